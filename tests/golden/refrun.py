@@ -1,0 +1,58 @@
+"""Run the UNMODIFIED reference PicketFence (stub-imported from /root/reference) on an
+ndarray and flatten what it computed into the same dict layout as oracle.pf_oracle.pf_analyze.
+Only usable where /root/reference exists (this container); used by make_pf_golden.py and
+tests/test_oracle_vs_reference.py."""
+from __future__ import annotations
+
+import io
+import types
+
+import numpy as np
+
+from oracle.refstub import FakeDicomDataset, import_reference
+
+
+def reference_pf(frame, pixel_spacing_mm, sid, ctor_kwargs=None, analyze_kwargs=None):
+    import_reference()
+    from pylinac import picketfence as rpf
+    from pylinac.core import image as rimage
+
+    ds = FakeDicomDataset(frame, pixel_spacing_mm, sid=sid)
+    old = rimage.retrieve_dicom_file, rimage.pixels
+    rimage.retrieve_dicom_file = lambda path: ds
+    rimage.pixels = types.SimpleNamespace(apply_rescale=lambda arr, md: arr)
+    try:
+        pf = rpf.PicketFence(io.BytesIO(b"fake"), **(ctor_kwargs or {}))
+    finally:
+        rimage.retrieve_dicom_file, rimage.pixels = old
+    pf.analyze(**(analyze_kwargs or {}))
+    rd = pf.results_data()
+    out = {}
+    out["shape"] = tuple(pf.image.shape)
+    out["dpmm"] = float(pf.image.dpmm)
+    out["orientation"] = 0 if pf.orientation == rpf.Orientation.UP_DOWN else 1
+    out["n_meas"] = len(pf.mlc_meas)
+    out["meas_leaf"] = np.array([m.leaf_num for m in pf.mlc_meas], dtype=np.int64)
+    out["meas_picket"] = np.array([m.picket_num for m in pf.mlc_meas], dtype=np.int64)
+    out["meas_position"] = np.array([list(m.position) for m in pf.mlc_meas], dtype=np.float64)
+    out["meas_error"] = np.array([list(m.error) for m in pf.mlc_meas], dtype=np.float64)
+    out["meas_width_mm"] = np.array([m.profile.field_width_mm for m in pf.mlc_meas], dtype=np.float64)
+    out["picket_idx"] = np.array(sorted({int(m._approximate_idx) for m in pf.mlc_meas}), dtype=np.int64)
+    out["picket_spacing"] = float(pf.mlc_meas[0]._spacing)
+    out["fits"] = np.array([np.asarray(p.fit.coefficients, dtype=float) for p in pf.pickets])
+    out["percent_passing"] = rd.percent_leaves_passing
+    out["max_error"] = rd.max_error_mm
+    out["abs_median_error"] = rd.absolute_median_error_mm
+    out["max_error_picket"] = int(rd.max_error_picket)
+    out["max_error_leaf"] = rd.max_error_leaf
+    out["passed"] = bool(rd.passed)
+    out["failed_leaves"] = list(rd.failed_leaves)
+    out["offsets_from_cax_mm"] = np.array(rd.offsets_from_cax_mm)
+    out["mean_picket_spacing"] = rd.mean_picket_spacing_mm
+    out["mlc_skew"] = rd.mlc_skew
+    out["number_of_pickets"] = rd.number_of_pickets
+    out["picket_widths"] = np.array([[rd.picket_widths[f"picket_{k}"][s] for s in ("max", "mean", "median", "min")]
+                                     for k in range(rd.number_of_pickets)])
+    out["mlc_positions_by_leaf"] = rd.mlc_positions_by_leaf
+    out["mlc_errors_by_leaf"] = rd.mlc_errors_by_leaf
+    return out
