@@ -1,0 +1,244 @@
+/* libepid -- B200-native (sm_100a) EPID image-analysis hot path.  C-ABI boundary.
+ *
+ * The reference (jrkerns/pylinac v3.46.0) is pure Python and has NO FFI of its own: its numerical
+ * work goes through numpy / scipy.ndimage / scipy.signal call sites inside pylinac/core/image.py,
+ * pylinac/core/array_utils.py, pylinac/core/profile.py and the module-level analyze() methods.
+ * Each entry point below replaces one of those call sites (cited as file:line of the reference);
+ * pylinac_b200/_native.py is the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - plain C, no exceptions; every function returns an int32 status (EPID_OK == 0, negative = error).
+ *  - images are row-major [row=y][col=x]; a "batch" is n equal-sized frames, contiguous.
+ *  - host pointers are owned by the caller; device memory is owned by ctx / batch handles.
+ *  - calls are synchronous unless stated otherwise (they return after the result is in host memory).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point returns EPID_ERR_NO_DEVICE.
+ */
+#ifndef EPID_H
+#define EPID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ----------------------------------------------------------------------------------------- status */
+enum {
+    EPID_OK = 0,
+    EPID_ERR_NO_DEVICE = -1,      /* no CUDA device / driver */
+    EPID_ERR_CUDA = -2,           /* CUDA runtime error, see epid_last_error() */
+    EPID_ERR_INVALID = -3,        /* bad argument (maps to ValueError) */
+    EPID_ERR_UNSUPPORTED = -4,    /* size / dtype outside what the kernels support */
+    EPID_ERR_NOMEM = -5,
+    EPID_ERR_NCCL = -6
+};
+
+/* element types of image batches (numpy dtypes the reference's operators preserve, core/array_utils.py) */
+enum { EPID_U8 = 0, EPID_U16 = 1, EPID_I32 = 2, EPID_F32 = 3, EPID_F64 = 4, EPID_I16 = 5, EPID_I64 = 6 };
+
+typedef struct epid_ctx epid_ctx;     /* one per device: stream(s), scratch, optional NCCL communicator */
+typedef struct epid_batch epid_batch; /* n frames resident in HBM */
+
+/* ----------------------------------------------------------------------------------------- context */
+int32_t epid_device_count(int32_t* count);                    /* EPID_OK with *count == 0 if no GPU */
+int32_t epid_ctx_create(int32_t device, epid_ctx** out);
+int32_t epid_ctx_destroy(epid_ctx* ctx);
+const char* epid_last_error(void);                             /* thread-local message of the last failure */
+int32_t epid_sync(epid_ctx* ctx);
+int32_t epid_device_info(epid_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, size_t* hbm_bytes);
+int32_t epid_launch_count(epid_ctx* ctx, int64_t* launches);   /* kernels launched by this ctx so far */
+int32_t epid_version(void);
+
+/* pinned host memory (for the H2D legs of the batched entry points) */
+int32_t epid_host_alloc(size_t bytes, void** out);
+int32_t epid_host_free(void* p);
+
+/* ----------------------------------------------------------------------------------------- batches */
+/* replaces: ArrayImage(array) / DicomImage pixel_array  (core/image.py:1818-1848, 1431-1444) */
+int32_t epid_batch_upload(epid_ctx* ctx, const void* host, int32_t dtype, int32_t n, int32_t h, int32_t w, epid_batch** out);
+int32_t epid_batch_alloc(epid_ctx* ctx, int32_t dtype, int32_t n, int32_t h, int32_t w, epid_batch** out);
+int32_t epid_batch_download(epid_batch* b, void* host);        /* whole batch, native dtype */
+int32_t epid_batch_free(epid_batch* b);
+int32_t epid_batch_shape(const epid_batch* b, int32_t* dtype, int32_t* n, int32_t* h, int32_t* w);
+int32_t epid_batch_device_ptr(const epid_batch* b, void** dptr);
+
+/* ----------------------------------------------------------------------------------------- frame statistics
+ * One streaming read of every frame: min, max, sum, row sums, column sums, exact order statistics.
+ * replaces: array.min()/max()/mean() (core/image.py:851,896; picketfence.py:231-232), np.percentile / np.median
+ * of a full frame (picketfence.py:233,1510; core/image.py:918-920; winston_lutz.py:709,775; starshot.py:227,286),
+ * np.sum/np.mean(image, axis) (picketfence.py:748-750,1513-1514; field_analysis.py:488-506).
+ * The view [r0:r0+vh, c0:c0+vw] of each frame is analysed (crop is a view: core/image.py:714-745).
+ * Integer dtypes U8/U16 only (exact integer histogram); q in percent, numpy 'linear' method.
+ * Outputs (host, may be NULL): min,max: double[n]; sum: double[n] (exact integer sums < 2^53);
+ * rowsum: double[n*vh] (sum over columns of each row); colsum: double[n*vw]; pct: double[n*nq]. */
+int32_t epid_frame_stats(epid_ctx* ctx, const epid_batch* b, int32_t r0, int32_t c0, int32_t vh, int32_t vw,
+                         const double* q_percent, int32_t nq,
+                         double* mn, double* mx, double* sum, double* rowsum, double* colsum, double* pct);
+/* full 65536-bin histogram of the view (uint32 counts [n][65536]); U8/U16 only */
+int32_t epid_frame_histogram(epid_ctx* ctx, const epid_batch* b, int32_t r0, int32_t c0, int32_t vh, int32_t vw, uint32_t* hist);
+
+/* ----------------------------------------------------------------------------------------- element-wise operators
+ * All write a NEW batch (the reference rebinds self.array to a fresh ndarray, core/image.py:712,757,798,852,866). */
+/* array_utils.invert  (core/array_utils.py:75-77): -a + max + min in the array's own dtype (modular for uints) */
+int32_t epid_invert(epid_ctx* ctx, const epid_batch* in, epid_batch** out);
+/* array_utils.bit_invert (core/array_utils.py:81-89): integer dtypes only, else EPID_ERR_INVALID */
+int32_t epid_bit_invert(epid_ctx* ctx, const epid_batch* in, epid_batch** out);
+/* array_utils.ground (core/array_utils.py:93-102): a - min + value, same dtype; mins: double[n] (may be NULL) */
+int32_t epid_ground(epid_ctx* ctx, const epid_batch* in, double value, epid_batch** out, double* mins);
+/* array_utils.normalize (core/array_utils.py:64-71): a / (value or max) -> F64; use_max != 0 ignores value */
+int32_t epid_normalize(epid_ctx* ctx, const epid_batch* in, int32_t use_max, double value, epid_batch** out);
+/* BaseImage.threshold (core/image.py:785-800): keep a >= t (kind 0, 'high') or a <= t (kind 1), else 0; same dtype */
+int32_t epid_threshold(epid_ctx* ctx, const epid_batch* in, double t, int32_t kind, epid_batch** out);
+/* BaseImage.as_binary (core/image.py:802-815): (a >= t) -> I64 0/1 */
+int32_t epid_binarize(epid_ctx* ctx, const epid_batch* in, double t, epid_batch** out);
+
+/* ----------------------------------------------------------------------------------------- stencils */
+/* scipy.ndimage.median_filter(a, size=k) as called by array_utils.filter (core/array_utils.py:131):
+ * full k x k footprint, mode='reflect', rank k*k/2, dtype preserved. */
+int32_t epid_median_filter(epid_ctx* ctx, const epid_batch* in, int32_t size, epid_batch** out);
+/* scipy.ndimage.gaussian_filter(a, sigma) as called by array_utils.filter (core/array_utils.py:133):
+ * separable, axis 0 then axis 1, radius int(4*sigma+0.5), mode='reflect', float64 accumulate,
+ * result of EACH pass cast to the input dtype (truncation for integers). */
+int32_t epid_gaussian_filter(epid_ctx* ctx, const epid_batch* in, double sigma, epid_batch** out);
+/* Same passes with caller-supplied correlate1d weights (2*radius+1 doubles).  The python binding passes the weights
+ * scipy itself computes (scipy/ndimage/_filters.py:_gaussian_kernel1d) so integer results are bit-exact.
+ * axes: 3 = axis 0 then axis 1 (2-D image), 1 = axis 0 only, 2 = axis 1 only (1-D profile stored as one row). */
+int32_t epid_correlate1d_passes(epid_ctx* ctx, const epid_batch* in, const double* weights, int32_t radius, int32_t axes, epid_batch** out);
+/* scipy.ndimage.sobel(a, axis) (core/image.py:1006-1007, BaseImage.gamma): reflect, same dtype semantics; out F32/F64 */
+int32_t epid_sobel(epid_ctx* ctx, const epid_batch* in, int32_t axis, epid_batch** out);
+
+/* ----------------------------------------------------------------------------------------- 1-D profiles
+ * pylinac.core.profile.find_peaks (core/profile.py:2545-2649) == scipy.signal.find_peaks(height, distance,
+ * prominence, width=min_width, rel_height = 1 - fwxm_height) + search-region trimming + top-max_number selection.
+ * values: host double[n].  Arguments follow the reference's python signature after _parse_peak_args has NOT yet
+ * been applied (threshold in [0,1] is a ratio of the range, separation in [0,1] a ratio of len, region <= 1 ratios).
+ * peak_sort: 0 = 'prominences', 1 = 'peak_heights'.  max_number <= 0: all.  required_prominence < 0: none.
+ * Outputs (capacity cap each): idx int64; heights, prominences, left_bases(int64), right_bases(int64), widths,
+ * width_heights, left_ips, right_ips double.  *count = number of peaks returned. */
+typedef struct {
+    double threshold;           /* -inf allowed */
+    double peak_separation;
+    int32_t max_number;
+    double fwxm_height;         /* 0..1 */
+    double min_width;
+    double search_lo, search_hi;
+    int32_t peak_sort;
+    double required_prominence; /* < 0: None */
+} epid_peak_params;
+
+int32_t epid_find_peaks(epid_ctx* ctx, const double* values, int32_t n, const epid_peak_params* p, int32_t cap,
+                        int64_t* idx, double* heights, double* prominences, int64_t* left_bases, int64_t* right_bases,
+                        double* widths, double* width_heights, double* left_ips, double* right_ips, int32_t* count);
+
+/* ----------------------------------------------------------------------------------------- Picket Fence
+ * PicketFence(image).analyze(**params) + the scalar set of results_data()  (picketfence.py:209-219, 280-329,
+ * 636-912, 1313-1363, 1501-1743, 1857-1923) for a batch of frames, one result per frame. */
+#define EPID_PF_MAX_PICKETS 32
+#define EPID_PF_MAX_LEAVES 160
+
+enum { /* per-frame status (maps to the reference's exceptions) */
+    EPID_PF_OK = 0,
+    EPID_PF_NO_PICKETS = 1,        /* ValueError "No pickets were found" (picketfence.py:760-764) */
+    EPID_PF_NO_MEASUREMENTS = 2,   /* ValueError "No MLC measurements were found" (picketfence.py:804-807) */
+    EPID_PF_TOO_MANY_PICKETS = 3,  /* more than EPID_PF_MAX_PICKETS peaks (unsupported) */
+    EPID_PF_WINDOW_NO_PEAK = 4,    /* reference would raise IndexError inside FWXMProfile.field_edge_idx */
+    EPID_PF_CAPACITY = 5,          /* measurement table capacity exceeded */
+    EPID_PF_FLAT_IMAGE = 6         /* max == min: the reference divides by zero */
+};
+
+typedef struct {
+    /* constructor (picketfence.py:280-329; PFDicomImage :209-219) */
+    double dpmm;                 /* image.dpmm (core/image.py:1534-1547) */
+    int32_t crop_px;             /* int(round(crop_mm * dpmm)) */
+    int32_t filter_size;         /* median filter size, 0 = None */
+    /* analyze() (picketfence.py:636-654) */
+    double tolerance;
+    double action_tolerance;     /* < 0: None */
+    int32_t num_pickets;         /* 0: None */
+    int32_t sag_px;              /* int(round(sag_adjustment * dpmm)) */
+    int32_t orientation;         /* -1 auto, 0 Up-Down, 1 Left-Right */
+    int32_t invert;
+    double leaf_analysis_width_ratio;
+    double picket_spacing;       /* < 0: None (auto) */
+    double height_threshold;
+    double edge_threshold;
+    int32_t peak_sort;           /* 0 'prominences', 1 'peak_heights' */
+    double required_prominence;
+    int32_t separate_leaves;
+    double nominal_gap_mm;
+    int32_t has_cax_override;    /* PFDicomImage.center override (picketfence.py:246-260) */
+    double cax_x_px, cax_y_px;   /* final centre in pixels when has_cax_override */
+    /* MLC arrangement (picketfence.py:68-135): centres (mm), widths (mm), leaf numbers, in the reference's order */
+    int32_t n_leaves;
+    double leaf_center_mm[EPID_PF_MAX_LEAVES];
+    double leaf_width_mm[EPID_PF_MAX_LEAVES];
+    int32_t leaf_num[EPID_PF_MAX_LEAVES];
+} epid_pf_params;
+
+typedef struct { /* one per frame */
+    int32_t status;
+    int32_t orientation;                 /* 0 Up-Down, 1 Left-Right */
+    int32_t noise_median_passes;         /* how often _check_for_noise filtered (picketfence.py:221-227) */
+    int32_t corner_inverted;             /* check_inversion fired (core/image.py:868-897) */
+    int32_t height, width;               /* analysed (cropped) shape */
+    int32_t n_pickets;
+    int32_t n_meas;                      /* rows of the measurement table that belong to this frame (after pruning) */
+    int32_t n_leaves_removed;            /* leaf rows dropped by the median-count rule (picketfence.py:810-828) */
+    int32_t passed;
+    int32_t max_error_picket;
+    int32_t max_error_leaf;              /* leaf number; for separate_leaves bank in max_error_bank (0 = A, 1 = B) */
+    int32_t max_error_bank;
+    int32_t n_failed;                    /* number of failing measurements (see table 'passed' flags) */
+    double picket_spacing_px;
+    double percent_passing;
+    double max_error_mm;
+    double abs_median_error_mm;
+    double mean_picket_spacing_mm;
+    double mlc_skew;
+    double cax_px;                       /* image.center component along leaf travel */
+    int32_t picket_idx[EPID_PF_MAX_PICKETS];      /* find_fwxm_peaks indices (bit-exact target) */
+    double picket_val[EPID_PF_MAX_PICKETS];
+    double fit_slope[EPID_PF_MAX_PICKETS];        /* np.polyfit(deg 1) of each picket */
+    double fit_intercept[EPID_PF_MAX_PICKETS];
+    double offsets_from_cax_mm[EPID_PF_MAX_PICKETS];
+    double picket_width_max[EPID_PF_MAX_PICKETS]; /* picket_width_stat (picketfence.py:471-491) */
+    double picket_width_mean[EPID_PF_MAX_PICKETS];
+    double picket_width_median[EPID_PF_MAX_PICKETS];
+    double picket_width_min[EPID_PF_MAX_PICKETS];
+} epid_pf_summary;
+
+typedef struct { /* one per kept MLCValue, leaf-major / picket-minor like PicketFence.mlc_meas */
+    int32_t leaf_num;
+    int32_t picket;
+    int32_t passed[2];
+    double position[2];      /* px along leaf travel; [1] only for separate_leaves */
+    double error[2];         /* mm */
+    double width_mm;         /* profile.field_width_mm */
+} epid_pf_meas;
+
+/* device-resident batch (uint16): results to host.  meas: [n][meas_cap].  Synchronous. */
+int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p,
+                        epid_pf_summary* summary, epid_pf_meas* meas, int32_t meas_cap);
+/* end-to-end: host frames [n][h][w] uint16 (pinned or pageable) -> chunked H2D overlapped with compute -> results. */
+int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, int32_t h, int32_t w,
+                             const epid_pf_params* p, epid_pf_summary* summary, epid_pf_meas* meas, int32_t meas_cap);
+/* timing hooks for bench.py: run the device-resident pipeline `iters` times back to back (results stay on the
+ * device except the last), return the CUDA-event time of the whole region and of the frame-statistics kernel. */
+int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters,
+                      float* total_ms, float* stats_kernel_ms, int64_t* launches);
+
+/* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
+ * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
+ * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */
+int32_t epid_comm_unique_id(void* id128);
+int32_t epid_comm_init(epid_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
+int32_t epid_comm_destroy(epid_ctx* ctx);
+/* all ranks contribute bytes_per_rank bytes (host); `all` (host, nranks*bytes_per_rank) is filled on every rank */
+int32_t epid_gather_results(epid_ctx* ctx, const void* local, size_t bytes_per_rank, void* all);
+int32_t epid_barrier(epid_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPID_H */

@@ -1,0 +1,376 @@
+"""ctypes binding of ``libepid.so`` (the C-ABI declared in ``include/epid.h``).
+
+This is the only module that touches the native library.  There is NO CPU fallback: if the shared
+library is missing, or no CUDA device is visible, the compute entry points raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libepid.so")
+
+EPID_OK = 0
+ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NCCL = -1, -2, -3, -4, -5, -6
+
+U8, U16, I32, F32, F64, I16, I64 = 0, 1, 2, 3, 4, 5, 6
+_NP2DT = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.int32): I32, np.dtype(np.float32): F32,
+          np.dtype(np.float64): F64, np.dtype(np.int16): I16, np.dtype(np.int64): I64}
+_DT2NP = {v: k for k, v in _NP2DT.items()}
+
+PF_MAX_PICKETS = 32
+PF_MAX_LEAVES = 160
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libepid error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class NoDeviceError(NativeError):
+    pass
+
+
+class PeakParams(C.Structure):
+    _fields_ = [("threshold", C.c_double), ("peak_separation", C.c_double), ("max_number", C.c_int32),
+                ("fwxm_height", C.c_double), ("min_width", C.c_double), ("search_lo", C.c_double),
+                ("search_hi", C.c_double), ("peak_sort", C.c_int32), ("required_prominence", C.c_double)]
+
+
+class PFParams(C.Structure):
+    _fields_ = [("dpmm", C.c_double), ("crop_px", C.c_int32), ("filter_size", C.c_int32), ("tolerance", C.c_double),
+                ("action_tolerance", C.c_double), ("num_pickets", C.c_int32), ("sag_px", C.c_int32),
+                ("orientation", C.c_int32), ("invert", C.c_int32), ("leaf_analysis_width_ratio", C.c_double),
+                ("picket_spacing", C.c_double), ("height_threshold", C.c_double), ("edge_threshold", C.c_double),
+                ("peak_sort", C.c_int32), ("required_prominence", C.c_double), ("separate_leaves", C.c_int32),
+                ("nominal_gap_mm", C.c_double), ("has_cax_override", C.c_int32), ("cax_x_px", C.c_double),
+                ("cax_y_px", C.c_double), ("n_leaves", C.c_int32), ("leaf_center_mm", C.c_double * PF_MAX_LEAVES),
+                ("leaf_width_mm", C.c_double * PF_MAX_LEAVES), ("leaf_num", C.c_int32 * PF_MAX_LEAVES)]
+
+
+class PFSummary(C.Structure):
+    _fields_ = [("status", C.c_int32), ("orientation", C.c_int32), ("noise_median_passes", C.c_int32),
+                ("corner_inverted", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_pickets", C.c_int32),
+                ("n_meas", C.c_int32), ("n_leaves_removed", C.c_int32), ("passed", C.c_int32),
+                ("max_error_picket", C.c_int32), ("max_error_leaf", C.c_int32), ("max_error_bank", C.c_int32),
+                ("n_failed", C.c_int32), ("picket_spacing_px", C.c_double), ("percent_passing", C.c_double),
+                ("max_error_mm", C.c_double), ("abs_median_error_mm", C.c_double), ("mean_picket_spacing_mm", C.c_double),
+                ("mlc_skew", C.c_double), ("cax_px", C.c_double), ("picket_idx", C.c_int32 * PF_MAX_PICKETS),
+                ("picket_val", C.c_double * PF_MAX_PICKETS), ("fit_slope", C.c_double * PF_MAX_PICKETS),
+                ("fit_intercept", C.c_double * PF_MAX_PICKETS), ("offsets_from_cax_mm", C.c_double * PF_MAX_PICKETS),
+                ("picket_width_max", C.c_double * PF_MAX_PICKETS), ("picket_width_mean", C.c_double * PF_MAX_PICKETS),
+                ("picket_width_median", C.c_double * PF_MAX_PICKETS), ("picket_width_min", C.c_double * PF_MAX_PICKETS)]
+
+
+class PFMeas(C.Structure):
+    _fields_ = [("leaf_num", C.c_int32), ("picket", C.c_int32), ("passed", C.c_int32 * 2), ("position", C.c_double * 2),
+                ("error", C.c_double * 2), ("width_mm", C.c_double)]
+
+
+PF_SUMMARY_DTYPE = np.dtype([
+    ("status", "<i4"), ("orientation", "<i4"), ("noise_median_passes", "<i4"), ("corner_inverted", "<i4"),
+    ("height", "<i4"), ("width", "<i4"), ("n_pickets", "<i4"), ("n_meas", "<i4"), ("n_leaves_removed", "<i4"),
+    ("passed", "<i4"), ("max_error_picket", "<i4"), ("max_error_leaf", "<i4"), ("max_error_bank", "<i4"),
+    ("n_failed", "<i4"), ("picket_spacing_px", "<f8"), ("percent_passing", "<f8"), ("max_error_mm", "<f8"),
+    ("abs_median_error_mm", "<f8"), ("mean_picket_spacing_mm", "<f8"), ("mlc_skew", "<f8"), ("cax_px", "<f8"),
+    ("picket_idx", "<i4", (PF_MAX_PICKETS,)), ("picket_val", "<f8", (PF_MAX_PICKETS,)),
+    ("fit_slope", "<f8", (PF_MAX_PICKETS,)), ("fit_intercept", "<f8", (PF_MAX_PICKETS,)),
+    ("offsets_from_cax_mm", "<f8", (PF_MAX_PICKETS,)), ("picket_width_max", "<f8", (PF_MAX_PICKETS,)),
+    ("picket_width_mean", "<f8", (PF_MAX_PICKETS,)), ("picket_width_median", "<f8", (PF_MAX_PICKETS,)),
+    ("picket_width_min", "<f8", (PF_MAX_PICKETS,))], align=True)
+PF_MEAS_DTYPE = np.dtype([("leaf_num", "<i4"), ("picket", "<i4"), ("passed", "<i4", (2,)), ("position", "<f8", (2,)),
+                          ("error", "<f8", (2,)), ("width_mm", "<f8")], align=True)
+assert PF_SUMMARY_DTYPE.itemsize == C.sizeof(PFSummary), (PF_SUMMARY_DTYPE.itemsize, C.sizeof(PFSummary))
+assert PF_MEAS_DTYPE.itemsize == C.sizeof(PFMeas)
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(force: bool = False) -> str:
+    """Compile libepid.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.run(["make", "-C", src, "clean"], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", src, "-j8"], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "epid_device_count": [C.POINTER(C.c_int32)],
+    "epid_ctx_create": [C.c_int32, C.POINTER(_P)],
+    "epid_ctx_destroy": [_P],
+    "epid_sync": [_P],
+    "epid_device_info": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_size_t)],
+    "epid_launch_count": [_P, C.POINTER(C.c_int64)],
+    "epid_version": [],
+    "epid_host_alloc": [C.c_size_t, C.POINTER(_P)],
+    "epid_host_free": [_P],
+    "epid_batch_upload": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)],
+    "epid_batch_alloc": [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)],
+    "epid_batch_download": [_P, _P],
+    "epid_batch_free": [_P],
+    "epid_batch_shape": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "epid_batch_device_ptr": [_P, C.POINTER(_P)],
+    "epid_frame_stats": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, _P, _P],
+    "epid_frame_histogram": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P],
+    "epid_invert": [_P, _P, C.POINTER(_P)],
+    "epid_bit_invert": [_P, _P, C.POINTER(_P)],
+    "epid_ground": [_P, _P, C.c_double, C.POINTER(_P), _P],
+    "epid_normalize": [_P, _P, C.c_int32, C.c_double, C.POINTER(_P)],
+    "epid_threshold": [_P, _P, C.c_double, C.c_int32, C.POINTER(_P)],
+    "epid_binarize": [_P, _P, C.c_double, C.POINTER(_P)],
+    "epid_median_filter": [_P, _P, C.c_int32, C.POINTER(_P)],
+    "epid_gaussian_filter": [_P, _P, C.c_double, C.POINTER(_P)],
+    "epid_correlate1d_passes": [_P, _P, _P, C.c_int32, C.c_int32, C.POINTER(_P)],
+    "epid_sobel": [_P, _P, C.c_int32, C.POINTER(_P)],
+    "epid_find_peaks": [_P, _P, C.c_int32, C.POINTER(PeakParams), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                        C.POINTER(C.c_int32)],
+    "epid_pf_analyze": [_P, _P, C.POINTER(PFParams), _P, _P, C.c_int32],
+    "epid_pf_analyze_host": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PFParams), _P, _P, C.c_int32],
+    "epid_pf_bench": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                      C.POINTER(C.c_int64)],
+    "epid_comm_unique_id": [_P],
+    "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
+    "epid_comm_destroy": [_P],
+    "epid_gather_results": [_P, _P, C.c_size_t, _P],
+    "epid_barrier": [_P],
+}
+
+
+def lib():
+    """Load libepid.so (once).  Raises if the native extension has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise ImportError(
+                        f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(pylinac_b200 has no CPU fallback).")
+                handle = C.CDLL(LIB_PATH)
+                for name, args in _SIGNATURES.items():
+                    fn = getattr(handle, name)
+                    fn.argtypes = args
+                    fn.restype = C.c_int32
+                handle.epid_last_error.argtypes = []
+                handle.epid_last_error.restype = C.c_char_p
+                _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGNATURES) + ["epid_last_error"])
+
+
+def check(rc):
+    if rc != EPID_OK:
+        msg = lib().epid_last_error().decode("utf-8", "replace")
+        if rc == ERR_NO_DEVICE:
+            raise NoDeviceError(rc, msg)
+        if rc == ERR_INVALID:
+            raise ValueError(msg)
+        raise NativeError(rc, msg)
+
+
+def device_count() -> int:
+    n = C.c_int32(0)
+    check(lib().epid_device_count(C.byref(n)))
+    return n.value
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One per device (epid_ctx)."""
+
+    _default = {}
+
+    def __init__(self, device: int = 0):
+        h = _P()
+        check(lib().epid_ctx_create(device, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    @classmethod
+    def default(cls, device: int | None = None) -> "Context":
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if device_count() > 1 else 0
+            if device >= device_count():
+                device = 0
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def close(self):
+        if self.handle:
+            lib().epid_ctx_destroy(self.handle)
+            self.handle = None
+
+    def sync(self):
+        check(lib().epid_sync(self.handle))
+
+    def info(self):
+        sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
+        check(lib().epid_device_info(self.handle, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": mem.value}
+
+    def launches(self) -> int:
+        n = C.c_int64()
+        check(lib().epid_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+
+class Batch:
+    """n frames resident in HBM (epid_batch)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.handle = handle
+
+    @classmethod
+    def upload(cls, ctx: Context, arr: np.ndarray) -> "Batch":
+        a = np.ascontiguousarray(arr)
+        if a.ndim == 2:
+            a = a[None]
+        if a.ndim != 3:
+            raise ValueError("expected [n, h, w] or [h, w]")
+        if a.dtype not in _NP2DT:
+            raise TypeError(f"unsupported dtype {a.dtype}")
+        h = _P()
+        check(lib().epid_batch_upload(ctx.handle, _ptr(a), _NP2DT[a.dtype], a.shape[0], a.shape[1], a.shape[2], C.byref(h)))
+        return cls(ctx, h)
+
+    @property
+    def shape_dtype(self):
+        dt, n, h, w = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(lib().epid_batch_shape(self.handle, C.byref(dt), C.byref(n), C.byref(h), C.byref(w)))
+        return (n.value, h.value, w.value), _DT2NP[dt.value]
+
+    def download(self) -> np.ndarray:
+        shape, dt = self.shape_dtype
+        out = np.empty(shape, dt)
+        check(lib().epid_batch_download(self.handle, _ptr(out)))
+        return out
+
+    def free(self):
+        if self.handle:
+            lib().epid_batch_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def _unary(self, fn, *args) -> "Batch":
+        h = _P()
+        check(fn(self.ctx.handle, self.handle, *args, C.byref(h)))
+        return Batch(self.ctx, h)
+
+
+def pinned_empty(shape, dtype=np.uint16) -> np.ndarray:
+    """numpy array backed by page-locked host memory (epid_host_alloc); freed when the array dies."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = _P()
+    check(lib().epid_host_alloc(nbytes, C.byref(p)))
+    buf = (C.c_char * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib().epid_host_free(self.ptr)
+            except Exception:
+                pass
+
+    _PINNED_OWNERS[arr.ctypes.data] = _Owner(p)
+    return arr
+
+
+_PINNED_OWNERS: dict = {}
+
+
+def frame_stats(ctx: Context, batch: Batch, view=None, percentiles=()):
+    (n, h, w), _ = batch.shape_dtype
+    r0, c0, vh, vw = view if view is not None else (0, 0, h, w)
+    q = np.asarray(percentiles, dtype=np.float64)
+    nq = q.size
+    mn, mx, sm = np.empty(n), np.empty(n), np.empty(n)
+    rows, cols = np.empty((n, vh)), np.empty((n, vw))
+    pct = np.empty((n, max(nq, 1)))
+    check(lib().epid_frame_stats(ctx.handle, batch.handle, r0, c0, vh, vw, _ptr(q) if nq else None, nq, _ptr(mn), _ptr(mx),
+                                 _ptr(sm), _ptr(rows), _ptr(cols), _ptr(pct)))
+    return {"min": mn, "max": mx, "sum": sm, "rowsum": rows, "colsum": cols, "percentiles": pct[:, :nq]}
+
+
+def frame_histogram(ctx: Context, batch: Batch, view=None) -> np.ndarray:
+    (n, h, w), _ = batch.shape_dtype
+    r0, c0, vh, vw = view if view is not None else (0, 0, h, w)
+    hist = np.empty((n, 65536), np.uint32)
+    check(lib().epid_frame_histogram(ctx.handle, batch.handle, r0, c0, vh, vw, _ptr(hist)))
+    return hist
+
+
+def find_peaks(ctx: Context, values, threshold=-np.inf, peak_separation=0, max_number=None, fwxm_height=0.5, min_width=0,
+               search_region=(0.0, 1.0), peak_sort="prominences", required_prominence=None):
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    n = v.size
+    p = PeakParams(float(threshold), float(peak_separation), int(max_number) if max_number else 0, float(fwxm_height),
+                   float(min_width), float(search_region[0]), float(search_region[1]), 1 if peak_sort == "peak_heights" else 0,
+                   -1.0 if required_prominence is None else float(required_prominence))
+    cap = n // 2 + 2
+    idx = np.empty(cap, np.int64)
+    lb, rb = np.empty(cap, np.int64), np.empty(cap, np.int64)
+    hts, prom, wid, wh, lip, rip = (np.empty(cap) for _ in range(6))
+    cnt = C.c_int32()
+    check(lib().epid_find_peaks(ctx.handle, _ptr(v), n, C.byref(p), cap, _ptr(idx), _ptr(hts), _ptr(prom), _ptr(lb), _ptr(rb),
+                                _ptr(wid), _ptr(wh), _ptr(lip), _ptr(rip), C.byref(cnt)))
+    c = cnt.value
+    props = {"peak_heights": hts[:c].copy(), "prominences": prom[:c].copy(), "left_bases": lb[:c].copy(),
+             "right_bases": rb[:c].copy(), "widths": wid[:c].copy(), "width_heights": wh[:c].copy(),
+             "left_ips": lip[:c].copy(), "right_ips": rip[:c].copy()}
+    return idx[:c].copy(), props
+
+
+def pf_analyze(ctx: Context, frames, params: PFParams, meas_cap: int = 1024, host_pipeline: bool = False):
+    """frames: a Batch (device-resident) or a uint16 ndarray [n,h,w] (host; chunked H2D overlapped with compute)."""
+    if isinstance(frames, Batch):
+        (n, _, _), _ = frames.shape_dtype
+        summ = np.zeros(n, PF_SUMMARY_DTYPE)
+        meas = np.zeros((n, meas_cap), PF_MEAS_DTYPE)
+        check(lib().epid_pf_analyze(ctx.handle, frames.handle, C.byref(params), _ptr(summ), _ptr(meas), meas_cap))
+        return summ, meas
+    a = frames
+    if a.dtype != np.uint16:
+        raise TypeError("picket fence frames must be uint16")
+    if a.ndim == 2:
+        a = a[None]
+    a = np.ascontiguousarray(a)
+    n, h, w = a.shape
+    summ = np.zeros(n, PF_SUMMARY_DTYPE)
+    meas = np.zeros((n, meas_cap), PF_MEAS_DTYPE)
+    check(lib().epid_pf_analyze_host(ctx.handle, _ptr(a), n, h, w, C.byref(params), _ptr(summ), _ptr(meas), meas_cap))
+    return summ, meas
+
+
+def pf_bench(ctx: Context, batch: Batch, params: PFParams, iters: int):
+    total, stats = C.c_float(), C.c_float()
+    launches = C.c_int64()
+    check(lib().epid_pf_bench(ctx.handle, batch.handle, C.byref(params), iters, C.byref(total), C.byref(stats), C.byref(launches)))
+    return total.value, stats.value, launches.value

@@ -1,0 +1,86 @@
+"""Host-side scalar geometry helpers (mirror of the parts of pylinac/core/geometry.py the hot path uses:
+Point :70-224, Line :497-584).  Scalar work stays in Python."""
+from __future__ import annotations
+
+import math
+from collections.abc import Iterable
+
+import numpy as np
+
+
+class Point:
+    """core/geometry.py:70-224 (the subset used on the hot path)."""
+
+    def __init__(self, x=0, y=0, z=0, idx=None, value=None, as_int: bool = False):
+        if isinstance(x, Point):
+            x, y, z, idx, value = x.x, x.y, x.z, x.idx, x.value
+        elif isinstance(x, Iterable) and not isinstance(x, (str, bytes)):
+            seq = list(x)
+            x = seq[0] if len(seq) > 0 else 0
+            y = seq[1] if len(seq) > 1 else y
+            z = seq[2] if len(seq) > 2 else z
+        if as_int:
+            x, y, z = int(round(x)), int(round(y)), int(round(z))
+        self.x, self.y, self.z, self.idx, self.value = x, y, z, idx, value
+
+    def distance_to(self, thing) -> float:
+        p = Point(thing)
+        return math.sqrt((self.x - p.x) ** 2 + (self.y - p.y) ** 2 + (self.z - p.z) ** 2)
+
+    def as_array(self, coords=("x", "y", "z")) -> np.ndarray:
+        return np.array([getattr(self, c) for c in coords])
+
+    def __add__(self, other):
+        o = Point(other)
+        return Point(self.x + o.x, self.y + o.y, self.z + o.z)
+
+    def __sub__(self, other):
+        o = Point(other)
+        return Point(self.x - o.x, self.y - o.y, self.z - o.z)
+
+    def __eq__(self, other):
+        o = Point(other)
+        return self.x == o.x and self.y == o.y and self.z == o.z
+
+    def __repr__(self):
+        return f"Point(x={self.x:3.2f}, y={self.y:3.2f}, z={self.z:3.2f})"
+
+
+class Line:
+    """core/geometry.py:497-584"""
+
+    def __init__(self, point1, point2):
+        self.point1 = Point(point1)
+        self.point2 = Point(point2)
+
+    @property
+    def m(self) -> float:
+        return (self.point1.y - self.point2.y) / (self.point1.x - self.point2.x)
+
+    @property
+    def b(self) -> float:
+        return self.point1.y - (self.m * self.point1.x)
+
+    def y(self, x) -> float:
+        return self.m * x + self.b
+
+    def x(self, y) -> float:
+        return (y - self.b) / self.m
+
+    @property
+    def center(self) -> Point:
+        mid_x = np.abs((self.point2.x - self.point1.x) / 2 + self.point1.x)
+        mid_y = (self.point2.y - self.point1.y) / 2 + self.point1.y
+        return Point(mid_x, mid_y)
+
+    @property
+    def length(self) -> float:
+        return self.point1.distance_to(self.point2)
+
+    def distance_to(self, point) -> float:
+        point = Point(point).as_array()
+        lp1 = self.point1.as_array()
+        lp2 = self.point2.as_array()
+        numerator = np.sqrt(np.sum(np.power(np.cross((lp2 - lp1), (lp1 - point)), 2)))
+        denominator = np.sqrt(np.sum(np.power(lp2 - lp1, 2)))
+        return numerator / denominator

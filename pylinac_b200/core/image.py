@@ -1,0 +1,341 @@
+"""Image classes mirroring ``pylinac.core.image`` (reference file cited per method) whose pixel arithmetic runs
+in hand-written CUDA through ``libepid.so``.  Pure re-indexing (crop / flip / roll / rot90) stays a numpy view
+operation exactly like the reference; everything that touches pixel values is a native call.
+"""
+from __future__ import annotations
+
+import io
+import os
+import os.path as osp
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+from .. import _native as nat
+from .. import dicom
+from . import array_utils as au
+from .geometry import Point
+
+MM_PER_INCH = 25.4
+
+
+def _is_array(obj: Any) -> bool:
+    return isinstance(obj, np.ndarray)
+
+
+def _is_dicom(path) -> bool:
+    try:
+        return dicom.is_dicom(path)
+    except Exception:
+        return False
+
+
+def load(path, **kwargs):
+    """core/image.py:244-286.  ndarray -> ArrayImage, DICOM -> DicomImage.  (TIFF/JPG FileImage is file-format
+    plumbing outside the hot path and not provided.)"""
+    if isinstance(path, BaseImage):
+        return path
+    if _is_array(path):
+        return ArrayImage(path, **kwargs)
+    if _is_dicom(path):
+        return DicomImage(path, **kwargs)
+    raise TypeError(f"The argument `{path}` was not found to be a valid DICOM file, Image file, or array")
+
+
+class BaseImage:
+    """core/image.py:453-1102 (operators).  ``array`` is a host ndarray; operators rebind it to a fresh array."""
+
+    array: np.ndarray
+
+    def __init__(self, path):
+        self.metrics = []
+        self.metric_values = {}
+        if isinstance(path, (str, Path)) and not osp.isfile(path):
+            raise FileExistsError(f"File `{path}` does not exist. Verify the file path name.")
+        elif isinstance(path, (str, Path)):
+            self.path = path
+            self.base_path = osp.basename(path)
+        else:
+            try:
+                path.seek(0)
+                self.path = str(Path(path.name))
+            except AttributeError:
+                self.path = ""
+
+    # ------------------------------------------------------------------ geometry helpers (host)
+    @property
+    def center(self) -> Point:  # core/image.py:526-533
+        return Point((self.shape[1] / 2) - 0.5, (self.shape[0] / 2) - 0.5)
+
+    @property
+    def physical_shape(self):  # core/image.py:535-538
+        return self.shape[0] / self.dpmm, self.shape[1] / self.dpmm
+
+    @property
+    def shape(self):
+        return self.array.shape
+
+    @property
+    def size(self):
+        return self.array.size
+
+    @property
+    def ndim(self):
+        return self.array.ndim
+
+    @property
+    def dtype(self):
+        return self.array.dtype
+
+    def sum(self):
+        return self.array.sum()
+
+    def ravel(self):
+        return self.array.ravel()
+
+    @property
+    def flat(self):
+        return self.array.flat
+
+    def __len__(self):  # core/image.py:1098-1099
+        return len(self.array)
+
+    def __getitem__(self, item):  # core/image.py:1101-1102
+        return self.array[item]
+
+    def as_type(self, dtype):
+        return self.array.astype(dtype)
+
+    # ------------------------------------------------------------------ operators
+    def filter(self, size=0.05, kind: str = "median") -> None:  # core/image.py:695-712
+        self.array = au.filter(self.array, size=size, kind=kind)
+
+    def crop(self, pixels: int = 15, edges=("top", "bottom", "left", "right")) -> None:  # core/image.py:714-745
+        if pixels < 0:
+            raise ValueError("Pixels to remove must be a positive number")
+        if pixels == 0:
+            return
+        if "top" in edges:
+            self.array = self.array[pixels:, :]
+        if "bottom" in edges:
+            self.array = self.array[:-pixels, :]
+        if "left" in edges:
+            self.array = self.array[:, pixels:]
+        if "right" in edges:
+            self.array = self.array[:, :-pixels]
+        if self.array.size == 0:
+            raise ValueError("Too many pixels removed; array is empty. Pass a smaller crop value.")
+
+    def flipud(self) -> None:
+        self.array = np.flipud(self.array)
+
+    def fliplr(self) -> None:
+        self.array = np.fliplr(self.array)
+
+    def invert(self) -> None:  # core/image.py:755-757
+        self.array = au.invert(self.array)
+
+    def bit_invert(self) -> None:  # core/image.py:759-761
+        self.array = au.bit_invert(self.array)
+
+    def roll(self, direction: str = "x", amount: int = 1) -> None:  # core/image.py:763-774
+        axis = 1 if direction == "x" else 0
+        self.array = np.roll(self.array, amount, axis=axis)
+
+    def rot90(self, n: int = 1) -> None:
+        self.array = np.rot90(self.array, n)
+
+    def threshold(self, threshold: float, kind: str = "high") -> None:  # core/image.py:785-800
+        self.array = au.threshold(self.array, threshold, kind)
+
+    def as_binary(self, threshold):  # core/image.py:802-815
+        return ArrayImage(au.binarize(self.array, threshold))
+
+    def dist2edge_min(self, point) -> float:  # core/image.py:817-837
+        if isinstance(point, tuple):
+            point = Point(point)
+        rows, cols = self.shape[0], self.shape[1]
+        return min(rows - point.y, cols - point.x, point.y, point.x)
+
+    def ground(self) -> float:  # core/image.py:839-853
+        new, mn = au.ground_with_min(self.array)
+        self.array = new
+        return mn
+
+    def normalize(self, norm_val=None) -> None:  # core/image.py:855-866
+        if norm_val == "max":
+            norm_val = None
+        self.array = au.normalize(self.array, value=norm_val)
+
+    def check_inversion(self, box_size: int = 20, position=(0.0, 0.0)) -> None:  # core/image.py:868-897
+        a = self.array
+        row_pos = max(int(position[0] * a.shape[0]), 1)
+        col_pos = max(int(position[1] * a.shape[1]), 1)
+        boxes = (a[row_pos : row_pos + box_size, col_pos : col_pos + box_size],
+                 a[-row_pos - box_size : -row_pos, col_pos : col_pos + box_size],
+                 a[row_pos : row_pos + box_size, -col_pos - box_size : -col_pos],
+                 a[-row_pos - box_size : -row_pos, -col_pos - box_size : -col_pos])
+        # 4 * box_size^2 corner pixels: a host reduction of a few hundred values; the frame mean is native
+        avg = np.mean(boxes)
+        if avg > au.frame_mean(a):
+            self.invert()
+
+    def check_inversion_by_histogram(self, percentiles=(5, 50, 95)) -> bool:  # core/image.py:899-926
+        p_low, p_mid, p_high = au.percentile(self.array, percentiles)
+        was_inverted = False
+        if abs(p_mid - p_low) > abs(p_mid - p_high):
+            was_inverted = True
+            self.invert()
+        return was_inverted
+
+
+class ArrayImage(BaseImage):
+    """core/image.py:1818-1867"""
+
+    def __init__(self, array: np.ndarray, *, dpi: float | None = None, sid: float | None = None, dtype=None):
+        self.metrics = []
+        self.metric_values = {}
+        if dtype is not None:
+            self.array = np.array(array, dtype=dtype)
+        else:
+            self.array = array
+        self._dpi = dpi
+        self.sid = sid
+        self.path = ""
+
+    @property
+    def dpmm(self) -> float | None:
+        try:
+            return self.dpi / MM_PER_INCH
+        except Exception:
+            return None
+
+    @property
+    def dpi(self) -> float | None:
+        dpi = None
+        if self._dpi is not None:
+            dpi = self._dpi
+            if self.sid is not None:
+                dpi *= self.sid / 1000
+        return dpi
+
+
+class DicomImage(BaseImage):
+    """core/image.py:1383-1580 with pylinac_b200.dicom instead of pydicom."""
+
+    def __init__(self, path, *, dtype=None, dpi: float = None, sid: float = None, sad: float = 1000, raw_pixels: bool = False,
+                 invert_pixels: bool | None = None):
+        super().__init__(path)
+        self._sid = sid
+        self._dpi = dpi
+        self._sad = sad
+        self.metadata = dicom.dcmread(path)
+        pix = self.metadata.pixel_array
+        self._original_dtype = pix.dtype
+        self._raw_pixels = raw_pixels
+        self._invert_pixels = invert_pixels
+        self.array = pix.astype(dtype) if dtype is not None else pix.copy()
+        self.array = _rescale_dicom_values(self.array, self.metadata, raw_pixels, invert_pixels)
+
+    @property
+    def sid(self) -> float:
+        try:
+            return float(self.metadata.RTImageSID)
+        except (AttributeError, ValueError, TypeError):
+            return self._sid
+
+    @property
+    def sad(self) -> float:
+        try:
+            return float(self.metadata.RadiationMachineSAD)
+        except (AttributeError, ValueError, TypeError):
+            return self._sad
+
+    @property
+    def dpi(self) -> float:
+        try:
+            return self.dpmm * MM_PER_INCH
+        except Exception:
+            return self._dpi
+
+    @property
+    def dpmm(self) -> float:  # core/image.py:1534-1547
+        dpmm = None
+        for tag in ("PixelSpacing", "ImagePlanePixelSpacing"):
+            mmpd = self.metadata.get(tag)
+            if mmpd is not None:
+                dpmm = 1 / mmpd[0]
+                break
+        if dpmm is not None and self.sid is not None:
+            dpmm *= self.sid / self.sad
+        elif dpmm is None and self._dpi is not None:
+            dpmm = self._dpi / MM_PER_INCH
+        return dpmm
+
+    @property
+    def cax(self) -> Point:  # core/image.py:1550-1580
+        try:
+            mag_factor = self.sid / self.sad
+            t = self.metadata.XRayImageReceptorTranslation
+            return Point(self.center.x - t[0] * self.dpmm / mag_factor, self.center.y + t[1] * self.dpmm / mag_factor)
+        except (AttributeError, ValueError, TypeError, KeyError):
+            return self.center
+
+
+def _rescale_dicom_values(unscaled, metadata, raw_pixels, invert_pixels):
+    """core/image.py:363-389 (pydicom apply_rescale: only when RescaleSlope/Intercept are present)."""
+    if raw_pixels:
+        return unscaled
+    slope, intercept = metadata.get("RescaleSlope"), metadata.get("RescaleIntercept")
+    scaled = unscaled
+    if slope is not None and intercept is not None:
+        # pydicom.pixels.apply_rescale: arr * slope + intercept -> float64 (kept integral dtype when the map is identity)
+        if not (float(slope) == 1.0 and float(intercept) == 0.0):
+            scaled = unscaled.astype(np.float64) * float(slope) + float(intercept)
+        else:
+            scaled = unscaled.astype(np.float64)
+    sign = metadata.get("PixelIntensityRelationshipSign")
+    if invert_pixels or (invert_pixels is None and sign == -1):
+        scaled = scaled.max() - scaled + scaled.min()
+    return scaled
+
+
+class LinacDicomImage(DicomImage):
+    """core/image.py:1583-1730: gantry / collimator / couch angles from tags or overrides."""
+
+    def __init__(self, path, use_filenames: bool = False, axes_precision: int | None = None, missing_axis_value=0, **kwargs):
+        self._axis_overrides = {}
+        for axis in ("gantry", "coll", "couch"):
+            if axis in kwargs:
+                self._axis_overrides[axis] = kwargs.pop(axis)
+        self._axes_precision = axes_precision
+        self._missing_axis_value = missing_axis_value
+        super().__init__(path, **kwargs)
+        self._use_filenames = use_filenames
+
+    def _axis(self, key, tag):
+        if key in self._axis_overrides and self._axis_overrides[key] is not None:
+            v = self._axis_overrides[key]
+        else:
+            v = self.metadata.get(tag)
+            if v is None:
+                if self._missing_axis_value == "raise":
+                    raise ValueError(f"Axis {key} was not found in the DICOM tags")
+                v = self._missing_axis_value
+        v = float(v)
+        if self._axes_precision is not None:
+            v = round(v, self._axes_precision)
+        return v % 360 if v >= 360 else v
+
+    @property
+    def gantry_angle(self) -> float:
+        return self._axis("gantry", "GantryAngle")
+
+    @property
+    def collimator_angle(self) -> float:
+        return self._axis("coll", "BeamLimitingDeviceAngle")
+
+    @property
+    def couch_angle(self) -> float:
+        return self._axis("couch", "PatientSupportAngle")

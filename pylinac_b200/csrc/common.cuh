@@ -1,0 +1,105 @@
+// Shared internals of libepid (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/epid.h"
+
+namespace epid {
+
+void set_error(const char* fmt, ...);
+
+#define EPID_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::epid::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return EPID_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define EPID_REQUIRE(cond, code, ...)              \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::epid::set_error(__VA_ARGS__);        \
+            return (code);                         \
+        }                                          \
+    } while (0)
+
+inline size_t dtype_size(int dt) {
+    switch (dt) {
+        case EPID_U8: return 1;
+        case EPID_U16: case EPID_I16: return 2;
+        case EPID_I32: case EPID_F32: return 4;
+        case EPID_F64: case EPID_I64: return 8;
+    }
+    return 0;
+}
+
+}  // namespace epid
+
+struct epid_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    cudaStream_t stream = nullptr;       // main stream
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    void* nccl_comm = nullptr;           // ncclComm_t
+    int nranks = 1, rank = 0;
+    // reusable device scratch (grown on demand, freed with the ctx)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct epid_batch {
+    epid_ctx* ctx = nullptr;
+    int dtype = EPID_U16;
+    int n = 0, h = 0, w = 0;
+    void* dptr = nullptr;
+    bool owns = true;
+    size_t bytes() const { return (size_t)n * h * w * epid::dtype_size(dtype); }
+};
+
+namespace epid {
+int ensure_scratch(epid_ctx* ctx, size_t bytes);   // grows ctx->scratch
+int ensure_pinned(epid_ctx* ctx, size_t bytes);
+
+// ------------------------------------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
+
+}  // namespace epid

@@ -1,0 +1,210 @@
+// Block-cooperative scipy.signal.find_peaks on one fp64 profile (device code, one CTA per profile).
+//
+// Reproduces, stage for stage, what pylinac.core.profile.find_peaks (core/profile.py:2545-2623) obtains from
+// scipy.signal.find_peaks(x, height, distance, prominence, width, rel_height)   (scipy/signal/_peak_finding.py:
+// _local_maxima_1d, _select_by_peak_distance, _peak_prominences, _peak_widths; restated in SURVEY.md appendix B):
+//   local maxima (plateau midpoint) -> height >= hmin -> distance (highest first; among equal heights the
+//   right-most survives) -> prominences (wlen=None) -> prominence >= pmin -> widths at rel_height -> width >= wmin
+//   -> keep the max_number largest by `peak_sort`, returned left to right.
+// All arithmetic is IEEE fp64 in the same operation order as the reference, so indices are bit-exact and the
+// interpolated positions agree to the last few ulps.
+#pragma once
+#include "common.cuh"
+
+namespace epid {
+
+struct PeakArgs {          // already parsed (= after _parse_peak_args, core/profile.py:2626-2649)
+    double hmin;           // height threshold (may be -inf)
+    int distance;          // ceil(distance); <= 1 disables the stage
+    double pmin;           // required prominence; < 0: none
+    double wmin;           // min width
+    double rel_height;     // 1 - fwxm_height
+    int max_number;        // <= 0: all
+    int sort_by_height;    // peak_sort == 'peak_heights'
+};
+
+struct PeakWork {          // caller-provided arrays (shared or global), each of capacity `cap`
+    int cap;
+    int* idx;
+    double* prom;
+    int* lbase;
+    int* rbase;
+    double* width_height;
+    double* lip;
+    double* rip;
+    // scratch
+    int* flag;             // cap
+    double* skey;          // cap2 = next pow2 >= cap
+    int* sidx;             // cap2
+    int* s_small;          // >= blockDim.x + 8 ints
+};
+
+__device__ __forceinline__ bool key_less(double ka, int ia, double kb, int ib) { return ka < kb || (ka == kb && ia < ib); }
+
+// ascending bitonic sort of (key, idx) pairs, m = power of two, all threads of the block participate
+__device__ inline void block_bitonic_sort(double* key, int* idx, int m) {
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const double ka = key[i], kb = key[l];
+                    const int ia = idx[i], ib = idx[l];
+                    const bool sw = up ? key_less(kb, ib, ka, ia) : key_less(ka, ia, kb, ib);
+                    if (sw) {
+                        key[i] = kb; key[l] = ka;
+                        idx[i] = ib; idx[l] = ia;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Order-preserving compaction of entries with flag != 0 (thread 0, sequential: peak counts are small).
+__device__ inline int compact_by_flag(PeakWork& w, int count, bool have_props) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int o = 0;
+        for (int i = 0; i < count; i++) {
+            if (w.flag[i]) {
+                if (o != i) {
+                    w.idx[o] = w.idx[i];
+                    if (have_props) {
+                        w.prom[o] = w.prom[i]; w.lbase[o] = w.lbase[i]; w.rbase[o] = w.rbase[i];
+                        w.width_height[o] = w.width_height[i]; w.lip[o] = w.lip[i]; w.rip[o] = w.rip[i];
+                    }
+                }
+                o++;
+            }
+        }
+        w.s_small[0] = o;
+    }
+    __syncthreads();
+    const int r = w.s_small[0];
+    __syncthreads();
+    return r;
+}
+
+// returns the number of peaks (>= 0) or -1 if the capacity was exceeded
+__device__ inline int block_find_peaks(const double* __restrict__ x, int n, const PeakArgs& a, PeakWork& w) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // ---- 1. local maxima + height filter, ordered
+    const int chunk = (n + nt - 1) / nt;
+    const int lo = max(1, tid * chunk), hi = min(n - 1, (tid + 1) * chunk);
+    int c = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int o = 0;
+        if (pass == 1) {
+            // exclusive scan of per-thread counts (sequential by thread 0; nt <= 1024)
+            w.s_small[tid + 1] = c;
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int t = 0; t < nt; t++) { int v = w.s_small[t + 1]; w.s_small[t + 1] = acc; acc += v; }
+                w.s_small[0] = acc;
+            }
+            __syncthreads();
+            o = w.s_small[tid + 1];
+            if (w.s_small[0] > w.cap) return -1;
+        }
+        for (int i = lo; i < hi; i++) {
+            if (x[i - 1] < x[i]) {
+                int ahead = i + 1;
+                while (ahead < n - 1 && x[ahead] == x[i]) ahead++;
+                if (x[ahead] < x[i]) {
+                    const int p = (i + ahead - 1) / 2;
+                    if (x[p] >= a.hmin) {
+                        if (pass == 1) w.idx[o] = p;
+                        o++;
+                    }
+                }
+            }
+        }
+        if (pass == 0) c = o;
+    }
+    __syncthreads();
+    int count = w.s_small[0];
+    __syncthreads();
+    if (count == 0) return 0;
+
+    // ---- 2. distance
+    if (a.distance > 1 && count > 1) {
+        int m = 1;
+        while (m < count) m <<= 1;
+        for (int i = tid; i < m; i += nt) {
+            if (i < count) { w.skey[i] = x[w.idx[i]]; w.sidx[i] = i; }
+            else { w.skey[i] = __longlong_as_double(0x7ff0000000000000LL); w.sidx[i] = i; }  // +inf padding sorts last
+            if (i < count) w.flag[i] = 1;
+        }
+        __syncthreads();
+        block_bitonic_sort(w.skey, w.sidx, m);
+        if (tid == 0) {
+            for (int i = count - 1; i >= 0; i--) {
+                const int j = w.sidx[i];
+                if (!w.flag[j]) continue;
+                int k = j - 1;
+                while (k >= 0 && w.idx[j] - w.idx[k] < a.distance) { w.flag[k] = 0; k--; }
+                k = j + 1;
+                while (k < count && w.idx[k] - w.idx[j] < a.distance) { w.flag[k] = 0; k++; }
+            }
+        }
+        count = compact_by_flag(w, count, false);
+    }
+
+    // ---- 3. prominences (wlen = None)
+    for (int i = tid; i < count; i += nt) {
+        const int p = w.idx[i];
+        const double xp = x[p];
+        int k = p, lb = p;
+        double lmin = xp;
+        while (k >= 0 && x[k] <= xp) { if (x[k] < lmin) { lmin = x[k]; lb = k; } k--; }
+        k = p;
+        int rb = p;
+        double rmin = xp;
+        while (k <= n - 1 && x[k] <= xp) { if (x[k] < rmin) { rmin = x[k]; rb = k; } k++; }
+        w.prom[i] = xp - fmax(lmin, rmin);
+        w.lbase[i] = lb;
+        w.rbase[i] = rb;
+    }
+    __syncthreads();
+    // ---- 4/5. widths (computed before the prominence filter is applied; independent per peak)
+    for (int i = tid; i < count; i += nt) {
+        const int p = w.idx[i];
+        const double h = x[p] - w.prom[i] * a.rel_height;
+        int k = p;
+        const int imin = w.lbase[i], imax = w.rbase[i];
+        while (imin < k && h < x[k]) k--;
+        double l = (double)k;
+        if (x[k] < h) l += (h - x[k]) / (x[k + 1] - x[k]);
+        k = p;
+        while (k < imax && h < x[k]) k++;
+        double r = (double)k;
+        if (x[k] < h) r -= (h - x[k]) / (x[k - 1] - x[k]);
+        w.width_height[i] = h;
+        w.lip[i] = l;
+        w.rip[i] = r;
+        w.flag[i] = ((a.pmin < 0 || w.prom[i] >= a.pmin) && (a.wmin <= r - l)) ? 1 : 0;
+    }
+    count = compact_by_flag(w, count, true);
+    if (count == 0) return 0;
+
+    // ---- 6. keep the max_number largest by the sort key, left to right (core/profile.py:2615-2623)
+    if (a.max_number > 0 && count > a.max_number) {
+        int m = 1;
+        while (m < count) m <<= 1;
+        for (int i = tid; i < m; i += nt) {
+            if (i < count) { w.skey[i] = a.sort_by_height ? x[w.idx[i]] : w.prom[i]; w.sidx[i] = i; w.flag[i] = 0; }
+            else { w.skey[i] = __longlong_as_double(0x7ff0000000000000LL); w.sidx[i] = i; }
+        }
+        __syncthreads();
+        block_bitonic_sort(w.skey, w.sidx, m);
+        for (int i = tid; i < a.max_number; i += nt) w.flag[w.sidx[count - 1 - i]] = 1;
+        count = compact_by_flag(w, count, true);
+    }
+    return count;
+}
+
+}  // namespace epid

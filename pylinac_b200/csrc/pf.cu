@@ -1,0 +1,1279 @@
+// Batched PicketFence.analyze() on the GPU.  One result per frame; frames never leave HBM between stages.
+//
+// Reference path reproduced (pylinac v3.46.0):
+//   PFDicomImage.__init__ crop / _check_for_noise / check_inversion      picketfence.py:209-238, core/image.py:868-897
+//   PicketFence.__init__ filter / ground / normalize                      picketfence.py:320-323
+//   PicketFence.analyze (orientation, picket search, per-leaf windows)    picketfence.py:636-912, 1501-1526
+//   MLCValue.get_peak_positions / error / marker_lines                    picketfence.py:1605-1628, 1701-1743
+//   Picket.get_fit / dist2cax / skew                                      picketfence.py:1881-1923
+//   aggregate results                                                      picketfence.py:439-562, 1313-1363, 1467-1469
+//
+// Exactness strategy: after ground()+normalize() the reference image is I = g / D with g = v - min (or max - v
+// when inverted) and D = max - min, a monotone affine map of the uint16 frame.  Every sum, median, threshold and
+// argmax is therefore evaluated EXACTLY on integers (g or 2g), and only the final 1-D profile arithmetic runs
+// in fp64 (same operation order as numpy/scipy, FMA contraction disabled).
+//
+// Stages (all stream-ordered, no host round trip unless a frame is flagged noisy):
+//   k_frame_stats   1 read   min/max/sum/row+col sums/corner boxes/exact p0.5,p99.5,median   (stats.cu)
+//   k_pf_decide     -        noise flag, corner inversion, D, median in g units
+//   k_pf_clamp_sums 1 read   row/col sums of max(2g, 2*median)  (orientation; skipped if orientation is given)
+//   k_pf_profile    -        orientation, leaf profile, find_peaks -> pickets, spacing, leaves in view
+//   k_pf_windows    ~0.5 read per (leaf, picket) window: validity, median profile, FWHM edges
+//   k_pf_finalize   -        leaf-row pruning, per-picket line fit, errors, aggregates
+#include <cmath>
+
+#include "filters.cuh"
+#include "peaks.cuh"
+#include "stats.cuh"
+
+namespace epid {
+
+constexpr int PF_P = EPID_PF_MAX_PICKETS;
+constexpr int PF_L = EPID_PF_MAX_LEAVES;
+constexpr int PROF_THREADS = 256;
+constexpr int PROF_MAXN = STATS_MAX_DIM;  // profile length
+constexpr int PROF_PEAK_CAP = 512;
+constexpr int WIN_WARPS = 4;
+constexpr int WIN_CAP_PX = 4096;          // staged pixels per window
+constexpr int WIN_MAX_NC = 1024;          // samples along leaf travel
+constexpr int WIN_MAX_NR = 64;            // samples across the leaf
+constexpr int FIN_THREADS = 256;
+
+struct PctPlan { int prev, next; double gamma; };
+
+struct PfConst {
+    epid_pf_params p;
+    int H, W;
+    int meas_cap;
+    int post_filter;       // stats were taken on an already inverted+filtered copy
+    PctPlan lo, hi;        // p0.5 / p99.5 of the frame (ranks live in StatsGeom slots 0..3)
+    PctPlan p85[2], p99[2];  // [0]: arrays of length W (np.sum(axis 0)), [1]: length H
+};
+
+struct PfFrame {
+    int status;
+    int noisy;
+    int inv;               // pixels are read as g = inv ? mx - v : v - mn
+    int corner_inverted;
+    int noise_passes;
+    uint32_t mn, mx, D;
+    uint32_t med2;         // 2 * median(g)
+    int orientation;
+    int n_pickets;
+    int n_inview;
+    int picket_idx[PF_P];
+    double picket_val[PF_P];
+    double spacing;
+    short inview[PF_L];    // indices into the leaf arrays, reference order
+};
+
+struct PfWin { int valid; double l, r; };  // per (in-view leaf, picket)
+
+// numpy _lerp (numpy/lib/_function_base_impl.py): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
+__device__ __forceinline__ double np_lerp(double a, double b, double t) {
+    const double d = b - a;
+    double r = a + d * t;
+    if (t >= 0.5) r = b - d * (1.0 - t);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ init
+__global__ void k_pf_init(const uint16_t* base, int n, int H0, int W0, int crop, FrameRef* refs, PfFrame* fr, int* counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { counters[0] = 0; counters[1] = 0; }
+    if (i >= n) return;
+    refs[i].origin = base + (size_t)i * H0 * W0 + (size_t)crop * W0 + crop;
+    refs[i].pitch = W0;
+    refs[i].pad = 0;
+    PfFrame& f = fr[i];
+    f.status = EPID_PF_OK;
+    f.noisy = 0;
+    f.inv = 0;
+    f.corner_inverted = 0;
+    f.noise_passes = 0;
+    f.n_pickets = 0;
+    f.n_inview = 0;
+    f.orientation = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decide
+// mode 0: first look (noise check only updates `noisy`), mode 1: after a noise-median pass (re-check noise),
+// both: corner inversion + median.  post_filter: only D / median, inversion already materialised.
+__global__ void k_pf_decide(const PfConst* __restrict__ cc, const FrameStats* __restrict__ st, PfFrame* fr, int n,
+                            const int* __restrict__ select, int check_noise, int* counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (select && !select[i]) return;
+    const PfConst& c = *cc;
+    const FrameStats& s = st[i];
+    PfFrame& f = fr[i];
+    f.mn = s.mn;
+    f.mx = s.mx;
+    f.D = s.mx - s.mn;
+    if (f.D == 0) { f.status = EPID_PF_FLAT_IMAGE; f.noisy = 0; return; }
+    if (!c.post_filter) {
+        // _has_noise (picketfence.py:229-238)
+        if (check_noise) {
+            const double near_min = np_lerp((double)s.ostat[0], (double)s.ostat[1], c.lo.gamma);
+            const double near_max = np_lerp((double)s.ostat[2], (double)s.ostat[3], c.hi.gamma);
+            const double mnv = (double)s.mn, mxv = (double)s.mx;
+            const bool max_is_extreme = mxv > near_max * 1.25;
+            const bool min_is_extreme = (mnv < near_min * 0.75) && (fabs(mnv - near_min) > 0.1 * (near_max - near_min));
+            f.noisy = (max_is_extreme || min_is_extreme) ? 1 : 0;
+            if (f.noisy) atomicAdd(&counters[0], 1);
+        }
+        // check_inversion(box_size=10, position=(0.01, 0.01)) (core/image.py:881-897)
+        const double avg = (double)s.corner_sum / (double)(4 * 10 * 10);
+        const double mean = (double)s.sum / (double)s.npix;
+        f.corner_inverted = avg > mean ? 1 : 0;
+    }
+    const int inv = (c.post_filter ? 0 : f.corner_inverted) ^ (c.p.invert ? 1 : 0);
+    f.inv = inv;
+    // median pair (raw order statistics a <= b) -> g units
+    const uint32_t a = s.ostat[4], b = s.ostat[5];
+    f.med2 = inv ? (s.mx - b) + (s.mx - a) : (a - s.mn) + (b - s.mn);
+}
+
+// ------------------------------------------------------------------------------------------------ clamped sums
+// PicketFence.orientation (picketfence.py:1509-1514): temp[temp < median] = median; np.sum(temp, 0); np.sum(temp, 1).
+// In 2g units: sum of max(2g, med2).  Same CTA-per-frame streaming structure as k_frame_stats.
+__global__ void __launch_bounds__(STATS_THREADS, 1)
+k_pf_clamp_sums(const StatsGeom g, const FrameRef* __restrict__ frames, const PfFrame* __restrict__ fr, int nframes,
+                uint32_t* __restrict__ rowsum2, uint32_t* __restrict__ colsum2) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* colpart = smem;                          // STATS_THREADS * 8
+    uint32_t* rowsum_sm = colpart + STATS_THREADS * 8; // H
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int grp = tid / g.vprp, jc = tid - grp * g.vprp;
+    const bool active_grp = grp < g.groups;
+    for (int fi = blockIdx.x; fi < nframes; fi += gridDim.x) {
+        const PfFrame& pf = fr[fi];
+        if (pf.status != EPID_PF_OK) continue;
+        const FrameRef frf = frames[fi];
+        const uint16_t* __restrict__ f = frf.origin;
+        const int pitch = frf.pitch;
+        const bool aligned = (pitch % 8) == 0;
+        const int mis = aligned ? (int)((reinterpret_cast<uintptr_t>(f) >> 1) & 7) : 0;
+        const int col_first = jc * 8 - mis;
+        uint32_t valid = 0;
+        if (active_grp) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = col_first + k;
+                if (c >= 0 && c < g.W) valid |= 1u << k;
+            }
+        }
+        const bool active = valid != 0;
+        const int inv = pf.inv;
+        const uint32_t mn = pf.mn, mx = pf.mx, med2 = pf.med2;
+        for (int i = tid; i < g.H; i += STATS_THREADS) rowsum_sm[i] = 0;
+        __syncthreads();
+        uint32_t csum[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) csum[k] = 0;
+        if (active_grp) {
+            constexpr int U = 4;
+            for (int r = grp; r < g.H; r += g.groups * U) {
+                uint4 q[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int rr = r + u * g.groups;
+                    q[u] = make_uint4(0, 0, 0, 0);
+                    if (rr < g.H && active) {
+                        const uint16_t* rowp = f + (size_t)rr * pitch;
+                        if (aligned) {
+                            q[u] = ldg_stream16(rowp + col_first);
+                        } else {
+                            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                if (valid >> k & 1) w[k >> 1] |= (uint32_t)__ldg(rowp + col_first + k) << ((k & 1) * 16);
+                            q[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int rr = r + u * g.groups;
+                    if (rr >= g.H) break;
+                    const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                    uint32_t rs = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (valid >> k & 1) {
+                            const uint32_t v = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                            const uint32_t g2 = 2u * (inv ? mx - v : v - mn);
+                            const uint32_t cl = max(g2, med2);
+                            csum[k] += cl;
+                            rs += cl;
+                        }
+                    }
+                    rs = warp_sum(rs);
+                    if (lane == 0) atomicAdd(&rowsum_sm[rr], rs);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) colpart[tid * 8 + k] = active ? csum[k] : 0u;
+        __syncthreads();
+        for (int x = tid; x < g.W; x += STATS_THREADS) {
+            const int ac = x + mis;
+            uint32_t s = 0;
+            for (int gg = 0; gg < g.groups; gg++) s += colpart[(gg * g.vprp) * 8 + ac];
+            colsum2[(size_t)fi * g.W + x] = s;
+        }
+        for (int y = tid; y < g.H; y += STATS_THREADS) rowsum2[(size_t)fi * g.H + y] = rowsum_sm[y];
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ profile / pickets
+__device__ inline void block_sort_u32(uint32_t* a, int m) {  // ascending bitonic, m power of two
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const uint32_t x = a[i], y = a[l];
+                    if (up ? (y < x) : (x < y)) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// (p99 - p85) of `src[0..n)` (np.percentile 'linear'), using `buf` (>= next pow2 of n) as sort space
+__device__ inline double block_pct_range(const uint32_t* __restrict__ src, int n, const PctPlan& p85, const PctPlan& p99, uint32_t* buf) {
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < n ? src[i] : 0xffffffffu;
+    __syncthreads();
+    block_sort_u32(buf, m);
+    const double v85 = np_lerp((double)buf[p85.prev], (double)buf[p85.next], p85.gamma);
+    const double v99 = np_lerp((double)buf[p99.prev], (double)buf[p99.next], p99.gamma);
+    __syncthreads();
+    return v99 - v85;
+}
+
+__global__ void __launch_bounds__(PROF_THREADS)
+k_pf_profile(const PfConst* __restrict__ cc, const FrameStats* __restrict__ st, PfFrame* fr,
+             const uint32_t* __restrict__ rowsum, const uint32_t* __restrict__ colsum,
+             const uint32_t* __restrict__ rowsum2, const uint32_t* __restrict__ colsum2) {
+    extern __shared__ unsigned char smraw[];
+    double* prof = reinterpret_cast<double*>(smraw);                 // PROF_MAXN doubles (aliased as sort buffer)
+    double* w_prom = prof + PROF_MAXN;
+    double* w_wh = w_prom + PROF_PEAK_CAP;
+    double* w_lip = w_wh + PROF_PEAK_CAP;
+    double* w_rip = w_lip + PROF_PEAK_CAP;
+    double* w_skey = w_rip + PROF_PEAK_CAP;
+    int* w_idx = reinterpret_cast<int*>(w_skey + PROF_PEAK_CAP);
+    int* w_lb = w_idx + PROF_PEAK_CAP;
+    int* w_rb = w_lb + PROF_PEAK_CAP;
+    int* w_flag = w_rb + PROF_PEAK_CAP;
+    int* w_sidx = w_flag + PROF_PEAK_CAP;
+    int* w_small = w_sidx + PROF_PEAK_CAP;                           // PROF_THREADS + 8
+    __shared__ double s_red[PROF_THREADS / 32];
+    __shared__ double s_bcast[2];
+
+    const int fi = blockIdx.x;
+    const PfConst& c = *cc;
+    PfFrame& f = fr[fi];
+    if (f.status != EPID_PF_OK) return;
+    const int H = c.H, W = c.W;
+    const int tid = threadIdx.x;
+
+    // ---- orientation (picketfence.py:1501-1526)
+    int orient = c.p.orientation;
+    if (orient < 0) {
+        uint32_t* buf = reinterpret_cast<uint32_t*>(prof);
+        const double row_range = block_pct_range(colsum2 + (size_t)fi * W, W, c.p85[0], c.p99[0], buf);  // np.sum(temp, 0)
+        const double col_range = block_pct_range(rowsum2 + (size_t)fi * H, H, c.p85[1], c.p99[1], buf);  // np.sum(temp, 1)
+        orient = (row_range < col_range) ? 1 : 0;
+    }
+    // ---- leaf profile: np.mean(image, axis) then / max   (picketfence.py:747-752)
+    const int n = orient == 0 ? W : H;
+    const int other = orient == 0 ? H : W;
+    const uint32_t* raw = orient == 0 ? colsum + (size_t)fi * W : rowsum + (size_t)fi * H;
+    // sum of g along the other axis: inv ? other*mx - raw : raw - other*mn   (exact integers)
+    const long long base = (long long)other * (long long)(f.inv ? f.mx : f.mn);
+    double lmax = 0.0;
+    for (int i = tid; i < n; i += PROF_THREADS) {
+        const long long sg = f.inv ? base - (long long)raw[i] : (long long)raw[i] - base;
+        const double v = (double)sg;
+        prof[i] = v;
+        lmax = fmax(lmax, v);
+    }
+    lmax = warp_max(lmax);
+    if ((tid & 31) == 0) s_red[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int i = 0; i < PROF_THREADS / 32; i++) m = fmax(m, s_red[i]);
+        s_bcast[0] = m;
+    }
+    __syncthreads();
+    const double pmax = s_bcast[0];
+    double lmin = 2.0;
+    for (int i = tid; i < n; i += PROF_THREADS) {
+        const double v = prof[i] / pmax;
+        prof[i] = v;
+        lmin = fmin(lmin, v);
+    }
+    lmin = warp_min(lmin);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = lmin;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 2.0;
+        for (int i = 0; i < PROF_THREADS / 32; i++) m = fmin(m, s_red[i]);
+        s_bcast[1] = m;
+    }
+    __syncthreads();
+    const double pmin = s_bcast[1];
+    // ---- find_fwxm_peaks(min_distance=0.02, threshold=height_threshold, max_number, peak_sort, required_prominence)
+    // _parse_peak_args (core/profile.py:2626-2649): max of the normalised profile is 1.0
+    PeakArgs a;
+    {
+        const double val_range = 1.0 - pmin;
+        double thr = c.p.height_threshold;
+        if (thr >= 0.0 && thr <= 1.0) thr = pmin + thr * val_range;
+        a.hmin = thr;
+        a.distance = max((int)(0.02 * (double)n), 1);
+        a.pmin = c.p.required_prominence;
+        a.wmin = 0.0;
+        a.rel_height = 1.0 - 0.5;
+        a.max_number = c.p.num_pickets;
+        a.sort_by_height = c.p.peak_sort == 1;
+    }
+    PeakWork w;
+    w.cap = PROF_PEAK_CAP;
+    w.idx = w_idx; w.prom = w_prom; w.lbase = w_lb; w.rbase = w_rb; w.width_height = w_wh; w.lip = w_lip; w.rip = w_rip;
+    w.flag = w_flag; w.skey = w_skey; w.sidx = w_sidx; w.s_small = w_small;
+    const int np = block_find_peaks(prof, n, a, w);
+    if (tid == 0) {
+        f.orientation = orient;
+        if (np < 0 || np > PF_P) {
+            f.status = EPID_PF_TOO_MANY_PICKETS;
+        } else if (np == 0) {
+            f.status = EPID_PF_NO_PICKETS;
+        } else {
+            f.n_pickets = np;
+            int sorted[PF_P];
+            for (int k = 0; k < np; k++) {
+                const double lt = w.lip[k], rt = w.rip[k];
+                const int idx = (int)rint(lt + (rt - lt) / 2.0);   // int(round(.)), banker's (core/profile.py:2167)
+                f.picket_idx[k] = idx;
+                f.picket_val[k] = prof[idx];
+                int j = k;
+                while (j > 0 && sorted[j - 1] > idx) { sorted[j] = sorted[j - 1]; j--; }
+                sorted[j] = idx;
+            }
+            // picket_spacing = np.median(np.diff(np.sort(peak_idxs)))   (picketfence.py:766-767)
+            double spacing = c.p.picket_spacing;
+            if (spacing < 0) {
+                const int nd = np - 1;
+                if (nd <= 0) {
+                    spacing = __longlong_as_double(0x7ff8000000000000LL);  // np.median([]) -> nan
+                } else {
+                    int d[PF_P];
+                    for (int k = 0; k < nd; k++) {
+                        const int v = sorted[k + 1] - sorted[k];
+                        int j = k;
+                        while (j > 0 && d[j - 1] > v) { d[j] = d[j - 1]; j--; }
+                        d[j] = v;
+                    }
+                    spacing = (nd & 1) ? (double)d[nd / 2] : ((double)d[nd / 2 - 1] + (double)d[nd / 2]) / 2.0;
+                }
+            }
+            f.spacing = spacing;
+            // _leaves_in_view (picketfence.py:888-912)
+            const double n_axis = (double)(orient == 0 ? H : W);
+            const double ratio = c.p.leaf_analysis_width_ratio;
+            double pixel_range = n_axis / 2.0;
+            pixel_range -= fmax(c.p.leaf_width_mm[0] * ratio, c.p.leaf_width_mm[c.p.n_leaves - 1] * ratio) * c.p.dpmm;
+            int cnt = 0;
+            for (int l = 0; l < c.p.n_leaves; l++)
+                if (fabs(c.p.leaf_center_mm[l]) < pixel_range / c.p.dpmm) f.inview[cnt++] = (short)l;
+            f.n_inview = cnt;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ windows
+// One warp per (leaf, picket) window.  Canonical window coordinates: i in [0, nr) across the leaf (the axis the
+// median collapses), j in [0, nc) along leaf travel.
+__global__ void __launch_bounds__(WIN_WARPS * 32)
+k_pf_windows(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWin* __restrict__ wins) {
+    __shared__ __align__(16) uint16_t s_px[WIN_WARPS][WIN_CAP_PX];     // staged g values; later aliased by the fp64 profile
+    __shared__ uint32_t s_m2[WIN_WARPS][WIN_MAX_NC];
+    const int fi = blockIdx.y;
+    const PfConst& c = *cc;
+    PfFrame& f = fr[fi];
+    if (f.status != EPID_PF_OK) return;
+    const int li = blockIdx.x;              // in-view leaf slot
+    if (li >= f.n_inview) return;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = c.H, W = c.W;
+    const int orient = f.orientation;
+    const int leaf = f.inview[li];
+    const double dpmm = c.p.dpmm;
+    const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
+    const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + (orient == 0 ? (double)H / 2.0 : (double)W / 2.0);
+    const FrameRef frf = frames[fi];
+    const int inv = f.inv;
+    const uint32_t mn = f.mn, mx = f.mx;
+    const double Dd = (double)f.D;
+    uint16_t* px = s_px[wid];
+    uint32_t* m2 = s_m2[wid];
+    double* xs = reinterpret_cast<double*>(px);
+
+    for (int pk = wid; pk < f.n_pickets; pk += WIN_WARPS) {
+        PfWin& out = wins[((size_t)fi * PF_L + li) * PF_P + pk];
+        const double pidx = (double)f.picket_idx[pk];
+        const double spacing = f.spacing;
+        // _get_mlc_window (picketfence.py:859-886): python int() truncates toward zero
+        int a0 = max((int)(pidx - spacing / 2.0), 0);                                   // along travel
+        int a1 = min((int)(pidx + spacing / 2.0), orient == 0 ? W : H);
+        int b0 = max((int)(lc_px - lw_px / 2.0), 0);                                    // across the leaf
+        int b1 = min((int)(lc_px + lw_px / 2.0), orient == 0 ? H : W);
+        const int nc = a1 - a0, nr = b1 - b0;
+        if (nc <= 0 || nr <= 0) {           // empty slice: np.max raises ValueError in the reference
+            if (lane == 0) { out.valid = 0; out.l = 0; out.r = 0; f.status = EPID_PF_WINDOW_NO_PEAK; }
+            continue;
+        }
+        if (nc > WIN_MAX_NC || nr > WIN_MAX_NR) {
+            if (lane == 0) { out.valid = 0; f.status = EPID_PF_CAPACITY; }
+            continue;
+        }
+        // The window is processed in chunks of `cw` travel samples so that any spacing fits the staging buffer:
+        // per chunk, stage g values (canonical layout px[i * cw + jj]), accumulate the validity statistics
+        // (max, per-row sum and sum of squares) and take the per-sample median across the leaf.
+        const int cw = min(nc, WIN_CAP_PX / nr);
+        const int sag = c.p.sag_px;
+        const int k1 = (nr - 1) / 2, k2 = nr / 2;
+        uint32_t gmax = 0;
+        unsigned long long rs1[2] = {0, 0}, rs2[2] = {0, 0};   // row i lives on lane i & 31, slot i >> 5
+        uint32_t lmin = 0xffffffffu, lmax = 0;
+        for (int j0 = 0; j0 < nc; j0 += cw) {
+            const int cn = min(cw, nc - j0);
+            __syncwarp();
+            // np.roll(sag) folded into the source index
+            if (orient == 0) {
+                for (int t = lane; t < nr * cn; t += 32) {
+                    const int i = t / cn, jj = t - i * cn;
+                    int row = b0 + i - sag;
+                    row %= H; if (row < 0) row += H;
+                    const uint32_t v = __ldg(frf.origin + (size_t)row * frf.pitch + a0 + j0 + jj);
+                    const uint32_t g = inv ? mx - v : v - mn;
+                    px[i * cn + jj] = (uint16_t)g;
+                    gmax = max(gmax, g);
+                }
+            } else {
+                for (int t = lane; t < nr * cn; t += 32) {
+                    const int jj = t / nr, i = t - jj * nr;   // lanes run along the memory-contiguous axis
+                    int col = b0 + i - sag;
+                    col %= W; if (col < 0) col += W;
+                    const uint32_t v = __ldg(frf.origin + (size_t)(a0 + j0 + jj) * frf.pitch + col);
+                    const uint32_t g = inv ? mx - v : v - mn;
+                    px[i * cn + jj] = (uint16_t)g;
+                    gmax = max(gmax, g);
+                }
+            }
+            __syncwarp();
+            for (int i = 0; i < nr; i++) {
+                unsigned long long s1 = 0, s2 = 0;
+                for (int jj = lane; jj < cn; jj += 32) {
+                    const unsigned long long g = px[i * cn + jj];
+                    s1 += g;
+                    s2 += g * g;
+                }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if ((i & 31) == lane) { rs1[i >> 5] += s1; rs2[i >> 5] += s2; }
+            }
+            // np.median(window, axis) -> 2*median per travel sample (picketfence.py:1605-1609)
+            for (int jj = lane; jj < cn; jj += 32) {
+                uint32_t va = 0, vb = 0;
+                for (int i = 0; i < nr; i++) {
+                    const uint32_t v = px[i * cn + jj];
+                    int rank = 0;
+                    for (int i2 = 0; i2 < nr; i2++) {
+                        const uint32_t o = px[i2 * cn + jj];
+                        rank += (o < v || (o == v && i2 < i)) ? 1 : 0;
+                    }
+                    if (rank == k1) va = v;
+                    if (rank == k2) vb = v;
+                }
+                const uint32_t m = va + vb;
+                m2[j0 + jj] = m;
+                lmin = min(lmin, m);
+                lmax = max(lmax, m);
+            }
+        }
+        gmax = warp_max(gmax);
+        __syncwarp();
+        // ---- _is_mlc_peak_in_window (picketfence.py:847-857)
+        // std across travel for each i: sqrt(nc*S2 - S1^2) / (nc * D), exact integer numerator
+        double sd[2] = {-1.0, -1.0};
+#pragma unroll
+        for (int sl = 0; sl < 2; sl++) {
+            if (sl * 32 + lane < nr) {
+                const double num = (double)((unsigned long long)nc * rs2[sl] - rs1[sl] * rs1[sl]);
+                sd[sl] = sqrt(num) / ((double)nc * Dd);
+            }
+        }
+        // max and median of the nr std values (rank counting through shuffles)
+        double sd_max = fmax(sd[0], sd[1]);
+        sd_max = warp_max(sd_max);
+        double med_a = 0.0, med_b = 0.0;
+        {
+            int rank[2] = {0, 0};
+            for (int t = 0; t < nr; t++) {
+                const double o = __shfl_sync(0xffffffffu, (t >> 5) ? sd[1] : sd[0], t & 31);
+#pragma unroll
+                for (int sl = 0; sl < 2; sl++) {
+                    const int me = sl * 32 + lane;
+                    if (me < nr && (o < sd[sl] || (o == sd[sl] && t < me))) rank[sl]++;
+                }
+            }
+            double ca = 0.0, cb = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < 2; sl++) {
+                const int me = sl * 32 + lane;
+                if (me < nr) {
+                    if (rank[sl] == k1) ca = sd[sl];
+                    if (rank[sl] == k2) cb = sd[sl];
+                }
+            }
+            // exactly one lane holds each; sum-reduce to broadcast (others contribute +0.0)
+            med_a = warp_sum(ca);
+            med_b = warp_sum(cb);
+        }
+        const double sd_med = (nr & 1) ? med_a : (med_a + med_b) / 2.0;
+        const bool above = ((double)gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
+        const bool not_edge = sd_max < c.p.edge_threshold * sd_med;
+        if (!(above && not_edge)) {
+            if (lane == 0) { out.valid = 0; out.l = 0; out.r = 0; }
+            __syncwarp();
+            continue;
+        }
+        lmin = warp_min(lmin);
+        lmax = warp_max(lmax);
+        __syncwarp();
+        if (lmax == lmin) {  // flat profile: the reference divides by zero and then finds no peak
+            if (lane == 0) { out.valid = 0; f.status = EPID_PF_WINDOW_NO_PEAK; }
+            continue;
+        }
+        // ---- FWXMProfilePhysical(ground=True, normalization=MAX) (core/profile.py:204-240)
+        const double den = (double)(lmax - lmin);
+        for (int j = lane; j < nc; j += 32) xs[j] = (double)(m2[j] - lmin) / den;
+        __syncwarp();
+        // ---- find_peaks(values, fwxm_height=0.5, max_number=1) by prominence (core/profile.py:602-611, 2545-2623)
+        double best_prom = -1.0;
+        int best_idx = -1, best_lb = 0, best_rb = 0;
+        for (int i = 1 + lane; i < nc - 1; i += 32) {
+            if (xs[i - 1] < xs[i]) {
+                int ahead = i + 1;
+                while (ahead < nc - 1 && xs[ahead] == xs[i]) ahead++;
+                if (xs[ahead] < xs[i]) {
+                    const int p = (i + ahead - 1) / 2;
+                    const double xp = xs[p];
+                    int k = p, lb = p;
+                    double lm = xp;
+                    while (k >= 0 && xs[k] <= xp) { if (xs[k] < lm) { lm = xs[k]; lb = k; } k--; }
+                    k = p;
+                    int rb = p;
+                    double rm = xp;
+                    while (k <= nc - 1 && xs[k] <= xp) { if (xs[k] < rm) { rm = xs[k]; rb = k; } k++; }
+                    const double prom = xp - fmax(lm, rm);
+                    if (prom > best_prom || (prom == best_prom && p > best_idx)) { best_prom = prom; best_idx = p; best_lb = lb; best_rb = rb; }
+                }
+            }
+        }
+        // warp arg-max by (prominence, index)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double op = __shfl_xor_sync(0xffffffffu, best_prom, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+            const int olb = __shfl_xor_sync(0xffffffffu, best_lb, o);
+            const int orb = __shfl_xor_sync(0xffffffffu, best_rb, o);
+            if (op > best_prom || (op == best_prom && oi > best_idx)) { best_prom = op; best_idx = oi; best_lb = olb; best_rb = orb; }
+        }
+        if (best_idx < 0) {
+            if (lane == 0) { out.valid = 0; f.status = EPID_PF_WINDOW_NO_PEAK; }
+            __syncwarp();
+            continue;
+        }
+        if (lane == 0) {
+            const int p = best_idx;
+            const double h = xs[p] - best_prom * 0.5;
+            int k = p;
+            while (best_lb < k && h < xs[k]) k--;
+            double l = (double)k;
+            if (xs[k] < h) l += (h - xs[k]) / (xs[k + 1] - xs[k]);
+            k = p;
+            while (k < best_rb && h < xs[k]) k++;
+            double r = (double)k;
+            if (xs[k] < h) r -= (h - xs[k]) / (xs[k - 1] - xs[k]);
+            out.valid = 1;
+            out.l = l;
+            out.r = r;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+__device__ inline void block_sort_f64(double* a, int m) {
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const double x = a[i], y = a[l];
+                    if (up ? (y < x) : (x < y)) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+k_pf_finalize(const PfConst* __restrict__ cc, PfFrame* fr, const PfWin* __restrict__ wins, epid_pf_summary* __restrict__ summ,
+              epid_pf_meas* __restrict__ meas_all) {
+    extern __shared__ double s_err[];                    // 2 * pow2(meas_cap) doubles for the median of |errors|
+    __shared__ int s_cnt[PF_L], s_off[PF_L], s_keep[PF_L];
+    __shared__ double s_fit[PF_P][2];
+    __shared__ int s_i[8];
+    __shared__ double s_wbuf[PF_L];
+
+    const int fi = blockIdx.x;
+    const PfConst& c = *cc;
+    PfFrame& f = fr[fi];
+    epid_pf_summary& S = summ[fi];
+    const int tid = threadIdx.x;
+    const int H = c.H, W = c.W;
+    if (tid == 0) {
+        S.status = f.status;
+        S.orientation = f.orientation;
+        S.noise_median_passes = f.noise_passes;
+        S.corner_inverted = f.corner_inverted;
+        S.height = H;
+        S.width = W;
+        S.n_pickets = f.n_pickets;
+        S.n_meas = 0;
+        S.n_leaves_removed = 0;
+        S.picket_spacing_px = f.spacing;
+        for (int k = 0; k < PF_P; k++) { S.picket_idx[k] = k < f.n_pickets ? f.picket_idx[k] : 0; S.picket_val[k] = k < f.n_pickets ? f.picket_val[k] : 0.0; }
+    }
+    if (f.status != EPID_PF_OK) return;
+    const int nl = f.n_inview, np = f.n_pickets;
+    const int orient = f.orientation;
+    const int npos = c.p.separate_leaves ? 2 : 1;
+    const double dpmm = c.p.dpmm;
+    const PfWin* wf = wins + (size_t)fi * PF_L * PF_P;
+    // ---- kisses per leaf row
+    for (int l = tid; l < nl; l += FIN_THREADS) {
+        int n = 0;
+        for (int p = 0; p < np; p++) n += wf[l * PF_P + p].valid ? 1 : 0;
+        s_cnt[l] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // median over the leaf rows that have at least one measurement (group_by on mlc_meas, picketfence.py:810-814)
+        int tmp[PF_L];
+        int ng = 0, total = 0;
+        for (int l = 0; l < nl; l++)
+            if (s_cnt[l] > 0) {
+                const int v = s_cnt[l];
+                int j = ng;
+                while (j > 0 && tmp[j - 1] > v) { tmp[j] = tmp[j - 1]; j--; }
+                tmp[j] = v;
+                ng++;
+                total += v;
+            }
+        int status = EPID_PF_OK;
+        int kept = 0, removed = 0;
+        if (total == 0) {
+            status = EPID_PF_NO_MEASUREMENTS;
+        } else {
+            const int med_twice = (ng & 1) ? 2 * tmp[ng / 2] : tmp[ng / 2 - 1] + tmp[ng / 2];  // 2 * statistics.median
+            int off = 0;
+            for (int l = 0; l < nl; l++) {
+                const bool keep = s_cnt[l] > 0 && 2 * s_cnt[l] == med_twice;
+                s_keep[l] = keep ? 1 : 0;
+                s_off[l] = off;
+                if (keep) { off += s_cnt[l]; kept++; }
+                else if (s_cnt[l] > 0) removed++;
+            }
+            if (off == 0) status = EPID_PF_NO_MEASUREMENTS;     // a .5 median drops every row (reference: polyfit of nothing)
+            else if (off > c.meas_cap) status = EPID_PF_CAPACITY;
+            s_i[1] = off;
+        }
+        s_i[0] = status;
+        S.n_leaves_removed = removed;
+        if (status != EPID_PF_OK) { S.status = status; f.status = status; }
+    }
+    __syncthreads();
+    if (s_i[0] != EPID_PF_OK) return;
+    const int M = s_i[1];
+    epid_pf_meas* meas = meas_all + (size_t)fi * c.meas_cap;
+    const double n_axis_half = (orient == 0 ? (double)H : (double)W) / 2.0;
+    // ---- measurement table, leaf-major / picket-minor (= PicketFence.mlc_meas order)
+    for (int l = tid; l < nl; l += FIN_THREADS) {
+        if (!s_keep[l]) continue;
+        int o = s_off[l];
+        const int leaf = f.inview[l];
+        for (int p = 0; p < np; p++) {
+            const PfWin w = wf[l * PF_P + p];
+            if (!w.valid) continue;
+            epid_pf_meas& m = meas[o++];
+            m.leaf_num = c.p.leaf_num[leaf];
+            m.picket = p;
+            const double offp = fmax((double)f.picket_idx[p] - f.spacing / 2.0, 0.0);   // picketfence.py:1618-1627
+            if (npos == 2) {
+                m.position[0] = w.l + offp;
+                m.position[1] = w.r + offp;
+            } else {
+                m.position[0] = fabs(w.r - w.l) / 2.0 + w.l + offp;                       // center_idx (core/profile.py:322-327)
+                m.position[1] = 0.0;
+            }
+            m.width_mm = (fmax(w.r, w.l) - fmin(w.r, w.l)) / dpmm;                        // field_width_px / dpmm
+            m.error[0] = m.error[1] = 0.0;
+            m.passed[0] = m.passed[1] = 1;
+        }
+    }
+    __syncthreads();
+    // ---- per-picket line fit np.polyfit(along-leaf-stack, along-travel, 1)  (picketfence.py:1881-1899)
+    const double ratio = c.p.leaf_analysis_width_ratio;
+    // marker line point1: across = lc - lw/2*ratio  (picketfence.py:1725-1743)
+    // The fit needs the across-leaf coordinate of each measurement; it is a function of the leaf only, so walk the
+    // kept leaves again (thread per picket, sequential over leaves: <= 160 x 2 points).
+    for (int p = tid; p < np; p += FIN_THREADS) {
+        double mx_ = 0, my_ = 0;
+        int n = 0;
+        for (int l = 0; l < nl; l++) {
+            if (!s_keep[l]) continue;
+            const PfWin w = wf[l * PF_P + p];
+            if (!w.valid) continue;
+            const int leaf = f.inview[l];
+            const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
+            const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + n_axis_half;
+            const double upper = lc_px - lw_px / 2.0 * ratio;
+            const double offp = fmax((double)f.picket_idx[p] - f.spacing / 2.0, 0.0);
+            if (npos == 2) {
+                mx_ += upper * 2.0; my_ += (w.l + offp) + (w.r + offp); n += 2;
+            } else {
+                mx_ += upper; my_ += fabs(w.r - w.l) / 2.0 + w.l + offp; n += 1;
+            }
+        }
+        if (n == 0) { s_fit[p][0] = __longlong_as_double(0x7ff8000000000000LL); s_fit[p][1] = s_fit[p][0]; continue; }
+        mx_ /= n; my_ /= n;
+        double sxx = 0, sxy = 0;
+        for (int l = 0; l < nl; l++) {
+            if (!s_keep[l]) continue;
+            const PfWin w = wf[l * PF_P + p];
+            if (!w.valid) continue;
+            const int leaf = f.inview[l];
+            const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
+            const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + n_axis_half;
+            const double upper = lc_px - lw_px / 2.0 * ratio;
+            const double offp = fmax((double)f.picket_idx[p] - f.spacing / 2.0, 0.0);
+            const double dx = upper - mx_;
+            if (npos == 2) {
+                sxx += 2.0 * dx * dx;
+                sxy += dx * ((w.l + offp) - my_) + dx * ((w.r + offp) - my_);
+            } else {
+                sxx += dx * dx;
+                sxy += dx * ((fabs(w.r - w.l) / 2.0 + w.l + offp) - my_);
+            }
+        }
+        const double slope = sxx > 0 ? sxy / sxx : 0.0;
+        s_fit[p][0] = slope;
+        s_fit[p][1] = my_ - slope * mx_;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int p = 0; p < np; p++)
+            if (s_fit[p][0] != s_fit[p][0]) { S.status = 7; f.status = 7; }   // a picket without measurements: polyfit([]) raises
+    }
+    __syncthreads();
+    if (f.status != EPID_PF_OK) return;
+    // ---- errors (picketfence.py:1701-1718)
+    int m2n = 1;
+    while (m2n < M * npos) m2n <<= 1;
+    for (int q = tid; q < m2n; q += FIN_THREADS) s_err[q] = __longlong_as_double(0x7ff0000000000000LL);
+    __syncthreads();
+    for (int l = tid; l < nl; l += FIN_THREADS) {
+        if (!s_keep[l]) continue;
+        const int leaf = f.inview[l];
+        const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
+        const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + n_axis_half;
+        const double upper = lc_px - lw_px / 2.0 * ratio;
+        const double lower = lc_px + lw_px / 2.0 * ratio;
+        const double centre = (lower - upper) / 2.0 + upper;          // Line.center (core/geometry.py:556-561)
+        for (int q = s_off[l]; q < s_off[l] + s_cnt[l]; q++) {
+            epid_pf_meas& m = meas[q];
+            const double fitv = s_fit[m.picket][0] * centre + s_fit[m.picket][1];
+            for (int s = 0; s < npos; s++) {
+                double picket_pos = fitv;
+                if (npos == 2) picket_pos += (s == 0 ? -1.0 : 1.0) * c.p.nominal_gap_mm / 2.0 * dpmm;
+                const double e = (m.position[s] - picket_pos) / dpmm;
+                m.error[s] = e;
+                m.passed[s] = fabs(e) < c.p.tolerance ? 1 : 0;
+                s_err[q * npos + s] = fabs(e);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- aggregates
+    if (tid == 0) {
+        int n_pass = 0, n_tot = 0, n_failed = 0;
+        double max_err = -1.0;
+        int arg = 0;
+        for (int q = 0; q < M; q++) {
+            const epid_pf_meas& m = meas[q];
+            double me = 0.0;
+            bool allp = true;
+            for (int s = 0; s < npos; s++) {
+                n_tot++;
+                if (m.passed[s]) n_pass++; else allp = false;
+                me = fmax(me, fabs(m.error[s]));
+            }
+            if (!allp) n_failed++;
+            if (me > max_err) { max_err = me; arg = q; }     // first maximum = stable descending sort .first()
+        }
+        S.n_meas = M;
+        S.percent_passing = 100.0 * (double)n_pass / (double)n_tot;
+        S.max_error_mm = max_err;
+        S.max_error_picket = meas[arg].picket;
+        S.max_error_leaf = meas[arg].leaf_num;
+        S.max_error_bank = (npos == 2 && !(fabs(meas[arg].error[0]) > fabs(meas[arg].error[1]))) ? 1 : 0;
+        S.passed = n_pass == n_tot ? 1 : 0;
+        S.n_failed = n_failed;
+        // dist2cax (picketfence.py:1905-1923) / image.center (core/image.py:526-533, PFDicomImage.center :246-260)
+        double cax;
+        if (c.p.has_cax_override) cax = orient == 0 ? c.p.cax_x_px : c.p.cax_y_px;
+        else cax = (orient == 0 ? (double)W : (double)H) / 2.0 - 0.5;
+        S.cax_px = cax;
+        const int length = orient == 0 ? H : W;
+        const double xmid = rint((double)length / 2.0);
+        double d2c[PF_P], srt[PF_P];
+        double skew = 0.0;
+        for (int p = 0; p < np; p++) {
+            S.fit_slope[p] = s_fit[p][0];
+            S.fit_intercept[p] = s_fit[p][1];
+            d2c[p] = (cax - (s_fit[p][0] * xmid + s_fit[p][1])) / dpmm;
+            S.offsets_from_cax_mm[p] = d2c[p];
+            skew += s_fit[p][0] * (180.0 / 3.14159265358979323846);
+            int j = p;
+            while (j > 0 && srt[j - 1] > d2c[p]) { srt[j] = srt[j - 1]; j--; }
+            srt[j] = d2c[p];
+        }
+        S.mlc_skew = skew / (double)np;
+        double sp = 0.0;
+        for (int p = 0; p + 1 < np; p++) sp += fabs(srt[p] - srt[p + 1]);
+        S.mean_picket_spacing_mm = np > 1 ? sp / (double)(np - 1) : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    // median of |errors| (np.median)
+    block_sort_f64(s_err, m2n);
+    if (tid == 0) {
+        const int ne = M * npos;
+        S.abs_median_error_mm = (ne & 1) ? s_err[ne / 2] : (s_err[ne / 2 - 1] + s_err[ne / 2]) / 2.0;
+    }
+    // ---- picket widths (picketfence.py:471-491): thread per picket, insertion sort of <= 160 widths in shared memory
+    __syncthreads();
+    for (int p = 0; p < np; p++) {
+        if (tid == 0) {
+            int n = 0;
+            double sum = 0.0;
+            for (int q = 0; q < M; q++) {
+                if (meas[q].picket != p) continue;
+                const double v = meas[q].width_mm;
+                int j = n;
+                while (j > 0 && s_wbuf[j - 1] > v) { s_wbuf[j] = s_wbuf[j - 1]; j--; }
+                s_wbuf[j] = v;
+                n++;
+                sum += v;
+            }
+            S.picket_width_max[p] = s_wbuf[n - 1];
+            S.picket_width_min[p] = s_wbuf[0];
+            S.picket_width_mean[p] = sum / (double)n;
+            S.picket_width_median[p] = (n & 1) ? s_wbuf[n / 2] : (s_wbuf[n / 2 - 1] + s_wbuf[n / 2]) / 2.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static PctPlan pct_plan(int n, double q_percent) {
+    // numpy 'linear' (numpy/lib/_function_base_impl.py: _compute_virtual_index, _get_indexes, _get_gamma)
+    const double q = q_percent / 100.0;
+    const double vi = (double)n * q + (1.0 + q * (1.0 - 1.0 - 1.0)) - 1.0;
+    double prev = floor(vi);
+    double next = prev + 1.0;
+    PctPlan p;
+    p.gamma = vi - prev;
+    if (prev < 0) prev = 0;
+    if (next < 0) next = 0;
+    if (prev > n - 1) prev = n - 1;
+    if (next > n - 1) next = n - 1;
+    p.prev = (int)prev;
+    p.next = (int)next;
+    return p;
+}
+
+struct PfWork {   // carved out of ctx->scratch
+    FrameRef* refs;
+    FrameRef* refs_b;        // ping-pong destination refs for median passes
+    ValueMap* maps;
+    PfFrame* fr;
+    FrameStats* stats;
+    uint32_t *rowsum, *colsum, *rowsum2, *colsum2;
+    PfWin* wins;
+    epid_pf_summary* summ;
+    epid_pf_meas* meas;
+    PfConst* cst;
+    int* counters;           // [0] noisy count
+    int* select;             // per-frame flags
+    size_t total;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void carve(PfWork& w, char* base, int n, int H, int W, int meas_cap) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + o : nullptr; o = align_up(o + bytes, 256); return p; };
+    w.refs = (FrameRef*)take(sizeof(FrameRef) * n);
+    w.refs_b = (FrameRef*)take(sizeof(FrameRef) * n);
+    w.maps = (ValueMap*)take(sizeof(ValueMap) * n);
+    w.fr = (PfFrame*)take(sizeof(PfFrame) * n);
+    w.stats = (FrameStats*)take(sizeof(FrameStats) * n);
+    w.rowsum = (uint32_t*)take(sizeof(uint32_t) * (size_t)n * H);
+    w.colsum = (uint32_t*)take(sizeof(uint32_t) * (size_t)n * W);
+    w.rowsum2 = (uint32_t*)take(sizeof(uint32_t) * (size_t)n * H);
+    w.colsum2 = (uint32_t*)take(sizeof(uint32_t) * (size_t)n * W);
+    w.wins = (PfWin*)take(sizeof(PfWin) * (size_t)n * PF_L * PF_P);
+    w.summ = (epid_pf_summary*)take(sizeof(epid_pf_summary) * n);
+    w.meas = (epid_pf_meas*)take(sizeof(epid_pf_meas) * (size_t)n * meas_cap);
+    w.cst = (PfConst*)take(sizeof(PfConst));
+    w.counters = (int*)take(sizeof(int) * 8);
+    w.select = (int*)take(sizeof(int) * n);
+    w.total = o;
+}
+
+__global__ void k_pf_mark_noisy(PfFrame* fr, int n, int* select, ValueMap* maps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = (fr[i].status == EPID_PF_OK && fr[i].noisy) ? 1 : 0;
+    select[i] = s;
+    maps[i].inv = 0; maps[i].mn = 0; maps[i].mx = 0;
+    if (s) fr[i].noise_passes++;
+}
+
+__global__ void k_pf_prepare_filter(PfFrame* fr, int n, int* select, ValueMap* maps, int user_invert) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    select[i] = fr[i].status == EPID_PF_OK ? 1 : 0;
+    // materialise check_inversion's invert() only (analyze(invert=True) is applied after normalisation)
+    maps[i].inv = fr[i].corner_inverted;
+    maps[i].mn = fr[i].mn;
+    maps[i].mx = fr[i].mx;
+    (void)user_invert;
+}
+
+__global__ void k_pf_swap_refs(FrameRef* refs, const FrameRef* refs_b, const int* select, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (select[i]) refs[i] = refs_b[i];
+}
+
+__global__ void k_pf_set_dst_refs(FrameRef* refs_b, uint16_t* pool, int n, int H, int Wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    refs_b[i].origin = pool + (size_t)i * H * Wp;
+    refs_b[i].pitch = Wp;
+    refs_b[i].pad = 0;
+}
+
+struct PfTimers { cudaEvent_t e0 = nullptr, e1 = nullptr; float stats_ms = 0; bool on = false; };
+
+// Enqueue the whole pipeline for one device-resident batch on `stream`; results land in w.summ / w.meas (device).
+static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int n, int H0, int W0, const epid_pf_params* p,
+                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm) {
+    const int crop = p->crop_px;
+    const int H = H0 - 2 * crop, W = W0 - 2 * crop;
+    StatsGeom g;
+    int rc = make_stats_geom(&g, H, W);
+    if (rc != EPID_OK) return rc;
+    PfConst hc;
+    memset(&hc, 0, sizeof(hc));
+    hc.p = *p;
+    hc.H = H;
+    hc.W = W;
+    hc.meas_cap = meas_cap;
+    hc.post_filter = 0;
+    const int npix = H * W;
+    hc.lo = pct_plan(npix, 0.5);
+    hc.hi = pct_plan(npix, 99.5);
+    hc.p85[0] = pct_plan(W, 85.0); hc.p99[0] = pct_plan(W, 99.0);
+    hc.p85[1] = pct_plan(H, 85.0); hc.p99[1] = pct_plan(H, 99.0);
+    g.nranks = 6;
+    g.ranks[0] = hc.lo.prev; g.ranks[1] = hc.lo.next;
+    g.ranks[2] = hc.hi.prev; g.ranks[3] = hc.hi.next;
+    g.ranks[4] = (npix - 1) / 2; g.ranks[5] = npix / 2;
+    g.box = 10;
+    g.rp = (int)(0.01 * H) > 1 ? (int)(0.01 * H) : 1;
+    g.cp = (int)(0.01 * W) > 1 ? (int)(0.01 * W) : 1;
+    EPID_CUDA(cudaMemcpyAsync(w.cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream));
+    const int tb = 128, nb = (n + tb - 1) / tb;
+    k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters);
+    ctx->launches++;
+    if (tm && tm->on) EPID_CUDA(cudaEventRecord(tm->e0, stream));
+    rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
+    if (rc != EPID_OK) return rc;
+    if (tm && tm->on) EPID_CUDA(cudaEventRecord(tm->e1, stream));
+    k_pf_decide<<<nb, tb, 0, stream>>>(w.cst, w.stats, w.fr, n, nullptr, 1, w.counters);
+    ctx->launches++;
+    // ---- _check_for_noise loop (picketfence.py:221-227): needs the host only to learn whether ANY frame is noisy
+    int n_noisy = 0;
+    EPID_CUDA(cudaMemcpyAsync(&n_noisy, w.counters, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    EPID_CUDA(cudaStreamSynchronize(stream));
+    if (tm && tm->on) { float ms = 0; cudaEventElapsedTime(&ms, tm->e0, tm->e1); tm->stats_ms += ms; }
+    const int Wp = (W + 7) / 8 * 8;
+    const size_t pool_bytes = sizeof(uint16_t) * (size_t)n * H * Wp;
+    int pass = 0;
+    uint16_t** pools = pool3;   // [0],[1]: ping-pong for the noise passes, [2]: PicketFence(filter=k)
+    auto ensure_pool = [&](int which) -> int {
+        if (!pools[which]) {
+            cudaError_t e = cudaMalloc(&pools[which], pool_bytes);
+            if (e != cudaSuccess) { set_error("cudaMalloc(%zu) for filtered frames failed: %s", pool_bytes, cudaGetErrorString(e)); return EPID_ERR_NOMEM; }
+        }
+        return EPID_OK;
+    };
+    int cur_pool = 0;
+    while (n_noisy > 0 && pass < 5) {
+        rc = ensure_pool(cur_pool);
+        if (rc != EPID_OK) return rc;
+        k_pf_mark_noisy<<<nb, tb, 0, stream>>>(w.fr, n, w.select, w.maps);
+        k_pf_set_dst_refs<<<nb, tb, 0, stream>>>(w.refs_b, pools[cur_pool], n, H, Wp);
+        ctx->launches += 2;
+        rc = launch_median_u16(ctx, stream, w.refs, w.refs_b, nullptr, w.select, n, H, W, 3);
+        if (rc != EPID_OK) return rc;
+        k_pf_swap_refs<<<nb, tb, 0, stream>>>(w.refs, w.refs_b, w.select, n);
+        ctx->launches++;
+        // statistics of the filtered frames only (the others keep theirs): a select-aware re-run over all slots
+        // would recompute identical numbers, so run it on all frames -- flagged ones are rare and this keeps
+        // one code path.
+        EPID_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int), stream));
+        rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
+        if (rc != EPID_OK) return rc;
+        k_pf_decide<<<nb, tb, 0, stream>>>(w.cst, w.stats, w.fr, n, w.select, 1, w.counters);
+        ctx->launches++;
+        EPID_CUDA(cudaMemcpyAsync(&n_noisy, w.counters, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        EPID_CUDA(cudaStreamSynchronize(stream));
+        cur_pool ^= 1;
+        pass++;
+    }
+    // ---- optional PicketFence(filter=k) median (picketfence.py:320-321) on the (corner-)inverted image
+    if (p->filter_size > 0) {
+        rc = ensure_pool(2);
+        if (rc != EPID_OK) return rc;
+        k_pf_prepare_filter<<<nb, tb, 0, stream>>>(w.fr, n, w.select, w.maps, p->invert);
+        k_pf_set_dst_refs<<<nb, tb, 0, stream>>>(w.refs_b, pools[2], n, H, Wp);
+        ctx->launches += 2;
+        rc = launch_median_u16(ctx, stream, w.refs, w.refs_b, w.maps, w.select, n, H, W, p->filter_size);
+        if (rc != EPID_OK) return rc;
+        k_pf_swap_refs<<<nb, tb, 0, stream>>>(w.refs, w.refs_b, w.select, n);
+        ctx->launches++;
+        hc.post_filter = 1;
+        EPID_CUDA(cudaMemcpyAsync(w.cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream));
+        StatsGeom g2 = g;
+        g2.box = 0;
+        rc = launch_frame_stats(ctx, stream, g2, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
+        if (rc != EPID_OK) return rc;
+        k_pf_decide<<<nb, tb, 0, stream>>>(w.cst, w.stats, w.fr, n, nullptr, 0, w.counters);
+        ctx->launches++;
+    }
+    // ---- orientation sums
+    if (p->orientation < 0) {
+        static bool attr = false;
+        const size_t smem = sizeof(uint32_t) * (size_t)(STATS_THREADS * 8 + H);
+        if (!attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_clamp_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+        const int grid = n < ctx->sm_count ? n : ctx->sm_count;
+        k_pf_clamp_sums<<<grid, STATS_THREADS, smem, stream>>>(g, w.refs, w.fr, n, w.rowsum2, w.colsum2);
+        ctx->launches++;
+    }
+    {
+        static bool attr = false;
+        const size_t smem = sizeof(double) * (PROF_MAXN + 5 * PROF_PEAK_CAP) + sizeof(int) * (5 * PROF_PEAK_CAP + PROF_THREADS + 8);
+        if (!attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.stats, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
+        ctx->launches++;
+    }
+    {
+        dim3 grid(p->n_leaves, n);
+        k_pf_windows<<<grid, WIN_WARPS * 32, 0, stream>>>(w.cst, w.refs, w.fr, w.wins);
+        ctx->launches++;
+    }
+    {
+        int m2 = 1;
+        while (m2 < 2 * meas_cap) m2 <<= 1;
+        const size_t smem = sizeof(double) * m2;
+        static size_t attr_set = 0;
+        if (smem > attr_set && smem > 48 * 1024) { EPID_CUDA(cudaFuncSetAttribute(k_pf_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; }
+        k_pf_finalize<<<n, FIN_THREADS, smem, stream>>>(w.cst, w.fr, w.wins, w.summ, w.meas);
+        ctx->launches++;
+    }
+    EPID_CUDA(cudaGetLastError());
+    return EPID_OK;
+}
+
+static int pf_validate(const epid_pf_params* p, int H0, int W0, int meas_cap) {
+    EPID_REQUIRE(p, EPID_ERR_INVALID, "params is NULL");
+    EPID_REQUIRE(p->dpmm > 0, EPID_ERR_INVALID, "dpmm must be positive");
+    EPID_REQUIRE(p->crop_px >= 0, EPID_ERR_INVALID, "Pixels to remove must be a positive number");
+    EPID_REQUIRE(H0 - 2 * p->crop_px > 0 && W0 - 2 * p->crop_px > 0, EPID_ERR_INVALID,
+                 "Too many pixels removed; array is empty. Pass a smaller crop value.");
+    EPID_REQUIRE(p->n_leaves > 0 && p->n_leaves <= PF_L, EPID_ERR_INVALID, "n_leaves %d outside 1..%d", p->n_leaves, PF_L);
+    EPID_REQUIRE(meas_cap > 0 && meas_cap <= 8192, EPID_ERR_INVALID, "meas_cap %d outside 1..8192", meas_cap);
+    EPID_REQUIRE(!(p->action_tolerance >= 0 && p->tolerance < p->action_tolerance), EPID_ERR_INVALID,
+                 "Tolerance cannot be lower than the action tolerance");
+    EPID_REQUIRE(p->filter_size >= 0 && p->filter_size <= 31, EPID_ERR_UNSUPPORTED, "median filter size %d outside 0..31", p->filter_size);
+    return EPID_OK;
+}
+
+}  // namespace epid
+
+using namespace epid;
+
+extern "C" {
+
+int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, epid_pf_summary* summary,
+                        epid_pf_meas* meas, int32_t meas_cap) {
+    EPID_REQUIRE(ctx && frames && summary && meas, EPID_ERR_INVALID, "NULL argument");
+    EPID_REQUIRE(frames->dtype == EPID_U16, EPID_ERR_UNSUPPORTED, "picket fence frames must be uint16");
+    int rc = pf_validate(p, frames->h, frames->w, meas_cap);
+    if (rc != EPID_OK) return rc;
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    const int n = frames->n, H = frames->h - 2 * p->crop_px, W = frames->w - 2 * p->crop_px;
+    PfWork w;
+    carve(w, nullptr, n, H, W, meas_cap);
+    rc = ensure_scratch(ctx, w.total);
+    if (rc != EPID_OK) return rc;
+    carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
+    uint16_t* pools[3] = {nullptr, nullptr, nullptr};
+    rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr);
+    if (rc == EPID_OK) {
+        cudaError_t e = cudaMemcpyAsync(summary, w.summ, sizeof(epid_pf_summary) * n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(meas, w.meas, sizeof(epid_pf_meas) * (size_t)n * meas_cap, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("PF result copy failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+    return rc;
+}
+
+int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* total_ms,
+                      float* stats_kernel_ms, int64_t* launches) {
+    EPID_REQUIRE(ctx && frames && p && iters > 0, EPID_ERR_INVALID, "bad argument");
+    EPID_REQUIRE(frames->dtype == EPID_U16, EPID_ERR_UNSUPPORTED, "picket fence frames must be uint16");
+    const int meas_cap = 1024;
+    int rc = pf_validate(p, frames->h, frames->w, meas_cap);
+    if (rc != EPID_OK) return rc;
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    const int n = frames->n, H = frames->h - 2 * p->crop_px, W = frames->w - 2 * p->crop_px;
+    PfWork w;
+    carve(w, nullptr, n, H, W, meas_cap);
+    rc = ensure_scratch(ctx, w.total);
+    if (rc != EPID_OK) return rc;
+    carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
+    PfTimers tm;
+    tm.on = true;
+    cudaEvent_t t0, t1;
+    EPID_CUDA(cudaEventCreate(&tm.e0));
+    EPID_CUDA(cudaEventCreate(&tm.e1));
+    EPID_CUDA(cudaEventCreate(&t0));
+    EPID_CUDA(cudaEventCreate(&t1));
+    uint16_t* pools[3] = {nullptr, nullptr, nullptr};
+    const int64_t l0 = ctx->launches;
+    EPID_CUDA(cudaStreamSynchronize(ctx->stream));
+    EPID_CUDA(cudaEventRecord(t0, ctx->stream));
+    for (int it = 0; it < iters && rc == EPID_OK; it++)
+        rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm);
+    cudaEventRecord(t1, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, t1);
+    if (total_ms) *total_ms = ms;
+    if (stats_kernel_ms) *stats_kernel_ms = tm.stats_ms;
+    if (launches) *launches = ctx->launches - l0;
+    cudaEventDestroy(tm.e0); cudaEventDestroy(tm.e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+    for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+    return rc;
+}
+
+int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, int32_t h, int32_t w_, const epid_pf_params* p,
+                             epid_pf_summary* summary, epid_pf_meas* meas, int32_t meas_cap) {
+    EPID_REQUIRE(ctx && frames && summary && meas, EPID_ERR_INVALID, "NULL argument");
+    EPID_REQUIRE(n > 0 && h > 0 && w_ > 0, EPID_ERR_INVALID, "empty batch");
+    int rc = pf_validate(p, h, w_, meas_cap);
+    if (rc != EPID_OK) return rc;
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    const int H = h - 2 * p->crop_px, W = w_ - 2 * p->crop_px;
+    const size_t fbytes = sizeof(uint16_t) * (size_t)h * w_;
+    // chunk size: ~64 MB of frames per chunk, double buffered
+    int chunk = (int)((64u << 20) / fbytes);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    PfWork wk;
+    carve(wk, nullptr, chunk, H, W, meas_cap);
+    const size_t work_bytes = align_up(wk.total, 256);
+    const size_t buf_bytes = align_up(fbytes * chunk, 256);
+    rc = ensure_scratch(ctx, 2 * work_bytes + 2 * buf_bytes);
+    if (rc != EPID_OK) return rc;
+    char* base = (char*)ctx->scratch;
+    PfWork works[2];
+    uint16_t* bufs[2];
+    for (int s = 0; s < 2; s++) {
+        carve(works[s], base + s * work_bytes, chunk, H, W, meas_cap);
+        bufs[s] = (uint16_t*)(base + 2 * work_bytes + s * buf_bytes);
+    }
+    cudaEvent_t copied[2], computed[2];
+    for (int s = 0; s < 2; s++) { EPID_CUDA(cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming)); EPID_CUDA(cudaEventCreateWithFlags(&computed[s], cudaEventDisableTiming)); }
+    uint16_t* pools[3] = {nullptr, nullptr, nullptr};
+    const int nchunks = (n + chunk - 1) / chunk;
+    // prologue: copy chunk 0
+    auto enqueue_copy = [&](int ci) -> int {
+        const int s = ci & 1;
+        const int cnt = (ci == nchunks - 1) ? n - ci * chunk : chunk;
+        // the buffer is free once the compute that last used it has finished
+        if (ci >= 2) EPID_CUDA(cudaStreamWaitEvent(ctx->copy_stream[0], computed[s], 0));
+        EPID_CUDA(cudaMemcpyAsync(bufs[s], frames + (size_t)ci * chunk * h * w_, fbytes * cnt, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+        EPID_CUDA(cudaEventRecord(copied[s], ctx->copy_stream[0]));
+        return EPID_OK;
+    };
+    rc = enqueue_copy(0);
+    for (int ci = 0; ci < nchunks && rc == EPID_OK; ci++) {
+        const int s = ci & 1;
+        const int cnt = (ci == nchunks - 1) ? n - ci * chunk : chunk;
+        if (ci + 1 < nchunks) { rc = enqueue_copy(ci + 1); if (rc != EPID_OK) break; }
+        EPID_CUDA(cudaStreamWaitEvent(ctx->stream, copied[s], 0));
+        rc = pf_run(ctx, ctx->stream, bufs[s], cnt, h, w_, p, meas_cap, works[s], pools, nullptr);
+        if (rc != EPID_OK) break;
+        EPID_CUDA(cudaMemcpyAsync(summary + (size_t)ci * chunk, works[s].summ, sizeof(epid_pf_summary) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        EPID_CUDA(cudaMemcpyAsync(meas + (size_t)ci * chunk * meas_cap, works[s].meas, sizeof(epid_pf_meas) * (size_t)cnt * meas_cap, cudaMemcpyDeviceToHost, ctx->stream));
+        EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
+    }
+    cudaStreamSynchronize(ctx->copy_stream[0]);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
+    for (int s = 0; s < 2; s++) { cudaEventDestroy(copied[s]); cudaEventDestroy(computed[s]); }
+    for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+// Fused frame statistics: ONE streaming read of a uint16 frame view produces min, max, sum, row sums,
+// column sums, the four check_inversion corner sums and EXACT order statistics (from a 65536-bin histogram
+// that never leaves shared memory).
+//
+// Replaces the reference's numpy passes: array.min()/max() (picketfence.py:231-232, core/image.py:851),
+// np.percentile / np.median of the full frame (picketfence.py:233,1510; core/image.py:918-920),
+// np.mean(image, axis) (picketfence.py:748-750), corner means (core/image.py:881-896).
+//
+// Design (B200): one persistent CTA of 1024 threads per SM, one frame per CTA at a time.  Each thread owns a
+// fixed 8-pixel column vector (128-bit ld.global.nc.L1::no_allocate, row pitch keeps it 16-byte aligned) and
+// strides over rows, so column sums live in registers, row sums are one warp-shuffle reduction + one shared
+// atomic per warp-row, and the histogram is 65536 packed 16-bit counters = 128 KB of shared memory updated
+// with ATOMS.ADD (1 or 0x10000 into the 32-bit word).  A packed counter can overflow only if > 65535 pixels of
+// a frame share one value; that is detected exactly (the decoded bin total then differs from the pixel count)
+// and the frame is re-run by the MODE 1 variant (32-bit counters over value>>1 plus a second pass resolving
+// the low bit), so results are always exact.
+#include "stats.cuh"
+
+namespace epid {
+
+constexpr int HIST_WORDS = 32768;
+
+int make_stats_geom(StatsGeom* g, int H, int W) {
+    if (H <= 0 || W <= 0 || H > STATS_MAX_DIM || W > STATS_MAX_DIM) {
+        set_error("frame view %d x %d outside the supported range (1..%d)", H, W, STATS_MAX_DIM);
+        return EPID_ERR_UNSUPPORTED;
+    }
+    memset(g, 0, sizeof(*g));
+    g->H = H;
+    g->W = W;
+    const int vpr = (W + 7 + 7) / 8;  // worst-case misalignment of 7 pixels
+    g->vprp = (vpr + 31) / 32 * 32;
+    g->groups = STATS_THREADS / g->vprp;
+    if (g->groups < 1) {
+        set_error("frame view too wide (%d)", W);
+        return EPID_ERR_UNSUPPORTED;
+    }
+    return EPID_OK;
+}
+
+__device__ __forceinline__ void block_scan_excl_1024(uint32_t v, uint32_t* s_warp, uint32_t& excl, uint32_t& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = s_warp[lane];
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;       // exclusive warp offsets
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    excl = s_warp[wid] + inc - v;
+    total = s_warp[32];
+    __syncthreads();
+}
+
+// MODE 0: packed u16 counters, all 65536 bins.  MODE 1: u32 counters over (v >> 1), low bit resolved by a 2nd pass.
+template <int MODE>
+__global__ void __launch_bounds__(STATS_THREADS, 1)
+k_frame_stats(const StatsGeom g, const FrameRef* __restrict__ frames, const int* __restrict__ out_index, int nframes,
+              FrameStats* __restrict__ stats, uint32_t* __restrict__ rowsum_out, uint32_t* __restrict__ colsum_out) {
+    extern __shared__ uint32_t smem[];
+    uint32_t* hist = smem;                                   // HIST_WORDS
+    uint32_t* colpart = hist + HIST_WORDS;                   // STATS_THREADS * 8
+    uint32_t* s_warp = colpart + STATS_THREADS * 8;          // 40
+    uint32_t* s_misc = s_warp + 40;                          // 8 + 3*STATS_MAX_RANKS (even word index: 64-bit atomics)
+    uint32_t* rowsum_sm = s_misc + 8 + 3 * STATS_MAX_RANKS;  // H
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int grp = tid / g.vprp;
+    const int jc = tid - grp * g.vprp;
+    const bool active_grp = grp < g.groups;
+
+    for (int fi = blockIdx.x; fi < nframes; fi += gridDim.x) {
+        const int slot = out_index ? out_index[fi] : fi;
+        if (MODE == 1 && stats[slot].overflow == 0) continue;
+        const FrameRef fr = frames[fi];
+        const uint16_t* __restrict__ f = fr.origin;
+        const int pitch = fr.pitch;
+        // aligned vector grid of this frame: vector j covers view columns [8j - mis, 8j - mis + 8)
+        const bool aligned = (pitch % 8) == 0;
+        const int mis = aligned ? (int)((reinterpret_cast<uintptr_t>(f) >> 1) & 7) : 0;
+        const int col_first = jc * 8 - mis;
+        uint32_t valid = 0;
+        if (active_grp) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int c = col_first + k;
+                if (c >= 0 && c < g.W) valid |= 1u << k;
+            }
+        }
+        const bool active = valid != 0;
+        for (int i = tid; i < HIST_WORDS; i += STATS_THREADS) hist[i] = 0;
+        for (int i = tid; i < g.H; i += STATS_THREADS) rowsum_sm[i] = 0;
+        __syncthreads();
+
+        uint32_t mn = 0xffffu, mx = 0, csum[8];
+        unsigned long long tsum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) csum[k] = 0;
+
+        if (active_grp) {
+            constexpr int U = 4;
+            for (int r = grp; r < g.H; r += g.groups * U) {
+                uint4 q[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int rr = r + u * g.groups;
+                    q[u] = make_uint4(0, 0, 0, 0);
+                    if (rr < g.H && active) {
+                        const uint16_t* rowp = f + (size_t)rr * pitch;
+                        if (aligned) {
+                            q[u] = ldg_stream16(rowp + col_first);
+                        } else {
+                            uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                if (valid >> k & 1) w[k >> 1] |= (uint32_t)__ldg(rowp + col_first + k) << ((k & 1) * 16);
+                            q[u] = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int rr = r + u * g.groups;
+                    if (rr >= g.H) break;  // warp-uniform
+                    uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+                    uint32_t rs = 0;
+                    if (valid == 0xffu) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t lo = w[k] & 0xffffu, hi = w[k] >> 16;
+                            if (MODE == 0) {
+                                atomicAdd(&hist[lo >> 1], (lo & 1) ? 0x10000u : 1u);
+                                atomicAdd(&hist[hi >> 1], (hi & 1) ? 0x10000u : 1u);
+                            } else {
+                                atomicAdd(&hist[lo >> 1], 1u);
+                                atomicAdd(&hist[hi >> 1], 1u);
+                            }
+                            mn = min(mn, min(lo, hi));
+                            mx = max(mx, max(lo, hi));
+                            csum[2 * k] += lo;
+                            csum[2 * k + 1] += hi;
+                            rs += lo + hi;
+                        }
+                    } else if (valid) {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            if (valid >> k & 1) {
+                                const uint32_t v = (w[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                                if (MODE == 0)
+                                    atomicAdd(&hist[v >> 1], (v & 1) ? 0x10000u : 1u);
+                                else
+                                    atomicAdd(&hist[v >> 1], 1u);
+                                mn = min(mn, v);
+                                mx = max(mx, v);
+                                csum[k] += v;
+                                rs += v;
+                            }
+                        }
+                    }
+                    tsum += rs;
+                    rs = warp_sum(rs);
+                    if (lane == 0) atomicAdd(&rowsum_sm[rr], rs);
+                }
+            }
+        }
+        // column partials -> shared
+#pragma unroll
+        for (int k = 0; k < 8; k++) colpart[tid * 8 + k] = active ? csum[k] : 0u;
+        // block reductions of min / max / sum
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        tsum = warp_sum(tsum);
+        __syncthreads();  // (also orders hist / rowsum / colpart writes)
+        if (tid == 0) { s_misc[0] = 0xffffu; s_misc[1] = 0; s_misc[2] = 0; s_misc[3] = 0; s_misc[4] = 0; s_misc[5] = 0; }
+        __syncthreads();
+        if (lane == 0) {
+            atomicMin(&s_misc[0], mn);
+            atomicMax(&s_misc[1], mx);
+            atomicAdd(reinterpret_cast<unsigned long long*>(&s_misc[2]), tsum);
+        }
+        // corner boxes (core/image.py:881-894): rows [rp, rp+box) and [H-rp-box, H-rp), cols [cp, cp+box) and [W-cp-box, W-cp)
+        if (g.box > 0) {
+            const int per = g.box * g.box;
+            unsigned long long cs = 0;
+            for (int i = tid; i < 4 * per; i += STATS_THREADS) {
+                const int b = i / per, o = i - b * per;
+                const int y = o / g.box, x = o - y * g.box;
+                const int rr = ((b & 2) ? g.H - g.rp - g.box : g.rp) + y;
+                const int cc = ((b & 1) ? g.W - g.cp - g.box : g.cp) + x;
+                if (rr >= 0 && rr < g.H && cc >= 0 && cc < g.W) cs += __ldg(f + (size_t)rr * pitch + cc);
+            }
+            cs = warp_sum(cs);
+            if (lane == 0 && cs) atomicAdd(reinterpret_cast<unsigned long long*>(&s_misc[4]), cs);
+        }
+        __syncthreads();
+        // outputs: sums
+        if (colsum_out) {
+            for (int x = tid; x < g.W; x += STATS_THREADS) {
+                const int ac = x + mis;  // position inside the per-row vector grid
+                uint32_t s = 0;
+                for (int gg = 0; gg < g.groups; gg++) s += colpart[(gg * g.vprp) * 8 + ac];
+                colsum_out[(size_t)slot * g.W + x] = s;
+            }
+        }
+        if (rowsum_out)
+            for (int y = tid; y < g.H; y += STATS_THREADS) rowsum_out[(size_t)slot * g.H + y] = rowsum_sm[y];
+
+        // ---- order statistics from the histogram
+        uint32_t cnt = 0;
+        {
+            const uint32_t* hw = hist + tid * 32;
+#pragma unroll 8
+            for (int i = 0; i < 32; i++) {
+                // rotate the start so that the 32 lanes of a warp hit 32 different banks
+                const uint32_t w = hw[(i + lane) & 31];
+                cnt += (MODE == 0) ? ((w & 0xffffu) + (w >> 16)) : w;
+            }
+        }
+        uint32_t excl, total;
+        block_scan_excl_1024(cnt, s_warp, excl, total);
+        const uint32_t npix = (uint32_t)g.H * (uint32_t)g.W;
+        const bool overflow = (MODE == 0) && (total != npix);
+        uint32_t* s_val = s_misc + 8;                       // value (MODE 0) or bin (MODE 1)
+        uint32_t* s_off = s_val + STATS_MAX_RANKS;          // MODE 1: rank offset inside the bin
+        uint32_t* s_cnt = s_off + STATS_MAX_RANKS;          // MODE 1: count of even values in the bin
+        if (!overflow) {
+            for (int qi = 0; qi < g.nranks; qi++) {
+                const uint32_t k = g.ranks[qi];
+                if (k >= excl && k < excl + cnt) {
+                    uint32_t acc = excl;
+                    const uint32_t* hw = hist + tid * 32;
+                    for (int i = 0; i < 32; i++) {
+                        const uint32_t w = hw[i];
+                        if (MODE == 0) {
+                            const uint32_t c0 = w & 0xffffu, c1 = w >> 16;
+                            if (k < acc + c0) { s_val[qi] = (tid * 32 + i) * 2; break; }
+                            acc += c0;
+                            if (k < acc + c1) { s_val[qi] = (tid * 32 + i) * 2 + 1; break; }
+                            acc += c1;
+                        } else {
+                            if (k < acc + w) { s_val[qi] = tid * 32 + i; s_off[qi] = k - acc; s_cnt[qi] = 0; break; }
+                            acc += w;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (MODE == 1 && g.nranks > 0) {
+            // second pass: how many pixels equal 2*bin (the even value of each target bin)?
+            uint32_t local[STATS_MAX_RANKS];
+#pragma unroll
+            for (int qi = 0; qi < STATS_MAX_RANKS; qi++) local[qi] = 0;
+            for (int i = tid; i < g.H * g.W; i += STATS_THREADS) {
+                const int rr = i / g.W, cc = i - rr * g.W;
+                const uint32_t v = __ldg(f + (size_t)rr * pitch + cc);
+#pragma unroll
+                for (int qi = 0; qi < STATS_MAX_RANKS; qi++)
+                    if (qi < g.nranks && v == 2u * s_val[qi]) local[qi]++;
+            }
+#pragma unroll
+            for (int qi = 0; qi < STATS_MAX_RANKS; qi++) {
+                if (qi < g.nranks) {
+                    uint32_t s = warp_sum(local[qi]);
+                    if (lane == 0 && s) atomicAdd(&s_cnt[qi], s);
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {
+            FrameStats& o = stats[slot];
+            o.mn = s_misc[0];
+            o.mx = s_misc[1];
+            o.npix = npix;
+            o.sum = *reinterpret_cast<unsigned long long*>(&s_misc[2]);
+            o.corner_sum = *reinterpret_cast<unsigned long long*>(&s_misc[4]);
+            o.overflow = overflow ? 1u : 0u;
+            if (!overflow)
+                for (int qi = 0; qi < g.nranks; qi++)
+                    o.ostat[qi] = (MODE == 0) ? s_val[qi] : (2u * s_val[qi] + (s_off[qi] >= s_cnt[qi] ? 1u : 0u));
+        }
+        __syncthreads();
+    }
+}
+
+static size_t stats_smem_bytes(const StatsGeom& g) {
+    return sizeof(uint32_t) * (size_t)(HIST_WORDS + STATS_THREADS * 8 + g.H + 40 + 8 + 3 * STATS_MAX_RANKS);
+}
+
+int launch_frame_stats(epid_ctx* ctx, cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames,
+                       const int* d_out_index, int n, FrameStats* d_stats, uint32_t* d_rowsum, uint32_t* d_colsum) {
+    static bool attr_set = false;
+    const size_t smem = stats_smem_bytes(g);
+    if (!attr_set) {
+        EPID_CUDA(cudaFuncSetAttribute(k_frame_stats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        EPID_CUDA(cudaFuncSetAttribute(k_frame_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    const int grid = n < ctx->sm_count ? n : ctx->sm_count;
+    k_frame_stats<0><<<grid, STATS_THREADS, smem, stream>>>(g, d_frames, d_out_index, n, d_stats, d_rowsum, d_colsum);
+    // exact fallback for frames whose packed counters overflowed (CTAs of other frames exit at once)
+    k_frame_stats<1><<<grid, STATS_THREADS, smem, stream>>>(g, d_frames, d_out_index, n, d_stats, d_rowsum, d_colsum);
+    ctx->launches += 2;
+    EPID_CUDA(cudaGetLastError());
+    return EPID_OK;
+}
+
+}  // namespace epid

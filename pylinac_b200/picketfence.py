@@ -1,0 +1,527 @@
+"""Picket-fence analysis -- drop-in for the hot path of ``pylinac.picketfence`` (reference file cited per item).
+
+``PicketFence(image).analyze(**kw)`` keeps the reference's signature and result accessors; underneath, the whole
+frame pipeline (crop view, noise check, inversion check, ground/normalise, orientation, picket search, per-leaf
+windows, FWHM positions, line fits, errors) runs in CUDA (pylinac_b200/csrc/pf.cu) with batch = 1.
+``analyze_batch(frames, ...)`` is the batched entry point the benchmark uses (one result per frame).
+
+Out of scope: plotting, PDF/QuAAC export, trajectory-log overlay (``log=``).
+"""
+from __future__ import annotations
+
+import enum
+import warnings
+from collections.abc import Sequence
+from pathlib import Path
+
+import numpy as np
+
+from . import _native as nat
+from .core import image
+from .core.geometry import Line, Point
+from .core.utilities import ResultBase, ResultsDataMixin, convert_to_enum
+
+LEFT_MLC_PREFIX = "A"
+RIGHT_MLC_PREFIX = "B"
+
+
+class Orientation(enum.Enum):
+    """picketfence.py:61-65"""
+
+    UP_DOWN = "Up-Down"
+    LEFT_RIGHT = "Left-Right"
+
+
+class MLCArrangement:
+    """picketfence.py:68-100"""
+
+    def __init__(self, leaf_arrangement: list[tuple[int, float]], offset: float = 0):
+        self.centers = []
+        self.widths = []
+        rolling_edge = 0
+        for leaf_num, width in leaf_arrangement:
+            self.centers += np.arange(start=rolling_edge + width / 2, stop=leaf_num * width + rolling_edge + width / 2,
+                                      step=width).tolist()
+            rolling_edge = self.centers[-1] + width / 2
+            self.widths += [width] * leaf_num
+        self.centers = [c - np.mean(self.centers) + offset for c in self.centers]
+
+    @property
+    def leaves(self) -> list[int]:
+        return np.arange(1, len(self.centers) + 1, dtype=int)[::-1].tolist()
+
+
+class MLC(enum.Enum):
+    """picketfence.py:103-135"""
+
+    MILLENNIUM = {"name": "Millennium", "arrangement": MLCArrangement([(10, 10), (40, 5), (10, 10)])}
+    HD_MILLENNIUM = {"name": "HD Millennium", "arrangement": MLCArrangement([(14, 5), (32, 2.5), (14, 5)])}
+    BMOD = {"name": "B Mod", "arrangement": MLCArrangement([(40, 4)])}
+    AGILITY = {"name": "Agility", "arrangement": MLCArrangement([(80, 5)])}
+    MLCI = {"name": "MLCi", "arrangement": MLCArrangement([(40, 10)])}
+    HALCYON_DISTAL = {"name": "Halcyon distal", "arrangement": MLCArrangement([(28, 10)])}
+    HALCYON_PROXIMAL = {"name": "Halcyon proximal", "arrangement": MLCArrangement([(29, 10)])}
+
+
+def _get_mlc_arrangement(value) -> MLCArrangement:  # picketfence.py:331-342
+    if isinstance(value, MLC):
+        return value.value["arrangement"]
+    if isinstance(value, MLCArrangement):
+        return value
+    if isinstance(value, str):
+        return [m.value["arrangement"] for _, m in MLC.__members__.items() if m.value["name"] == value][0]
+    raise TypeError("mlc must be an MLC, MLCArrangement or str")
+
+
+class PFResult(ResultBase):
+    """picketfence.py:138-201"""
+
+    tolerance_mm: float
+    action_tolerance_mm: float | None
+    percent_leaves_passing: float
+    number_of_pickets: int
+    absolute_median_error_mm: float
+    max_error_mm: float
+    max_error_picket: int
+    max_error_leaf: str | int
+    mean_picket_spacing_mm: float
+    offsets_from_cax_mm: list[float]
+    passed: bool
+    failed_leaves: list[str] | list[int]
+    mlc_skew: float
+    picket_widths: dict[str, dict[str, float]]
+    mlc_positions_by_leaf: dict[str, list[float]]
+    mlc_errors_by_leaf: dict[str, list[float]]
+    cax: dict
+
+
+STATUS_EXCEPTIONS = {
+    1: (ValueError, "No pickets were found. This can mean either an incorrect orientation or incorrect inversion. "
+                    "Try passing the correct orientation; if that fails, also set invert=True."),
+    2: (ValueError, "No MLC measurements were found. This may be due to an incorrect inversion. Try setting invert=True. "
+                    "Or, you may have passed an incorrect orientation."),
+    3: (NotImplementedError, f"More than {nat.PF_MAX_PICKETS} pickets were detected; unsupported."),
+    4: (IndexError, "An MLC window profile has no peak (the reference raises IndexError in FWXMProfile.field_edge_idx)."),
+    5: (MemoryError, "Measurement table / window capacity exceeded."),
+    6: (ValueError, "The image is flat (max == min); cannot normalize."),
+    7: (TypeError, "expected non-empty vector for x (a picket has no MLC measurements)."),
+}
+
+
+def make_params(dpmm: float, shape, *, crop_mm=3, filter=None, mlc=MLC.MILLENNIUM, tolerance=0.5, action_tolerance=None,
+                num_pickets=None, sag_adjustment=0, orientation=None, invert=False, leaf_analysis_width_ratio=0.4,
+                picket_spacing=None, height_threshold=0.5, edge_threshold=1.5, peak_sort="peak_heights",
+                required_prominence=0.2, fwxm=50, separate_leaves=False, nominal_gap_mm=3, central_axis=None) -> nat.PFParams:
+    """Translate the reference's constructor + analyze() keyword arguments (picketfence.py:280-289, 636-654) into the
+    C-ABI parameter block.  ``fwxm`` is accepted and ignored exactly like the reference does (it stores the value,
+    picketfence.py:1563, but never forwards it to FWXMProfilePhysical, :1610-1615)."""
+    if action_tolerance is not None and tolerance < action_tolerance:
+        raise ValueError("Tolerance cannot be lower than the action tolerance")
+    arr = _get_mlc_arrangement(mlc)
+    n = len(arr.centers)
+    if n > nat.PF_MAX_LEAVES:
+        raise NotImplementedError(f"MLC arrangements with more than {nat.PF_MAX_LEAVES} leaves are not supported")
+    p = nat.PFParams()
+    p.dpmm = float(dpmm)
+    p.crop_px = int(round(crop_mm * dpmm))
+    p.filter_size = int(filter) if isinstance(filter, int) and not isinstance(filter, bool) else 0
+    p.tolerance = float(tolerance)
+    p.action_tolerance = -1.0 if action_tolerance is None else float(action_tolerance)
+    p.num_pickets = int(num_pickets) if num_pickets else 0
+    p.sag_px = int(round(sag_adjustment * dpmm)) if sag_adjustment != 0 else 0
+    if orientation is None:
+        p.orientation = -1
+    else:
+        p.orientation = 0 if convert_to_enum(orientation, Orientation) == Orientation.UP_DOWN else 1
+    p.invert = 1 if invert else 0
+    p.leaf_analysis_width_ratio = float(leaf_analysis_width_ratio)
+    p.picket_spacing = -1.0 if picket_spacing is None else float(picket_spacing)
+    p.height_threshold = float(height_threshold)
+    p.edge_threshold = float(edge_threshold)
+    p.peak_sort = 1 if peak_sort == "peak_heights" else 0
+    p.required_prominence = -1.0 if required_prominence is None else float(required_prominence)
+    p.separate_leaves = 1 if separate_leaves else 0
+    p.nominal_gap_mm = float(nominal_gap_mm)
+    if central_axis is not None:
+        # PFDicomImage.center (picketfence.py:246-260) on the CROPPED image
+        h = shape[0] - 2 * p.crop_px
+        w = shape[1] - 2 * p.crop_px
+        cx = (w / 2 - 0.5) + central_axis.x * dpmm
+        cy = (h / 2 - 0.5) + central_axis.y * dpmm
+        cy = 2 * (h // 2) - cy
+        p.has_cax_override = 1
+        p.cax_x_px = cx
+        p.cax_y_px = cy
+    p.n_leaves = n
+    for i in range(n):
+        p.leaf_center_mm[i] = float(arr.centers[i])
+        p.leaf_width_mm[i] = float(arr.widths[i])
+        p.leaf_num[i] = int(arr.leaves[i])
+    return p
+
+
+class PFFrameResult:
+    """Lazy, per-frame view over the struct-of-arrays the GPU returned (no Python objects per MLC kiss until asked)."""
+
+    def __init__(self, summary, meas, params: nat.PFParams, tolerance, action_tolerance, separate_leaves):
+        self.s = summary
+        self.m = meas[: int(summary["n_meas"])] if int(summary["status"]) == 0 else meas[:0]
+        self.params = params
+        self.tolerance = tolerance
+        self.action_tolerance = action_tolerance
+        self.separate_leaves = bool(separate_leaves)
+
+    @property
+    def status(self) -> int:
+        return int(self.s["status"])
+
+    def raise_for_status(self):
+        if self.status:
+            exc, msg = STATUS_EXCEPTIONS.get(self.status, (RuntimeError, f"picket fence status {self.status}"))
+            raise exc(msg)
+
+    @property
+    def orientation(self) -> Orientation:
+        return Orientation.UP_DOWN if int(self.s["orientation"]) == 0 else Orientation.LEFT_RIGHT
+
+    @property
+    def num_pickets(self) -> int:
+        return int(self.s["n_pickets"])
+
+    @property
+    def picket_idx(self) -> np.ndarray:
+        return self.s["picket_idx"][: self.num_pickets].astype(np.int64)
+
+    def _npos(self):
+        return 2 if self.separate_leaves else 1
+
+    def _leaf_name(self, leaf, bank):
+        if not self.separate_leaves:
+            return int(leaf)
+        return f"{LEFT_MLC_PREFIX if bank == 0 else RIGHT_MLC_PREFIX}{int(leaf)}"
+
+    def failed_leaves(self):
+        out = []
+        for row in self.m:
+            ok = [bool(row["passed"][k]) for k in range(self._npos())]
+            if all(ok):
+                continue
+            names = [int(row["leaf_num"])] if not self.separate_leaves else [self._leaf_name(row["leaf_num"], k) for k in range(2) if not ok[k]]
+            for nme in names:
+                if nme not in out:
+                    out.append(nme)
+        return out
+
+    @property
+    def max_error_leaf(self):
+        if not self.separate_leaves:
+            return int(self.s["max_error_leaf"])
+        return self._leaf_name(self.s["max_error_leaf"], int(self.s["max_error_bank"]))
+
+    def results_data(self) -> PFResult:
+        self.raise_for_status()
+        s = self.s
+        npk = self.num_pickets
+        dpmm = self.params.dpmm
+        cax_phys = float(s["cax_px"]) / dpmm
+        positions, errors = {}, {}
+        npos = self._npos()
+        for row in self.m:  # leaf-major, picket-minor (picketfence.py:1329-1338)
+            for k in range(npos):
+                name = str(self._leaf_name(row["leaf_num"], k))
+                positions.setdefault(name, []).append(cax_phys - float(row["position"][k]) / dpmm)
+                errors.setdefault(name, []).append(float(row["error"][k]))
+        h, w = int(s["height"]), int(s["width"])
+        if self.params.has_cax_override:
+            cax = {"x": self.params.cax_x_px, "y": self.params.cax_y_px, "z": 0}
+        else:
+            cax = {"x": w / 2 - 0.5, "y": h / 2 - 0.5, "z": 0}
+        return PFResult(
+            tolerance_mm=self.tolerance,
+            action_tolerance_mm=self.action_tolerance,
+            percent_leaves_passing=float(s["percent_passing"]),
+            number_of_pickets=npk,
+            absolute_median_error_mm=float(s["abs_median_error_mm"]),
+            max_error_mm=float(s["max_error_mm"]),
+            max_error_picket=int(s["max_error_picket"]),
+            max_error_leaf=self.max_error_leaf,
+            mean_picket_spacing_mm=float(s["mean_picket_spacing_mm"]),
+            offsets_from_cax_mm=[float(v) for v in s["offsets_from_cax_mm"][:npk]],
+            passed=bool(s["passed"]),
+            failed_leaves=self.failed_leaves(),
+            mlc_skew=float(s["mlc_skew"]),
+            picket_widths={f"picket_{k}": {"max": float(s["picket_width_max"][k]), "mean": float(s["picket_width_mean"][k]),
+                                           "median": float(s["picket_width_median"][k]), "min": float(s["picket_width_min"][k])}
+                           for k in range(npk)},
+            mlc_positions_by_leaf=dict(sorted(positions.items())),
+            mlc_errors_by_leaf=dict(sorted(errors.items())),
+            cax=cax,
+        )
+
+
+class PFBatchResult(Sequence):
+    def __init__(self, summary, meas, params, tolerance, action_tolerance, separate_leaves):
+        self.summary = summary
+        self.meas = meas
+        self.params = params
+        self._args = (tolerance, action_tolerance, separate_leaves)
+
+    def __len__(self):
+        return len(self.summary)
+
+    def __getitem__(self, i) -> PFFrameResult:
+        return PFFrameResult(self.summary[i], self.meas[i], self.params, *self._args)
+
+
+def analyze_batch(frames, dpmm: float, *, device: int | None = None, meas_cap: int = 1024, crop_mm=3, filter=None,
+                  mlc=MLC.MILLENNIUM, **analyze_kwargs) -> PFBatchResult:
+    """Batched ``PicketFence(frame, filter=, mlc=, crop_mm=).analyze(**analyze_kwargs)`` over frames[n, h, w] uint16.
+
+    ``frames`` may be a host ndarray (chunked H2D copies overlapped with compute) or a device-resident
+    ``_native.Batch``.  Returns one lazily materialised result per frame.
+    """
+    ctx = nat.Context.default(device)
+    if isinstance(frames, nat.Batch):
+        (n, h, w), dt = frames.shape_dtype
+    else:
+        frames = np.asarray(frames)
+        if frames.ndim == 2:
+            frames = frames[None]
+        n, h, w = frames.shape
+    params = make_params(dpmm, (h, w), crop_mm=crop_mm, filter=filter, mlc=mlc, **analyze_kwargs)
+    summ, meas = nat.pf_analyze(ctx, frames, params, meas_cap=meas_cap)
+    return PFBatchResult(summ, meas, params, analyze_kwargs.get("tolerance", 0.5), analyze_kwargs.get("action_tolerance"),
+                         analyze_kwargs.get("separate_leaves", False))
+
+
+class PFImageMixin:
+    """PFDicomImage behaviour (picketfence.py:204-260) that is not pixel arithmetic: the CAX override."""
+
+    _central_axis: Point | None = None
+
+
+class _PicketView:
+    """The parts of ``Picket`` (picketfence.py:1857-1923) user code reads: fit, skew(), dist2cax, mlc_meas."""
+
+    def __init__(self, fit, dist2cax, meas):
+        self.fit = np.poly1d(fit)
+        self.dist2cax = dist2cax
+        self.mlc_meas = meas
+
+    def skew(self) -> float:
+        return float(np.rad2deg(self.fit.coefficients[0]))
+
+
+class _MLCValueView:
+    """The parts of ``MLCValue`` (picketfence.py:1529-1743) that are data."""
+
+    def __init__(self, row, npos, dpmm, leaf_center_px, leaf_width_px, ratio, orientation, separate):
+        self.leaf_num = int(row["leaf_num"])
+        self.picket_num = int(row["picket"])
+        self.position = tuple(float(row["position"][k]) for k in range(npos))
+        self.error = [float(row["error"][k]) for k in range(npos)]
+        self.passed = [bool(row["passed"][k]) for k in range(npos)]
+        self.field_width_mm = float(row["width_mm"])
+        self._dpmm = dpmm
+        self.leaf_center_px = leaf_center_px
+        self.leaf_width_px = leaf_width_px
+        self._analysis_ratio = ratio
+        self._orientation = orientation
+        self._separate_leaves = separate
+
+    @property
+    def position_mm(self):
+        return [p / self._dpmm for p in self.position]
+
+    @property
+    def full_leaf_nums(self):
+        if not self._separate_leaves:
+            return [self.leaf_num]
+        return [f"{LEFT_MLC_PREFIX}{self.leaf_num}", f"{RIGHT_MLC_PREFIX}{self.leaf_num}"]
+
+    @property
+    def max_abs_error(self) -> float:
+        return float(np.max(np.abs(self.error)))
+
+    @property
+    def marker_lines(self) -> list[Line]:  # picketfence.py:1725-1743
+        upper = self.leaf_center_px - self.leaf_width_px / 2 * self._analysis_ratio
+        lower = self.leaf_center_px + self.leaf_width_px / 2 * self._analysis_ratio
+        lines = []
+        for p in self.position:
+            if self._orientation == Orientation.UP_DOWN:
+                lines.append(Line((p, upper), (p, lower)))
+            else:
+                lines.append(Line((upper, p), (lower, p)))
+        return lines
+
+    def __repr__(self):
+        return f"Leaf: {self.leaf_num}, Picket: {self.picket_num}"
+
+
+class PicketFence(ResultsDataMixin[PFResult]):
+    """picketfence.py:263-329, 439-562, 636-845, 1292-1363 -- same constructor / analyze() signature."""
+
+    def __init__(self, filename, filter: int | None = None, log: str | None = None, use_filename: bool = False,
+                 mlc=MLC.MILLENNIUM, crop_mm: int = 3, image_kwargs: dict | None = None):
+        if log is not None:
+            raise NotImplementedError("trajectory-log overlay (log=) is outside the accelerated hot path")
+        img_kwargs = dict(image_kwargs or {})
+        self._central_axis = img_kwargs.pop("central_axis", None)
+        if isinstance(filename, np.ndarray):
+            self._raw = image.ArrayImage(filename, **img_kwargs)
+        elif isinstance(filename, image.BaseImage):
+            self._raw = filename
+        else:
+            self._raw = image.LinacDicomImage(filename, use_filenames=use_filename, **img_kwargs)
+        if self._raw.dpmm is None:
+            raise ValueError("The image has no dpmm; pass image_kwargs={'dpi': ..., 'sid': ...} for array input")
+        self._filter = filter
+        self._crop_mm = crop_mm
+        self.mlc = _get_mlc_arrangement(mlc)
+        self._mlc_arg = mlc
+        self._is_analyzed = False
+        self._result: PFFrameResult | None = None
+        self._warnings: list = []
+
+    @classmethod
+    def from_multiple_images(cls, *a, **k):
+        raise NotImplementedError("load_multiples is an ingest feature outside the accelerated hot path (SURVEY.md 8f)")
+
+    # the frame the GPU analyses: uint16, un-cropped (the crop is a device-side view)
+    def _frame_u16(self) -> np.ndarray:
+        a = self._raw.array
+        if a.dtype == np.uint16:
+            return a
+        if a.dtype == np.uint8:
+            return a.astype(np.uint16)
+        af = np.asarray(a)
+        if af.dtype.kind in "fiu" and af.min() >= 0 and af.max() <= 65535 and np.array_equal(af, np.floor(af)):
+            return af.astype(np.uint16)  # integer-valued pixels stored as another dtype (e.g. DICOM rescale 1.0/0.0)
+        raise NotImplementedError("the GPU picket-fence path takes integer-valued pixel data in [0, 65535]")
+
+    def analyze(self, tolerance: float = 0.5, action_tolerance: float | None = None, num_pickets: int | None = None,
+                sag_adjustment: float | int = 0, orientation=None, invert: bool = False,
+                leaf_analysis_width_ratio: float = 0.4, picket_spacing: float | None = None, height_threshold: float = 0.5,
+                edge_threshold: float = 1.5, peak_sort: str = "peak_heights", required_prominence: float = 0.2,
+                fwxm: int = 50, separate_leaves: bool = False, nominal_gap_mm: float = 3, central_axis: Point | None = None) -> None:
+        """picketfence.py:636-845"""
+        if action_tolerance is not None and tolerance < action_tolerance:
+            raise ValueError("Tolerance cannot be lower than the action tolerance")
+        self.tolerance = tolerance
+        self.action_tolerance = action_tolerance
+        self.leaf_analysis_width = leaf_analysis_width_ratio
+        self.separate_leaves = separate_leaves
+        if central_axis:
+            self._central_axis = central_axis
+        frame = self._frame_u16()
+        dpmm = self._raw.dpmm
+        batch = analyze_batch(frame, dpmm, crop_mm=self._crop_mm, filter=self._filter, mlc=self._mlc_arg, tolerance=tolerance,
+                              action_tolerance=action_tolerance, num_pickets=num_pickets, sag_adjustment=sag_adjustment,
+                              orientation=orientation, invert=invert, leaf_analysis_width_ratio=leaf_analysis_width_ratio,
+                              picket_spacing=picket_spacing, height_threshold=height_threshold, edge_threshold=edge_threshold,
+                              peak_sort=peak_sort, required_prominence=required_prominence, fwxm=fwxm,
+                              separate_leaves=separate_leaves, nominal_gap_mm=nominal_gap_mm, central_axis=self._central_axis)
+        res = batch[0]
+        res.raise_for_status()
+        self._result = res
+        if int(res.s["n_leaves_removed"]) > 0:
+            warnings.warn("Some leaves were removed from analysis because they were not detected for all pickets. If some valid "
+                          "leaves are missing try adjusting height_threshold or edge_threshold")
+        self._is_analyzed = True
+
+    # ------------------------------------------------------------------ accessors (picketfence.py:439-562)
+    def _need(self) -> PFFrameResult:
+        if not self._is_analyzed:
+            raise ValueError("It appears the PF image has not been analyzed yet. Use .analyze() first.")
+        return self._result
+
+    @property
+    def orientation(self) -> Orientation:
+        return self._need().orientation
+
+    @property
+    def passed(self) -> bool:
+        return bool(self._need().s["passed"])
+
+    @property
+    def percent_passing(self) -> float:
+        return float(self._need().s["percent_passing"])
+
+    @property
+    def max_error(self) -> float:
+        return float(self._need().s["max_error_mm"])
+
+    @property
+    def max_error_picket(self) -> int:
+        return int(self._need().s["max_error_picket"])
+
+    @property
+    def max_error_leaf(self):
+        return self._need().max_error_leaf
+
+    @property
+    def abs_median_error(self) -> float:
+        return float(self._need().s["abs_median_error_mm"])
+
+    @property
+    def num_pickets(self) -> int:
+        return self._need().num_pickets
+
+    @property
+    def mean_picket_spacing(self) -> float:
+        return float(self._need().s["mean_picket_spacing_mm"])
+
+    def mlc_skew(self) -> float:
+        return float(self._need().s["mlc_skew"])
+
+    def failed_leaves(self):
+        return self._need().failed_leaves()
+
+    def picket_width_stat(self, picket: int, metric: str = "max") -> float:
+        return float(self._need().s[f"picket_width_{metric}"][picket])
+
+    @property
+    def mlc_meas(self) -> list[_MLCValueView]:
+        r = self._need()
+        p = r.params
+        n_axis = r.s["height"] if r.orientation == Orientation.UP_DOWN else r.s["width"]
+        centers = {int(p.leaf_num[i]): (p.leaf_center_mm[i], p.leaf_width_mm[i]) for i in range(p.n_leaves)}
+        out = []
+        for row in r.m:
+            c_mm, w_mm = centers[int(row["leaf_num"])]
+            out.append(_MLCValueView(row, r._npos(), p.dpmm, c_mm * p.dpmm + n_axis / 2, w_mm * p.dpmm,
+                                     p.leaf_analysis_width_ratio, r.orientation, r.separate_leaves))
+        return out
+
+    @property
+    def pickets(self) -> list[_PicketView]:
+        r = self._need()
+        meas = self.mlc_meas
+        return [_PicketView([float(r.s["fit_slope"][k]), float(r.s["fit_intercept"][k])], float(r.s["offsets_from_cax_mm"][k]),
+                            [m for m in meas if m.picket_num == k]) for k in range(r.num_pickets)]
+
+    def results(self, as_list: bool = False):
+        """picketfence.py:1292-1311"""
+        r = self._need()
+        offsets = " ".join(f"{float(v):.1f}" for v in r.s["offsets_from_cax_mm"][: r.num_pickets])
+        gantry = getattr(self._raw, "gantry_angle", 0.0)
+        coll = getattr(self._raw, "collimator_angle", 0.0)
+        results = [
+            "Picket Fence Results:",
+            f"Gantry Angle (\N{DEGREE SIGN}): {gantry:2.1f}",
+            f"Collimator Angle (\N{DEGREE SIGN}): {coll:2.1f}",
+            f"Tolerance (mm): {self.tolerance}",
+            f"Leaves passing (%): {self.percent_passing:2.1f}",
+            f"Absolute median error (mm): {self.abs_median_error:2.3f}mm",
+            f"Mean picket spacing (mm): {self.mean_picket_spacing:2.1f}mmn",
+            f"Picket offsets from CAX (mm): {offsets}",
+            f"Max Error: {self.max_error:2.3f}mm on Picket: {self.max_error_picket}, Leaf: {self.max_error_leaf}",
+            f"MLC Skew: {self.mlc_skew():2.3f} degrees",
+        ]
+        if self.failed_leaves():
+            results.append(f"Failing leaves: {self.failed_leaves()}")
+        return results if as_list else "\n".join(results)
+
+    def _generate_results_data(self) -> PFResult:
+        return self._need().results_data()

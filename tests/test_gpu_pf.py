@@ -1,0 +1,128 @@
+"""GPU parity: PicketFence pipeline in CUDA (through the C-ABI) vs the committed reference goldens and the oracle port.
+
+Bars (BASELINE.json north_star): bit-exact for orientation, picket indices, leaf / picket / kiss counts, pass flags;
+<= 0.01 px for sub-pixel positions (we assert 1e-6 px; the fp64 profile arithmetic mirrors scipy's operation order)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from tests.golden.pf_cases import CASES, case_frame
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load("tests/golden/pf_golden.npz")
+POS_TOL_PX = 1e-6     # required: 0.01 px
+ERR_TOL_MM = 1e-6
+
+
+def gpu_run(name):
+    from pylinac_b200 import picketfence as pf
+
+    a, ps, sid, ck, ak = case_frame(name)
+    dpmm = (1 / ps) * sid / 1000.0
+    ck = dict(ck)
+    if ck.get("mlc") == "HD":
+        ck["mlc"] = pf.MLC.HD_MILLENNIUM
+    res = pf.analyze_batch(a[None], dpmm, **ck, **ak)
+    return res[0], dpmm
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pf_matches_reference_golden(name):
+    r, dpmm = gpu_run(name)
+    if f"{name}/raises" in GOLD:
+        assert r.status != 0
+        with pytest.raises(ValueError):
+            r.raise_for_status()
+        return
+    assert r.status == 0, r.status
+    g = lambda k: GOLD[f"{name}/{k}"]
+    s = r.s
+    # ---- bit-exact integers
+    assert int(s["orientation"]) == int(g("orientation"))
+    assert int(s["n_pickets"]) == int(g("number_of_pickets"))
+    assert int(s["n_meas"]) == int(g("n_meas"))
+    assert tuple(int(v) for v in (s["height"], s["width"])) == tuple(int(v) for v in g("shape"))
+    # the golden stores the set of picket indices that produced measurements (sorted)
+    assert sorted(int(v) for v in r.picket_idx) == [int(v) for v in g("picket_idx")]
+    assert np.array_equal(r.m["leaf_num"], g("meas_leaf"))
+    assert np.array_equal(r.m["picket"], g("meas_picket"))
+    assert bool(s["passed"]) == bool(g("passed"))
+    assert int(s["max_error_picket"]) == int(g("max_error_picket"))
+    assert str(r.max_error_leaf) == str(g("max_error_leaf"))
+    assert [str(x) for x in r.failed_leaves()] == [str(x) for x in g("failed_leaves")]
+    # ---- sub-pixel quantities
+    npos = g("meas_position").shape[1]
+    np.testing.assert_allclose(r.m["position"][:, :npos], g("meas_position"), rtol=0, atol=POS_TOL_PX)
+    np.testing.assert_allclose(r.m["error"][:, :npos], g("meas_error"), rtol=0, atol=ERR_TOL_MM)
+    np.testing.assert_allclose(r.m["width_mm"], g("meas_width_mm"), rtol=0, atol=ERR_TOL_MM)
+    npk = int(s["n_pickets"])
+    np.testing.assert_allclose(s["picket_spacing_px"], g("picket_spacing"), rtol=0, atol=0)
+    fits = np.stack([s["fit_slope"][:npk], s["fit_intercept"][:npk]], axis=1)
+    np.testing.assert_allclose(fits[:, 0], g("fits")[:, 0], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(fits[:, 1], g("fits")[:, 1], rtol=0, atol=POS_TOL_PX)
+    np.testing.assert_allclose(s["offsets_from_cax_mm"][:npk], g("offsets_from_cax_mm"), rtol=0, atol=ERR_TOL_MM)
+    for key, gk in [("percent_passing", "percent_passing"), ("max_error_mm", "max_error"), ("abs_median_error_mm", "abs_median_error"),
+                    ("mean_picket_spacing_mm", "mean_picket_spacing"), ("mlc_skew", "mlc_skew")]:
+        np.testing.assert_allclose(float(s[key]), float(g(gk)), rtol=0, atol=ERR_TOL_MM, err_msg=key)
+    pw = np.stack([s["picket_width_max"][:npk], s["picket_width_mean"][:npk], s["picket_width_median"][:npk], s["picket_width_min"][:npk]], axis=1)
+    np.testing.assert_allclose(pw, g("picket_widths"), rtol=0, atol=ERR_TOL_MM)
+
+
+def test_pf_batch_matches_oracle_and_is_frame_independent():
+    """A mixed batch: every frame's result equals its single-frame result and the oracle's."""
+    from oracle import pf_oracle, synth
+    from pylinac_b200 import picketfence as pf
+
+    frames = np.stack([synth.bench_pf_frame(i) for i in range(20, 26)])
+    res = pf.analyze_batch(frames, 2.56)
+    for i in range(len(frames)):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o = pf_oracle.pf_analyze(frames[i], 2.56)
+        r = res[i]
+        assert r.status == 0
+        assert np.array_equal(np.sort(r.picket_idx), np.sort(o["picket_idx"]))
+        assert int(r.s["n_meas"]) == o["n_meas"]
+        np.testing.assert_allclose(r.m["position"][:, :1], o["meas_position"], rtol=0, atol=POS_TOL_PX)
+        np.testing.assert_allclose(r.m["error"][:, :1], o["meas_error"], rtol=0, atol=ERR_TOL_MM)
+        single = pf.analyze_batch(frames[i][None], 2.56)[0]
+        assert np.array_equal(single.m["position"], r.m["position"])
+
+
+def test_pf_host_pipeline_equals_device_resident():
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    frames = np.stack([synth.bench_pf_frame(i) for i in range(40, 43)] * 30)  # 90 frames -> several chunks
+    ctx = nat.Context.default()
+    params = pf.make_params(2.56, frames.shape[1:])
+    s1, m1 = nat.pf_analyze(ctx, frames, params)
+    b = nat.Batch.upload(ctx, frames)
+    s2, m2 = nat.pf_analyze(ctx, b, params)
+    b.free()
+    assert np.array_equal(s1["picket_idx"], s2["picket_idx"])
+    assert np.array_equal(m1["position"], m2["position"])
+    assert np.array_equal(s1["max_error_mm"], s2["max_error_mm"])
+
+
+def test_picketfence_class_api():
+    from oracle import synth
+    from pylinac_b200.picketfence import MLC, Orientation, PicketFence
+
+    a = synth.bench_pf_frame(0)
+    pfo = PicketFence(a, image_kwargs={"dpi": 25.4 / 0.390625, "sid": 1000})
+    pfo.analyze()
+    assert pfo.num_pickets == 10
+    assert pfo.orientation == Orientation.UP_DOWN
+    assert pfo.passed
+    rd = pfo.results_data()
+    assert rd.number_of_pickets == 10
+    assert abs(rd.max_error_mm - float(GOLD["bench0/max_error"])) < 1e-6
+    assert len(rd.mlc_positions_by_leaf) == 50
+    assert "Picket Fence Results" in pfo.results()
+    assert len(pfo.mlc_meas) == 500 and len(pfo.pickets) == 10
+    d = pfo.results_data(as_dict=True)
+    assert d["percent_leaves_passing"] == 100.0
