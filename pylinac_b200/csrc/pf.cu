@@ -22,60 +22,9 @@
 //   k_pf_finalize   -        leaf-row pruning, per-picket line fit, errors, aggregates
 #include <cmath>
 
-#include "filters.cuh"
-#include "peaks.cuh"
-#include "stats.cuh"
+#include "pf_common.cuh"
 
 namespace epid {
-
-constexpr int PF_P = EPID_PF_MAX_PICKETS;
-constexpr int PF_L = EPID_PF_MAX_LEAVES;
-constexpr int PROF_THREADS = 256;
-constexpr int PROF_MAXN = STATS_MAX_DIM;  // profile length
-constexpr int PROF_PEAK_CAP = 512;
-constexpr int WIN_WARPS = 4;
-constexpr int WIN_CAP_PX = 4096;          // staged pixels per window
-constexpr int WIN_MAX_NC = 1024;          // samples along leaf travel
-constexpr int WIN_MAX_NR = 64;            // samples across the leaf
-constexpr int FIN_THREADS = 256;
-
-struct PctPlan { int prev, next; double gamma; };
-
-struct PfConst {
-    epid_pf_params p;
-    int H, W;
-    int meas_cap;
-    int post_filter;       // stats were taken on an already inverted+filtered copy
-    PctPlan lo, hi;        // p0.5 / p99.5 of the frame (ranks live in StatsGeom slots 0..3)
-    PctPlan p85[2], p99[2];  // [0]: arrays of length W (np.sum(axis 0)), [1]: length H
-};
-
-struct PfFrame {
-    int status;
-    int noisy;
-    int inv;               // pixels are read as g = inv ? mx - v : v - mn
-    int corner_inverted;
-    int noise_passes;
-    uint32_t mn, mx, D;
-    uint32_t med2;         // 2 * median(g)
-    int orientation;
-    int n_pickets;
-    int n_inview;
-    int picket_idx[PF_P];
-    double picket_val[PF_P];
-    double spacing;
-    short inview[PF_L];    // indices into the leaf arrays, reference order
-};
-
-struct PfWin { int valid; double l, r; };  // per (in-view leaf, picket)
-
-// numpy _lerp (numpy/lib/_function_base_impl.py): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
-__device__ __forceinline__ double np_lerp(double a, double b, double t) {
-    const double d = b - a;
-    double r = a + d * t;
-    if (t >= 0.5) r = b - d * (1.0 - t);
-    return r;
-}
 
 // ------------------------------------------------------------------------------------------------ init
 __global__ void k_pf_init(const uint16_t* base, int n, int H0, int W0, int crop, FrameRef* refs, PfFrame* fr, int* counters) {
@@ -228,176 +177,14 @@ k_pf_clamp_sums(const StatsGeom g, const FrameRef* __restrict__ frames, const Pf
 }
 
 // ------------------------------------------------------------------------------------------------ profile / pickets
-__device__ inline void block_sort_u32(uint32_t* a, int m) {  // ascending bitonic, m power of two
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const uint32_t x = a[i], y = a[l];
-                    if (up ? (y < x) : (x < y)) { a[i] = y; a[l] = x; }
-                }
-            }
-            __syncthreads();
-        }
-}
-
-// (p99 - p85) of `src[0..n)` (np.percentile 'linear'), using `buf` (>= next pow2 of n) as sort space
-__device__ inline double block_pct_range(const uint32_t* __restrict__ src, int n, const PctPlan& p85, const PctPlan& p99, uint32_t* buf) {
-    int m = 1;
-    while (m < n) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < n ? src[i] : 0xffffffffu;
-    __syncthreads();
-    block_sort_u32(buf, m);
-    const double v85 = np_lerp((double)buf[p85.prev], (double)buf[p85.next], p85.gamma);
-    const double v99 = np_lerp((double)buf[p99.prev], (double)buf[p99.next], p99.gamma);
-    __syncthreads();
-    return v99 - v85;
-}
-
 __global__ void __launch_bounds__(PROF_THREADS)
-k_pf_profile(const PfConst* __restrict__ cc, const FrameStats* __restrict__ st, PfFrame* fr,
-             const uint32_t* __restrict__ rowsum, const uint32_t* __restrict__ colsum,
+k_pf_profile(const PfConst* __restrict__ cc, PfFrame* fr, const uint32_t* __restrict__ rowsum, const uint32_t* __restrict__ colsum,
              const uint32_t* __restrict__ rowsum2, const uint32_t* __restrict__ colsum2) {
-    extern __shared__ unsigned char smraw[];
-    double* prof = reinterpret_cast<double*>(smraw);                 // PROF_MAXN doubles (aliased as sort buffer)
-    double* w_prom = prof + PROF_MAXN;
-    double* w_wh = w_prom + PROF_PEAK_CAP;
-    double* w_lip = w_wh + PROF_PEAK_CAP;
-    double* w_rip = w_lip + PROF_PEAK_CAP;
-    double* w_skey = w_rip + PROF_PEAK_CAP;
-    int* w_idx = reinterpret_cast<int*>(w_skey + PROF_PEAK_CAP);
-    int* w_lb = w_idx + PROF_PEAK_CAP;
-    int* w_rb = w_lb + PROF_PEAK_CAP;
-    int* w_flag = w_rb + PROF_PEAK_CAP;
-    int* w_sidx = w_flag + PROF_PEAK_CAP;
-    int* w_small = w_sidx + PROF_PEAK_CAP;                           // PROF_THREADS + 8
-    __shared__ double s_red[PROF_THREADS / 32];
-    __shared__ double s_bcast[2];
-
+    extern __shared__ __align__(16) unsigned char smraw[];
     const int fi = blockIdx.x;
     const PfConst& c = *cc;
-    PfFrame& f = fr[fi];
-    if (f.status != EPID_PF_OK) return;
-    const int H = c.H, W = c.W;
-    const int tid = threadIdx.x;
-
-    // ---- orientation (picketfence.py:1501-1526)
-    int orient = c.p.orientation;
-    if (orient < 0) {
-        uint32_t* buf = reinterpret_cast<uint32_t*>(prof);
-        const double row_range = block_pct_range(colsum2 + (size_t)fi * W, W, c.p85[0], c.p99[0], buf);  // np.sum(temp, 0)
-        const double col_range = block_pct_range(rowsum2 + (size_t)fi * H, H, c.p85[1], c.p99[1], buf);  // np.sum(temp, 1)
-        orient = (row_range < col_range) ? 1 : 0;
-    }
-    // ---- leaf profile: np.mean(image, axis) then / max   (picketfence.py:747-752)
-    const int n = orient == 0 ? W : H;
-    const int other = orient == 0 ? H : W;
-    const uint32_t* raw = orient == 0 ? colsum + (size_t)fi * W : rowsum + (size_t)fi * H;
-    // sum of g along the other axis: inv ? other*mx - raw : raw - other*mn   (exact integers)
-    const long long base = (long long)other * (long long)(f.inv ? f.mx : f.mn);
-    double lmax = 0.0;
-    for (int i = tid; i < n; i += PROF_THREADS) {
-        const long long sg = f.inv ? base - (long long)raw[i] : (long long)raw[i] - base;
-        const double v = (double)sg;
-        prof[i] = v;
-        lmax = fmax(lmax, v);
-    }
-    lmax = warp_max(lmax);
-    if ((tid & 31) == 0) s_red[tid >> 5] = lmax;
-    __syncthreads();
-    if (tid == 0) {
-        double m = 0.0;
-        for (int i = 0; i < PROF_THREADS / 32; i++) m = fmax(m, s_red[i]);
-        s_bcast[0] = m;
-    }
-    __syncthreads();
-    const double pmax = s_bcast[0];
-    double lmin = 2.0;
-    for (int i = tid; i < n; i += PROF_THREADS) {
-        const double v = prof[i] / pmax;
-        prof[i] = v;
-        lmin = fmin(lmin, v);
-    }
-    lmin = warp_min(lmin);
-    __syncthreads();
-    if ((tid & 31) == 0) s_red[tid >> 5] = lmin;
-    __syncthreads();
-    if (tid == 0) {
-        double m = 2.0;
-        for (int i = 0; i < PROF_THREADS / 32; i++) m = fmin(m, s_red[i]);
-        s_bcast[1] = m;
-    }
-    __syncthreads();
-    const double pmin = s_bcast[1];
-    // ---- find_fwxm_peaks(min_distance=0.02, threshold=height_threshold, max_number, peak_sort, required_prominence)
-    // _parse_peak_args (core/profile.py:2626-2649): max of the normalised profile is 1.0
-    PeakArgs a;
-    {
-        const double val_range = 1.0 - pmin;
-        double thr = c.p.height_threshold;
-        if (thr >= 0.0 && thr <= 1.0) thr = pmin + thr * val_range;
-        a.hmin = thr;
-        a.distance = max((int)(0.02 * (double)n), 1);
-        a.pmin = c.p.required_prominence;
-        a.wmin = 0.0;
-        a.rel_height = 1.0 - 0.5;
-        a.max_number = c.p.num_pickets;
-        a.sort_by_height = c.p.peak_sort == 1;
-    }
-    PeakWork w;
-    w.cap = PROF_PEAK_CAP;
-    w.idx = w_idx; w.prom = w_prom; w.lbase = w_lb; w.rbase = w_rb; w.width_height = w_wh; w.lip = w_lip; w.rip = w_rip;
-    w.flag = w_flag; w.skey = w_skey; w.sidx = w_sidx; w.s_small = w_small;
-    const int np = block_find_peaks(prof, n, a, w);
-    if (tid == 0) {
-        f.orientation = orient;
-        if (np < 0 || np > PF_P) {
-            f.status = EPID_PF_TOO_MANY_PICKETS;
-        } else if (np == 0) {
-            f.status = EPID_PF_NO_PICKETS;
-        } else {
-            f.n_pickets = np;
-            int sorted[PF_P];
-            for (int k = 0; k < np; k++) {
-                const double lt = w.lip[k], rt = w.rip[k];
-                const int idx = (int)rint(lt + (rt - lt) / 2.0);   // int(round(.)), banker's (core/profile.py:2167)
-                f.picket_idx[k] = idx;
-                f.picket_val[k] = prof[idx];
-                int j = k;
-                while (j > 0 && sorted[j - 1] > idx) { sorted[j] = sorted[j - 1]; j--; }
-                sorted[j] = idx;
-            }
-            // picket_spacing = np.median(np.diff(np.sort(peak_idxs)))   (picketfence.py:766-767)
-            double spacing = c.p.picket_spacing;
-            if (spacing < 0) {
-                const int nd = np - 1;
-                if (nd <= 0) {
-                    spacing = __longlong_as_double(0x7ff8000000000000LL);  // np.median([]) -> nan
-                } else {
-                    int d[PF_P];
-                    for (int k = 0; k < nd; k++) {
-                        const int v = sorted[k + 1] - sorted[k];
-                        int j = k;
-                        while (j > 0 && d[j - 1] > v) { d[j] = d[j - 1]; j--; }
-                        d[j] = v;
-                    }
-                    spacing = (nd & 1) ? (double)d[nd / 2] : ((double)d[nd / 2 - 1] + (double)d[nd / 2]) / 2.0;
-                }
-            }
-            f.spacing = spacing;
-            // _leaves_in_view (picketfence.py:888-912)
-            const double n_axis = (double)(orient == 0 ? H : W);
-            const double ratio = c.p.leaf_analysis_width_ratio;
-            double pixel_range = n_axis / 2.0;
-            pixel_range -= fmax(c.p.leaf_width_mm[0] * ratio, c.p.leaf_width_mm[c.p.n_leaves - 1] * ratio) * c.p.dpmm;
-            int cnt = 0;
-            for (int l = 0; l < c.p.n_leaves; l++)
-                if (fabs(c.p.leaf_center_mm[l]) < pixel_range / c.p.dpmm) f.inview[cnt++] = (short)l;
-            f.n_inview = cnt;
-        }
-    }
+    pf_profile_block(c, fr[fi], rowsum + (size_t)fi * c.H, colsum + (size_t)fi * c.W, rowsum2 + (size_t)fi * c.H,
+                     colsum2 + (size_t)fi * c.W, smraw);
 }
 
 // ------------------------------------------------------------------------------------------------ windows
@@ -1107,9 +894,9 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     }
     {
         static bool attr = false;
-        const size_t smem = sizeof(double) * (PROF_MAXN + 5 * PROF_PEAK_CAP) + sizeof(int) * (5 * PROF_PEAK_CAP + PROF_THREADS + 8);
+        const size_t smem = pf_profile_smem_bytes(PROF_THREADS);
         if (!attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-        k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.stats, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
+        k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
         ctx->launches++;
     }
     {

@@ -104,7 +104,12 @@ def test_pf_host_pipeline_equals_device_resident():
     s2, m2 = nat.pf_analyze(ctx, b, params)
     b.free()
     assert np.array_equal(s1["picket_idx"], s2["picket_idx"])
-    assert np.array_equal(m1["position"], m2["position"])
+    assert np.array_equal(s1["n_meas"], s2["n_meas"])
+    for i in range(len(frames)):   # rows beyond n_meas are unspecified
+        k = int(s1["n_meas"][i])
+        assert k == 500
+        assert np.array_equal(m1["position"][i, :k], m2["position"][i, :k])
+        assert np.array_equal(m1["error"][i, :k], m2["error"][i, :k])
     assert np.array_equal(s1["max_error_mm"], s2["max_error_mm"])
 
 
