@@ -191,7 +191,7 @@ k_pf_profile(const PfConst* __restrict__ cc, PfFrame* fr, const uint32_t* __rest
 // One warp per (leaf, picket) window.  Canonical window coordinates: i in [0, nr) across the leaf (the axis the
 // median collapses), j in [0, nc) along leaf travel.
 __global__ void __launch_bounds__(WIN_WARPS * 32)
-k_pf_windows(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWin* __restrict__ wins) {
+k_pf_windows(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWin* __restrict__ wins, int todo_only) {
     __shared__ __align__(16) uint16_t s_px[WIN_WARPS][WIN_CAP_PX];     // staged g values; later aliased by the fp64 profile
     __shared__ uint32_t s_m2[WIN_WARPS][WIN_MAX_NC];
     const int fi = blockIdx.y;
@@ -217,6 +217,7 @@ k_pf_windows(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames
 
     for (int pk = wid; pk < f.n_pickets; pk += WIN_WARPS) {
         PfWin& out = wins[((size_t)fi * PF_L + li) * PF_P + pk];
+        if (todo_only && out.valid != -1) continue;   // already done by k_pf_windows_fast
         const double pidx = (double)f.picket_idx[pk];
         const double spacing = f.spacing;
         // _get_mlc_window (picketfence.py:859-886): python int() truncates toward zero
@@ -900,8 +901,11 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
         ctx->launches++;
     }
     {
+        // fast path for ordinary window sizes, then the generic kernel for whatever it left marked (valid == -1)
+        rc = launch_pf_windows_fast(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
+        if (rc != EPID_OK) return rc;
         dim3 grid(p->n_leaves, n);
-        k_pf_windows<<<grid, WIN_WARPS * 32, 0, stream>>>(w.cst, w.refs, w.fr, w.wins);
+        k_pf_windows<<<grid, WIN_WARPS * 32, 0, stream>>>(w.cst, w.refs, w.fr, w.wins, 1);
         ctx->launches++;
     }
     {

@@ -57,6 +57,9 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
     return r;
 }
 
+// pf_windows.cu
+int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
+
 // ------------------------------------------------------------------------------------------------ profile / pickets
 __device__ inline void block_sort_u32(uint32_t* a, int m) {  // ascending bitonic, m power of two
     for (int k = 2; k <= m; k <<= 1)
