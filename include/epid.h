@@ -49,6 +49,13 @@ int32_t epid_sync(epid_ctx* ctx);
 int32_t epid_device_info(epid_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, size_t* hbm_bytes);
 int32_t epid_launch_count(epid_ctx* ctx, int64_t* launches);   /* kernels launched by this ctx so far */
 int32_t epid_version(void);
+/* options / diagnostic counters (no reference counterpart: the reference has a single CPU code path).
+ * EPID_OPT_PF_EXACT_ONLY: 1 = always use the exact-histogram PicketFence pipeline (default 0: fused sample-guided front
+ * kernel with automatic per-batch fallback to the exact pipeline).  EPID_CTR_PF_FALLBACKS: batches / chunks re-run exactly. */
+enum { EPID_OPT_PF_EXACT_ONLY = 1 };
+enum { EPID_CTR_PF_FALLBACKS = 1 };
+int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value);
+int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value);
 
 /* pinned host memory (for the H2D legs of the batched entry points) */
 int32_t epid_host_alloc(size_t bytes, void** out);

@@ -23,6 +23,8 @@ _NP2DT = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.int32): 
           np.dtype(np.float64): F64, np.dtype(np.int16): I16, np.dtype(np.int64): I64}
 _DT2NP = {v: k for k, v in _NP2DT.items()}
 
+OPT_PF_EXACT_ONLY = 1
+CTR_PF_FALLBACKS = 1
 PF_MAX_PICKETS = 32
 PF_MAX_LEAVES = 160
 
@@ -112,6 +114,8 @@ _SIGNATURES = {
     "epid_device_info": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_size_t)],
     "epid_launch_count": [_P, C.POINTER(C.c_int64)],
     "epid_version": [],
+    "epid_set_option": [_P, C.c_int32, C.c_int64],
+    "epid_get_counter": [_P, C.c_int32, C.POINTER(C.c_int64)],
     "epid_host_alloc": [C.c_size_t, C.POINTER(_P)],
     "epid_host_free": [_P],
     "epid_batch_upload": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)],
@@ -224,6 +228,14 @@ class Context:
         sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_size_t()
         check(lib().epid_device_info(self.handle, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
         return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": mem.value}
+
+    def set_option(self, key: int, value: int) -> None:
+        check(lib().epid_set_option(self.handle, key, value))
+
+    def counter(self, key: int) -> int:
+        v = C.c_int64()
+        check(lib().epid_get_counter(self.handle, key, C.byref(v)))
+        return v.value
 
     def launches(self) -> int:
         n = C.c_int64()

@@ -57,6 +57,9 @@ struct epid_ctx {
     size_t scratch_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // options / diagnostics (epid_set_option / epid_get_counter)
+    int pf_exact_only = 0;               // 1: never use the fused sample-guided front kernel
+    int64_t pf_fallbacks = 0;            // batches (or chunks) re-run by the exact pipeline
 };
 
 struct epid_batch {

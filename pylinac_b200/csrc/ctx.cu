@@ -134,6 +134,24 @@ int32_t epid_launch_count(epid_ctx* ctx, int64_t* launches) {
     return EPID_OK;
 }
 
+int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value) {
+    EPID_REQUIRE(ctx, EPID_ERR_INVALID, "ctx is NULL");
+    switch (key) {
+        case EPID_OPT_PF_EXACT_ONLY: ctx->pf_exact_only = value ? 1 : 0; return EPID_OK;
+    }
+    set_error("unknown option %d", key);
+    return EPID_ERR_INVALID;
+}
+
+int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value) {
+    EPID_REQUIRE(ctx && value, EPID_ERR_INVALID, "NULL argument");
+    switch (key) {
+        case EPID_CTR_PF_FALLBACKS: *value = ctx->pf_fallbacks; return EPID_OK;
+    }
+    set_error("unknown counter %d", key);
+    return EPID_ERR_INVALID;
+}
+
 int32_t epid_host_alloc(size_t bytes, void** out) {
     EPID_REQUIRE(out, EPID_ERR_INVALID, "out is NULL");
     cudaError_t e = cudaMallocHost(out, bytes);

@@ -53,34 +53,7 @@ __global__ void k_pf_decide(const PfConst* __restrict__ cc, const FrameStats* __
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (select && !select[i]) return;
-    const PfConst& c = *cc;
-    const FrameStats& s = st[i];
-    PfFrame& f = fr[i];
-    f.mn = s.mn;
-    f.mx = s.mx;
-    f.D = s.mx - s.mn;
-    if (f.D == 0) { f.status = EPID_PF_FLAT_IMAGE; f.noisy = 0; return; }
-    if (!c.post_filter) {
-        // _has_noise (picketfence.py:229-238)
-        if (check_noise) {
-            const double near_min = np_lerp((double)s.ostat[0], (double)s.ostat[1], c.lo.gamma);
-            const double near_max = np_lerp((double)s.ostat[2], (double)s.ostat[3], c.hi.gamma);
-            const double mnv = (double)s.mn, mxv = (double)s.mx;
-            const bool max_is_extreme = mxv > near_max * 1.25;
-            const bool min_is_extreme = (mnv < near_min * 0.75) && (fabs(mnv - near_min) > 0.1 * (near_max - near_min));
-            f.noisy = (max_is_extreme || min_is_extreme) ? 1 : 0;
-            if (f.noisy) atomicAdd(&counters[0], 1);
-        }
-        // check_inversion(box_size=10, position=(0.01, 0.01)) (core/image.py:881-897)
-        const double avg = (double)s.corner_sum / (double)(4 * 10 * 10);
-        const double mean = (double)s.sum / (double)s.npix;
-        f.corner_inverted = avg > mean ? 1 : 0;
-    }
-    const int inv = (c.post_filter ? 0 : f.corner_inverted) ^ (c.p.invert ? 1 : 0);
-    f.inv = inv;
-    // median pair (raw order statistics a <= b) -> g units
-    const uint32_t a = s.ostat[4], b = s.ostat[5];
-    f.med2 = inv ? (s.mx - b) + (s.mx - a) : (a - s.mn) + (b - s.mn);
+    pf_decide_frame(*cc, st[i], fr[i], check_noise, counters);
 }
 
 // ------------------------------------------------------------------------------------------------ clamped sums
@@ -785,11 +758,34 @@ __global__ void k_pf_set_dst_refs(FrameRef* refs_b, uint16_t* pool, int n, int H
     refs_b[i].pad = 0;
 }
 
-struct PfTimers { cudaEvent_t e0 = nullptr, e1 = nullptr; float stats_ms = 0; bool on = false; };
+struct PfTimers {   // CUDA-event pairs around the frame-streaming kernel of every pipeline pass (bench only)
+    std::vector<cudaEvent_t> ev;
+    bool on = false;
+    int record(cudaStream_t s) {
+        cudaEvent_t e;
+        EPID_CUDA(cudaEventCreate(&e));
+        EPID_CUDA(cudaEventRecord(e, s));
+        ev.push_back(e);
+        return EPID_OK;
+    }
+    float total_ms() {   // call after the stream has been synchronised
+        float t = 0;
+        for (size_t i = 0; i + 1 < ev.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t += ms; }
+        return t;
+    }
+    void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); }
+};
 
 // Enqueue the whole pipeline for one device-resident batch on `stream`; results land in w.summ / w.meas (device).
+// pf_front.cu
+bool pf_front_supported(int H, int W, int pitch);
+int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, const StatsGeom& g, const FrameRef* refs, int n, PfFrame* fr,
+                    FrameStats* stats, int* counters);
+
+// fast == true: fused front kernel (sample-guided exact selection), no host round trip; frames it cannot certify
+// (counters[1]) or that _check_for_noise flags (counters[0]) make the caller re-run the batch with fast == false.
 static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int n, int H0, int W0, const epid_pf_params* p,
-                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm) {
+                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm, bool fast) {
     const int crop = p->crop_px;
     const int H = H0 - 2 * crop, W = W0 - 2 * crop;
     StatsGeom g;
@@ -818,17 +814,18 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     const int tb = 128, nb = (n + tb - 1) / tb;
     k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters);
     ctx->launches++;
-    if (tm && tm->on) EPID_CUDA(cudaEventRecord(tm->e0, stream));
-    rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
+    if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
+    if (fast) rc = launch_pf_front(ctx, stream, w.cst, g, w.refs, n, w.fr, w.stats, w.counters);
+    else rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
     if (rc != EPID_OK) return rc;
-    if (tm && tm->on) EPID_CUDA(cudaEventRecord(tm->e1, stream));
+    if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
+    if (!fast) {
     k_pf_decide<<<nb, tb, 0, stream>>>(w.cst, w.stats, w.fr, n, nullptr, 1, w.counters);
     ctx->launches++;
     // ---- _check_for_noise loop (picketfence.py:221-227): needs the host only to learn whether ANY frame is noisy
     int n_noisy = 0;
     EPID_CUDA(cudaMemcpyAsync(&n_noisy, w.counters, sizeof(int), cudaMemcpyDeviceToHost, stream));
     EPID_CUDA(cudaStreamSynchronize(stream));
-    if (tm && tm->on) { float ms = 0; cudaEventElapsedTime(&ms, tm->e0, tm->e1); tm->stats_ms += ms; }
     const int Wp = (W + 7) / 8 * 8;
     const size_t pool_bytes = sizeof(uint16_t) * (size_t)n * H * Wp;
     int pass = 0;
@@ -900,6 +897,7 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
         k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
         ctx->launches++;
     }
+    }   // !fast
     {
         // fast path for ordinary window sizes, then the generic kernel for whatever it left marked (valid == -1)
         rc = launch_pf_windows_fast(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
@@ -939,6 +937,24 @@ static int pf_validate(const epid_pf_params* p, int H0, int W0, int meas_cap) {
 
 using namespace epid;
 
+namespace {
+
+struct PfResultCopy {   // async D2H of one chunk's results + the two fallback counters
+    static int enqueue(cudaStream_t st, const PfWork& w, int cnt, int meas_cap, epid_pf_summary* summ, epid_pf_meas* meas, int* counters2) {
+        EPID_CUDA(cudaMemcpyAsync(summ, w.summ, sizeof(epid_pf_summary) * cnt, cudaMemcpyDeviceToHost, st));
+        EPID_CUDA(cudaMemcpyAsync(meas, w.meas, sizeof(epid_pf_meas) * (size_t)cnt * meas_cap, cudaMemcpyDeviceToHost, st));
+        EPID_CUDA(cudaMemcpyAsync(counters2, w.counters, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        return EPID_OK;
+    }
+};
+
+bool pf_fast_ok(const epid_ctx* ctx, const epid_pf_params* p, int H0, int W0) {
+    const int H = H0 - 2 * p->crop_px, W = W0 - 2 * p->crop_px;
+    return !ctx->pf_exact_only && p->filter_size == 0 && pf_front_supported(H, W, W0);
+}
+
+}  // namespace
+
 extern "C" {
 
 int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, epid_pf_summary* summary,
@@ -955,14 +971,20 @@ int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_p
     if (rc != EPID_OK) return rc;
     carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
     uint16_t* pools[3] = {nullptr, nullptr, nullptr};
-    rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr);
-    if (rc == EPID_OK) {
-        cudaError_t e = cudaMemcpyAsync(summary, w.summ, sizeof(epid_pf_summary) * n, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(meas, w.meas, sizeof(epid_pf_meas) * (size_t)n * meas_cap, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { set_error("PF result copy failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
-    } else {
-        cudaStreamSynchronize(ctx->stream);
+    bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr, fast);
+        int cnt2[2] = {0, 0};
+        if (rc == EPID_OK) {
+            rc = PfResultCopy::enqueue(ctx->stream, w, n, meas_cap, summary, meas, cnt2);
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            if (rc == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
+        } else {
+            cudaStreamSynchronize(ctx->stream);
+        }
+        if (rc != EPID_OK || !fast || (cnt2[0] == 0 && cnt2[1] == 0)) break;
+        ctx->pf_fallbacks++;
+        fast = false;   // a frame was flagged noisy or could not be certified: exact pipeline for the whole batch
     }
     for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
     return rc;
@@ -982,27 +1004,34 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
     rc = ensure_scratch(ctx, w.total);
     if (rc != EPID_OK) return rc;
     carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
-    PfTimers tm;
-    tm.on = true;
+    uint16_t* pools[3] = {nullptr, nullptr, nullptr};
+    bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
     cudaEvent_t t0, t1;
-    EPID_CUDA(cudaEventCreate(&tm.e0));
-    EPID_CUDA(cudaEventCreate(&tm.e1));
     EPID_CUDA(cudaEventCreate(&t0));
     EPID_CUDA(cudaEventCreate(&t1));
-    uint16_t* pools[3] = {nullptr, nullptr, nullptr};
-    const int64_t l0 = ctx->launches;
-    EPID_CUDA(cudaStreamSynchronize(ctx->stream));
-    EPID_CUDA(cudaEventRecord(t0, ctx->stream));
-    for (int it = 0; it < iters && rc == EPID_OK; it++)
-        rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm);
-    cudaEventRecord(t1, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, t0, t1);
-    if (total_ms) *total_ms = ms;
-    if (stats_kernel_ms) *stats_kernel_ms = tm.stats_ms;
-    if (launches) *launches = ctx->launches - l0;
-    cudaEventDestroy(tm.e0); cudaEventDestroy(tm.e1); cudaEventDestroy(t0); cudaEventDestroy(t1);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        PfTimers tm;
+        tm.on = true;
+        const int64_t l0 = ctx->launches;
+        EPID_CUDA(cudaStreamSynchronize(ctx->stream));
+        EPID_CUDA(cudaEventRecord(t0, ctx->stream));
+        for (int it = 0; it < iters && rc == EPID_OK; it++)
+            rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm, fast);
+        cudaEventRecord(t1, ctx->stream);
+        int cnt2[2] = {0, 0};
+        cudaMemcpyAsync(cnt2, w.counters, sizeof(cnt2), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (total_ms) *total_ms = ms;
+        if (stats_kernel_ms) *stats_kernel_ms = tm.total_ms();
+        if (launches) *launches = ctx->launches - l0;
+        tm.destroy();
+        if (rc != EPID_OK || !fast || (cnt2[0] == 0 && cnt2[1] == 0)) break;
+        ctx->pf_fallbacks++;
+        fast = false;
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
     for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
     return rc;
 }
@@ -1016,49 +1045,79 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
     EPID_CUDA(cudaSetDevice(ctx->device));
     const int H = h - 2 * p->crop_px, W = w_ - 2 * p->crop_px;
     const size_t fbytes = sizeof(uint16_t) * (size_t)h * w_;
-    // chunk size: ~64 MB of frames per chunk, double buffered
-    int chunk = (int)((64u << 20) / fbytes);
+    // chunk: ~256 MB of frames (one CTA per frame needs >= 148 frames in flight to fill the GPU), double buffered
+    int chunk = (int)((256u << 20) / fbytes);
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
+    const int nchunks = (n + chunk - 1) / chunk;
     PfWork wk;
     carve(wk, nullptr, chunk, H, W, meas_cap);
     const size_t work_bytes = align_up(wk.total, 256);
     const size_t buf_bytes = align_up(fbytes * chunk, 256);
     rc = ensure_scratch(ctx, 2 * work_bytes + 2 * buf_bytes);
     if (rc != EPID_OK) return rc;
+    // pinned staging for the results of two chunks in flight
+    const size_t res_bytes = align_up(sizeof(epid_pf_summary) * chunk, 256) + align_up(sizeof(epid_pf_meas) * (size_t)chunk * meas_cap, 256) + 256;
+    rc = ensure_pinned(ctx, 2 * res_bytes);
+    if (rc != EPID_OK) return rc;
     char* base = (char*)ctx->scratch;
     PfWork works[2];
     uint16_t* bufs[2];
+    epid_pf_summary* h_summ[2];
+    epid_pf_meas* h_meas[2];
+    int* h_cnt[2];
     for (int s = 0; s < 2; s++) {
         carve(works[s], base + s * work_bytes, chunk, H, W, meas_cap);
         bufs[s] = (uint16_t*)(base + 2 * work_bytes + s * buf_bytes);
+        char* r = (char*)ctx->pinned + s * res_bytes;
+        h_summ[s] = (epid_pf_summary*)r;
+        h_meas[s] = (epid_pf_meas*)(r + align_up(sizeof(epid_pf_summary) * chunk, 256));
+        h_cnt[s] = (int*)(r + res_bytes - 256);
     }
     cudaEvent_t copied[2], computed[2];
     for (int s = 0; s < 2; s++) { EPID_CUDA(cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming)); EPID_CUDA(cudaEventCreateWithFlags(&computed[s], cudaEventDisableTiming)); }
     uint16_t* pools[3] = {nullptr, nullptr, nullptr};
-    const int nchunks = (n + chunk - 1) / chunk;
-    // prologue: copy chunk 0
+    const bool fast = pf_fast_ok(ctx, p, h, w_);
+    auto count_of = [&](int ci) { return (ci == nchunks - 1) ? n - ci * chunk : chunk; };
     auto enqueue_copy = [&](int ci) -> int {
         const int s = ci & 1;
-        const int cnt = (ci == nchunks - 1) ? n - ci * chunk : chunk;
-        // the buffer is free once the compute that last used it has finished
-        if (ci >= 2) EPID_CUDA(cudaStreamWaitEvent(ctx->copy_stream[0], computed[s], 0));
-        EPID_CUDA(cudaMemcpyAsync(bufs[s], frames + (size_t)ci * chunk * h * w_, fbytes * cnt, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+        // the buffer is free once the compute that last used it has finished (finish(ci - 2) already waited for it)
+        EPID_CUDA(cudaMemcpyAsync(bufs[s], frames + (size_t)ci * chunk * h * w_, fbytes * count_of(ci), cudaMemcpyHostToDevice, ctx->copy_stream[0]));
         EPID_CUDA(cudaEventRecord(copied[s], ctx->copy_stream[0]));
+        return EPID_OK;
+    };
+    auto enqueue_run = [&](int ci, bool use_fast) -> int {
+        const int s = ci & 1, cnt = count_of(ci);
+        int r = pf_run(ctx, ctx->stream, bufs[s], cnt, h, w_, p, meas_cap, works[s], pools, nullptr, use_fast);
+        if (r != EPID_OK) return r;
+        r = PfResultCopy::enqueue(ctx->stream, works[s], cnt, meas_cap, h_summ[s], h_meas[s], h_cnt[s]);
+        if (r != EPID_OK) return r;
+        EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
+        return EPID_OK;
+    };
+    auto finish = [&](int ci) -> int {   // wait for chunk ci, redo it exactly if flagged, hand the results to the caller
+        const int s = ci & 1, cnt = count_of(ci);
+        EPID_CUDA(cudaEventSynchronize(computed[s]));
+        if (fast && (h_cnt[s][0] != 0 || h_cnt[s][1] != 0)) {
+            ctx->pf_fallbacks++;
+            int r = enqueue_run(ci, false);
+            if (r != EPID_OK) return r;
+            EPID_CUDA(cudaEventSynchronize(computed[s]));
+        }
+        memcpy(summary + (size_t)ci * chunk, h_summ[s], sizeof(epid_pf_summary) * cnt);
+        memcpy(meas + (size_t)ci * chunk * meas_cap, h_meas[s], sizeof(epid_pf_meas) * (size_t)cnt * meas_cap);
         return EPID_OK;
     };
     rc = enqueue_copy(0);
     for (int ci = 0; ci < nchunks && rc == EPID_OK; ci++) {
         const int s = ci & 1;
-        const int cnt = (ci == nchunks - 1) ? n - ci * chunk : chunk;
-        if (ci + 1 < nchunks) { rc = enqueue_copy(ci + 1); if (rc != EPID_OK) break; }
         EPID_CUDA(cudaStreamWaitEvent(ctx->stream, copied[s], 0));
-        rc = pf_run(ctx, ctx->stream, bufs[s], cnt, h, w_, p, meas_cap, works[s], pools, nullptr);
+        rc = enqueue_run(ci, fast);
         if (rc != EPID_OK) break;
-        EPID_CUDA(cudaMemcpyAsync(summary + (size_t)ci * chunk, works[s].summ, sizeof(epid_pf_summary) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-        EPID_CUDA(cudaMemcpyAsync(meas + (size_t)ci * chunk * meas_cap, works[s].meas, sizeof(epid_pf_meas) * (size_t)cnt * meas_cap, cudaMemcpyDeviceToHost, ctx->stream));
-        EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
+        if (ci >= 1) { rc = finish(ci - 1); if (rc != EPID_OK) break; }
+        if (ci + 1 < nchunks) rc = enqueue_copy(ci + 1);
     }
+    if (rc == EPID_OK) rc = finish(nchunks - 1);
     cudaStreamSynchronize(ctx->copy_stream[0]);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (rc == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }

@@ -57,6 +57,38 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
     return r;
 }
 
+// noise flag (_has_noise), corner inversion, D, median in g units for one frame from its statistics.
+// check_noise: evaluate the noise criterion (and count noisy frames in counters[0]); post_filter: statistics were taken
+// on an already inverted + filtered copy, only D / median are refreshed.
+__device__ inline void pf_decide_frame(const PfConst& c, const FrameStats& s, PfFrame& f, int check_noise, int* counters) {
+    f.mn = s.mn;
+    f.mx = s.mx;
+    f.D = s.mx - s.mn;
+    if (f.D == 0) { f.status = EPID_PF_FLAT_IMAGE; f.noisy = 0; return; }
+    if (!c.post_filter) {
+        // _has_noise (picketfence.py:229-238)
+        if (check_noise) {
+            const double near_min = np_lerp((double)s.ostat[0], (double)s.ostat[1], c.lo.gamma);
+            const double near_max = np_lerp((double)s.ostat[2], (double)s.ostat[3], c.hi.gamma);
+            const double mnv = (double)s.mn, mxv = (double)s.mx;
+            const bool max_is_extreme = mxv > near_max * 1.25;
+            const bool min_is_extreme = (mnv < near_min * 0.75) && (fabs(mnv - near_min) > 0.1 * (near_max - near_min));
+            f.noisy = (max_is_extreme || min_is_extreme) ? 1 : 0;
+            if (f.noisy) atomicAdd(&counters[0], 1);
+        }
+        // check_inversion(box_size=10, position=(0.01, 0.01)) (core/image.py:881-897)
+        const double avg = (double)s.corner_sum / (double)(4 * 10 * 10);
+        const double mean = (double)s.sum / (double)s.npix;
+        f.corner_inverted = avg > mean ? 1 : 0;
+    }
+    const int inv = (c.post_filter ? 0 : f.corner_inverted) ^ (c.p.invert ? 1 : 0);
+    f.inv = inv;
+    // median pair (raw order statistics a <= b) -> g units
+    const uint32_t a = s.ostat[4], b = s.ostat[5];
+    f.med2 = inv ? (s.mx - b) + (s.mx - a) : (a - s.mn) + (b - s.mn);
+}
+
+
 // pf_windows.cu
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
 

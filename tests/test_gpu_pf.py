@@ -131,3 +131,62 @@ def test_picketfence_class_api():
     assert len(pfo.mlc_meas) == 500 and len(pfo.pickets) == 10
     d = pfo.results_data(as_dict=True)
     assert d["percent_leaves_passing"] == 100.0
+
+
+def _variants():
+    """Adversarial inputs for the sample-guided selection of the fused front kernel."""
+    from oracle import synth
+
+    out = {}
+    a = synth.bench_pf_frame(11)
+    out["plain"] = (a, {})
+    out["crop5_misaligned"] = (a, {"crop_mm": 2})                       # 5 px crop: the view is not 16-byte aligned
+    out["crop0"] = (a, {"crop_mm": 0})
+    out["quantised_8bit"] = ((a >> 8) << 8, {})                         # 256 heavy values
+    out["saturated"] = (np.minimum(a.astype(np.uint32) * 2, 65535).astype(np.uint16), {})   # clipped ceiling
+    out["offset_floor"] = ((a // 2 + 20000).astype(np.uint16), {})      # heavy floor value that is not zero
+    out["left_right"] = (np.ascontiguousarray(a.T), {})
+    out["inverted"] = ((a.max() - a).astype(np.uint16), {})
+    rng = np.random.default_rng(3)
+    out["strong_noise"] = (np.clip(a.astype(np.int64) + rng.normal(0, 1500, a.shape), 0, 65535).astype(np.uint16), {})
+    out["given_orientation"] = (a, {"orientation": "Up-Down"})
+    return out
+
+
+@pytest.mark.parametrize("name", list(_variants()))
+def test_fast_front_kernel_equals_exact_pipeline(name):
+    """The fused sample-guided front kernel must give bit-identical results to the exact-histogram pipeline
+    (which is pinned to the reference by the golden tests above), whichever path ends up being used."""
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    a, kw = _variants()[name]
+    frames = np.stack([a, a[::-1].copy(), a])
+    ctx = nat.Context.default()
+    try:
+        ctx.set_option(nat.OPT_PF_EXACT_ONLY, 1)
+        exact = pf.analyze_batch(frames, 2.56, **kw)
+        ctx.set_option(nat.OPT_PF_EXACT_ONLY, 0)
+        fast = pf.analyze_batch(frames, 2.56, **kw)
+    finally:
+        ctx.set_option(nat.OPT_PF_EXACT_ONLY, 0)
+    for k in exact.summary.dtype.names:
+        np.testing.assert_array_equal(exact.summary[k], fast.summary[k], err_msg=k)
+    for i in range(len(frames)):
+        if int(exact.summary["status"][i]) == 0:
+            m = int(exact.summary["n_meas"][i])
+            for k in exact.meas.dtype.names:
+                np.testing.assert_array_equal(exact.meas[k][i, :m], fast.meas[k][i, :m], err_msg=k)
+
+
+def test_fast_front_kernel_is_used_for_the_benchmark_frames():
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    ctx = nat.Context.default()
+    before = ctx.counter(nat.CTR_PF_FALLBACKS)
+    frames = np.stack([synth.bench_pf_frame(i) for i in range(60, 66)])
+    res = pf.analyze_batch(frames, 2.56)
+    assert all(int(s) == 0 for s in res.summary["status"])
+    assert ctx.counter(nat.CTR_PF_FALLBACKS) == before, "the fused front kernel fell back to the exact pipeline"
