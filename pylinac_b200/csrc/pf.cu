@@ -42,6 +42,7 @@ __global__ void k_pf_init(const uint16_t* base, int n, int H0, int W0, int crop,
     f.noise_passes = 0;
     f.n_pickets = 0;
     f.n_inview = 0;
+    f.todo = 0;
     f.orientation = 0;
 }
 
@@ -171,9 +172,9 @@ k_pf_windows(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames
     const PfConst& c = *cc;
     PfFrame& f = fr[fi];
     if (f.status != EPID_PF_OK) return;
-    const int li = blockIdx.x;              // in-view leaf slot
-    if (li >= f.n_inview) return;
+    if (todo_only && !f.todo) return;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int li = blockIdx.x; li < f.n_inview; li += gridDim.x) {   // in-view leaf slot
     const int H = c.H, W = c.W;
     const int orient = f.orientation;
     const int leaf = f.inview[li];
@@ -383,288 +384,7 @@ k_pf_windows(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames
         }
         __syncwarp();
     }
-}
-
-// ------------------------------------------------------------------------------------------------ finalize
-__device__ inline void block_sort_f64(double* a, int m) {
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const double x = a[i], y = a[l];
-                    if (up ? (y < x) : (x < y)) { a[i] = y; a[l] = x; }
-                }
-            }
-            __syncthreads();
-        }
-}
-
-__global__ void __launch_bounds__(FIN_THREADS)
-k_pf_finalize(const PfConst* __restrict__ cc, PfFrame* fr, const PfWin* __restrict__ wins, epid_pf_summary* __restrict__ summ,
-              epid_pf_meas* __restrict__ meas_all) {
-    extern __shared__ double s_err[];                    // 2 * pow2(meas_cap) doubles for the median of |errors|
-    __shared__ int s_cnt[PF_L], s_off[PF_L], s_keep[PF_L];
-    __shared__ double s_fit[PF_P][2];
-    __shared__ int s_i[8];
-    __shared__ double s_wbuf[PF_L];
-
-    const int fi = blockIdx.x;
-    const PfConst& c = *cc;
-    PfFrame& f = fr[fi];
-    epid_pf_summary& S = summ[fi];
-    const int tid = threadIdx.x;
-    const int H = c.H, W = c.W;
-    if (tid == 0) {
-        S.status = f.status;
-        S.orientation = f.orientation;
-        S.noise_median_passes = f.noise_passes;
-        S.corner_inverted = f.corner_inverted;
-        S.height = H;
-        S.width = W;
-        S.n_pickets = f.n_pickets;
-        S.n_meas = 0;
-        S.n_leaves_removed = 0;
-        S.picket_spacing_px = f.spacing;
-        for (int k = 0; k < PF_P; k++) { S.picket_idx[k] = k < f.n_pickets ? f.picket_idx[k] : 0; S.picket_val[k] = k < f.n_pickets ? f.picket_val[k] : 0.0; }
-    }
-    if (f.status != EPID_PF_OK) return;
-    const int nl = f.n_inview, np = f.n_pickets;
-    const int orient = f.orientation;
-    const int npos = c.p.separate_leaves ? 2 : 1;
-    const double dpmm = c.p.dpmm;
-    const PfWin* wf = wins + (size_t)fi * PF_L * PF_P;
-    // ---- kisses per leaf row
-    for (int l = tid; l < nl; l += FIN_THREADS) {
-        int n = 0;
-        for (int p = 0; p < np; p++) n += wf[l * PF_P + p].valid ? 1 : 0;
-        s_cnt[l] = n;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        // median over the leaf rows that have at least one measurement (group_by on mlc_meas, picketfence.py:810-814)
-        int tmp[PF_L];
-        int ng = 0, total = 0;
-        for (int l = 0; l < nl; l++)
-            if (s_cnt[l] > 0) {
-                const int v = s_cnt[l];
-                int j = ng;
-                while (j > 0 && tmp[j - 1] > v) { tmp[j] = tmp[j - 1]; j--; }
-                tmp[j] = v;
-                ng++;
-                total += v;
-            }
-        int status = EPID_PF_OK;
-        int kept = 0, removed = 0;
-        if (total == 0) {
-            status = EPID_PF_NO_MEASUREMENTS;
-        } else {
-            const int med_twice = (ng & 1) ? 2 * tmp[ng / 2] : tmp[ng / 2 - 1] + tmp[ng / 2];  // 2 * statistics.median
-            int off = 0;
-            for (int l = 0; l < nl; l++) {
-                const bool keep = s_cnt[l] > 0 && 2 * s_cnt[l] == med_twice;
-                s_keep[l] = keep ? 1 : 0;
-                s_off[l] = off;
-                if (keep) { off += s_cnt[l]; kept++; }
-                else if (s_cnt[l] > 0) removed++;
-            }
-            if (off == 0) status = EPID_PF_NO_MEASUREMENTS;     // a .5 median drops every row (reference: polyfit of nothing)
-            else if (off > c.meas_cap) status = EPID_PF_CAPACITY;
-            s_i[1] = off;
-        }
-        s_i[0] = status;
-        S.n_leaves_removed = removed;
-        if (status != EPID_PF_OK) { S.status = status; f.status = status; }
-    }
-    __syncthreads();
-    if (s_i[0] != EPID_PF_OK) return;
-    const int M = s_i[1];
-    epid_pf_meas* meas = meas_all + (size_t)fi * c.meas_cap;
-    const double n_axis_half = (orient == 0 ? (double)H : (double)W) / 2.0;
-    // ---- measurement table, leaf-major / picket-minor (= PicketFence.mlc_meas order)
-    for (int l = tid; l < nl; l += FIN_THREADS) {
-        if (!s_keep[l]) continue;
-        int o = s_off[l];
-        const int leaf = f.inview[l];
-        for (int p = 0; p < np; p++) {
-            const PfWin w = wf[l * PF_P + p];
-            if (!w.valid) continue;
-            epid_pf_meas& m = meas[o++];
-            m.leaf_num = c.p.leaf_num[leaf];
-            m.picket = p;
-            const double offp = fmax((double)f.picket_idx[p] - f.spacing / 2.0, 0.0);   // picketfence.py:1618-1627
-            if (npos == 2) {
-                m.position[0] = w.l + offp;
-                m.position[1] = w.r + offp;
-            } else {
-                m.position[0] = fabs(w.r - w.l) / 2.0 + w.l + offp;                       // center_idx (core/profile.py:322-327)
-                m.position[1] = 0.0;
-            }
-            m.width_mm = (fmax(w.r, w.l) - fmin(w.r, w.l)) / dpmm;                        // field_width_px / dpmm
-            m.error[0] = m.error[1] = 0.0;
-            m.passed[0] = m.passed[1] = 1;
-        }
-    }
-    __syncthreads();
-    // ---- per-picket line fit np.polyfit(along-leaf-stack, along-travel, 1)  (picketfence.py:1881-1899)
-    const double ratio = c.p.leaf_analysis_width_ratio;
-    // marker line point1: across = lc - lw/2*ratio  (picketfence.py:1725-1743)
-    // The fit needs the across-leaf coordinate of each measurement; it is a function of the leaf only, so walk the
-    // kept leaves again (thread per picket, sequential over leaves: <= 160 x 2 points).
-    for (int p = tid; p < np; p += FIN_THREADS) {
-        double mx_ = 0, my_ = 0;
-        int n = 0;
-        for (int l = 0; l < nl; l++) {
-            if (!s_keep[l]) continue;
-            const PfWin w = wf[l * PF_P + p];
-            if (!w.valid) continue;
-            const int leaf = f.inview[l];
-            const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
-            const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + n_axis_half;
-            const double upper = lc_px - lw_px / 2.0 * ratio;
-            const double offp = fmax((double)f.picket_idx[p] - f.spacing / 2.0, 0.0);
-            if (npos == 2) {
-                mx_ += upper * 2.0; my_ += (w.l + offp) + (w.r + offp); n += 2;
-            } else {
-                mx_ += upper; my_ += fabs(w.r - w.l) / 2.0 + w.l + offp; n += 1;
-            }
-        }
-        if (n == 0) { s_fit[p][0] = __longlong_as_double(0x7ff8000000000000LL); s_fit[p][1] = s_fit[p][0]; continue; }
-        mx_ /= n; my_ /= n;
-        double sxx = 0, sxy = 0;
-        for (int l = 0; l < nl; l++) {
-            if (!s_keep[l]) continue;
-            const PfWin w = wf[l * PF_P + p];
-            if (!w.valid) continue;
-            const int leaf = f.inview[l];
-            const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
-            const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + n_axis_half;
-            const double upper = lc_px - lw_px / 2.0 * ratio;
-            const double offp = fmax((double)f.picket_idx[p] - f.spacing / 2.0, 0.0);
-            const double dx = upper - mx_;
-            if (npos == 2) {
-                sxx += 2.0 * dx * dx;
-                sxy += dx * ((w.l + offp) - my_) + dx * ((w.r + offp) - my_);
-            } else {
-                sxx += dx * dx;
-                sxy += dx * ((fabs(w.r - w.l) / 2.0 + w.l + offp) - my_);
-            }
-        }
-        const double slope = sxx > 0 ? sxy / sxx : 0.0;
-        s_fit[p][0] = slope;
-        s_fit[p][1] = my_ - slope * mx_;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        for (int p = 0; p < np; p++)
-            if (s_fit[p][0] != s_fit[p][0]) { S.status = 7; f.status = 7; }   // a picket without measurements: polyfit([]) raises
-    }
-    __syncthreads();
-    if (f.status != EPID_PF_OK) return;
-    // ---- errors (picketfence.py:1701-1718)
-    int m2n = 1;
-    while (m2n < M * npos) m2n <<= 1;
-    for (int q = tid; q < m2n; q += FIN_THREADS) s_err[q] = __longlong_as_double(0x7ff0000000000000LL);
-    __syncthreads();
-    for (int l = tid; l < nl; l += FIN_THREADS) {
-        if (!s_keep[l]) continue;
-        const int leaf = f.inview[l];
-        const double lw_px = c.p.leaf_width_mm[leaf] * dpmm;
-        const double lc_px = c.p.leaf_center_mm[leaf] * dpmm + n_axis_half;
-        const double upper = lc_px - lw_px / 2.0 * ratio;
-        const double lower = lc_px + lw_px / 2.0 * ratio;
-        const double centre = (lower - upper) / 2.0 + upper;          // Line.center (core/geometry.py:556-561)
-        for (int q = s_off[l]; q < s_off[l] + s_cnt[l]; q++) {
-            epid_pf_meas& m = meas[q];
-            const double fitv = s_fit[m.picket][0] * centre + s_fit[m.picket][1];
-            for (int s = 0; s < npos; s++) {
-                double picket_pos = fitv;
-                if (npos == 2) picket_pos += (s == 0 ? -1.0 : 1.0) * c.p.nominal_gap_mm / 2.0 * dpmm;
-                const double e = (m.position[s] - picket_pos) / dpmm;
-                m.error[s] = e;
-                m.passed[s] = fabs(e) < c.p.tolerance ? 1 : 0;
-                s_err[q * npos + s] = fabs(e);
-            }
-        }
-    }
-    __syncthreads();
-    // ---- aggregates
-    if (tid == 0) {
-        int n_pass = 0, n_tot = 0, n_failed = 0;
-        double max_err = -1.0;
-        int arg = 0;
-        for (int q = 0; q < M; q++) {
-            const epid_pf_meas& m = meas[q];
-            double me = 0.0;
-            bool allp = true;
-            for (int s = 0; s < npos; s++) {
-                n_tot++;
-                if (m.passed[s]) n_pass++; else allp = false;
-                me = fmax(me, fabs(m.error[s]));
-            }
-            if (!allp) n_failed++;
-            if (me > max_err) { max_err = me; arg = q; }     // first maximum = stable descending sort .first()
-        }
-        S.n_meas = M;
-        S.percent_passing = 100.0 * (double)n_pass / (double)n_tot;
-        S.max_error_mm = max_err;
-        S.max_error_picket = meas[arg].picket;
-        S.max_error_leaf = meas[arg].leaf_num;
-        S.max_error_bank = (npos == 2 && !(fabs(meas[arg].error[0]) > fabs(meas[arg].error[1]))) ? 1 : 0;
-        S.passed = n_pass == n_tot ? 1 : 0;
-        S.n_failed = n_failed;
-        // dist2cax (picketfence.py:1905-1923) / image.center (core/image.py:526-533, PFDicomImage.center :246-260)
-        double cax;
-        if (c.p.has_cax_override) cax = orient == 0 ? c.p.cax_x_px : c.p.cax_y_px;
-        else cax = (orient == 0 ? (double)W : (double)H) / 2.0 - 0.5;
-        S.cax_px = cax;
-        const int length = orient == 0 ? H : W;
-        const double xmid = rint((double)length / 2.0);
-        double d2c[PF_P], srt[PF_P];
-        double skew = 0.0;
-        for (int p = 0; p < np; p++) {
-            S.fit_slope[p] = s_fit[p][0];
-            S.fit_intercept[p] = s_fit[p][1];
-            d2c[p] = (cax - (s_fit[p][0] * xmid + s_fit[p][1])) / dpmm;
-            S.offsets_from_cax_mm[p] = d2c[p];
-            skew += s_fit[p][0] * (180.0 / 3.14159265358979323846);
-            int j = p;
-            while (j > 0 && srt[j - 1] > d2c[p]) { srt[j] = srt[j - 1]; j--; }
-            srt[j] = d2c[p];
-        }
-        S.mlc_skew = skew / (double)np;
-        double sp = 0.0;
-        for (int p = 0; p + 1 < np; p++) sp += fabs(srt[p] - srt[p + 1]);
-        S.mean_picket_spacing_mm = np > 1 ? sp / (double)(np - 1) : __longlong_as_double(0x7ff8000000000000LL);
-    }
-    // median of |errors| (np.median)
-    block_sort_f64(s_err, m2n);
-    if (tid == 0) {
-        const int ne = M * npos;
-        S.abs_median_error_mm = (ne & 1) ? s_err[ne / 2] : (s_err[ne / 2 - 1] + s_err[ne / 2]) / 2.0;
-    }
-    // ---- picket widths (picketfence.py:471-491): thread per picket, insertion sort of <= 160 widths in shared memory
-    __syncthreads();
-    for (int p = 0; p < np; p++) {
-        if (tid == 0) {
-            int n = 0;
-            double sum = 0.0;
-            for (int q = 0; q < M; q++) {
-                if (meas[q].picket != p) continue;
-                const double v = meas[q].width_mm;
-                int j = n;
-                while (j > 0 && s_wbuf[j - 1] > v) { s_wbuf[j] = s_wbuf[j - 1]; j--; }
-                s_wbuf[j] = v;
-                n++;
-                sum += v;
-            }
-            S.picket_width_max[p] = s_wbuf[n - 1];
-            S.picket_width_min[p] = s_wbuf[0];
-            S.picket_width_mean[p] = sum / (double)n;
-            S.picket_width_median[p] = (n & 1) ? s_wbuf[n / 2] : (s_wbuf[n / 2 - 1] + s_wbuf[n / 2]) / 2.0;
-        }
-    }
+    }   // leaf slots
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -902,19 +622,12 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
         // fast path for ordinary window sizes, then the generic kernel for whatever it left marked (valid == -1)
         rc = launch_pf_windows_fast(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
         if (rc != EPID_OK) return rc;
-        dim3 grid(p->n_leaves, n);
+        dim3 grid(p->n_leaves < 8 ? p->n_leaves : 8, n);   // exits at once unless the fast kernel left work (PfFrame.todo)
         k_pf_windows<<<grid, WIN_WARPS * 32, 0, stream>>>(w.cst, w.refs, w.fr, w.wins, 1);
         ctx->launches++;
     }
-    {
-        int m2 = 1;
-        while (m2 < 2 * meas_cap) m2 <<= 1;
-        const size_t smem = sizeof(double) * m2;
-        static size_t attr_set = 0;
-        if (smem > attr_set && smem > 48 * 1024) { EPID_CUDA(cudaFuncSetAttribute(k_pf_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = smem; }
-        k_pf_finalize<<<n, FIN_THREADS, smem, stream>>>(w.cst, w.fr, w.wins, w.summ, w.meas);
-        ctx->launches++;
-    }
+    rc = launch_pf_finalize(ctx, stream, w.cst, w.fr, w.wins, w.summ, w.meas, n, meas_cap);
+    if (rc != EPID_OK) return rc;
     EPID_CUDA(cudaGetLastError());
     return EPID_OK;
 }

@@ -41,6 +41,7 @@ struct PfFrame {
     int orientation;
     int n_pickets;
     int n_inview;
+    int todo;              // windows left to the generic kernel (set by k_pf_windows_fast)
     int picket_idx[PF_P];
     double picket_val[PF_P];
     double spacing;
@@ -91,6 +92,9 @@ __device__ inline void pf_decide_frame(const PfConst& c, const FrameStats& s, Pf
 
 // pf_windows.cu
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
+// pf_finalize.cu
+int launch_pf_finalize(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, PfFrame* fr, const PfWin* wins, epid_pf_summary* summ,
+                       epid_pf_meas* meas, int n, int meas_cap);
 
 // ------------------------------------------------------------------------------------------------ profile / pickets
 __device__ inline void block_sort_u32(uint32_t* a, int m) {  // ascending bitonic, m power of two

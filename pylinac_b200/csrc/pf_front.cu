@@ -605,6 +605,7 @@ k_pf_front(const PfConst* __restrict__ cc, const StatsGeom g, const FrameRef* __
             f.noise_passes = 0;
             f.n_pickets = 0;
             f.n_inview = 0;
+            f.todo = 0;
             f.orientation = 0;
             if (sh->fallback) atomicAdd(&counters[1], 1);
             pf_decide_frame(c, sh->st, f, 1, counters);

@@ -15,6 +15,7 @@ frames = np.concatenate([uniq] * (n // 8))
 ctx = nat.Context.default(0)
 b = nat.Batch.upload(ctx, frames)
 params = pf.make_params(2.56, (1024, 1024))
+nat.pf_bench(ctx, b, params, 1)   # warm-up: module load, attribute calls, scratch allocation
 total, stats, launches = nat.pf_bench(ctx, b, params, iters)
 print(f"{n} frames x {iters} iters: {total / iters:.3f} ms/iter -> {n * iters / total * 1e3:.0f} fps; stats kernel {stats / iters:.3f} ms; launches {launches}")
 s, m = nat.pf_analyze(ctx, b, params)
