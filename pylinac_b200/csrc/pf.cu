@@ -418,6 +418,7 @@ struct PfWork {   // carved out of ctx->scratch
     PfConst* cst;
     int* counters;           // [0] noisy count
     int* select;             // per-frame flags
+    void* front;             // partial sums / thresholds of the single-pass front end (pf_stream.cu)
     size_t total;
 };
 
@@ -441,6 +442,7 @@ static void carve(PfWork& w, char* base, int n, int H, int W, int meas_cap) {
     w.cst = (PfConst*)take(sizeof(PfConst));
     w.counters = (int*)take(sizeof(int) * 8);
     w.select = (int*)take(sizeof(int) * n);
+    w.front = (void*)take(pf_front_scratch_bytes(n, H, W));
     w.total = o;
 }
 
@@ -500,7 +502,7 @@ struct PfTimers {   // CUDA-event pairs around the frame-streaming kernel of eve
 // pf_front.cu
 bool pf_front_supported(int H, int W, int pitch);
 int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, const StatsGeom& g, const FrameRef* refs, int n, PfFrame* fr,
-                    FrameStats* stats, int* counters);
+                    FrameStats* stats, int* counters, void* scratch);
 
 // fast == true: fused front kernel (sample-guided exact selection), no host round trip; frames it cannot certify
 // (counters[1]) or that _check_for_noise flags (counters[0]) make the caller re-run the batch with fast == false.
@@ -535,7 +537,7 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters);
     ctx->launches++;
     if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
-    if (fast) rc = launch_pf_front(ctx, stream, w.cst, g, w.refs, n, w.fr, w.stats, w.counters);
+    if (fast) rc = launch_pf_front(ctx, stream, w.cst, g, w.refs, n, w.fr, w.stats, w.counters, w.front);
     else rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
     if (rc != EPID_OK) return rc;
     if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }

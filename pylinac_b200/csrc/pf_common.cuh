@@ -92,6 +92,8 @@ __device__ inline void pf_decide_frame(const PfConst& c, const FrameStats& s, Pf
 
 // pf_windows.cu
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
+// pf_stream.cu
+size_t pf_front_scratch_bytes(int n, int H, int W);
 // pf_finalize.cu
 int launch_pf_finalize(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, PfFrame* fr, const PfWin* wins, epid_pf_summary* summ,
                        epid_pf_meas* meas, int n, int meas_cap);
@@ -133,9 +135,12 @@ __host__ __device__ inline size_t pf_profile_smem_bytes(int threads) {
 // Orientation, leaf profile, picket search, spacing, leaves in view for ONE frame, executed by the whole block.
 // rowsum/colsum: raw pixel sums of THIS frame (rowsum[y] = sum over x); rowsum2/colsum2: clamped sums (may be null if
 // the orientation is given).  smraw: pf_profile_smem_bytes(blockDim.x) bytes of shared memory, 8-byte aligned.
+// d_colsum2 / d_rowsum2 > 0: the clamped sums are only known to within [0, d] per element (certified clamp level, see
+// pf_stream.cu); the orientation is then decided with that margin and an undecidable frame is counted in counters[1].
 __device__ inline void pf_profile_block(const PfConst& c, PfFrame& f, const uint32_t* __restrict__ rowsum,
                                         const uint32_t* __restrict__ colsum, const uint32_t* __restrict__ rowsum2,
-                                        const uint32_t* __restrict__ colsum2, unsigned char* smraw) {
+                                        const uint32_t* __restrict__ colsum2, unsigned char* smraw, double d_colsum2 = 0.0,
+                                        double d_rowsum2 = 0.0, int* counters = nullptr) {
     double* prof = reinterpret_cast<double*>(smraw);                 // PROF_MAXN doubles (aliased as sort buffer)
     double* w_prom = prof + PROF_MAXN;
     double* w_wh = w_prom + PROF_PEAK_CAP;
@@ -164,6 +169,12 @@ __device__ inline void pf_profile_block(const PfConst& c, PfFrame& f, const uint
         const double row_range = block_pct_range(colsum2, W, c.p85[0], c.p99[0], buf);  // np.sum(temp, 0)
         const double col_range = block_pct_range(rowsum2, H, c.p85[1], c.p99[1], buf);  // np.sum(temp, 1)
         orient = (row_range < col_range) ? 1 : 0;
+        if (counters && (d_colsum2 > 0.0 || d_rowsum2 > 0.0)) {
+            // every percentile of a sum vector moves by at most its d, so each range moves by at most d (+1: lerp rounding)
+            const bool sure_lr = row_range + d_colsum2 + 1.0 < col_range - d_rowsum2;
+            const bool sure_ud = row_range - d_colsum2 >= col_range + d_rowsum2 + 1.0;
+            if (!sure_lr && !sure_ud && threadIdx.x == 0) atomicAdd(&counters[1], 1);
+        }
     }
     // ---- leaf profile: np.mean(image, axis) then / max   (picketfence.py:747-752)
     const int n = orient == 0 ? W : H;
