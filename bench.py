@@ -8,7 +8,8 @@ A "step" is one pass of the whole PicketFence pipeline over one batch of synthet
   value  : whole-job frames/s with the batch already resident in HBM (CUDA events, max over ranks)
   e2e    : the same metric through the public API `pylinac_b200.picketfence.analyze_batch` with HOST (pinned)
            frames -- chunked H2D copies and the D2H of the results are inside the timed region
-  roofline: the dominant kernel (k_frame_stats: one read of every frame) vs the measured HBM copy bandwidth
+  roofline: the frame-streaming kernel (k_pf_stream: ONE read of every frame through a TMA ring) vs the measured HBM
+           copy bandwidth; its time comes from CUDA events around that kernel inside the timed region
   cpu_baseline: the oracle port (numpy/scipy restatement of the reference, bit-identical to it on the golden
            cases) on all host cores for a bounded sample of the same frames
 """
@@ -284,7 +285,9 @@ def main():
         ach = alg_bytes / (stats_ms / args.steps * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "frame_stats_traffic.json"))).get("dram_bytes_per_launch")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "stream_traffic.json")))
+            # ncu dram__bytes_read + dram__bytes_write of one k_pf_stream launch, scaled from the captured batch size
+            traffic = tj["dram_bytes_per_launch"] * n / tj["frames"]
         except Exception:
             pass
         frames_total = world * n * args.steps
@@ -301,7 +304,7 @@ def main():
                     "api": "pylinac_b200.picketfence.analyze_batch(host uint16 frames) -> per-frame results"
                            + (" + ncclAllGather of the summaries" if world > 1 else "")},
             "gpu_launches": int(launches_timed),
-            "roofline": {"bound": "hbm", "kernel": "k_frame_stats<0>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "roofline": {"bound": "hbm", "kernel": "k_pf_stream<4>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": stats_ms / args.steps,
                          "kernel_share_of_step": stats_ms / total_ms},

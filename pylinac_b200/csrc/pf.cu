@@ -480,29 +480,11 @@ __global__ void k_pf_set_dst_refs(FrameRef* refs_b, uint16_t* pool, int n, int H
     refs_b[i].pad = 0;
 }
 
-struct PfTimers {   // CUDA-event pairs around the frame-streaming kernel of every pipeline pass (bench only)
-    std::vector<cudaEvent_t> ev;
-    bool on = false;
-    int record(cudaStream_t s) {
-        cudaEvent_t e;
-        EPID_CUDA(cudaEventCreate(&e));
-        EPID_CUDA(cudaEventRecord(e, s));
-        ev.push_back(e);
-        return EPID_OK;
-    }
-    float total_ms() {   // call after the stream has been synchronised
-        float t = 0;
-        for (size_t i = 0; i + 1 < ev.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t += ms; }
-        return t;
-    }
-    void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); }
-};
-
 // Enqueue the whole pipeline for one device-resident batch on `stream`; results land in w.summ / w.meas (device).
 // pf_front.cu
 bool pf_front_supported(int H, int W, int pitch);
 int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, const StatsGeom& g, const FrameRef* refs, int n, PfFrame* fr,
-                    FrameStats* stats, int* counters, void* scratch);
+                    FrameStats* stats, int* counters, void* scratch, PfTimers* tm);
 
 // fast == true: fused front kernel (sample-guided exact selection), no host round trip; frames it cannot certify
 // (counters[1]) or that _check_for_noise flags (counters[0]) make the caller re-run the batch with fast == false.
@@ -536,11 +518,15 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     const int tb = 128, nb = (n + tb - 1) / tb;
     k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters);
     ctx->launches++;
-    if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
-    if (fast) rc = launch_pf_front(ctx, stream, w.cst, g, w.refs, n, w.fr, w.stats, w.counters, w.front);
-    else rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
+    // bench timers: around the frame-streaming kernel only (k_pf_stream inside launch_pf_front, k_frame_stats otherwise)
+    if (fast) {
+        rc = launch_pf_front(ctx, stream, w.cst, g, w.refs, n, w.fr, w.stats, w.counters, w.front, tm);
+    } else {
+        if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
+        rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
+        if (rc == EPID_OK && tm && tm->on) rc = tm->record(stream);
+    }
     if (rc != EPID_OK) return rc;
-    if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
     if (!fast) {
     k_pf_decide<<<nb, tb, 0, stream>>>(w.cst, w.stats, w.fr, n, nullptr, 1, w.counters);
     ctx->launches++;
@@ -613,9 +599,9 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
         ctx->launches++;
     }
     {
-        static bool attr = false;
-        const size_t smem = pf_profile_smem_bytes(PROF_THREADS);
-        if (!attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        static size_t attr = 0;
+        const size_t smem = pf_profile_smem_bytes(PROF_THREADS, H, W);
+        if (smem > attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
         k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
         ctx->launches++;
     }

@@ -90,6 +90,25 @@ __device__ inline void pf_decide_frame(const PfConst& c, const FrameStats& s, Pf
 }
 
 
+// bench only: CUDA-event pairs around the frame-streaming kernel of every pipeline pass
+struct PfTimers {
+    std::vector<cudaEvent_t> ev;
+    bool on = false;
+    int record(cudaStream_t s) {
+        cudaEvent_t e;
+        EPID_CUDA(cudaEventCreate(&e));
+        EPID_CUDA(cudaEventRecord(e, s));
+        ev.push_back(e);
+        return EPID_OK;
+    }
+    float total_ms() {   // call after the stream has been synchronised
+        float t = 0;
+        for (size_t i = 0; i + 1 < ev.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t += ms; }
+        return t;
+    }
+    void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); }
+};
+
 // pf_windows.cu
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
 // pf_stream.cu
@@ -99,50 +118,57 @@ int launch_pf_finalize(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, P
                        epid_pf_meas* meas, int n, int meas_cap);
 
 // ------------------------------------------------------------------------------------------------ profile / pickets
-__device__ inline void block_sort_u32(uint32_t* a, int m) {  // ascending bitonic, m power of two
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const uint32_t x = a[i], y = a[l];
-                    if (up ? (y < x) : (x < y)) { a[i] = y; a[l] = x; }
-                }
-            }
-            __syncthreads();
-        }
+// r-th smallest (0-based) of src[0..n): value bisection by ONE warp, no block barriers (32 steps, n / 32 compares per lane)
+__device__ __forceinline__ uint32_t warp_select_u32(const uint32_t* __restrict__ src, int n, int r) {
+    const int lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = 0xffffffffu;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t cnt = 0;
+        for (int i = lane; i < n; i += 32) cnt += src[i] <= mid ? 1u : 0u;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= (uint32_t)r + 1u) hi = mid; else lo = mid + 1u;
+    }
+    return lo;
 }
 
-// (p99 - p85) of `src[0..n)` (np.percentile 'linear'), using `buf` (>= next pow2 of n) as sort space
-__device__ inline double block_pct_range(const uint32_t* __restrict__ src, int n, const PctPlan& p85, const PctPlan& p99, uint32_t* buf) {
-    int m = 1;
-    while (m < n) m <<= 1;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = i < n ? src[i] : 0xffffffffu;
+// (p99 - p85) of two arrays at once (np.percentile 'linear'): the 8 order statistics are independent selection problems,
+// one per warp.  `sel` : 8 words of shared scratch.
+__device__ inline void block_pct_ranges2(const uint32_t* __restrict__ a0, int n0, const PctPlan& p85_0, const PctPlan& p99_0,
+                                         const uint32_t* __restrict__ a1, int n1, const PctPlan& p85_1, const PctPlan& p99_1,
+                                         uint32_t* sel, double& range0, double& range1) {
+    const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
-    block_sort_u32(buf, m);
-    const double v85 = np_lerp((double)buf[p85.prev], (double)buf[p85.next], p85.gamma);
-    const double v99 = np_lerp((double)buf[p99.prev], (double)buf[p99.next], p99.gamma);
+    for (int s = wid; s < 8; s += nw) {
+        const bool second = s >= 4;
+        const PctPlan& pp = (s & 2) ? (second ? p99_1 : p99_0) : (second ? p85_1 : p85_0);
+        const int r = (s & 1) ? pp.next : pp.prev;
+        const uint32_t v = warp_select_u32(second ? a1 : a0, second ? n1 : n0, r);
+        if (lane == 0) sel[s] = v;
+    }
     __syncthreads();
-    return v99 - v85;
+    range0 = np_lerp((double)sel[2], (double)sel[3], p99_0.gamma) - np_lerp((double)sel[0], (double)sel[1], p85_0.gamma);
+    range1 = np_lerp((double)sel[6], (double)sel[7], p99_1.gamma) - np_lerp((double)sel[4], (double)sel[5], p85_1.gamma);
+    __syncthreads();
 }
 
 // smem needed by pf_profile_block for a block of `threads` threads
-__host__ __device__ inline size_t pf_profile_smem_bytes(int threads) {
-    return sizeof(double) * (PROF_MAXN + 5 * PROF_PEAK_CAP) + sizeof(int) * (5 * PROF_PEAK_CAP + threads + 8) + 64 * sizeof(double);
+__host__ __device__ inline int pf_profile_len(int H, int W) { return ((H > W ? H : W) + 3) & ~3; }
+__host__ __device__ inline size_t pf_profile_smem_bytes(int threads, int H, int W) {
+    return sizeof(double) * (pf_profile_len(H, W) + 5 * PROF_PEAK_CAP) + sizeof(int) * (5 * PROF_PEAK_CAP + threads + 8) + 64 * sizeof(double);
 }
 
 // Orientation, leaf profile, picket search, spacing, leaves in view for ONE frame, executed by the whole block.
 // rowsum/colsum: raw pixel sums of THIS frame (rowsum[y] = sum over x); rowsum2/colsum2: clamped sums (may be null if
-// the orientation is given).  smraw: pf_profile_smem_bytes(blockDim.x) bytes of shared memory, 8-byte aligned.
+// the orientation is given).  smraw: pf_profile_smem_bytes(blockDim.x, H, W) bytes of shared memory, 8-byte aligned.
 // d_colsum2 / d_rowsum2 > 0: the clamped sums are only known to within [0, d] per element (certified clamp level, see
 // pf_stream.cu); the orientation is then decided with that margin and an undecidable frame is counted in counters[1].
 __device__ inline void pf_profile_block(const PfConst& c, PfFrame& f, const uint32_t* __restrict__ rowsum,
                                         const uint32_t* __restrict__ colsum, const uint32_t* __restrict__ rowsum2,
                                         const uint32_t* __restrict__ colsum2, unsigned char* smraw, double d_colsum2 = 0.0,
                                         double d_rowsum2 = 0.0, int* counters = nullptr) {
-    double* prof = reinterpret_cast<double*>(smraw);                 // PROF_MAXN doubles (aliased as sort buffer)
-    double* w_prom = prof + PROF_MAXN;
+    double* prof = reinterpret_cast<double*>(smraw);                 // max(H, W) doubles (also selection scratch)
+    double* w_prom = prof + pf_profile_len(c.H, c.W);
     double* w_wh = w_prom + PROF_PEAK_CAP;
     double* w_lip = w_wh + PROF_PEAK_CAP;
     double* w_rip = w_lip + PROF_PEAK_CAP;
@@ -166,8 +192,8 @@ __device__ inline void pf_profile_block(const PfConst& c, PfFrame& f, const uint
     int orient = c.p.orientation;
     if (orient < 0) {
         uint32_t* buf = reinterpret_cast<uint32_t*>(prof);
-        const double row_range = block_pct_range(colsum2, W, c.p85[0], c.p99[0], buf);  // np.sum(temp, 0)
-        const double col_range = block_pct_range(rowsum2, H, c.p85[1], c.p99[1], buf);  // np.sum(temp, 1)
+        double row_range, col_range;   // of np.sum(temp, 0) and np.sum(temp, 1)
+        block_pct_ranges2(colsum2, W, c.p85[0], c.p99[0], rowsum2, H, c.p85[1], c.p99[1], buf, row_range, col_range);
         orient = (row_range < col_range) ? 1 : 0;
         if (counters && (d_colsum2 > 0.0 || d_rowsum2 > 0.0)) {
             // every percentile of a sum vector moves by at most its d, so each range moves by at most d (+1: lerp rounding)

@@ -1,6 +1,6 @@
 // Single-pass front end of the batched PicketFence pipeline (replaces the two-sweep kernel of round 1a):
 //
-//   k_pf_pilot   every 16th row (6 % of the frame): sample-guided thresholds  u_lo, [a1, b1], l_hi  around the ranks of
+//   k_pf_pilot   every 32nd row (3 % of the frame): sample-guided thresholds  u_lo, [a1, b1], l_hi  around the ranks of
 //                p0.5, the median pair and p99.5
 //   k_pf_stream  ONE read of every frame through a TMA (cp.async.bulk) ring: min / max, raw row + column sums, row +
 //                column sums of max(v, a1), and the exact pixel counts #(v < a1), #(v <= b1), #(v <= u_lo), #(v >= l_hi)
@@ -41,7 +41,7 @@ constexpr int ST_KMAX = 8;                 // max row blocks (items) per frame
 constexpr int ST_MAXROWS = 1024;           // rows per item
 constexpr int PILOT_THREADS = 256;
 constexpr int PILOT_BINS = 2048;
-constexpr int PILOT_STEP = 16, PILOT_OFF = 8;
+constexpr int PILOT_STEP = 32, PILOT_OFF = 16;
 constexpr int TAIL_THREADS = 256;
 
 struct PilotOut {            // thresholds of one frame (raw pixel values)
@@ -681,7 +681,7 @@ k_pf_tail(const PfConst* __restrict__ cc, const StatsGeom g, const StreamGeom sg
 // ------------------------------------------------------------------------------------------------ host side
 size_t pf_tail_smem_bytes(int H, int W) {
     const int Hp = (H + 3) & ~3, Wp = (W + 3) & ~3;
-    return sizeof(uint32_t) * (size_t)(2 * Hp + 2 * Wp) + pf_profile_smem_bytes(TAIL_THREADS) + 64;
+    return sizeof(uint32_t) * (size_t)(2 * Hp + 2 * Wp) + pf_profile_smem_bytes(TAIL_THREADS, H, W) + 64;
 }
 
 static int stream_vpl(int nvec, int* nstrips) {
@@ -720,7 +720,7 @@ static int launch_stream(cudaStream_t stream, int grid, size_t smem, const Strea
 }
 
 int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, const StatsGeom& g, const FrameRef* refs, int n, PfFrame* fr,
-                    FrameStats* stats, int* counters, void* scratch) {
+                    FrameStats* stats, int* counters, void* scratch, PfTimers* tm) {
     const int H = g.H, W = g.W;
     StreamGeom sg;
     sg.H = H;
@@ -752,6 +752,7 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
     const size_t smem = 256 + (size_t)ST_NST * sg.rps * sg.row_bytes + sizeof(uint32_t) * (size_t)ST_NCW * vpl * 256;
     const int grid = nitems < ctx->sm_count ? nitems : ctx->sm_count;
     int rc = EPID_OK;
+    if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
     switch (vpl) {
         case 1: rc = launch_stream<1>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
         case 2: rc = launch_stream<2>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
@@ -760,6 +761,7 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
     }
     if (rc != EPID_OK) return rc;
     ctx->launches++;
+    if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
     {
         static size_t attr = 0;
         const size_t tsm = pf_tail_smem_bytes(H, W);

@@ -383,32 +383,106 @@ k_pf_windows_fast(const PfConst* __restrict__ cc, const FrameRef* __restrict__ f
         // find_peaks(values, fwxm_height=0.5, max_number=1) by prominence (core/profile.py:602-611, 2545-2623)
         double best_prom = -1.0;
         int best_idx = -1, best_lb = 0, best_rb = 0;
-        for (int i = 1 + lane; i < nc - 1; i += 32) {
-            if (xs[i - 1] < xs[i]) {
-                int ahead = i + 1;
-                while (ahead < nc - 1 && xs[ahead] == xs[i]) ahead++;
-                if (xs[ahead] < xs[i]) {
-                    const int p = (i + ahead - 1) / 2;
-                    const double xp = xs[p];
-                    int k = p, lb = p;
-                    double lm = xp;
-                    while (k >= 0 && xs[k] <= xp) { if (xs[k] < lm) { lm = xs[k]; lb = k; } k--; }
-                    k = p;
-                    int rb = p;
-                    double rm = xp;
-                    while (k <= nc - 1 && xs[k] <= xp) { if (xs[k] < rm) { rm = xs[k]; rb = k; } k++; }
-                    const double prom = xp - fmax(lm, rm);
-                    if (prom > best_prom || (prom == best_prom && p > best_idx)) { best_prom = prom; best_idx = p; best_lb = lb; best_rb = rb; }
+        if (nc <= 128) {
+            // xs is a strictly monotone map of the integers m2, so local maxima, nearest higher samples and range minima
+            // are found on the integers, warp-wide and without divergent walks.  Candidates are visited from the highest
+            // down; a candidate of height h cannot have a prominence above h - min(profile), which ends the search after
+            // a few candidates.  The winner is chosen on the fp64 prominences exactly like the sequential formulation.
+            uint32_t mv[4], ck[4];
+#pragma unroll
+            for (int sl = 0; sl < 4; sl++) {
+                const int i = lane + 32 * sl;
+                mv[sl] = i < nc ? m2[i] : 0u;
+                ck[sl] = 0;
+                if (i >= 1 && i < nc - 1 && m2[i - 1] < mv[sl]) {
+                    int ahead = i + 1;
+                    while (ahead < nc - 1 && m2[ahead] == mv[sl]) ahead++;
+                    if (m2[ahead] < mv[sl]) ck[sl] = (mv[sl] << 8) | (uint32_t)((i + ahead - 1) / 2);
                 }
             }
-        }
+            int best_int = -1;
+            while (true) {
+                const uint32_t key = __reduce_max_sync(0xffffffffu, max(max(ck[0], ck[1]), max(ck[2], ck[3])));
+                if (key == 0) break;
+                const uint32_t hp = key >> 8;
+                const int p = (int)(key & 255u);
+                if ((int)(hp - lmin) < best_int) break;
+                uint32_t gt[4];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {   // warp arg-max by (prominence, index)
-            const double op = __shfl_xor_sync(0xffffffffu, best_prom, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-            const int olb = __shfl_xor_sync(0xffffffffu, best_lb, o);
-            const int orb = __shfl_xor_sync(0xffffffffu, best_rb, o);
-            if (op > best_prom || (op == best_prom && oi > best_idx)) { best_prom = op; best_idx = oi; best_lb = olb; best_rb = orb; }
+                for (int sl = 0; sl < 4; sl++) {
+                    if (ck[sl] == key) ck[sl] = 0;
+                    gt[sl] = __ballot_sync(0xffffffffu, mv[sl] > hp);
+                }
+                int L = -1, R = nc;       // nearest strictly higher sample on each side
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) {
+                    const int lo = 32 * sl;
+                    uint32_t m = gt[sl];
+                    if (p <= lo) m = 0; else if (p < lo + 32) m &= (1u << (p - lo)) - 1u;
+                    if (m) L = lo + 31 - __clz(m);
+                }
+#pragma unroll
+                for (int sl = 3; sl >= 0; sl--) {
+                    const int lo = 32 * sl;
+                    uint32_t m = gt[sl];
+                    if (p >= lo + 32) m = 0; else if (p >= lo) m &= ~((2u << (p - lo)) - 1u);
+                    if (m) R = lo + __ffs(m) - 1;
+                }
+                uint32_t lmv = 0xffffffffu, rmv = 0xffffffffu;
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) {
+                    const int j = lane + 32 * sl;
+                    if (j > L && j <= p) lmv = min(lmv, mv[sl]);
+                    if (j >= p && j < R && j < nc) rmv = min(rmv, mv[sl]);
+                }
+                lmv = __reduce_min_sync(0xffffffffu, lmv);
+                rmv = __reduce_min_sync(0xffffffffu, rmv);
+                // bases: the occurrence of each minimum that is closest to the peak
+                int lb = p, rb = p;
+#pragma unroll
+                for (int sl = 0; sl < 4; sl++) {
+                    const int j = lane + 32 * sl;
+                    const uint32_t el = __ballot_sync(0xffffffffu, j > L && j <= p && mv[sl] == lmv);
+                    if (el) lb = 32 * sl + 31 - __clz(el);
+                }
+#pragma unroll
+                for (int sl = 3; sl >= 0; sl--) {
+                    const int j = lane + 32 * sl;
+                    const uint32_t er = __ballot_sync(0xffffffffu, j >= p && j < R && j < nc && mv[sl] == rmv);
+                    if (er) rb = 32 * sl + __ffs(er) - 1;
+                }
+                const double prom = xs[p] - fmax(xs[lb], xs[rb]);
+                if (prom > best_prom || (prom == best_prom && p > best_idx)) { best_prom = prom; best_idx = p; best_lb = lb; best_rb = rb; }
+                best_int = max(best_int, (int)(hp - max(lmv, rmv)));
+            }
+        } else {
+            for (int i = 1 + lane; i < nc - 1; i += 32) {
+                if (xs[i - 1] < xs[i]) {
+                    int ahead = i + 1;
+                    while (ahead < nc - 1 && xs[ahead] == xs[i]) ahead++;
+                    if (xs[ahead] < xs[i]) {
+                        const int p = (i + ahead - 1) / 2;
+                        const double xp = xs[p];
+                        int k = p, lb = p;
+                        double lm = xp;
+                        while (k >= 0 && xs[k] <= xp) { if (xs[k] < lm) { lm = xs[k]; lb = k; } k--; }
+                        k = p;
+                        int rb = p;
+                        double rm = xp;
+                        while (k <= nc - 1 && xs[k] <= xp) { if (xs[k] < rm) { rm = xs[k]; rb = k; } k++; }
+                        const double prom = xp - fmax(lm, rm);
+                        if (prom > best_prom || (prom == best_prom && p > best_idx)) { best_prom = prom; best_idx = p; best_lb = lb; best_rb = rb; }
+                    }
+                }
+            }
+    #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {   // warp arg-max by (prominence, index)
+                const double op = __shfl_xor_sync(0xffffffffu, best_prom, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+                const int olb = __shfl_xor_sync(0xffffffffu, best_lb, o);
+                const int orb = __shfl_xor_sync(0xffffffffu, best_rb, o);
+                if (op > best_prom || (op == best_prom && oi > best_idx)) { best_prom = op; best_idx = oi; best_lb = olb; best_rb = orb; }
+            }
         }
         if (best_idx < 0) {
             if (lane == 0) { out.valid = 0; f.status = EPID_PF_WINDOW_NO_PEAK; }
