@@ -3,7 +3,8 @@
 //   k_pf_pilot   every 32nd row (3 % of the frame): sample-guided thresholds  u_lo, [a1, b1], l_hi  around the ranks of
 //                p0.5, the median pair and p99.5
 //   k_pf_stream  ONE read of every frame through a TMA (cp.async.bulk) ring: min / max, raw row + column sums, row +
-//                column sums of max(v, a1), and the exact pixel counts #(v < a1), #(v <= b1), #(v <= u_lo), #(v >= l_hi)
+//                column sums of max(v, a1), the exact pixel counts #(v < a1), #(v <= b1) and lower bounds of #(v <= u_lo),
+//                #(v >= l_hi) (counts of 4-pixel groups whose minimum / maximum passes the threshold)
 //   k_pf_tail    per frame: combine the partial sums, CERTIFY every decision of the reference's front end from the exact
 //                counts, then orientation / leaf profile / picket search (pf_profile_block)
 //
@@ -190,7 +191,8 @@ k_pf_pilot(const StatsGeom g, const FrameRef* __restrict__ frames, int nframes, 
     if (tid < 4) {
         // t0: band 0 upper, t1: band 1 lower, t2: band 1 upper, t3: band 2 upper (flipped); margins 5 sigma
         const int b = tid == 0 ? 0 : (tid == 3 ? 2 : 1);
-        const double fq = (double)(tid == 1 ? k_lo[b] : k_hi[b]) / (double)npix;
+        // bands 0 / 2 are taken on the minima / maxima of 4-pixel groups: the rank sits at a 4x higher quantile there
+        const double fq = fmin((b == 1 ? 1.0 : 4.0) * (double)(tid == 1 ? k_lo[b] : k_hi[b]) / (double)npix, 0.999);
         const double sg = sqrt(fq * (1.0 - fq) * (double)nT0);
         const double ctr = fq * (double)nT0;
         double rr = (tid == 1) ? ctr - 5.0 * sg - 2.0 : ctr + 5.0 * sg + 3.0;
@@ -254,32 +256,33 @@ k_pf_pilot(const StatsGeom g, const FrameRef* __restrict__ frames, int nframes, 
     const uint32_t sh[3] = {shs[0], shs[1], shs[2]};
     uint32_t below[3] = {0, 0, 0}, eq[3] = {0, 0, 0};
     const int np_rows = pilot_rows_of(H);
-    const bool aligned = (frf.pitch & 7) == 0;
-    const int mis = aligned ? (int)((reinterpret_cast<uintptr_t>(frf.origin) >> 1) & 7) : 0;
+    const bool aligned = true;    // pf_front_supported(): pitch % 8 == 0
+    const int mis = (int)((reinterpret_cast<uintptr_t>(frf.origin) >> 1) & 7);
     const int jf = (mis + 7) / 8, jl = (W + mis) / 8;                       // full vectors [jf, jl) cover view columns [cl, cr)
     const int cl = aligned ? min(W, max(0, jf * 8 - mis)) : 0;
     const int cr = aligned ? (jl > jf ? jl * 8 - mis : cl) : 0;
-    auto px = [&](uint32_t v) {
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            const uint32_t vv = j == 2 ? 65535u - v : v;
-            const int u = (int)vv - (int)a0[j];
-            below[j] += (uint32_t)u >> 31;
-            eq[j] += u == 0 ? 1u : 0u;
-            if ((uint32_t)(u - 1) < wd[j]) atomicAdd(&hist[j][(uint32_t)u >> sh[j]], 1u);
-        }
+    // band 1 (median): every pixel; bands 0 / 2 (extremes): the minimum / maximum of each group of 4 alternate pixels of an
+    // aligned vector -- the statistic whose count the stream kernel certifies (#groups with min <= u_lo is a lower bound of
+    // #pixels <= u_lo)
+    auto put = [&](int j, uint32_t vv) {
+        const int u = (int)vv - (int)a0[j];
+        below[j] += (uint32_t)u >> 31;
+        eq[j] += u == 0 ? 1u : 0u;
+        if ((uint32_t)(u - 1) < wd[j]) atomicAdd(&hist[j][(uint32_t)u >> sh[j]], 1u);
     };
     for (int ri = wid; ri < np_rows; ri += PILOT_THREADS / 32) {
         const uint16_t* rowp = frf.origin + (size_t)(PILOT_OFF + PILOT_STEP * ri) * frf.pitch;
-        if (aligned) {
-            for (int j = jf + lane; j < jl; j += 32) {
-                const uint4 q = ldg_stream16(rowp - mis + j * 8);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int j = jf + lane; j < jl; j += 32) {
+            const uint4 q = ldg_stream16(rowp - mis + j * 8);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            const uint32_t vm = __vminu2(__vminu2(w[0], w[1]), __vminu2(w[2], w[3]));
+            const uint32_t vM = __vmaxu2(__vmaxu2(w[0], w[1]), __vmaxu2(w[2], w[3]));
+            put(0, vm & 0xffffu);
+            put(0, vm >> 16);
+            put(2, 65535u - (vM & 0xffffu));
+            put(2, 65535u - (vM >> 16));
 #pragma unroll
-                for (int t = 0; t < 4; t++) { px(w[t] & 0xffffu); px(w[t] >> 16); }
-            }
-        } else {
-            for (int cidx = lane; cidx < W; cidx += 32) px(__ldg(rowp + cidx));
+            for (int t = 0; t < 4; t++) { put(1, w[t] & 0xffffu); put(1, w[t] >> 16); }
         }
     }
 #pragma unroll
@@ -296,13 +299,16 @@ k_pf_pilot(const StatsGeom g, const FrameRef* __restrict__ frames, int nframes, 
     uint32_t thr_lo[3], thr_hi[3];      // band domain: lower-edge threshold for k_lo, upper-edge threshold for k_hi
     for (int j = 0; j < 3; j++) {
         const uint32_t nb = (wd[j] >> sh[j]) + 1;
+        // population of the pilot statistic: pixels (band 1) or 4-pixel groups (bands 0 / 2); an absolute full-frame count k
+        // is expected at k * n_p / npix in either population
         const double scale = (double)n_p / (double)npix;
-        const double fq = ((double)k_lo[j] + 0.5) / (double)npix;
-        const double sg = sqrt(fq * (1.0 - fq) * (double)n_p);
+        const double pop = j == 1 ? (double)n_p : (double)n_p / 4.0;
+        const double fq = fmin((j == 1 ? 1.0 : 4.0) * ((double)k_lo[j] + 0.5) / (double)npix, 1.0);
+        const double sg = sqrt(fq * (1.0 - fq) * pop);
         const double rl = (double)k_lo[j] * scale - 5.0 * sg - 2.0;
         const double ru = (double)k_hi[j] * scale + 5.0 * sg + 3.0;
         const uint32_t r_l = rl <= 0.0 ? 0u : (uint32_t)rl;
-        const uint32_t r_u = (uint32_t)fmin(ru, (double)(n_p > 0 ? n_p - 1 : 0));
+        const uint32_t r_u = (uint32_t)fmin(ru, fmax(pop - 1.0, 0.0));
         const uint32_t xa = pilot_find(hist[j], nb, below_s[j], r_l, s_red, &s_found);
         const uint32_t xb = pilot_find(hist[j], nb, below_s[j], r_u, s_red, &s_found);
         // lower threshold: lower edge of bin xa (rank below the band: the band's lower edge; beyond: its upper edge)
@@ -416,8 +422,14 @@ k_pf_stream(const StreamGeom sg, const FrameRef* __restrict__ frames, const Pilo
                 for (int v = 0; v < VPL; v++) {
                     if (full[v]) {
                         const uint32_t w[4] = {q[v].x, q[v].y, q[v].z, q[v].w};
-                        mn2 = __vminu2(mn2, __vminu2(__vminu2(w[0], w[1]), __vminu2(w[2], w[3])));
-                        mx2 = __vmaxu2(mx2, __vmaxu2(__vmaxu2(w[0], w[1]), __vmaxu2(w[2], w[3])));
+                        // packed min / max of the vector: each half = a group of 4 alternate pixels
+                        const uint32_t vm = __vminu2(__vminu2(w[0], w[1]), __vminu2(w[2], w[3]));
+                        const uint32_t vM = __vmaxu2(__vmaxu2(w[0], w[1]), __vmaxu2(w[2], w[3]));
+                        mn2 = __vminu2(mn2, vm);
+                        mx2 = __vmaxu2(mx2, vM);
+                        // groups whose minimum is <= u_lo / whose maximum is >= l_hi: lower bounds of the pixel counts
+                        cL = __dp2a_lo(__vminu2(__vmaxu2(vm, Up) - vm, 0x00010001u), 0x0101u, cL);
+                        cH = __dp2a_lo(__vminu2(vM - __vminu2(vM, Lp), 0x00010001u), 0x0101u, cH);
 #pragma unroll
                         for (int t = 0; t < 4; t++) {
                             const uint32_t x = w[t];
@@ -430,8 +442,6 @@ k_pf_stream(const StreamGeom sg, const FrameRef* __restrict__ frames, const Pilo
                             rc = __dp2a_lo(xa, 0x0101u, rc);
                             cA = __dp2a_lo(__vminu2(xa - x, 0x00010001u), 0x0101u, cA);
                             cB = __dp2a_lo(__vminu2(__vmaxu2(x, Bp) - x, 0x00010001u), 0x0101u, cB);
-                            cL = __dp2a_lo(__vminu2(__vmaxu2(x, Up) - x, 0x00010001u), 0x0101u, cL);
-                            cH = __dp2a_lo(__vminu2(x - __vminu2(x, Lp), 0x00010001u), 0x0101u, cH);
                         }
                     }
                 }
