@@ -56,3 +56,41 @@ def reference_pf(frame, pixel_spacing_mm, sid, ctor_kwargs=None, analyze_kwargs=
     out["mlc_positions_by_leaf"] = rd.mlc_positions_by_leaf
     out["mlc_errors_by_leaf"] = rd.mlc_errors_by_leaf
     return out
+
+
+def reference_starshot(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
+    """Run the UNMODIFIED reference Starshot on an ndarray -> the dict layout of oracle.starshot_oracle.starshot_analyze."""
+    import_reference()
+    from pylinac import starshot as rs
+
+    s = rs.Starshot(np.array(frame), dpi=25.4 / pixel_spacing_mm, sid=sid)
+    # instrument the loop count of _get_reasonable_wobble without touching the reference: count StarProfile constructions
+    count = {"n": 0}
+    orig = rs.StarProfile
+
+    class Counting(orig):
+        def __init__(self, *a, **k):
+            count["n"] += 1
+            super().__init__(*a, **k)
+
+    rs.StarProfile = Counting
+    try:
+        auto, local_max = None, None
+        s.analyze(**(analyze_kwargs or {}))
+    finally:
+        rs.StarProfile = orig
+    cp = s.circle_profile
+    out = {
+        "iterations": count["n"],
+        "radius_px": float(cp.radius),
+        "profile_len": len(cp.values),
+        "peak_idx": np.array([int(p.idx) for p in cp.peaks], dtype=np.int64),
+        "peak_xy": np.array([[float(p.x), float(p.y)] for p in cp.peaks]),
+        "wobble_center": np.array([s.wobble.center.x, s.wobble.center.y], dtype=float),
+        "wobble_radius_px": float(s.wobble.radius),
+        "wobble_radius_mm": float(s.wobble.radius_mm),
+        "angles": np.array(s.angles, dtype=float),
+        "n_lines": len(s.lines),
+        "passed": bool(s.passed),
+    }
+    return out
