@@ -235,6 +235,57 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
 int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters,
                       float* total_ms, float* stats_kernel_ms, int64_t* launches);
 
+
+/* ----------------------------------------------------------------------------------------- Starshot
+ * Starshot(image).analyze(**params)  (starshot.py:105-125, 197-401, 701-834; CollapsedCircleProfile core/profile.py:
+ * 2244-2283, 2405-2483) for a batch of uint16 frames, one result per frame. */
+#define EPID_STAR_MAX_PEAKS 64
+
+enum { /* per-frame status (maps to the reference's exceptions) */
+    EPID_STAR_OK = 0,
+    EPID_STAR_NO_WOBBLE = 1,       /* RuntimeError "unable to determine a reasonable wobble" (starshot.py:372-376) */
+    EPID_STAR_NO_LINES = 2,        /* RuntimeError "unable to properly detect the radiation lines" (starshot.py:339-342) */
+    EPID_STAR_NO_START_POINT = 3,  /* no FW80M peak in the central third (reference: IndexError) */
+    EPID_STAR_CAPACITY = 4,        /* profile / peak capacity exceeded */
+    EPID_STAR_FLAT_IMAGE = 5
+};
+
+typedef struct {
+    double dpmm;                  /* image.dpmm */
+    double radius;                /* analyze() arguments (starshot.py:230-240) */
+    double min_peak_height;
+    double max_wobble_diameter;
+    double tolerance;
+    int32_t has_start_point;
+    double start_x, start_y;
+    int32_t fwhm;
+    int32_t recursive;
+    int32_t invert;
+} epid_star_params;
+
+typedef struct { /* one per frame */
+    int32_t status;
+    int32_t hist_inverted;        /* check_inversion_by_histogram([4, 50, 96]) fired */
+    int32_t start_x, start_y;     /* _get_reasonable_start_point (bit-exact target) */
+    double local_max;             /* np.percentile(central third, 90) */
+    int32_t iterations;           /* StarProfile constructions of _get_reasonable_wobble */
+    int32_t profile_len;
+    double radius_px;             /* circle_profile.radius */
+    int32_t n_peaks, n_lines;
+    int32_t peak_idx[EPID_STAR_MAX_PEAKS];   /* find_fwxm_peaks indices on the rolled profile (bit-exact target) */
+    double peak_x[EPID_STAR_MAX_PEAKS], peak_y[EPID_STAR_MAX_PEAKS];
+    double wobble_x, wobble_y;    /* wobble.center (px) */
+    double wobble_radius_px, wobble_radius_mm;
+    double angles[EPID_STAR_MAX_PEAKS / 2];
+    int32_t passed;
+    int32_t pad;
+} epid_star_result;
+
+/* gauss_weights / gauss_offsets: scipy _gaussian_kernel1d tables for sigma = 1 .. max_sigma (host; weights of sigma s start at
+ * gauss_offsets[s], 2 * int(4 s + 0.5) + 1 doubles each), computed by the binding exactly like scipy does. */
+int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_star_params* p, const double* gauss_weights,
+                              const int32_t* gauss_offsets, int32_t max_sigma, epid_star_result* results);
+
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
  * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */

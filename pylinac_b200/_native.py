@@ -92,6 +92,32 @@ PF_MEAS_DTYPE = np.dtype([("leaf_num", "<i4"), ("picket", "<i4"), ("passed", "<i
 assert PF_SUMMARY_DTYPE.itemsize == C.sizeof(PFSummary), (PF_SUMMARY_DTYPE.itemsize, C.sizeof(PFSummary))
 assert PF_MEAS_DTYPE.itemsize == C.sizeof(PFMeas)
 
+STAR_MAX_PEAKS = 64
+
+
+class StarParams(C.Structure):
+    _fields_ = [("dpmm", C.c_double), ("radius", C.c_double), ("min_peak_height", C.c_double), ("max_wobble_diameter", C.c_double),
+                ("tolerance", C.c_double), ("has_start_point", C.c_int32), ("start_x", C.c_double), ("start_y", C.c_double),
+                ("fwhm", C.c_int32), ("recursive", C.c_int32), ("invert", C.c_int32)]
+
+
+class StarResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("hist_inverted", C.c_int32), ("start_x", C.c_int32), ("start_y", C.c_int32),
+                ("local_max", C.c_double), ("iterations", C.c_int32), ("profile_len", C.c_int32), ("radius_px", C.c_double),
+                ("n_peaks", C.c_int32), ("n_lines", C.c_int32), ("peak_idx", C.c_int32 * STAR_MAX_PEAKS),
+                ("peak_x", C.c_double * STAR_MAX_PEAKS), ("peak_y", C.c_double * STAR_MAX_PEAKS), ("wobble_x", C.c_double),
+                ("wobble_y", C.c_double), ("wobble_radius_px", C.c_double), ("wobble_radius_mm", C.c_double),
+                ("angles", C.c_double * (STAR_MAX_PEAKS // 2)), ("passed", C.c_int32), ("pad", C.c_int32)]
+
+
+STAR_RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("hist_inverted", "<i4"), ("start_x", "<i4"), ("start_y", "<i4"), ("local_max", "<f8"),
+    ("iterations", "<i4"), ("profile_len", "<i4"), ("radius_px", "<f8"), ("n_peaks", "<i4"), ("n_lines", "<i4"),
+    ("peak_idx", "<i4", (STAR_MAX_PEAKS,)), ("peak_x", "<f8", (STAR_MAX_PEAKS,)), ("peak_y", "<f8", (STAR_MAX_PEAKS,)),
+    ("wobble_x", "<f8"), ("wobble_y", "<f8"), ("wobble_radius_px", "<f8"), ("wobble_radius_mm", "<f8"),
+    ("angles", "<f8", (STAR_MAX_PEAKS // 2,)), ("passed", "<i4"), ("pad", "<i4")], align=True)
+assert STAR_RESULT_DTYPE.itemsize == C.sizeof(StarResult), (STAR_RESULT_DTYPE.itemsize, C.sizeof(StarResult))
+
 _lib = None
 _lock = threading.Lock()
 
@@ -142,6 +168,7 @@ _SIGNATURES = {
     "epid_pf_analyze_host": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PFParams), _P, _P, C.c_int32],
     "epid_pf_bench": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                       C.POINTER(C.c_int64)],
+    "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -386,3 +413,42 @@ def pf_bench(ctx: Context, batch: Batch, params: PFParams, iters: int):
     launches = C.c_int64()
     check(lib().epid_pf_bench(ctx.handle, batch.handle, C.byref(params), iters, C.byref(total), C.byref(stats), C.byref(launches)))
     return total.value, stats.value, launches.value
+
+
+def gaussian_kernel_table(max_sigma: int):
+    """scipy/ndimage/_filters.py:_gaussian_kernel1d (order 0, truncate 4) for sigma = 1 .. max_sigma, concatenated.
+    Host-side table of filter weights (the same numpy expression scipy evaluates); offsets[s] = start of sigma s."""
+    offsets = np.zeros(max_sigma + 1, np.int32)
+    chunks = []
+    pos = 0
+    for s in range(1, max_sigma + 1):
+        sd = float(s)
+        lw = int(4.0 * sd + 0.5)
+        x = np.arange(-lw, lw + 1)
+        phi = np.exp(-0.5 / (sd * sd) * x**2)
+        w = (phi / phi.sum())[::-1]
+        offsets[s] = pos
+        chunks.append(np.ascontiguousarray(w, dtype=np.float64))
+        pos += w.size
+    return np.concatenate(chunks), offsets
+
+
+def starshot_analyze(ctx: Context, frames, params: StarParams) -> np.ndarray:
+    """frames: a Batch (device-resident, uint16) or a uint16 ndarray [n,h,w] / [h,w]; one STAR_RESULT_DTYPE row per frame."""
+    own = None
+    if not isinstance(frames, Batch):
+        a = np.asarray(frames)
+        if a.dtype != np.uint16:
+            raise TypeError("starshot frames must be uint16")
+        own = frames = Batch.upload(ctx, a)
+    (n, h, w), _ = frames.shape_dtype
+    # CollapsedCircleProfile length <= 2 pi * 1.1 * 0.95 * (dim / 2) * 3; sigma = round(0.003 * length)
+    max_sigma = max(int(round(0.003 * (10 * max(h, w) + 64))) + 1, 2)
+    gw, go = gaussian_kernel_table(max_sigma)
+    res = np.zeros(n, STAR_RESULT_DTYPE)
+    try:
+        check(lib().epid_starshot_analyze(ctx.handle, frames.handle, C.byref(params), _ptr(gw), _ptr(go), max_sigma, _ptr(res)))
+    finally:
+        if own is not None:
+            own.free()
+    return res
