@@ -1,0 +1,66 @@
+"""Multi-GPU plumbing of the batched entry points.
+
+Frames are independent, so a batch shards by frame index with no data-path collective; the only exchange is the
+final gather of the fixed-size per-frame result rows.  One process per GPU (torchrun: RANK / LOCAL_RANK / WORLD_SIZE).
+``torch.distributed`` is plumbing only (rendezvous, barrier, the gloo fallback of the gather used by the CPU tests);
+on GPUs the gather is ONE ``ncclAllGather`` issued by libepid (``epid_gather_results``).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def world_info():
+    """(world_size, rank, local_rank) from the torchrun environment (1, 0, 0 when launched plainly)."""
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block of frame indices owned by `rank`: sizes differ by at most one, earlier ranks take the remainder."""
+    if not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside 0..{world - 1}")
+    base, rem = divmod(n_total, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(n_total: int, world: int) -> list[int]:
+    return [shard_range(n_total, world, r)[1] - shard_range(n_total, world, r)[0] for r in range(world)]
+
+
+def gather_rows(rows: np.ndarray, n_total: int, *, dist=None, ctx=None) -> np.ndarray:
+    """All ranks contribute their shard's result rows (a numpy structured array); every rank receives all n_total rows in
+    frame order.  Shards are padded to the largest shard so that the exchange is one fixed-size all-gather.
+
+    ctx  : a pylinac_b200._native.Context whose NCCL communicator is initialised -> ncclAllGather (the GPU path)
+    dist : an initialised torch.distributed module (gloo) -> all_gather of byte tensors (CPU tests / no NCCL)
+    """
+    world, rank, _ = world_info() if dist is None else (dist.get_world_size(), dist.get_rank(), 0)
+    if world == 1:
+        return rows
+    sizes = shard_sizes(n_total, world)
+    if len(rows) != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {len(rows)} rows, its shard has {sizes[rank]}")
+    width = max(sizes)
+    padded = np.zeros(width, rows.dtype)
+    padded[: len(rows)] = rows
+    if ctx is not None:
+        from . import _native as nat
+
+        allbuf = np.empty(world * width, rows.dtype)
+        nat.check(nat.lib().epid_gather_results(ctx.handle, padded.ctypes.data, padded.nbytes, allbuf.ctypes.data))
+    else:
+        import torch
+
+        mine = torch.from_numpy(padded.view(np.uint8).copy())
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        allbuf = np.concatenate([p.numpy() for p in parts]).view(rows.dtype)
+    out = np.empty(n_total, rows.dtype)
+    pos = 0
+    for r in range(world):
+        out[pos: pos + sizes[r]] = allbuf[r * width: r * width + sizes[r]]
+        pos += sizes[r]
+    return out
