@@ -94,3 +94,25 @@ def reference_starshot(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
         "passed": bool(s.passed),
     }
     return out
+
+
+def reference_field(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
+    """Run the UNMODIFIED reference FieldAnalysis on an ndarray -> flat dict of its _results / _extra_results.
+    (central_roi_* need skimage.draw.polygon, absent here, and are not part of the golden.)"""
+    import_reference()
+    from pylinac import field_analysis as fa
+
+    kw = dict(analyze_kwargs or {})
+    if "protocol" in kw:
+        kw["protocol"] = fa.Protocol[kw["protocol"]]
+    f = fa.FieldAnalysis(np.array(frame), image_kwargs=dict(dpi=25.4 / pixel_spacing_mm, sid=sid))
+    f.analyze(**kw)
+    out = {}
+    for k, v in f._results.items():
+        out[k] = np.asarray(v, dtype=float)
+    for k, v in f._extra_results.items():
+        out[k] = float(v)
+    out["strip_rows"] = np.array([f._upper_h_index, f._lower_h_index])
+    out["strip_cols"] = np.array([f._left_v_index, f._right_v_index])
+    out["profile_len"] = np.array([len(f.horiz_profile.values), len(f.vert_profile.values)])
+    return out
