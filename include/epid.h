@@ -286,6 +286,58 @@ typedef struct { /* one per frame */
 int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_star_params* p, const double* gauss_weights,
                               const int32_t* gauss_offsets, int32_t max_sigma, epid_star_result* results);
 
+
+/* ----------------------------------------------------------------------------------------- Field analysis
+ * FieldAnalysis(image).analyze(**params)  (field_analysis.py:445-864, 1069-1117; protocol functions :37-231; SingleProfile
+ * core/profile.py:1125-1937) for a batch of uint16 frames, one result per frame.  Interpolation NONE / LINEAR, edge
+ * detection FWHM / INFLECTION_DERIVATIVE, every normalisation, protocols NONE / VARIAN / SIEMENS / ELEKTA. */
+enum { /* per-frame status */
+    EPID_FIELD_OK = 0,
+    EPID_FIELD_NO_EDGES = 1,     /* a profile without a usable peak / inflection (reference: IndexError in find_peaks output) */
+    EPID_FIELD_FLAT_IMAGE = 2
+};
+
+typedef struct {
+    double dpmm;                       /* image.dpmm */
+    int32_t protocol;                  /* 0 NONE, 1 VARIAN, 2 SIEMENS, 3 ELEKTA (field_analysis.py:233-289) */
+    int32_t centering;                 /* 0 MANUAL, 1 BEAM_CENTER, 2 GEOMETRIC_CENTER (core/profile.py:187-192) */
+    double vert_position, horiz_position, vert_width, horiz_width;
+    double in_field_ratio, slope_exclusion_ratio;
+    int32_t invert;
+    double penumbra_lower, penumbra_upper;
+    int32_t interpolation;             /* 0 NONE, 1 LINEAR */
+    double interpolation_resolution_mm;
+    int32_t ground;
+    int32_t normalization;             /* 0 NONE, 1 GEOMETRIC_CENTER, 2 BEAM_CENTER, 3 MAX */
+    int32_t edge;                      /* 0 FWHM, 1 INFLECTION_DERIVATIVE */
+    double edge_smoothing_ratio;
+} epid_field_params;
+
+typedef struct { /* one per frame: FieldAnalysis._results + protocol results (field_analysis.py:755-863) */
+    int32_t status;
+    int32_t hist_inverted;             /* check_inversion_by_histogram() fired (field_analysis.py:472) */
+    int32_t strip_rows[2];             /* rows [bottom, top) averaged into the horizontal profile */
+    int32_t strip_cols[2];             /* columns [left, right) averaged into the vertical profile */
+    int32_t profile_len[2];            /* samples of the horizontal / vertical SingleProfile */
+    double top_penumbra_mm, bottom_penumbra_mm, left_penumbra_mm, right_penumbra_mm;
+    double geometric_center_index_x_y[2], beam_center_index_x_y[2];
+    double field_size_vertical_mm, field_size_horizontal_mm;
+    double beam_center_to_top_mm, beam_center_to_bottom_mm, beam_center_to_left_mm, beam_center_to_right_mm;
+    double cax_to_top_mm, cax_to_bottom_mm, cax_to_left_mm, cax_to_right_mm;
+    double top_position_index_x_y[2];
+    double top_horizontal_distance_from_cax_mm, top_vertical_distance_from_cax_mm;
+    double top_horizontal_distance_from_beam_center_mm, top_vertical_distance_from_beam_center_mm;
+    double left_slope_percent_mm, right_slope_percent_mm, top_slope_percent_mm, bottom_slope_percent_mm;
+    double symmetry_horizontal, symmetry_vertical, flatness_horizontal, flatness_vertical;
+} epid_field_result;
+
+/* samples of SingleProfile(values of length n0, dpmm, interpolation, resolution) (core/profile.py:1306-1322) */
+int32_t epid_field_profile_len(int32_t n0, double dpmm, int32_t interpolation, double resolution_mm);
+/* gauss_h / gauss_v: scipy gaussian_filter1d weights (2 * lw + 1 doubles, already reversed for correlate1d) for
+ * sigma = edge_smoothing_ratio * profile length of the horizontal / vertical profile; may be NULL when edge == 0. */
+int32_t epid_field_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_field_params* p, const double* gauss_h, int32_t lw_h,
+                           const double* gauss_v, int32_t lw_v, epid_field_result* results);
+
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
  * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */

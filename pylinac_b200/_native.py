@@ -118,6 +118,43 @@ STAR_RESULT_DTYPE = np.dtype([
     ("angles", "<f8", (STAR_MAX_PEAKS // 2,)), ("passed", "<i4"), ("pad", "<i4")], align=True)
 assert STAR_RESULT_DTYPE.itemsize == C.sizeof(StarResult), (STAR_RESULT_DTYPE.itemsize, C.sizeof(StarResult))
 
+class FieldParams(C.Structure):
+    _fields_ = [("dpmm", C.c_double), ("protocol", C.c_int32), ("centering", C.c_int32), ("vert_position", C.c_double),
+                ("horiz_position", C.c_double), ("vert_width", C.c_double), ("horiz_width", C.c_double),
+                ("in_field_ratio", C.c_double), ("slope_exclusion_ratio", C.c_double), ("invert", C.c_int32),
+                ("penumbra_lower", C.c_double), ("penumbra_upper", C.c_double), ("interpolation", C.c_int32),
+                ("interpolation_resolution_mm", C.c_double), ("ground", C.c_int32), ("normalization", C.c_int32),
+                ("edge", C.c_int32), ("edge_smoothing_ratio", C.c_double)]
+
+
+_FIELD_DOUBLES = ["top_penumbra_mm", "bottom_penumbra_mm", "left_penumbra_mm", "right_penumbra_mm"]
+_FIELD_LAYOUT = [
+    ("status", "<i4"), ("hist_inverted", "<i4"), ("strip_rows", "<i4", (2,)), ("strip_cols", "<i4", (2,)), ("profile_len", "<i4", (2,)),
+    ("top_penumbra_mm", "<f8"), ("bottom_penumbra_mm", "<f8"), ("left_penumbra_mm", "<f8"), ("right_penumbra_mm", "<f8"),
+    ("geometric_center_index_x_y", "<f8", (2,)), ("beam_center_index_x_y", "<f8", (2,)),
+    ("field_size_vertical_mm", "<f8"), ("field_size_horizontal_mm", "<f8"),
+    ("beam_center_to_top_mm", "<f8"), ("beam_center_to_bottom_mm", "<f8"), ("beam_center_to_left_mm", "<f8"),
+    ("beam_center_to_right_mm", "<f8"), ("cax_to_top_mm", "<f8"), ("cax_to_bottom_mm", "<f8"), ("cax_to_left_mm", "<f8"),
+    ("cax_to_right_mm", "<f8"), ("top_position_index_x_y", "<f8", (2,)),
+    ("top_horizontal_distance_from_cax_mm", "<f8"), ("top_vertical_distance_from_cax_mm", "<f8"),
+    ("top_horizontal_distance_from_beam_center_mm", "<f8"), ("top_vertical_distance_from_beam_center_mm", "<f8"),
+    ("left_slope_percent_mm", "<f8"), ("right_slope_percent_mm", "<f8"), ("top_slope_percent_mm", "<f8"),
+    ("bottom_slope_percent_mm", "<f8"), ("symmetry_horizontal", "<f8"), ("symmetry_vertical", "<f8"),
+    ("flatness_horizontal", "<f8"), ("flatness_vertical", "<f8")]
+FIELD_RESULT_DTYPE = np.dtype(_FIELD_LAYOUT, align=True)
+
+
+def _struct_from_layout(name, layout):
+    fields = []
+    for item in layout:
+        ct = C.c_int32 if item[1] == "<i4" else C.c_double
+        fields.append((item[0], ct * item[2][0] if len(item) == 3 else ct))
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+FieldResult = _struct_from_layout("FieldResult", _FIELD_LAYOUT)
+assert FIELD_RESULT_DTYPE.itemsize == C.sizeof(FieldResult), (FIELD_RESULT_DTYPE.itemsize, C.sizeof(FieldResult))
+
 _lib = None
 _lock = threading.Lock()
 
@@ -169,6 +206,8 @@ _SIGNATURES = {
     "epid_pf_bench": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                       C.POINTER(C.c_int64)],
     "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
+    "epid_field_profile_len": [C.c_int32, C.c_double, C.c_int32, C.c_double],
+    "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -448,6 +487,41 @@ def starshot_analyze(ctx: Context, frames, params: StarParams) -> np.ndarray:
     res = np.zeros(n, STAR_RESULT_DTYPE)
     try:
         check(lib().epid_starshot_analyze(ctx.handle, frames.handle, C.byref(params), _ptr(gw), _ptr(go), max_sigma, _ptr(res)))
+    finally:
+        if own is not None:
+            own.free()
+    return res
+
+
+def gaussian_kernel1d(sigma: float, truncate: float = 4.0):
+    """scipy/ndimage/_filters.py:_gaussian_kernel1d (order 0), reversed as gaussian_filter1d hands it to correlate1d."""
+    sd = float(sigma)
+    lw = int(truncate * sd + 0.5)
+    x = np.arange(-lw, lw + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x**2)
+    return np.ascontiguousarray((phi / phi.sum())[::-1], dtype=np.float64), lw
+
+
+def field_analyze(ctx: Context, frames, params: FieldParams) -> np.ndarray:
+    """frames: a Batch (device-resident, uint16) or a uint16 ndarray [n,h,w] / [h,w]; one FIELD_RESULT_DTYPE row per frame."""
+    own = None
+    if not isinstance(frames, Batch):
+        a = np.asarray(frames)
+        if a.dtype != np.uint16:
+            raise TypeError("field analysis frames must be uint16")
+        own = frames = Batch.upload(ctx, a)
+    (n, h, w), _ = frames.shape_dtype
+    gh = gv = None
+    lh = lv = 0
+    if params.edge != 0:
+        # gaussian_filter1d(values, sigma=edge_smoothing_ratio * len(values)) (core/profile.py:1655-1659): one table per profile length
+        nh = lib().epid_field_profile_len(w, params.dpmm, params.interpolation, params.interpolation_resolution_mm)
+        nv = lib().epid_field_profile_len(h, params.dpmm, params.interpolation, params.interpolation_resolution_mm)
+        gh, lh = gaussian_kernel1d(params.edge_smoothing_ratio * nh)
+        gv, lv = gaussian_kernel1d(params.edge_smoothing_ratio * nv)
+    res = np.zeros(n, FIELD_RESULT_DTYPE)
+    try:
+        check(lib().epid_field_analyze(ctx.handle, frames.handle, C.byref(params), _ptr(gh), lh, _ptr(gv), lv, _ptr(res)))
     finally:
         if own is not None:
             own.free()

@@ -1,0 +1,271 @@
+"""Field (flatness / symmetry) analysis -- drop-in for the hot path of ``pylinac.field_analysis`` (reference file cited per item).
+
+``FieldAnalysis(image, filter=None, image_kwargs=None).analyze(**kw)`` keeps the reference's signature and result accessors;
+underneath, the whole per-frame pipeline (histogram inversion check, beam-centre search on the row / column sums, strip
+profiles, SingleProfile interpolation / normalisation / edge detection, penumbra, field sizes, slopes, protocol flatness and
+symmetry) runs in CUDA (pylinac_b200/csrc/field.cu).  ``analyze_batch(frames, dpmm, ...)`` is the batched entry point.
+
+Supported: interpolation NONE / LINEAR, edge detection FWHM / INFLECTION_DERIVATIVE, every normalisation, protocols NONE /
+VARIAN / SIEMENS / ELEKTA.  Not on the GPU path: SPLINE interpolation, INFLECTION_HILL, the central ROI statistics
+(skimage polygon rasterisation), plotting / PDF export.  The ``top_*`` results are the exact vertex of the fitted parabola (the
+reference's L-BFGS-B run is noise-limited).
+"""
+from __future__ import annotations
+
+import enum
+import warnings
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _native as nat
+from .core import image
+from .core.profile import Centering, Edge, Interpolation, Normalization
+from .core.utilities import ResultBase, ResultsDataMixin, convert_to_enum
+
+
+class Protocol(enum.Enum):
+    """field_analysis.py:233-289 (the calculation tables live in csrc/field.cu)."""
+
+    NONE = "NONE"
+    VARIAN = "VARIAN"
+    SIEMENS = "SIEMENS"
+    ELEKTA = "ELEKTA"
+
+
+_PROTOCOL_CODE = {Protocol.NONE: 0, Protocol.VARIAN: 1, Protocol.SIEMENS: 2, Protocol.ELEKTA: 3}
+_CENTERING_CODE = {Centering.MANUAL: 0, Centering.BEAM_CENTER: 1, Centering.GEOMETRIC_CENTER: 2}
+_NORM_CODE = {Normalization.NONE: 0, Normalization.GEOMETRIC_CENTER: 1, Normalization.BEAM_CENTER: 2, Normalization.MAX: 3}
+_RESULT_KEYS = ["top_penumbra_mm", "bottom_penumbra_mm", "left_penumbra_mm", "right_penumbra_mm", "geometric_center_index_x_y",
+                "beam_center_index_x_y", "field_size_vertical_mm", "field_size_horizontal_mm", "beam_center_to_top_mm",
+                "beam_center_to_bottom_mm", "beam_center_to_left_mm", "beam_center_to_right_mm", "cax_to_top_mm", "cax_to_bottom_mm",
+                "cax_to_left_mm", "cax_to_right_mm", "top_position_index_x_y", "top_horizontal_distance_from_cax_mm",
+                "top_vertical_distance_from_cax_mm", "top_horizontal_distance_from_beam_center_mm",
+                "top_vertical_distance_from_beam_center_mm", "left_slope_percent_mm", "right_slope_percent_mm",
+                "top_slope_percent_mm", "bottom_slope_percent_mm"]
+
+
+class FieldResult(ResultBase):
+    """field_analysis.py:291-439 (without the central ROI statistics)."""
+
+    protocol: str
+    protocol_results: dict
+    centering_method: str | None
+    normalization_method: str | None
+    interpolation_method: str | None
+    edge_detection_method: str
+    top_penumbra_mm: float
+    bottom_penumbra_mm: float
+    left_penumbra_mm: float
+    right_penumbra_mm: float
+    geometric_center_index_x_y: tuple[float, float]
+    beam_center_index_x_y: tuple[float, float]
+    field_size_vertical_mm: float
+    field_size_horizontal_mm: float
+    beam_center_to_top_mm: float
+    beam_center_to_bottom_mm: float
+    beam_center_to_left_mm: float
+    beam_center_to_right_mm: float
+    cax_to_top_mm: float
+    cax_to_bottom_mm: float
+    cax_to_left_mm: float
+    cax_to_right_mm: float
+    top_position_index_x_y: tuple[float, float]
+    top_horizontal_distance_from_cax_mm: float
+    top_vertical_distance_from_cax_mm: float
+    top_horizontal_distance_from_beam_center_mm: float
+    top_vertical_distance_from_beam_center_mm: float
+    left_slope_percent_mm: float
+    right_slope_percent_mm: float
+    top_slope_percent_mm: float
+    bottom_slope_percent_mm: float
+
+
+def make_params(dpmm: float, *, protocol=Protocol.VARIAN, centering=Centering.BEAM_CENTER, vert_position: float = 0.5,
+                horiz_position: float = 0.5, vert_width: float = 0, horiz_width: float = 0, in_field_ratio: float = 0.8,
+                slope_exclusion_ratio: float = 0.2, invert: bool = False, is_FFF: bool = False, penumbra=(20, 80),
+                interpolation=Interpolation.LINEAR, interpolation_resolution_mm: float = 0.1, ground: bool = True,
+                normalization_method=Normalization.BEAM_CENTER, edge_detection_method=Edge.INFLECTION_DERIVATIVE,
+                edge_smoothing_ratio: float = 0.003, hill_window_ratio: float = 0.15) -> nat.FieldParams:
+    """analyze() arguments (field_analysis.py:565-586) -> the C-ABI struct."""
+    protocol = Protocol[protocol] if isinstance(protocol, str) else protocol
+    edge = convert_to_enum(edge_detection_method, Edge)
+    interp = convert_to_enum(interpolation, Interpolation)
+    norm = convert_to_enum(normalization_method, Normalization)
+    cent = convert_to_enum(centering, Centering)
+    if is_FFF and edge == Edge.FWHM:
+        warnings.warn("Using FWHM for an FFF beam is not advised. Consider using INFLECTION_DERIVATIVE or INFLECTION_HILL")
+    if edge == Edge.INFLECTION_HILL:
+        raise NotImplementedError("Edge.INFLECTION_HILL (Hill-function fits) is outside the accelerated hot path")
+    if interp == Interpolation.SPLINE:
+        raise NotImplementedError("Interpolation.SPLINE (cubic interp1d) is outside the accelerated hot path")
+    if slope_exclusion_ratio >= in_field_ratio or slope_exclusion_ratio >= 1.0:
+        raise ValueError("The exclusion region must be smaller than the field ratio")
+    if penumbra[0] > penumbra[1]:
+        raise ValueError("Upper penumbra value must be larger than the lower penumbra value")
+    p = nat.FieldParams()
+    p.dpmm = float(dpmm)
+    p.protocol = _PROTOCOL_CODE[protocol]
+    p.centering = _CENTERING_CODE[cent]
+    p.vert_position, p.horiz_position = float(vert_position), float(horiz_position)
+    p.vert_width, p.horiz_width = float(vert_width), float(horiz_width)
+    p.in_field_ratio, p.slope_exclusion_ratio = float(in_field_ratio), float(slope_exclusion_ratio)
+    p.invert = 1 if invert else 0
+    p.penumbra_lower, p.penumbra_upper = float(penumbra[0]), float(penumbra[1])
+    p.interpolation = 0 if interp == Interpolation.NONE else 1
+    p.interpolation_resolution_mm = float(interpolation_resolution_mm)
+    p.ground = 1 if ground else 0
+    p.normalization = _NORM_CODE[norm]
+    p.edge = 0 if edge == Edge.FWHM else 1
+    p.edge_smoothing_ratio = float(edge_smoothing_ratio)
+    return p
+
+
+class FieldFrameResult:
+    """One frame's results (a row of the struct-of-arrays the GPU returns)."""
+
+    def __init__(self, row, protocol: Protocol):
+        self.r = row
+        self.protocol = protocol
+
+    @property
+    def status(self) -> int:
+        return int(self.r["status"])
+
+    def raise_for_status(self):
+        if self.status == 1:
+            raise IndexError("no field edges were found in a profile (the image is likely inverted or empty)")
+        if self.status == 2:
+            raise ValueError("the image is flat (max == min)")
+
+    def results_dict(self) -> dict:
+        out = {}
+        for k in _RESULT_KEYS:
+            v = self.r[k]
+            out[k] = tuple(float(x) for x in v) if np.ndim(v) else float(v)
+        return out
+
+    def protocol_results(self) -> dict:
+        if self.protocol == Protocol.NONE:
+            return {}
+        return {k: float(self.r[k]) for k in ("symmetry_horizontal", "symmetry_vertical", "flatness_horizontal", "flatness_vertical")}
+
+
+class FieldBatchResult(Sequence):
+    def __init__(self, rows: np.ndarray, protocol: Protocol):
+        self.rows = rows
+        self.protocol = protocol
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __getitem__(self, i) -> FieldFrameResult:
+        return FieldFrameResult(self.rows[i], self.protocol)
+
+
+def analyze_batch(frames, dpmm: float, *, device: int | None = None, filter: int | None = None, **kwargs) -> FieldBatchResult:
+    """FieldAnalysis(frame, filter=filter).analyze(**kwargs) for every frame of ``frames`` (uint16 [n,h,w] ndarray or Batch)."""
+    ctx = nat.Context.default(device)
+    params = make_params(dpmm, **kwargs)
+    protocol = kwargs.get("protocol", Protocol.VARIAN)
+    protocol = Protocol[protocol] if isinstance(protocol, str) else protocol
+    own = None
+    if not isinstance(frames, nat.Batch):
+        a = np.asarray(frames)
+        if a.dtype != np.uint16:
+            raise TypeError("field analysis frames must be uint16")
+        own = frames = nat.Batch.upload(ctx, a)
+    try:
+        if filter:
+            filtered = frames._unary(nat.lib().epid_median_filter, int(filter))   # image.filter(size=filter) (field_analysis.py:466)
+            try:
+                rows = nat.field_analyze(ctx, filtered, params)
+            finally:
+                filtered.free()
+        else:
+            rows = nat.field_analyze(ctx, frames, params)
+    finally:
+        if own is not None:
+            own.free()
+    return FieldBatchResult(rows, protocol)
+
+
+class FieldAnalysis(ResultsDataMixin[FieldResult]):
+    """field_analysis.py:442-472, 565-864, 866-983 -- same constructor / analyze() signature."""
+
+    def __init__(self, path, filter: int | None = None, image_kwargs: dict | None = None):
+        img_kwargs = image_kwargs or {}
+        self._path = path
+        if isinstance(path, np.ndarray):
+            self.image = image.ArrayImage(path, **img_kwargs)
+        elif isinstance(path, image.BaseImage):
+            self.image = path
+        else:
+            self.image = image.load(path, **img_kwargs)
+        self._filter = filter
+        self._is_analyzed = False
+
+    def _frame_u16(self) -> np.ndarray:
+        a = np.asarray(self.image.array)
+        if a.dtype == np.uint16:
+            return a
+        if a.dtype == np.uint8:
+            return a.astype(np.uint16)
+        if a.dtype.kind in "fiu" and a.min() >= 0 and a.max() <= 65535 and np.array_equal(a, np.floor(a)):
+            return a.astype(np.uint16)
+        raise NotImplementedError("the GPU field-analysis path takes integer-valued pixel data in [0, 65535]")
+
+    def analyze(self, protocol=Protocol.VARIAN, centering=Centering.BEAM_CENTER, vert_position: float = 0.5, horiz_position: float = 0.5,
+                vert_width: float = 0, horiz_width: float = 0, in_field_ratio: float = 0.8, slope_exclusion_ratio: float = 0.2,
+                invert: bool = False, is_FFF: bool = False, penumbra=(20, 80), interpolation=Interpolation.LINEAR,
+                interpolation_resolution_mm: float = 0.1, ground: bool = True, normalization_method=Normalization.BEAM_CENTER,
+                edge_detection_method=Edge.INFLECTION_DERIVATIVE, edge_smoothing_ratio: float = 0.003,
+                hill_window_ratio: float = 0.15, **kwargs) -> None:
+        """field_analysis.py:565-642"""
+        if self.image.dpmm is None:
+            raise ValueError("The image has no dpmm; pass image_kwargs={'dpi': ..., 'sid': ...} for array input")
+        self._protocol = Protocol[protocol] if isinstance(protocol, str) else protocol
+        self._centering = convert_to_enum(centering, Centering)
+        self._norm = convert_to_enum(normalization_method, Normalization)
+        self._interp = convert_to_enum(interpolation, Interpolation)
+        self._edge = convert_to_enum(edge_detection_method, Edge)
+        self._penumbra = penumbra
+        res = analyze_batch(self._frame_u16(), self.image.dpmm, filter=self._filter, protocol=self._protocol, centering=centering,
+                            vert_position=vert_position, horiz_position=horiz_position, vert_width=vert_width,
+                            horiz_width=horiz_width, in_field_ratio=in_field_ratio, slope_exclusion_ratio=slope_exclusion_ratio,
+                            invert=invert, is_FFF=is_FFF, penumbra=penumbra, interpolation=interpolation,
+                            interpolation_resolution_mm=interpolation_resolution_mm, ground=ground,
+                            normalization_method=normalization_method, edge_detection_method=edge_detection_method,
+                            edge_smoothing_ratio=edge_smoothing_ratio, hill_window_ratio=hill_window_ratio)[0]
+        res.raise_for_status()
+        self._result = res
+        self._results = res.results_dict()
+        self._extra_results = res.protocol_results()
+        self._is_analyzed = True
+
+    def results(self, as_str: bool = True):
+        """field_analysis.py:866-955 (the numeric lines)."""
+        if not self._is_analyzed:
+            raise ValueError("Image is not analyzed yet. Use analyze() first.")
+        r = self._results
+        out = ["Field Analysis Results", "----------------------", f"File: {self._path if not isinstance(self._path, np.ndarray) else 'array'}",
+               f"Protocol: {self._protocol.name}", f"Centering method: {self._centering.value}",
+               f"Normalization method: {self._norm.value}", f"Interpolation: {self._interp.value}",
+               f"Edge detection method: {self._edge.value}", "",
+               f"Penumbra width ({self._penumbra[0]}/{self._penumbra[1]}):", f"Left: {r['left_penumbra_mm']:3.1f}mm",
+               f"Right: {r['right_penumbra_mm']:3.1f}mm", f"Top: {r['top_penumbra_mm']:3.1f}mm", f"Bottom: {r['bottom_penumbra_mm']:3.1f}mm", "",
+               "Field Size:", f"Horizontal: {r['field_size_horizontal_mm']:3.1f}mm", f"Vertical: {r['field_size_vertical_mm']:3.1f}mm", "",
+               "CAX to edge distances:", f"CAX -> Top edge: {r['cax_to_top_mm']:3.1f}mm", f"CAX -> Bottom edge: {r['cax_to_bottom_mm']:3.1f}mm",
+               f"CAX -> Left edge: {r['cax_to_left_mm']:3.1f}mm", f"CAX -> Right edge: {r['cax_to_right_mm']:3.1f}mm", ""]
+        for name in ("symmetry", "flatness"):
+            if f"{name}_horizontal" in self._extra_results:
+                out += [f"Vertical {name}: {self._extra_results[name + '_vertical']:3.3f}",
+                        f"Horizontal {name}: {self._extra_results[name + '_horizontal']:3.3f}", ""]
+        return "\n".join(out) if as_str else out
+
+    def _generate_results_data(self) -> FieldResult:
+        if not self._is_analyzed:
+            raise ValueError("Image is not analyzed yet. Use analyze() first.")
+        return FieldResult(**self._results, protocol=self._protocol.name, centering_method=self._centering.value,
+                           normalization_method=self._norm.value, interpolation_method=self._interp.value,
+                           edge_detection_method=self._edge.value, protocol_results=self._extra_results)

@@ -1,0 +1,90 @@
+"""GPU parity: FieldAnalysis pipeline in CUDA (through the C-ABI) vs the committed reference goldens.
+
+Bars (BASELINE.json north_star): bit-exact for the integer quantities (strip bounds, profile lengths); <= 0.01 px for edge
+indices / beam centre (we assert 1e-6 px / mm / %).  The top_* fields are outside the bar: the reference's L-BFGS-B run on the
+fitted parabola is noise-limited (tests/test_oracle_field.py); ours is the exact vertex and is compared with the oracle."""
+import warnings
+
+import numpy as np
+import pytest
+
+from tests.golden.field_cases import CASES, case_frame
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load("tests/golden/field_golden.npz")
+TOL = 1e-6
+TOP_KEYS = {"top_position_index_x_y", "top_horizontal_distance_from_cax_mm", "top_vertical_distance_from_cax_mm",
+            "top_horizontal_distance_from_beam_center_mm", "top_vertical_distance_from_beam_center_mm"}
+META = {"input_sha1", "strip_rows", "strip_cols", "profile_len"}
+
+
+def gpu_kwargs(ak):
+    ak = dict(ak)
+    if "interpolation" in ak and ak["interpolation"] is None:
+        from pylinac_b200.core.profile import Interpolation
+
+        ak["interpolation"] = Interpolation.NONE
+    return ak
+
+
+def gpu_run(name):
+    from pylinac_b200 import field_analysis as fa
+
+    a, ps, sid, ak = case_frame(name)
+    dpmm = (25.4 / ps) / 25.4 * sid / 1000.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fa.analyze_batch(a[None], dpmm, **gpu_kwargs(ak))[0], dpmm, ak
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_field_matches_reference_golden(name):
+    r, dpmm, ak = gpu_run(name)
+    assert r.status == 0, r.status
+    row = r.r
+    assert np.array_equal(row["strip_rows"], GOLD[f"{name}/strip_rows"])
+    assert np.array_equal(row["strip_cols"], GOLD[f"{name}/strip_cols"])
+    assert np.array_equal(row["profile_len"], GOLD[f"{name}/profile_len"])
+    keys = [k.split("/", 1)[1] for k in GOLD.files if k.startswith(name + "/") and k.split("/", 1)[1] not in META | TOP_KEYS]
+    assert len(keys) >= 20
+    for k in keys:
+        np.testing.assert_allclose(np.asarray(row[k], dtype=float), GOLD[f"{name}/{k}"], rtol=0, atol=TOL, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["as1200_150", "as1200_offset", "fwhm_edges", "no_interp"])
+def test_field_top_matches_oracle_vertex(name):
+    from oracle import field_oracle
+
+    r, dpmm, ak = gpu_run(name)
+    ak = dict(ak)
+    ak.pop("is_FFF", None)
+    if "interpolation" in ak and ak["interpolation"] is not None:
+        ak["interpolation"] = "Linear"
+    a = case_frame(name)[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = field_oracle.field_analyze(a, dpmm, **ak)
+    for k in TOP_KEYS:
+        np.testing.assert_allclose(np.asarray(r.r[k], dtype=float), np.asarray(o[k], dtype=float), rtol=0, atol=1e-5, err_msg=k)
+
+
+def test_field_batch_is_frame_independent_and_class_api():
+    from pylinac_b200 import field_analysis as fa
+
+    names = ["as1200_150", "as1200_offset", "inverted", "fff"]
+    frames = np.stack([case_frame(n)[0] for n in names])
+    dpmm = (25.4 / 0.336) / 25.4
+    res = fa.analyze_batch(frames, dpmm)
+    for i, n in enumerate(names):
+        single = fa.analyze_batch(frames[i][None], dpmm)[0]
+        for k in res.rows.dtype.names:
+            np.testing.assert_array_equal(res.rows[k][i], single.r[k], err_msg=f"{n}/{k}")
+    f = fa.FieldAnalysis(frames[0], image_kwargs={"dpi": 25.4 / 0.336, "sid": 1000})
+    f.analyze()
+    rd = f.results_data()
+    assert abs(rd.field_size_horizontal_mm - float(GOLD["as1200_150/field_size_horizontal_mm"])) < TOL
+    assert abs(rd.protocol_results["flatness_vertical"] - float(GOLD["as1200_150/flatness_vertical"])) < TOL
+    assert "Field Analysis Results" in f.results()
+    with pytest.raises(NotImplementedError):
+        f.analyze(edge_detection_method=fa.Edge.INFLECTION_HILL)
