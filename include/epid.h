@@ -287,6 +287,15 @@ int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames, const epi
                               const int32_t* gauss_offsets, int32_t max_sigma, epid_star_result* results);
 
 
+/* CircleProfile / CollapsedCircleProfile._profile + x / y locations (core/profile.py:2179-2283, 2405-2483) of ONE image
+ * (batch of 1; U8 / U16 / F32 / F64): nearest-neighbour samples (scipy.ndimage.map_coordinates order=0, 0 outside) on
+ * radians = arange(start_angle, 2 pi + start_angle - interval, interval)[::-1 if ccw], interval = 2 pi / (pi * r_max * 2 *
+ * sampling_ratio); collapsed != 0: mean over num_profiles radii linspace(r (1 - width_ratio), r (1 + width_ratio)).
+ * cap: capacity of the three output arrays; *count = number of samples. */
+int32_t epid_circle_profile(epid_ctx* ctx, const epid_batch* image, double cx, double cy, double radius, double start_angle,
+                            int32_t ccw, double sampling_ratio, int32_t collapsed, double width_ratio, int32_t num_profiles,
+                            int32_t cap, double* profile, double* x_locations, double* y_locations, int32_t* count);
+
 /* ----------------------------------------------------------------------------------------- Field analysis
  * FieldAnalysis(image).analyze(**params)  (field_analysis.py:445-864, 1069-1117; protocol functions :37-231; SingleProfile
  * core/profile.py:1125-1937) for a batch of uint16 frames, one result per frame.  Interpolation NONE / LINEAR, edge

@@ -206,6 +206,8 @@ _SIGNATURES = {
     "epid_pf_bench": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                       C.POINTER(C.c_int64)],
     "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
+    "epid_circle_profile": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_double,
+                            C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)],
     "epid_field_profile_len": [C.c_int32, C.c_double, C.c_int32, C.c_double],
     "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
     "epid_comm_unique_id": [_P],
@@ -526,3 +528,24 @@ def field_analyze(ctx: Context, frames, params: FieldParams) -> np.ndarray:
         if own is not None:
             own.free()
     return res
+
+
+def circle_profile(ctx: Context, image: np.ndarray, center, radius: float, start_angle: float = 0.0, ccw: bool = True,
+                   sampling_ratio: float = 1.0, collapsed: bool = False, width_ratio: float = 0.1, num_profiles: int = 20):
+    """(profile, x_locations, y_locations) of a CircleProfile / CollapsedCircleProfile of one image."""
+    a = np.ascontiguousarray(image)
+    if a.dtype not in (np.uint8, np.uint16, np.float32, np.float64):
+        a = a.astype(np.float64)
+    b = Batch.upload(ctx, a)
+    rmax = radius * (1 + width_ratio) if collapsed else radius
+    cap = int(np.ceil(2 * np.pi * rmax * sampling_ratio)) + 8
+    prof, xl, yl = np.empty(cap), np.empty(cap), np.empty(cap)
+    cnt = C.c_int32()
+    try:
+        check(lib().epid_circle_profile(ctx.handle, b.handle, float(center[0]), float(center[1]), float(radius), float(start_angle),
+                                        1 if ccw else 0, float(sampling_ratio), 1 if collapsed else 0, float(width_ratio),
+                                        int(num_profiles), cap, _ptr(prof), _ptr(xl), _ptr(yl), C.byref(cnt)))
+    finally:
+        b.free()
+    c = cnt.value
+    return prof[:c].copy(), xl[:c].copy(), yl[:c].copy()

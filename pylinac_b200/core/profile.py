@@ -115,6 +115,75 @@ class MultiProfile(ProfileMixin):
         return np.array(idxs), np.array(vals)
 
 
+class CircleProfile(MultiProfile):
+    """core/profile.py:2179-2402: a profile sampled on a circle (nearest neighbour), peaks mapped back to image coordinates."""
+
+    def __init__(self, center, radius: float, image_array: np.ndarray, start_angle: float = 0, ccw: bool = True,
+                 sampling_ratio: float = 1.0):
+        self.center = Point(center)
+        self.radius = radius
+        self.image_array = image_array
+        self.start_angle = start_angle
+        self.ccw = ccw
+        self.sampling_ratio = sampling_ratio
+        prof, self.x_locations, self.y_locations = self._sample()
+        super().__init__(prof)
+
+    def _sample(self):
+        return nat.circle_profile(nat.Context.default(), self.image_array, (self.center.x, self.center.y), self.radius,
+                                  start_angle=self.start_angle, ccw=self.ccw, sampling_ratio=self.sampling_ratio)
+
+    @property
+    def size(self) -> float:
+        return np.pi * self.radius * 2 * self.sampling_ratio
+
+    def _map_peaks(self) -> None:
+        for peak in self.peaks:
+            peak.x = self.x_locations[int(peak.idx)]
+            peak.y = self.y_locations[int(peak.idx)]
+
+    def find_peaks(self, threshold=0.3, min_distance=0.05, max_number=None, search_region=(0.0, 1.0)):
+        out = super().find_peaks(threshold, min_distance, max_number, search_region)
+        self._map_peaks()
+        return out
+
+    def find_valleys(self, threshold=0.3, min_distance=0.05, max_number=None, search_region=(0.0, 1.0)):
+        out = super().find_valleys(threshold, min_distance, max_number, search_region)
+        self._map_peaks()
+        return out
+
+    def find_fwxm_peaks(self, threshold=0.3, min_distance=0.05, max_number=None, search_region=(0.0, 1.0)):
+        out = super().find_fwxm_peaks(threshold, min_distance, max_number, search_region=search_region)
+        self._map_peaks()
+        return out
+
+    def roll(self, amount: int) -> None:
+        self.values = np.roll(self.values, -amount)
+        self.x_locations = np.roll(self.x_locations, -amount)
+        self.y_locations = np.roll(self.y_locations, -amount)
+
+
+class CollapsedCircleProfile(CircleProfile):
+    """core/profile.py:2405-2483: mean of `num_profiles` circle profiles in a band of relative width `width_ratio`."""
+
+    def __init__(self, center, radius: float, image_array: np.ndarray, start_angle: float = 0, ccw: bool = True,
+                 sampling_ratio: float = 1.0, width_ratio: float = 0.1, num_profiles: int = 20):
+        if not 0 <= width_ratio <= 1:
+            raise ValueError("width_ratio must be between 0 and 1")
+        self.width_ratio = width_ratio
+        self.num_profiles = num_profiles
+        super().__init__(center, radius, image_array, start_angle, ccw, sampling_ratio)
+
+    def _sample(self):
+        return nat.circle_profile(nat.Context.default(), self.image_array, (self.center.x, self.center.y), self.radius,
+                                  start_angle=self.start_angle, ccw=self.ccw, sampling_ratio=self.sampling_ratio, collapsed=True,
+                                  width_ratio=self.width_ratio, num_profiles=self.num_profiles)
+
+    @property
+    def size(self) -> float:
+        return np.pi * self.radius * (1 + self.width_ratio) * 2 * self.sampling_ratio
+
+
 def utils_negate(values) -> np.ndarray:
     """-values for find_valleys: a sign flip of the stored samples (no arithmetic on magnitudes)."""
     return np.negative(np.asarray(values, dtype=np.float64))

@@ -507,6 +507,35 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
 
 }  // namespace epid
 
+// ------------------------------------------------------------------------------------------------ circle profiles
+// CircleProfile / CollapsedCircleProfile._profile (core/profile.py:2244-2283, 2446-2483) of ONE image: for every sample angle
+// radians[i] the sum over `nprof` radii of scipy.ndimage.map_coordinates(image, [y, x], order=0) (nearest neighbour, 0 outside),
+// divided by nprof for the collapsed profile.  Also returns x / y locations on the nominal radius.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_circle_profile(const T* __restrict__ img, int H, int W, double cx, double cy, double radius, double r_lo, double r_hi, int nprof,
+                 int collapsed, double first, double delta, int n, int ccw, double* __restrict__ prof, double* __restrict__ xloc,
+                 double* __restrict__ yloc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = ccw ? n - 1 - i : i;                          // rads[::-1] when counter-clockwise
+    const double rad = k == 0 ? first : first + (double)k * delta;   // np.arange: first + i * delta
+    const double cs = cos(rad), sn = sin(rad);
+    const double rstep = nprof > 1 ? (r_hi - r_lo) / (double)(nprof - 1) : 0.0;
+    double acc = 0.0;
+    for (int p = 0; p < nprof; p++) {
+        const double rk = !collapsed ? radius : (p == nprof - 1 && nprof > 1 ? r_hi : (double)p * rstep + r_lo);
+        const double yc = sn * rk + cy, xc = cs * rk + cx;
+        double v = 0.0;
+        if (yc >= 0.0 && yc <= (double)(H - 1) && xc >= 0.0 && xc <= (double)(W - 1))
+            v = (double)img[(size_t)((int)floor(yc + 0.5)) * W + (int)floor(xc + 0.5)];
+        acc += v;
+    }
+    prof[i] = collapsed ? acc / (double)nprof : acc;
+    xloc[i] = cs * radius + cx;
+    yloc[i] = sn * radius + cy;
+}
+
 using namespace epid;
 
 namespace {
@@ -632,5 +661,52 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
     EPID_CUDA(cudaMemcpyAsync(results, d_res, sizeof(epid_star_result) * n, cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("starshot pipeline failed: %s", cudaGetErrorString(e)); return EPID_ERR_CUDA; }
+    return EPID_OK;
+}
+
+extern "C" int32_t epid_circle_profile(epid_ctx* ctx, const epid_batch* image, double cx, double cy, double radius, double start_angle,
+                                       int32_t ccw, double sampling_ratio, int32_t collapsed, double width_ratio, int32_t num_profiles,
+                                       int32_t cap, double* profile, double* x_locations, double* y_locations, int32_t* count) {
+    EPID_REQUIRE(ctx && image && profile && x_locations && y_locations && count, EPID_ERR_INVALID, "NULL argument");
+    EPID_REQUIRE(image->n == 1, EPID_ERR_INVALID, "circle profiles are taken from a single image");
+    EPID_REQUIRE(image->dtype == EPID_U16 || image->dtype == EPID_F64 || image->dtype == EPID_U8 || image->dtype == EPID_F32,
+                 EPID_ERR_UNSUPPORTED, "image dtype not supported");
+    EPID_REQUIRE(radius > 0 && sampling_ratio > 0, EPID_ERR_INVALID, "radius and sampling_ratio must be positive");
+    EPID_REQUIRE(!collapsed || (num_profiles >= 1 && width_ratio >= 0 && width_ratio <= 1), EPID_ERR_INVALID, "bad band parameters");
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    const int H = image->h, W = image->w;
+    // Array size check of CircleProfile.__init__ (core/profile.py:2228-2230, 2395-2402)
+    EPID_REQUIRE(!((double)W < radius + cx || (double)H < radius + cy), EPID_ERR_INVALID, "Array size not large enough to compute profile");
+    const double PI = 3.141592653589793;
+    const double r_lo = radius * (1 - width_ratio), r_hi = radius * (1 + width_ratio);
+    const double rmax = collapsed ? (r_hi > r_lo ? r_hi : r_lo) : radius;     // max(np.linspace(r_lo, r_hi, num))
+    const double size = PI * rmax * 2 * sampling_ratio;
+    const double interval = (2 * PI) / size;
+    const double start = 0 + start_angle, stop = (2 * PI) + start_angle - interval;
+    const double span = (stop - start) / interval;                             // np.arange length
+    const int n = span > 0 ? (int)ceil(span) : 0;
+    EPID_REQUIRE(n >= 1, EPID_ERR_INVALID, "empty profile");
+    EPID_REQUIRE(n <= cap, EPID_ERR_INVALID, "output capacity %d too small for %d samples", cap, n);
+    const double first = start, delta = (start + interval) - start;           // np.arange fills first + i * (next - first)
+    int rc = ensure_scratch(ctx, sizeof(double) * 3 * (size_t)n + 1024);
+    if (rc != EPID_OK) return rc;
+    double* d_p = (double*)ctx->scratch;
+    double* d_x = d_p + n;
+    double* d_y = d_x + n;
+    const int grid = (n + 255) / 256;
+    const int np_ = collapsed ? num_profiles : 1;
+    switch (image->dtype) {
+        case EPID_U16: k_circle_profile<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)image->dptr, H, W, cx, cy, radius, r_lo, r_hi, np_, collapsed, first, delta, n, ccw, d_p, d_x, d_y); break;
+        case EPID_U8: k_circle_profile<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)image->dptr, H, W, cx, cy, radius, r_lo, r_hi, np_, collapsed, first, delta, n, ccw, d_p, d_x, d_y); break;
+        case EPID_F32: k_circle_profile<float><<<grid, 256, 0, ctx->stream>>>((const float*)image->dptr, H, W, cx, cy, radius, r_lo, r_hi, np_, collapsed, first, delta, n, ccw, d_p, d_x, d_y); break;
+        default: k_circle_profile<double><<<grid, 256, 0, ctx->stream>>>((const double*)image->dptr, H, W, cx, cy, radius, r_lo, r_hi, np_, collapsed, first, delta, n, ccw, d_p, d_x, d_y); break;
+    }
+    ctx->launches++;
+    EPID_CUDA(cudaGetLastError());
+    EPID_CUDA(cudaMemcpyAsync(profile, d_p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    EPID_CUDA(cudaMemcpyAsync(x_locations, d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    EPID_CUDA(cudaMemcpyAsync(y_locations, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    EPID_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count = n;
     return EPID_OK;
 }

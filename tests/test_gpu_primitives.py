@@ -183,3 +183,37 @@ def test_find_peaks_and_profile_classes_match_the_reference_semantics():
     _, rp3 = ref_find_peaks(single, fwxm_height=0.8, max_number=1)
     assert abs(fw.center_idx - (abs(rp3["right_ips"][0] - rp3["left_ips"][0]) / 2 + rp3["left_ips"][0])) < 1e-12
     assert abs(fw.field_width_px - (rp3["right_ips"][0] - rp3["left_ips"][0])) < 1e-12
+
+
+def test_circle_profiles_match_map_coordinates(frame):
+    """CircleProfile / CollapsedCircleProfile (core/profile.py:2179-2283, 2405-2483) vs the reference expression."""
+    from pylinac_b200.core.profile import CircleProfile, CollapsedCircleProfile
+
+    img = frame
+    for cls, kw in ((CircleProfile, dict(sampling_ratio=1.0)), (CircleProfile, dict(sampling_ratio=2.0, start_angle=0.3, ccw=False)),
+                    (CollapsedCircleProfile, dict(sampling_ratio=3, width_ratio=0.1, num_profiles=20)),
+                    (CollapsedCircleProfile, dict(sampling_ratio=1, width_ratio=0.25, num_profiles=7, start_angle=1.0))):
+        cx, cy, r = 500.3, 520.7, 371.5
+        p = cls((cx, cy), r, img, **kw)
+        collapsed = cls is CollapsedCircleProfile
+        wr, nprof = kw.get("width_ratio", 0.0), kw.get("num_profiles", 1)
+        radii = np.linspace(r * (1 - wr), r * (1 + wr), nprof) if collapsed else np.array([r])
+        size = np.pi * max(radii) * 2 * kw.get("sampling_ratio", 1.0)
+        interval = (2 * np.pi) / size
+        sa = kw.get("start_angle", 0)
+        rads = np.arange(0 + sa, (2 * np.pi) + sa - interval, interval)
+        if kw.get("ccw", True):
+            rads = rads[::-1]
+        ref = np.zeros(len(rads))
+        for rr in radii:
+            ref += ndimage.map_coordinates(img, [np.sin(rads) * rr + cy, np.cos(rads) * rr + cx], order=0)
+        if collapsed:
+            ref /= nprof
+        assert len(p.values) == len(rads)
+        # cos / sin of the device agree with numpy to ~1 ulp: a sample can flip only when it sits on a pixel boundary
+        mism = np.flatnonzero(p.values != ref)
+        assert len(mism) <= 2, len(mism)
+        np.testing.assert_allclose(p.x_locations, np.cos(rads) * r + cx, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(p.y_locations, np.sin(rads) * r + cy, rtol=0, atol=1e-9)
+    with pytest.raises(ValueError):
+        CircleProfile((900, 900), 400, img)
