@@ -63,29 +63,36 @@ __device__ inline void block_bitonic_sort(double* key, int* idx, int m) {
     }
 }
 
-// Order-preserving compaction of entries with flag != 0 (thread 0, sequential: peak counts are small).
+// Order-preserving compaction of entries with flag != 0: chunks of blockDim.x entries, ballot + warp totals for the output
+// positions; every source of a chunk is in registers before the first write (destinations never pass their sources).
 __device__ inline int compact_by_flag(PeakWork& w, int count, bool have_props) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int o = 0;
-        for (int i = 0; i < count; i++) {
-            if (w.flag[i]) {
-                if (o != i) {
-                    w.idx[o] = w.idx[i];
-                    if (have_props) {
-                        w.prom[o] = w.prom[i]; w.lbase[o] = w.lbase[i]; w.rbase[o] = w.rbase[i];
-                        w.width_height[o] = w.width_height[i]; w.lip[o] = w.lip[i]; w.rip[o] = w.rip[i];
-                    }
-                }
-                o++;
-            }
+    int out = 0;
+    for (int base = 0; base < count; base += nt) {
+        const int i = base + tid;
+        const bool keep = i < count && w.flag[i] != 0;
+        int idx = 0, lb = 0, rb = 0;
+        double prom = 0, wh = 0, lip = 0, rip = 0;
+        if (keep) {
+            idx = w.idx[i];
+            if (have_props) { prom = w.prom[i]; lb = w.lbase[i]; rb = w.rbase[i]; wh = w.width_height[i]; lip = w.lip[i]; rip = w.rip[i]; }
         }
-        w.s_small[0] = o;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) w.s_small[1 + wid] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+        for (int k = 0; k < nw; k++) { const int c = w.s_small[1 + k]; if (k < wid) woff += c; total += c; }
+        __syncthreads();
+        if (keep) {
+            const int o = out + woff + __popc(bal & ((1u << lane) - 1u));
+            w.idx[o] = idx;
+            if (have_props) { w.prom[o] = prom; w.lbase[o] = lb; w.rbase[o] = rb; w.width_height[o] = wh; w.lip[o] = lip; w.rip[o] = rip; }
+        }
+        out += total;
     }
     __syncthreads();
-    const int r = w.s_small[0];
-    __syncthreads();
-    return r;
+    return out;
 }
 
 // returns the number of peaks (>= 0) or -1 if the capacity was exceeded
@@ -192,7 +199,40 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
     if (count == 0) return 0;
 
     // ---- 6. keep the max_number largest by the sort key, left to right (core/profile.py:2615-2623)
-    if (a.max_number > 0 && count > a.max_number) {
+    if (a.max_number == 1 && count > 1) {
+        // the single largest entry by (key, position): what the last element of the ascending sort below would be
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        double bk = -__longlong_as_double(0x7ff0000000000000LL);
+        int bi = -1;
+        for (int i = tid; i < count; i += nt) {
+            const double k = a.sort_by_height ? x[w.idx[i]] : w.prom[i];
+            if (bi < 0 || key_less(bk, bi, k, i)) { bk = k; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || key_less(bk, bi, ok, oi))) { bk = ok; bi = oi; }
+        }
+        __syncthreads();
+        if (lane == 0) { w.s_small[1 + 3 * wid] = __double2hiint(bk); w.s_small[2 + 3 * wid] = __double2loint(bk); w.s_small[3 + 3 * wid] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double gk = 0;
+            int gi = -1;
+            for (int k = 0; k < nw; k++) {
+                const int oi = w.s_small[3 + 3 * k];
+                const double ok = __hiloint2double(w.s_small[1 + 3 * k], w.s_small[2 + 3 * k]);
+                if (oi >= 0 && (gi < 0 || key_less(gk, gi, ok, oi))) { gk = ok; gi = oi; }
+            }
+            w.s_small[0] = gi;
+        }
+        __syncthreads();
+        const int win = w.s_small[0];
+        __syncthreads();
+        for (int i = tid; i < count; i += nt) w.flag[i] = i == win ? 1 : 0;
+        count = compact_by_flag(w, count, true);
+    } else if (a.max_number > 0 && count > a.max_number) {
         int m = 1;
         while (m < count) m <<= 1;
         for (int i = tid; i < m; i += nt) {
