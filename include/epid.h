@@ -347,6 +347,42 @@ int32_t epid_field_profile_len(int32_t n0, double dpmm, int32_t interpolation, d
 int32_t epid_field_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_field_params* p, const double* gauss_h, int32_t lw_h,
                            const double* gauss_v, int32_t lw_v, epid_field_result* results);
 
+/* SingleProfile(values, dpmm, interpolation, ground, ..., edge_detection_method, ...) and its query methods for ONE host
+ * profile (core/profile.py:1125-1937): fwxm_data(x), beam_center(), geometric_center(), inflection_data(), penumbra(lower,
+ * upper), field_data(in_field_ratio, slope_exclusion_ratio), all evaluated in one launch.  Indices are in the units of the
+ * original samples (x_values = range(len(values))); the interpolated abscissae are linspace(x_start, x_stop, n). */
+typedef struct {
+    double dpmm;                       /* <= 0: None (interpolation_factor is used) */
+    int32_t interpolation;             /* 0 NONE, 1 LINEAR */
+    double interpolation_resolution_mm, interpolation_factor;
+    int32_t ground, normalization, edge, centering;   /* codes as in epid_field_params; centering 2 = GEOMETRIC_CENTER */
+    double edge_smoothing_ratio;
+} epid_sp_params;
+
+typedef struct {
+    int32_t status;                    /* 0 ok, 1: no usable peak while normalising */
+    int32_t n;                         /* samples after interpolation */
+    double x_start, x_stop;
+    double values_max;
+    double geometric_center_index, geometric_center_value;
+    int32_t beam_ok, fwxm_ok, infl_ok, pen_ok, fd_ok, fd_field_values_n;
+    double beam_center_index, beam_center_value_at_rounded;
+    double fwxm_left, fwxm_right, fwxm_center_value_at_rounded, fwxm_left_value_at_rounded, fwxm_right_value_at_rounded;
+    double infl_left, infl_right, infl_left_value_exact, infl_right_value_exact, infl_left_value_rounded, infl_right_value_rounded;
+    double pen_left_lower, pen_left_upper, pen_right_lower, pen_right_upper;
+    double fd_width, fd_beam_center, fd_cax, fd_left, fd_right, fd_inner_left, fd_inner_right;
+    double fd_left_slope, fd_left_intercept, fd_right_slope, fd_right_intercept;
+    double fd_top_index, fd_top_value, fd_top_params[3];
+    double fd_beam_center_value, fd_cax_value, fd_left_value, fd_right_value;
+} epid_sp_result;
+
+/* gauss: gaussian_filter1d weights for sigma = edge_smoothing_ratio * n_expect (NULL when edge == 0).  values_out (cap):
+ * the interpolated / grounded / normalised values; field_values_out (cap): field_data()["field values"]. */
+int32_t epid_single_profile(epid_ctx* ctx, const double* values, int32_t n0, const epid_sp_params* p, const double* gauss, int32_t lw,
+                            int32_t n_expect, double fwxm_x, double pen_lower, double pen_upper, double in_field_ratio,
+                            double slope_exclusion_ratio, epid_sp_result* result, double* values_out, double* field_values_out,
+                            int32_t cap);
+
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
  * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */

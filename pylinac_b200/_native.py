@@ -155,6 +155,28 @@ def _struct_from_layout(name, layout):
 FieldResult = _struct_from_layout("FieldResult", _FIELD_LAYOUT)
 assert FIELD_RESULT_DTYPE.itemsize == C.sizeof(FieldResult), (FIELD_RESULT_DTYPE.itemsize, C.sizeof(FieldResult))
 
+class SpParams(C.Structure):
+    _fields_ = [("dpmm", C.c_double), ("interpolation", C.c_int32), ("interpolation_resolution_mm", C.c_double),
+                ("interpolation_factor", C.c_double), ("ground", C.c_int32), ("normalization", C.c_int32), ("edge", C.c_int32),
+                ("centering", C.c_int32), ("edge_smoothing_ratio", C.c_double)]
+
+
+_SP_LAYOUT = [
+    ("status", "<i4"), ("n", "<i4"), ("x_start", "<f8"), ("x_stop", "<f8"), ("values_max", "<f8"),
+    ("geometric_center_index", "<f8"), ("geometric_center_value", "<f8"),
+    ("beam_ok", "<i4"), ("fwxm_ok", "<i4"), ("infl_ok", "<i4"), ("pen_ok", "<i4"), ("fd_ok", "<i4"), ("fd_field_values_n", "<i4"),
+    ("beam_center_index", "<f8"), ("beam_center_value_at_rounded", "<f8"),
+    ("fwxm_left", "<f8"), ("fwxm_right", "<f8"), ("fwxm_center_value_at_rounded", "<f8"), ("fwxm_left_value_at_rounded", "<f8"),
+    ("fwxm_right_value_at_rounded", "<f8"),
+    ("infl_left", "<f8"), ("infl_right", "<f8"), ("infl_left_value_exact", "<f8"), ("infl_right_value_exact", "<f8"),
+    ("infl_left_value_rounded", "<f8"), ("infl_right_value_rounded", "<f8"),
+    ("pen_left_lower", "<f8"), ("pen_left_upper", "<f8"), ("pen_right_lower", "<f8"), ("pen_right_upper", "<f8"),
+    ("fd_width", "<f8"), ("fd_beam_center", "<f8"), ("fd_cax", "<f8"), ("fd_left", "<f8"), ("fd_right", "<f8"),
+    ("fd_inner_left", "<f8"), ("fd_inner_right", "<f8"), ("fd_left_slope", "<f8"), ("fd_left_intercept", "<f8"),
+    ("fd_right_slope", "<f8"), ("fd_right_intercept", "<f8"), ("fd_top_index", "<f8"), ("fd_top_value", "<f8"),
+    ("fd_top_params", "<f8", (3,)), ("fd_beam_center_value", "<f8"), ("fd_cax_value", "<f8"), ("fd_left_value", "<f8"),
+    ("fd_right_value", "<f8")]
+SP_RESULT_DTYPE = np.dtype(_SP_LAYOUT, align=True)
 _lib = None
 _lock = threading.Lock()
 
@@ -208,6 +230,8 @@ _SIGNATURES = {
     "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
     "epid_circle_profile": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_double,
                             C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)],
+    "epid_single_profile": [_P, _P, C.c_int32, C.POINTER(SpParams), _P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                            C.c_double, C.c_double, _P, _P, _P, C.c_int32],
     "epid_field_profile_len": [C.c_int32, C.c_double, C.c_int32, C.c_double],
     "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
     "epid_comm_unique_id": [_P],
@@ -549,3 +573,23 @@ def circle_profile(ctx: Context, image: np.ndarray, center, radius: float, start
         b.free()
     c = cnt.value
     return prof[:c].copy(), xl[:c].copy(), yl[:c].copy()
+
+
+def single_profile(ctx: Context, values, params: SpParams, *, fwxm_x=50.0, penumbra=(20.0, 80.0), in_field_ratio=0.8,
+                   slope_exclusion_ratio=0.2):
+    """SingleProfile(values, ...) + every query method in one launch -> (result row, values, field values)."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    n0 = v.size
+    if params.interpolation:
+        n = int(round(n0 / (params.dpmm * params.interpolation_resolution_mm))) if params.dpmm > 0 else int(round(n0 * params.interpolation_factor))
+    else:
+        n = n0
+    gw, lw = (gaussian_kernel1d(params.edge_smoothing_ratio * n) if params.edge != 0 else (None, 0))
+    res = np.zeros(1, SP_RESULT_DTYPE)
+    cap = n + 8
+    vals, fv = np.empty(cap), np.empty(cap)
+    check(lib().epid_single_profile(ctx.handle, _ptr(v), n0, C.byref(params), _ptr(gw), lw, n, float(fwxm_x), float(penumbra[0]),
+                                    float(penumbra[1]), float(in_field_ratio), float(slope_exclusion_ratio), _ptr(res), _ptr(vals),
+                                    _ptr(fv), cap))
+    r = res[0]
+    return r, vals[: int(r["n"])].copy(), fv[: int(r["fd_field_values_n"])].copy()

@@ -384,7 +384,7 @@ __device__ inline void sp_window(const Sp& s, double a, double b, int* start_out
 }
 
 // scipy.stats.linregress slope of (x_indices[i], y_at(x_indices[i])) over [start, stop)
-__device__ inline double sp_window_slope(const Sp& s, int start, int stop) {
+__device__ inline double sp_window_slope(const Sp& s, int start, int stop, double* intercept = nullptr) {
     const int tid = threadIdx.x, m = stop - start;
     double sx = 0, sy = 0;
     for (int i = start + tid; i < stop; i += FA_THREADS) { sx += sp_x(s, i); sy += sp_y_at(s, s.v, sp_x(s, i)); }
@@ -396,12 +396,15 @@ __device__ inline double sp_window_slope(const Sp& s, int start, int stop) {
         sxy += dx * (sp_y_at(s, s.v, sp_x(s, i)) - ym);
     }
     const double ssxm = block_sum(sxx, s.red) / m, ssxym = block_sum(sxy, s.red) / m;
-    return ssxym / ssxm;
+    const double slope = ssxym / ssxm;
+    if (intercept) *intercept = ym - slope * xm;
+    return slope;
 }
 
 struct SpField {
     bool ok;
     double width, beam_center, cax, beam_center_val, left, right, left_slope, right_slope, top;
+    double inner_left, inner_right, left_intercept, right_intercept, top_val, top_params[3];
     int fv_n;               // number of "field values" left in s.t1
 };
 
@@ -411,6 +414,8 @@ __device__ inline SpField sp_field_data(const Sp& s, double ifr, double ser) {
     f.ok = false;
     f.fv_n = 0;
     f.width = f.beam_center = f.cax = f.beam_center_val = f.left = f.right = f.left_slope = f.right_slope = f.top = 0.0;
+    f.inner_left = f.inner_right = f.left_intercept = f.right_intercept = f.top_val = 0.0;
+    f.top_params[0] = f.top_params[1] = f.top_params[2] = 0.0;
     const int tid = threadIdx.x;
     double full_width;
     if (s.edge == 0) {
@@ -433,9 +438,11 @@ __device__ inline SpField sp_field_data(const Sp& s, double ifr, double ser) {
     const double ir = center + ser * fw / 2;
     int a0, a1;
     sp_window(s, fl, il, &a0, &a1);
-    f.left_slope = sp_window_slope(s, a0, a1);
+    f.left_slope = sp_window_slope(s, a0, a1, &f.left_intercept);
     sp_window(s, ir, fr, &a0, &a1);
-    f.right_slope = sp_window_slope(s, a0, a1);
+    f.right_slope = sp_window_slope(s, a0, a1, &f.right_intercept);
+    f.inner_left = il;
+    f.inner_right = ir;
     // top: np.polyfit(top_x, top_y, 2) as least squares on u = (x - mean) / max|x - mean|, vertex clipped to the window
     sp_window(s, il, ir, &a0, &a1);
     {
@@ -472,6 +479,11 @@ __device__ inline SpField sp_field_data(const Sp& s, double ifr, double ser) {
             }
         }
         f.top = best_u * sc + xm;
+        f.top_val = best_v;
+        // coefficients of np.polyfit in the abscissa itself: u = (x - xm) / sc
+        f.top_params[0] = c2 / (sc * sc);
+        f.top_params[1] = c1 / sc - 2 * c2 * xm / (sc * sc);
+        f.top_params[2] = c0 - c1 * xm / sc + c2 * xm * xm / (sc * sc);
     }
     // field values: y_at(x_indices_shifted[imin .. imax]) with the pixel-offset shift (core/profile.py:1563-1574)
     const double off = center - rint(center);
@@ -781,6 +793,119 @@ k_field_profile(const FieldConst* __restrict__ cc, const double* __restrict__ gw
     }
 }
 
+// ------------------------------------------------------------------------------------------------ SingleProfile (one profile)
+// SingleProfile(values, dpmm, ...) and its query methods for ONE host profile (core/profile.py:1125-1937): the same engine as
+// k_field_profile, every query evaluated in one launch.
+__global__ void __launch_bounds__(FA_THREADS)
+k_single_profile(const epid_sp_params p, const double* __restrict__ raw, int n0, int nmax, int pcap, const double* __restrict__ gw, int lw,
+                 int n_expect, double fwxm_x, double pen_lower, double pen_upper, double ifr, double ser, double* __restrict__ work,
+                 epid_sp_result* __restrict__ out, double* __restrict__ values_out, double* __restrict__ fv_out) {
+    __shared__ int s_small[FA_THREADS + 8];
+    __shared__ BlockRed s_red;
+    __shared__ double s_bc[8];
+    __shared__ int s_status;
+    const int tid = threadIdx.x;
+    PeakWork w;
+    peak_work_at(w, work + 3 * (size_t)nmax, pcap, s_small);
+    Sp s;
+    s.dpmm = p.dpmm;
+    s.edge = p.edge;
+    s.centering = p.centering;
+    s.smoothing = p.edge_smoothing_ratio;
+    s.gw = gw;
+    s.lw = lw;
+    s.v = work;
+    s.t1 = work + nmax;
+    s.t2 = work + 2 * (size_t)nmax;
+    s.w = &w;
+    s.red = &s_red;
+    s.bc = s_bc;
+    s.status = &s_status;
+    epid_sp_result R;
+    memset(&R, 0, sizeof(R));
+    const bool use_dpmm = p.dpmm > 0;
+    bool ok = sp_build(s, raw, n0, p.interpolation != 0, use_dpmm, use_dpmm ? p.interpolation_resolution_mm : p.interpolation_factor,
+                       p.ground != 0, p.normalization);
+    if (ok && s.edge == 1 && s.n != n_expect) ok = false;
+    R.status = ok ? 0 : 1;
+    R.n = s.n;
+    R.x_start = s.start;
+    R.x_stop = s.stop;
+    if (ok) {
+        for (int i = tid; i < s.n; i += FA_THREADS) values_out[i] = s.v[i];
+        double vmax = -INFINITY;
+        for (int i = tid; i < s.n; i += FA_THREADS) vmax = fmax(vmax, s.v[i]);
+        R.values_max = block_max(vmax, s.red);
+        R.geometric_center_index = sp_geom_index(s);
+        R.geometric_center_value = (s.n % 2 == 0) ? (s.v[s.n / 2] + s.v[s.n / 2 - 1]) / 2.0 : s.v[(s.n - 1) / 2];
+        // fwxm_data(x)
+        double l, r;
+        if (sp_fwxm(s, fwxm_x, &l, &r)) {
+            R.fwxm_ok = 1;
+            R.fwxm_left = l;
+            R.fwxm_right = r;
+            const double c = (r - l) / 2 + l;
+            R.fwxm_center_value_at_rounded = sp_y_at(s, s.v, rint(c));
+            R.fwxm_left_value_at_rounded = sp_y_at(s, s.v, rint(l));
+            R.fwxm_right_value_at_rounded = sp_y_at(s, s.v, rint(r));
+        }
+        // inflection_data()
+        if (s.edge == 1) {
+            double il, ir;
+            if (sp_inflection(s, &il, &ir)) {
+                R.infl_ok = 1;
+                R.infl_left = il;
+                R.infl_right = ir;
+                R.infl_left_value_exact = sp_y_at(s, s.v, il);
+                R.infl_right_value_exact = sp_y_at(s, s.v, ir);
+                R.infl_left_value_rounded = sp_y_at(s, s.v, rint(il));
+                R.infl_right_value_rounded = sp_y_at(s, s.v, rint(ir));
+            }
+        }
+        // beam_center()
+        const SpBeam b = sp_beam_center(s);
+        if (b.ok) { R.beam_ok = 1; R.beam_center_index = b.idx; R.beam_center_value_at_rounded = b.val_at_rounded; }
+        // penumbra(lower, upper)
+        {
+            double ll = 0, lr = 0, ul = 0, ur = 0, dummy;
+            bool pk;
+            if (s.edge == 0) {
+                pk = sp_fwxm(s, pen_upper, &ul, &ur) && sp_fwxm(s, pen_lower, &ll, &lr);
+            } else {
+                pk = R.infl_ok != 0;
+                if (pk) {
+                    const double lo_l = fmax(R.infl_left_value_exact / R.values_max * pen_lower / 50 * 100, 1.0);
+                    const double up_l = fmin(R.infl_left_value_exact / R.values_max * pen_upper / 50 * 100, 99.0);
+                    const double lo_r = fmax(R.infl_right_value_exact / R.values_max * pen_lower / 50 * 100, 1.0);
+                    const double up_r = fmin(R.infl_right_value_exact / R.values_max * pen_upper / 50 * 100, 99.0);
+                    pk = sp_fwxm(s, up_l, &ul, &dummy) && sp_fwxm(s, lo_l, &ll, &dummy) && sp_fwxm(s, up_r, &dummy, &ur) && sp_fwxm(s, lo_r, &dummy, &lr);
+                }
+            }
+            if (pk) { R.pen_ok = 1; R.pen_left_lower = ll; R.pen_left_upper = ul; R.pen_right_lower = lr; R.pen_right_upper = ur; }
+        }
+        // field_data(in_field_ratio, slope_exclusion_ratio)
+        if (ser < ifr) {
+            const SpField f = sp_field_data(s, ifr, ser);
+            if (f.ok) {
+                R.fd_ok = 1;
+                R.fd_width = f.width; R.fd_beam_center = f.beam_center; R.fd_cax = f.cax; R.fd_left = f.left; R.fd_right = f.right;
+                R.fd_inner_left = f.inner_left; R.fd_inner_right = f.inner_right;
+                R.fd_left_slope = f.left_slope; R.fd_left_intercept = f.left_intercept;
+                R.fd_right_slope = f.right_slope; R.fd_right_intercept = f.right_intercept;
+                R.fd_top_index = f.top; R.fd_top_value = f.top_val;
+                R.fd_top_params[0] = f.top_params[0]; R.fd_top_params[1] = f.top_params[1]; R.fd_top_params[2] = f.top_params[2];
+                R.fd_beam_center_value = f.beam_center_val;
+                R.fd_cax_value = sp_y_at(s, s.v, rint(f.cax));
+                R.fd_left_value = sp_y_at(s, s.v, rint(f.left));
+                R.fd_right_value = sp_y_at(s, s.v, rint(f.right));
+                R.fd_field_values_n = f.fv_n;
+                for (int i = tid; i < f.fv_n; i += FA_THREADS) fv_out[i] = s.t1[i];
+            }
+        }
+    }
+    if (tid == 0) *out = R;
+}
+
 }  // namespace epid
 
 using namespace epid;
@@ -902,5 +1027,45 @@ extern "C" int32_t epid_field_analyze(epid_ctx* ctx, const epid_batch* frames, c
     EPID_CUDA(cudaMemcpyAsync(results, d_res, sizeof(epid_field_result) * n, cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { set_error("field analysis pipeline failed: %s", cudaGetErrorString(e)); return EPID_ERR_CUDA; }
+    return EPID_OK;
+}
+
+extern "C" int32_t epid_single_profile(epid_ctx* ctx, const double* values, int32_t n0, const epid_sp_params* p, const double* gauss,
+                                       int32_t lw, int32_t n_expect, double fwxm_x, double pen_lower, double pen_upper,
+                                       double in_field_ratio, double slope_exclusion_ratio, epid_sp_result* result, double* values_out,
+                                       double* field_values_out, int32_t cap) {
+    EPID_REQUIRE(ctx && values && p && result && values_out && field_values_out, EPID_ERR_INVALID, "NULL argument");
+    EPID_REQUIRE(n0 >= 3, EPID_ERR_INVALID, "profile too short");
+    EPID_REQUIRE(p->edge == 0 || gauss, EPID_ERR_INVALID, "gaussian weights missing");
+    EPID_REQUIRE(fwxm_x >= 0 && fwxm_x <= 100, EPID_ERR_INVALID, "x must be between 0 and 100");
+    EPID_REQUIRE(pen_lower <= pen_upper, EPID_ERR_INVALID, "Upper penumbra value must be larger than the lower penumbra value");
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    int n = n0;
+    if (p->interpolation) n = (int)rint(p->dpmm > 0 ? (double)n0 / (p->dpmm * p->interpolation_resolution_mm) : (double)n0 * p->interpolation_factor);
+    EPID_REQUIRE(n >= 3 && n <= cap, EPID_ERR_INVALID, "output capacity %d too small for %d samples", cap, n);
+    const int nmax = n + 16;
+    int pcap = 1;
+    while (pcap < nmax / 2 + 8) pcap <<= 1;
+    size_t o = 0;
+    auto sz = [&](size_t b) { const size_t r = o; o += (b + 255) / 256 * 256; return r; };
+    const size_t o_raw = sz(sizeof(double) * n0), o_gw = sz(sizeof(double) * (size_t)(2 * lw + 1)), o_res = sz(sizeof(epid_sp_result));
+    const size_t o_val = sz(sizeof(double) * n), o_fv = sz(sizeof(double) * n), o_wk = sz(sizeof(double) * (3 * (size_t)nmax + 8 * (size_t)pcap));
+    int rc = ensure_scratch(ctx, o);
+    if (rc != EPID_OK) return rc;
+    char* base = (char*)ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    EPID_CUDA(cudaMemcpyAsync(base + o_raw, values, sizeof(double) * n0, cudaMemcpyHostToDevice, st));
+    if (p->edge != 0) EPID_CUDA(cudaMemcpyAsync(base + o_gw, gauss, sizeof(double) * (size_t)(2 * lw + 1), cudaMemcpyHostToDevice, st));
+    k_single_profile<<<1, FA_THREADS, 0, st>>>(*p, (const double*)(base + o_raw), n0, nmax, pcap, (const double*)(base + o_gw), lw, n_expect, fwxm_x,
+                                               pen_lower, pen_upper, in_field_ratio, slope_exclusion_ratio, (double*)(base + o_wk),
+                                               (epid_sp_result*)(base + o_res), (double*)(base + o_val), (double*)(base + o_fv));
+    ctx->launches++;
+    EPID_CUDA(cudaGetLastError());
+    EPID_CUDA(cudaMemcpyAsync(result, base + o_res, sizeof(epid_sp_result), cudaMemcpyDeviceToHost, st));
+    EPID_CUDA(cudaStreamSynchronize(st));
+    EPID_CUDA(cudaMemcpyAsync(values_out, base + o_val, sizeof(double) * result->n, cudaMemcpyDeviceToHost, st));
+    if (result->fd_field_values_n > 0)
+        EPID_CUDA(cudaMemcpyAsync(field_values_out, base + o_fv, sizeof(double) * result->fd_field_values_n, cudaMemcpyDeviceToHost, st));
+    EPID_CUDA(cudaStreamSynchronize(st));
     return EPID_OK;
 }
