@@ -116,3 +116,23 @@ def reference_field(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
     out["strip_cols"] = np.array([f._left_v_index, f._right_v_index])
     out["profile_len"] = np.array([len(f.horiz_profile.values), len(f.vert_profile.values)])
     return out
+
+
+def reference_wl2d(frame, pixel_spacing_mm, sid, gantry, coll, couch, analyze_kwargs=None):
+    """Run the UNMODIFIED reference WinstonLutz2D (skimage calls served by oracle/skimage_shim.py) on an ndarray."""
+    from oracle import skimage_shim
+    from oracle.refstub import reference_image_from_array
+
+    skimage_shim.install()
+    from pylinac import winston_lutz as wl
+
+    img = reference_image_from_array(wl.WinstonLutz2D, np.array(frame), pixel_spacing_mm, sid=sid, gantry=gantry, coll=coll, couch=couch)
+    img.analyze(**(analyze_kwargs or {}))
+    rd = img.results_data()
+    return {
+        "shape": np.array(img.shape), "field_cax": np.array([img.field_cax.x, img.field_cax.y], dtype=float),
+        "bb": np.array([img.bb.x, img.bb.y], dtype=float), "epid": np.array([img.epid.x, img.epid.y], dtype=float),
+        "cax2bb_vector": np.array([rd.cax2bb_vector.x, rd.cax2bb_vector.y], dtype=float), "cax2bb_distance": float(rd.cax2bb_distance),
+        "cax2epid_vector": np.array([rd.cax2epid_vector.x, rd.cax2epid_vector.y], dtype=float),
+        "cax2epid_distance": float(rd.cax2epid_distance), "variable_axis": np.array(str(rd.variable_axis)),
+    }
