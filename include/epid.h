@@ -383,6 +383,44 @@ int32_t epid_single_profile(epid_ctx* ctx, const double* values, int32_t n0, con
                             double slope_exclusion_ratio, epid_sp_result* result, double* values_out, double* field_values_out,
                             int32_t cap);
 
+/* ----------------------------------------------------------------------------------------- Winston-Lutz (per image)
+ * WinstonLutz2D(image).analyze(bb_size_mm, low_density_bb, open_field, bb_proximity_mm) (winston_lutz.py:668-829, 1109-1231;
+ * SizedDiskLocator / find_features metrics/image.py:564-612, metrics/utils.py:66-190; predicates metrics/features.py:7-68) for a
+ * batch of uint16 frames, one result per frame.  BB arrangement ISO (nominal BB position = EPID centre), no shift vector. */
+enum { /* per-frame status (maps to the reference's exceptions) */
+    EPID_WL_OK = 0,
+    EPID_WL_NO_BB = 1,        /* ValueError "Couldn't find the minimum number of disks" / BB_ERROR_MESSAGE */
+    EPID_WL_MISMATCH = 2,     /* ValueError "The number of detected fields and BBs do not match" */
+    EPID_WL_NO_FIELD = 3,     /* ValueError "No fields were detected" */
+    EPID_WL_CAPACITY = 4,     /* search window / field / region larger than the kernels' shared-memory tiles */
+    EPID_WL_FLAT_IMAGE = 5
+};
+
+typedef struct {
+    double dpmm;
+    double bb_size_mm;
+    int32_t low_density_bb;
+    int32_t open_field;
+    double bb_proximity_mm;
+} epid_wl_params;
+
+typedef struct { /* one per frame */
+    int32_t status;
+    int32_t inverted;             /* check_inversion_by_histogram((0.01, 50, 99.99)) fired */
+    int32_t crop_px;              /* pixels _clean_edges removed from every edge */
+    int32_t height, width;        /* analysed (cropped) shape */
+    int32_t n_bbs;                /* BB candidates accepted at the first successful threshold */
+    int32_t threshold_passes;     /* thresholds visited by find_features */
+    int32_t pad;
+    double bb_x, bb_y;            /* matched BB (weighted centroid), pixels of the cropped image */
+    double field_x, field_y;      /* field CAX (centre of mass of the filled field mask) */
+    double epid_x, epid_y;        /* image centre */
+    double cax2bb_x, cax2bb_y, cax2bb_distance;         /* mm */
+    double cax2epid_x, cax2epid_y, cax2epid_distance;   /* mm */
+} epid_wl_result;
+
+int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_wl_params* p, epid_wl_result* results);
+
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
  * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */

@@ -177,6 +177,21 @@ _SP_LAYOUT = [
     ("fd_top_params", "<f8", (3,)), ("fd_beam_center_value", "<f8"), ("fd_cax_value", "<f8"), ("fd_left_value", "<f8"),
     ("fd_right_value", "<f8")]
 SP_RESULT_DTYPE = np.dtype(_SP_LAYOUT, align=True)
+
+
+class WlParams(C.Structure):
+    _fields_ = [("dpmm", C.c_double), ("bb_size_mm", C.c_double), ("low_density_bb", C.c_int32), ("open_field", C.c_int32),
+                ("bb_proximity_mm", C.c_double)]
+
+
+(WL_OK, WL_NO_BB, WL_MISMATCH, WL_NO_FIELD, WL_CAPACITY, WL_FLAT_IMAGE) = range(6)
+_WL_LAYOUT = [
+    ("status", "<i4"), ("inverted", "<i4"), ("crop_px", "<i4"), ("height", "<i4"), ("width", "<i4"), ("n_bbs", "<i4"),
+    ("threshold_passes", "<i4"), ("pad", "<i4"), ("bb_x", "<f8"), ("bb_y", "<f8"), ("field_x", "<f8"), ("field_y", "<f8"),
+    ("epid_x", "<f8"), ("epid_y", "<f8"), ("cax2bb_x", "<f8"), ("cax2bb_y", "<f8"), ("cax2bb_distance", "<f8"),
+    ("cax2epid_x", "<f8"), ("cax2epid_y", "<f8"), ("cax2epid_distance", "<f8")]
+WL_RESULT_DTYPE = np.dtype(_WL_LAYOUT, align=True)
+assert WL_RESULT_DTYPE.itemsize == 128
 _lib = None
 _lock = threading.Lock()
 
@@ -234,6 +249,7 @@ _SIGNATURES = {
                             C.c_double, C.c_double, _P, _P, _P, C.c_int32],
     "epid_field_profile_len": [C.c_int32, C.c_double, C.c_int32, C.c_double],
     "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
+    "epid_wl2d_analyze": [_P, _P, C.POINTER(WlParams), _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -548,6 +564,24 @@ def field_analyze(ctx: Context, frames, params: FieldParams) -> np.ndarray:
     res = np.zeros(n, FIELD_RESULT_DTYPE)
     try:
         check(lib().epid_field_analyze(ctx.handle, frames.handle, C.byref(params), _ptr(gh), lh, _ptr(gv), lv, _ptr(res)))
+    finally:
+        if own is not None:
+            own.free()
+    return res
+
+
+def wl2d_analyze(ctx: Context, frames, params: WlParams) -> np.ndarray:
+    """frames: a Batch (device-resident, uint16) or a uint16 ndarray [n,h,w] / [h,w]; one WL_RESULT_DTYPE row per frame."""
+    own = None
+    if not isinstance(frames, Batch):
+        a = np.asarray(frames)
+        if a.dtype != np.uint16:
+            raise TypeError("Winston-Lutz frames must be uint16")
+        own = frames = Batch.upload(ctx, a)
+    (n, _, _), _ = frames.shape_dtype
+    res = np.zeros(n, WL_RESULT_DTYPE)
+    try:
+        check(lib().epid_wl2d_analyze(ctx.handle, frames.handle, C.byref(params), _ptr(res)))
     finally:
         if own is not None:
             own.free()

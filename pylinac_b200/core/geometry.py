@@ -46,6 +46,44 @@ class Point:
         return f"Point(x={self.x:3.2f}, y={self.y:3.2f}, z={self.z:3.2f})"
 
 
+class Vector:
+    """core/geometry.py:408-480 (x, y, z triple with scalar length and component arithmetic)."""
+
+    def __init__(self, x: float = 0, y: float = 0, z: float = 0):
+        self.x, self.y, self.z = x, y, z
+
+    def as_scalar(self) -> float:
+        return math.sqrt(self.x**2 + self.y**2 + self.z**2)
+
+    def as_point(self) -> Point:
+        return Point(self.x, self.y, self.z)
+
+    def dict(self) -> dict:
+        return {"x": self.x, "y": self.y, "z": self.z}
+
+    def distance_to(self, thing) -> float:
+        p = Point(thing)
+        return math.sqrt((self.x - p.x) ** 2 + (self.y - p.y) ** 2 + (self.z - p.z) ** 2)
+
+    def __sub__(self, other):
+        return Vector(self.x - other.x, self.y - other.y, self.z - other.z)
+
+    def __add__(self, other):
+        return Vector(self.x + other.x, self.y + other.y, self.z + other.z)
+
+    def __neg__(self):
+        return Vector(-self.x, -self.y, -self.z)
+
+    def __truediv__(self, k: float):
+        return Vector(self.x / k, self.y / k, self.z / k)
+
+    def __mul__(self, k: float):
+        return Vector(self.x * k, self.y * k, self.z * k)
+
+    def __repr__(self):
+        return f"Vector(x={self.x:.2f}, y={self.y:.2f}, z={self.z:.2f})"
+
+
 class Line:
     """core/geometry.py:497-584"""
 
