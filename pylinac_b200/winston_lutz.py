@@ -5,9 +5,10 @@ inversion check, edge clean-up, ground / normalize, field mask centre of mass, B
 region properties and the five detection predicates, field / BB matching, CAX->BB and CAX->EPID vectors) runs in CUDA
 (pylinac_b200/csrc/wl.cu).  ``analyze_batch(frames, dpmm, ...)`` is the batched entry point (one result per frame).
 
-Scope: BB arrangement ISO, one field and one BB per image.  Out of scope here: the
-set-level 3-D solve of ``WinstonLutz`` (a32: host-side scipy minimisation over N small vectors), multi-target arrangements,
-``shift_vector`` virtual shifts, plotting / PDF / QuAAC.
+Scope: BB arrangement ISO, one field and one BB per image; ``WinstonLutz`` analyses a
+whole set as one GPU batch and does the set-level solve (3-D BB / field positions, isocentre sizes, statistics) on the host
+from the N result rows, as the reference does.  Out of scope here: multi-target arrangements, ``shift_vector`` virtual
+shifts, plotting / PDF / QuAAC.
 
 The reference delegates labelling and region properties to scikit-image, which is absent from the build container: the CUDA
 kernels follow the published algorithms (see oracle/skimage_shim.py); that boundary is unpinned against skimage itself.
@@ -15,6 +16,7 @@ kernels follow the published algorithms (see oracle/skimage_shim.py); that bound
 from __future__ import annotations
 
 import enum
+import math
 from collections.abc import Sequence
 
 import numpy as np
@@ -278,3 +280,383 @@ class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
         return WinstonLutz2DResult(variable_axis=self.variable_axis.value, cax2bb_vector=ser(r.cax2bb_vector),
                                    cax2epid_vector=ser(r.cax2epid_vector), cax2bb_distance=r.cax2bb_distance,
                                    cax2epid_distance=r.cax2epid_distance, bb_location=ser(r.bb), field_cax=ser(r.field_cax))
+
+
+# ---------------------------------------------------------------------------------------------------------------- set level
+class MachineScale(enum.Enum):
+    """core/scale.py:30-72 (axis conversions relative to IEC 61217)."""
+
+    IEC61217 = "IEC61217"
+    ELEKTA_IEC = "ELEKTA_IEC"
+    VARIAN_IEC = "VARIAN_IEC"
+    VARIAN_STANDARD = "VARIAN_STANDARD"
+
+
+def _to_iec(scale: MachineScale, gantry: float, coll: float, rotation: float):
+    if scale == MachineScale.IEC61217:
+        return gantry, coll, rotation
+    if scale in (MachineScale.ELEKTA_IEC, MachineScale.VARIAN_IEC):
+        return gantry, coll, wrap360(-rotation)
+    return wrap360(180 - gantry), wrap360(180 - coll), wrap360(180 - rotation)
+
+
+def convert_scale(input_scale: MachineScale, output_scale: MachineScale, gantry: float, collimator: float, rotation: float):
+    """core/scale.py:75-92: every conversion is its own inverse, so to-IEC followed by from-IEC."""
+    g, c, r = _to_iec(input_scale, gantry, collimator, rotation)
+    return _to_iec(output_scale, g, c, r)
+
+
+def _cosd(deg: float) -> float:
+    return math.cos(math.radians(deg))
+
+
+def _sind(deg: float) -> float:
+    return math.sin(math.radians(deg))
+
+
+def solve_3d_shift_vector_from_2d_planes(xs, ys, thetas, phis, scale: MachineScale = MachineScale.IEC61217) -> Vector:
+    """Low et al. equations 6-9 generalised (winston_lutz.py:3492-3577): least-squares (pseudo-inverse) solve of the 2 n x 3
+    system built from the in-plane offsets and the gantry / couch angles in Varian Standard scale."""
+    if not (len(xs) == len(ys) == len(thetas) == len(phis)):
+        raise ValueError("The x, y, theta, and phi arrays must all be the same length.")
+    n = len(xs)
+    A = np.zeros((2 * n, 3))
+    xi = np.zeros(2 * n)
+    for i in range(n):
+        th, _, ph = convert_scale(scale, MachineScale.VARIAN_STANDARD, thetas[i], 0, phis[i])
+        A[2 * i, :] = [-_cosd(ph), -_sind(ph), 0]
+        A[2 * i + 1, :] = [-_cosd(th) * _sind(ph), _cosd(th) * _cosd(ph), -_sind(th)]
+        xi[2 * i] = ys[i]
+        xi[2 * i + 1] = -xs[i]
+    long, lat, vert = np.linalg.pinv(A).dot(xi).squeeze()
+    return Vector(x=lat, y=-long, z=vert)
+
+
+def solve_3d_position_from_2d_planes(xs, ys, thetas, phis, scale: MachineScale = MachineScale.IEC61217) -> Vector:
+    """winston_lutz.py:3580-3590"""
+    return -solve_3d_shift_vector_from_2d_planes(xs, ys, thetas, phis, scale)
+
+
+def straight_ray(vector: Vector, gantry_angle: float):
+    """winston_lutz.py:3463-3489: the 40 mm back-projection segment through ``vector`` for a gantry angle."""
+    from .core.geometry import Line
+
+    c, s = _cosd(gantry_angle), _sind(gantry_angle)
+    p1 = Point(vector.x * c + 20 * s, vector.y, vector.x * -s + 20 * c)
+    p2 = Point(vector.x * c - 20 * s, vector.y, vector.x * -s - 20 * c)
+    return Line(p1, p2)
+
+
+def max_distance_to_lines(p, lines) -> float:
+    """winston_lutz.py:3395-3398"""
+    point = Point(p[0], p[1], p[2])
+    return max(line.distance_to(point) for line in lines)
+
+
+class WinstonLutzResult(ResultBase):
+    """winston_lutz.py:456-541"""
+
+    max_2d_cax_to_bb_mm: float
+    median_2d_cax_to_bb_mm: float
+    mean_2d_cax_to_bb_mm: float
+    max_2d_cax_to_epid_mm: float
+    median_2d_cax_to_epid_mm: float
+    mean_2d_cax_to_epid_mm: float
+    gantry_3d_iso_diameter_mm: float
+    coll_2d_iso_diameter_mm: float
+    couch_2d_iso_diameter_mm: float
+    gantry_coll_3d_iso_diameter_mm: float
+    num_total_images: int
+    num_gantry_images: int
+    num_coll_images: int
+    num_couch_images: int
+    num_gantry_coll_images: int
+    max_gantry_rms_deviation_mm: float
+    max_epid_rms_deviation_mm: float
+    max_coll_rms_deviation_mm: float
+    max_couch_rms_deviation_mm: float
+    bb_shift_vector: dict
+    image_details: list[WinstonLutz2DResult]
+    keyed_image_details: dict[str, WinstonLutz2DResult]
+
+
+class _SetImage:
+    """One image of an analysed set: the GPU result row + the axis values (the WinstonLutz2D accessors of the reference)."""
+
+    def __init__(self, row: WLFrameResult, dpmm: float, gantry: float, coll: float, couch: float, refs):
+        self.r = row
+        self.dpmm = dpmm
+        self.gantry_angle, self.collimator_angle, self.couch_angle = gantry, coll, couch
+        self._refs = refs
+
+    bb = property(lambda self: self.r.bb)
+    field_cax = property(lambda self: self.r.field_cax)
+    epid = property(lambda self: self.r.epid)
+    cax2bb_vector = property(lambda self: self.r.cax2bb_vector)
+    cax2bb_distance = property(lambda self: self.r.cax2bb_distance)
+    cax2epid_vector = property(lambda self: self.r.cax2epid_vector)
+    cax2epid_distance = property(lambda self: self.r.cax2epid_distance)
+
+    @property
+    def variable_axis(self) -> Axis:
+        return variable_axis(self.gantry_angle, self.collimator_angle, self.couch_angle, **self._refs)
+
+    # BBFieldMatch vectors in coordinate space (y flipped; winston_lutz.py:265-285)
+    def _coord(self, a: Point, b: Point) -> Vector:
+        return Vector((a.x - b.x) / self.dpmm, -((a.y - b.y) / self.dpmm), (a.z - b.z) / self.dpmm)
+
+    @property
+    def bb_field_vector_mm(self) -> Vector:
+        return self._coord(self.bb, self.field_cax)
+
+    @property
+    def bb_epid_vector_mm(self) -> Vector:
+        return self._coord(self.bb, self.epid)
+
+    @property
+    def field_epid_vector_mm(self) -> Vector:
+        return self._coord(self.field_cax, self.epid)
+
+    @property
+    def bb_epid_distance_mm(self) -> float:
+        """winston_lutz.py:292-295"""
+        return self.epid.distance_to(self.bb) / self.dpmm
+
+    @property
+    def bb_to_field_projection(self):
+        return straight_ray(self.bb_field_vector_mm, self.gantry_angle)
+
+    def results_data(self) -> WinstonLutz2DResult:
+        def ser(p):
+            return {"x": p.x, "y": p.y, "z": p.z}
+
+        return WinstonLutz2DResult(variable_axis=self.variable_axis.value, cax2bb_vector=ser(self.cax2bb_vector),
+                                   cax2epid_vector=ser(self.cax2epid_vector), cax2bb_distance=self.cax2bb_distance,
+                                   cax2epid_distance=self.cax2epid_distance, bb_location=ser(self.bb),
+                                   field_cax=ser(self.field_cax))
+
+
+class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
+    """winston_lutz.py:1234-1611, 1614-1850, 2548-2609 -- a set of EPID images analysed as one batch on the GPU; the set-level
+    quantities (3-D gantry isocentre, 2-D collimator / couch isocentres, BB shift vector, distance statistics) are scalar
+    host work on N result rows, as in the reference.
+
+    ``WinstonLutz(directory_or_paths)`` loads DICOM files like the reference; ``WinstonLutz.from_arrays(frames, axes, dpmm=)``
+    takes frames already in memory (uint16 [n,h,w]) with one (gantry, collimator, couch) triple per frame."""
+
+    def __init__(self, directory, use_filenames: bool = False, axis_mapping: dict | None = None, axes_precision: int | None = None,
+                 dpi: float | None = None, sid: float | None = None, missing_axis_value=0):
+        import os
+
+        if use_filenames:
+            raise NotImplementedError("axis values from file names are an ingest feature outside the accelerated hot path")
+        if isinstance(directory, (list, tuple)):
+            paths = [str(p) for p in directory]
+        else:
+            paths = sorted(os.path.join(directory, f) for f in os.listdir(directory) if not f.startswith("."))
+        if len(paths) < 2:
+            raise ValueError("<2 valid WL images were found in the folder/file or passed. Ensure you chose the correct folder/file")
+        frames, axes, dpmm = [], [], None
+        for pth in paths:
+            img = image.LinacDicomImage(pth, axes_precision=axes_precision, missing_axis_value=missing_axis_value)
+            key = os.path.basename(pth)
+            if axis_mapping and key in axis_mapping:
+                axes.append(tuple(float(v) for v in axis_mapping[key]))
+            else:
+                axes.append((float(img.gantry_angle), float(img.collimator_angle), float(img.couch_angle)))
+            frames.append(np.asarray(img.array))
+            dpmm = img.dpmm if dpmm is None else dpmm
+        self._setup(np.stack(frames), axes, dpmm)
+
+    @classmethod
+    def from_arrays(cls, frames: np.ndarray, axes, *, dpmm: float):
+        self = cls.__new__(cls)
+        self._setup(np.asarray(frames), [tuple(float(v) for v in a) for a in axes], float(dpmm))
+        return self
+
+    def _setup(self, frames: np.ndarray, axes, dpmm: float):
+        if frames.ndim != 3 or len(axes) != frames.shape[0]:
+            raise ValueError("frames must be [n,h,w] with one (gantry, collimator, couch) triple per frame")
+        if frames.dtype != np.uint16:
+            if frames.dtype.kind in "iu" and frames.min() >= 0 and frames.max() <= 65535:
+                frames = frames.astype(np.uint16)
+            else:
+                raise NotImplementedError("the GPU Winston-Lutz path takes integer-valued pixel data in [0, 65535]")
+        self._frames, self._axes, self.dpmm = frames, axes, dpmm
+        self.images: list[_SetImage] = []
+        self._is_analyzed = False
+        self.machine_scale = MachineScale.IEC61217
+        self._minimized = {}
+
+    def analyze(self, bb_size_mm: float = 5, machine_scale: MachineScale = MachineScale.IEC61217, low_density_bb: bool = False,
+                open_field: bool = False, apply_virtual_shift: bool = False, snap_tolerance: float = 3, gantry_reference: float = 0,
+                collimator_reference: float = 0, couch_reference: float = 0, bb_proximity_mm: float = 20) -> None:
+        """winston_lutz.py:1519-1611"""
+        if apply_virtual_shift:
+            raise NotImplementedError("virtual BB shifts are outside the accelerated per-image path")
+        self.machine_scale = machine_scale
+        rows = analyze_batch(self._frames, self.dpmm, bb_size_mm=bb_size_mm, low_density_bb=low_density_bb, open_field=open_field,
+                             bb_proximity_mm=bb_proximity_mm)
+        refs = dict(snap_tolerance=snap_tolerance, gantry_reference=gantry_reference, collimator_reference=collimator_reference,
+                    couch_reference=couch_reference)
+        self.images = []
+        for k, (g, c, p) in enumerate(self._axes):
+            rows[k].raise_for_status()
+            self.images.append(_SetImage(rows[k], self.dpmm, g, c, p, refs))
+        self._minimized = {}
+        self._bb_diameter = bb_size_mm
+        self._is_analyzed = True
+
+    # ---- BB3D (winston_lutz.py:313-362)
+    def _solve(self, which: str) -> Point:
+        vs = [getattr(m, which) for m in self.images]
+        v = solve_3d_position_from_2d_planes([t.x for t in vs], [t.y for t in vs], [m.gantry_angle for m in self.images],
+                                             [m.couch_angle for m in self.images], self.machine_scale)
+        return Point(v.x, v.y, v.z)
+
+    @property
+    def measured_bb_position(self) -> Point:
+        return self._solve("bb_epid_vector_mm")
+
+    @property
+    def measured_field_position(self) -> Point:
+        return self._solve("field_epid_vector_mm")
+
+    @property
+    def bb_shift_vector(self) -> Vector:
+        """winston_lutz.py:1703-1711"""
+        d = self.measured_field_position - self.measured_bb_position
+        return Vector(d.x, d.y, d.z)
+
+    def bb_shift_instructions(self, couch_vrt: float | None = None, couch_lng: float | None = None,
+                              couch_lat: float | None = None) -> str:
+        """winston_lutz.py:1713-1745"""
+        sv = self.bb_shift_vector
+        x_dir = "LEFT" if sv.x < 0 else "RIGHT"
+        y_dir = "IN" if sv.y > 0 else "OUT"
+        z_dir = "UP" if sv.z > 0 else "DOWN"
+        move = f"{x_dir} {abs(sv.x):2.2f}mm; {y_dir} {abs(sv.y):2.2f}mm; {z_dir} {abs(sv.z):2.2f}mm"
+        if all(val is not None for val in [couch_vrt, couch_lat, couch_lng]):
+            new_lat = round(couch_lat + sv.x / 10, 2)
+            new_vrt = round(couch_vrt + sv.z / 10, 2)
+            new_lng = round(couch_lng + sv.y / 10, 2)
+            move += f"\nNew couch coordinates (cm): VRT: {new_vrt:3.2f}; LNG: {new_lng:3.2f}; LAT: {new_lat:3.2f}"
+        return move
+
+    # ---- isocentre sizes (winston_lutz.py:1614-1700)
+    def _get_images(self, axis=(Axis.GANTRY,)):
+        if isinstance(axis, Axis):
+            axis = (axis,)
+        imgs = [im for im in self.images if im.variable_axis in axis]
+        return len(imgs), imgs
+
+    def _minimize_axis(self, axes=(Axis.GANTRY,)):
+        from scipy import optimize
+
+        if isinstance(axes, Axis):
+            axes = (axes,)
+        if axes in self._minimized:
+            return self._minimized[axes]
+        things = [im.bb_to_field_projection for im in self.images if im.variable_axis in (axes + (Axis.REFERENCE,))]
+        if len(things) <= 1:
+            raise ValueError("Not enough images of the given type to identify the axis isocenter")
+        result = optimize.minimize(max_distance_to_lines, np.array([0, 0, 0]), args=things, bounds=[(-20, 20)] * 3,
+                                   options={"eps": 1e-7})
+        self._minimized[axes] = result
+        return result
+
+    @property
+    def gantry_iso_size(self) -> float:
+        if self._get_images((Axis.GANTRY, Axis.REFERENCE))[0] > 1:
+            return self._minimize_axis(Axis.GANTRY).fun * 2
+        return 0
+
+    @property
+    def gantry_coll_iso_size(self) -> float:
+        if self._get_images((Axis.GANTRY, Axis.COLLIMATOR, Axis.GB_COMBO, Axis.REFERENCE))[0] > 1:
+            return self._minimize_axis((Axis.GANTRY, Axis.COLLIMATOR, Axis.GB_COMBO)).fun * 2
+        return 0
+
+    @staticmethod
+    def _find_max_distance_between_points(images) -> float:
+        pts = [Point(im.cax2bb_vector.x, im.cax2bb_vector.y) for im in images]
+        return max(p1.distance_to(p2) for p1 in pts for p2 in pts)
+
+    @property
+    def collimator_iso_size(self) -> float:
+        n, imgs = self._get_images((Axis.COLLIMATOR, Axis.REFERENCE))
+        return self._find_max_distance_between_points(imgs) if n > 1 else 0
+
+    @property
+    def couch_iso_size(self) -> float:
+        n, imgs = self._get_images((Axis.COUCH, Axis.REFERENCE))
+        return self._find_max_distance_between_points(imgs) if n > 1 else 0
+
+    def axis_rms_deviation(self, axis=Axis.GANTRY, value: str = "all"):
+        """winston_lutz.py:1747-1774"""
+        if isinstance(axis, (tuple, list)):
+            axis = tuple(Axis(a) if not isinstance(a, Axis) else a for a in axis)
+        elif not isinstance(axis, Axis):
+            axis = Axis(axis)
+        attr = "cax2bb_vector"
+        if axis == Axis.EPID:
+            attr = "cax2epid_vector"
+            axis = (Axis.GANTRY, Axis.COLLIMATOR, Axis.REFERENCE)
+        imgs = self._get_images(axis=axis)[1]
+        if len(imgs) <= 1:
+            return (0,)
+        rms = [getattr(im, attr).as_scalar() for im in imgs]
+        if value == "range":
+            rms = max(rms) - min(rms)
+        return rms
+
+    def _metric(self, values, metric: str) -> float:
+        import statistics
+
+        if metric == "max":
+            return max(values)
+        if metric == "median":
+            return statistics.median(values)
+        if metric == "mean":
+            return statistics.mean(values)
+        raise ValueError("metric must be one of 'max', 'median', 'mean'")
+
+    def cax2bb_distance(self, metric: str = "max") -> float:
+        """winston_lutz.py:1776-1792"""
+        return self._metric([im.cax2bb_distance for im in self.images], metric)
+
+    def cax2epid_distance(self, metric: str = "max") -> float:
+        """winston_lutz.py:1794-1810 -- as in the reference this aggregates ``epid_to_bb_distances()`` (EPID centre to BB,
+        winston_lutz.py:838-843), not the per-image CAX-to-EPID distance."""
+        return self._metric([im.bb_epid_distance_mm for im in self.images], metric)
+
+    def _generate_results_data(self) -> WinstonLutzResult:
+        """winston_lutz.py:2548-2609"""
+        if not self._is_analyzed:
+            raise ValueError("The set is not analyzed. Use .analyze() first.")
+        details = [im.results_data() for im in self.images]
+        keyed = {}
+        for k, im in enumerate(self.images):
+            key = f"G{im.gantry_angle}B{im.collimator_angle}P{im.couch_angle}"
+            suffix, idx = "", 1
+            while key + suffix in keyed:
+                suffix = f"_{idx}"
+                idx += 1
+            keyed[key + suffix] = details[k]
+        sv = self.bb_shift_vector
+        return WinstonLutzResult(
+            num_total_images=len(self.images),
+            num_gantry_images=self._get_images((Axis.GANTRY, Axis.REFERENCE))[0],
+            num_coll_images=self._get_images((Axis.COLLIMATOR, Axis.REFERENCE))[0],
+            num_gantry_coll_images=self._get_images((Axis.GANTRY, Axis.COLLIMATOR, Axis.GB_COMBO, Axis.REFERENCE))[0],
+            num_couch_images=self._get_images((Axis.COUCH, Axis.REFERENCE))[0],
+            max_2d_cax_to_bb_mm=self.cax2bb_distance("max"), median_2d_cax_to_bb_mm=self.cax2bb_distance("median"),
+            mean_2d_cax_to_bb_mm=self.cax2bb_distance("mean"), max_2d_cax_to_epid_mm=self.cax2epid_distance("max"),
+            median_2d_cax_to_epid_mm=self.cax2epid_distance("median"), mean_2d_cax_to_epid_mm=self.cax2epid_distance("mean"),
+            coll_2d_iso_diameter_mm=self.collimator_iso_size, couch_2d_iso_diameter_mm=self.couch_iso_size,
+            gantry_3d_iso_diameter_mm=self.gantry_iso_size, gantry_coll_3d_iso_diameter_mm=self.gantry_coll_iso_size,
+            max_gantry_rms_deviation_mm=max(self.axis_rms_deviation((Axis.GANTRY, Axis.REFERENCE))),
+            max_coll_rms_deviation_mm=max(self.axis_rms_deviation((Axis.COLLIMATOR, Axis.REFERENCE))),
+            max_couch_rms_deviation_mm=max(self.axis_rms_deviation((Axis.COUCH, Axis.REFERENCE))),
+            max_epid_rms_deviation_mm=max(self.axis_rms_deviation(Axis.EPID)),
+            bb_shift_vector={"x": sv.x, "y": sv.y, "z": sv.z}, image_details=details, keyed_image_details=keyed)

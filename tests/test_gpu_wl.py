@@ -107,3 +107,21 @@ def test_wl2d_class_api():
     assert rd.variable_axis == str(GOLD["couch45/variable_axis"])
     np.testing.assert_allclose([img.bb.x, img.bb.y], GOLD["couch45/bb"], rtol=0, atol=1e-7)
     np.testing.assert_allclose(rd.cax2bb_distance, float(GOLD["couch45/cax2bb_distance"]), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["standard", "gantry_only", "combo"])
+def test_wl_set_matches_reference_golden(name):
+    """WinstonLutz (set level, winston_lutz.py:1519-1850): per-image rows from the GPU, set-level solve on the host."""
+    from pylinac_b200 import winston_lutz as wl
+    from tests.golden.wlset_cases import set_frames
+    from tests.test_wlset_host import GOLD as SGOLD
+    from tests.test_wlset_host import check_set
+
+    frames, ps, sid, axes = set_frames(name)
+    st = wl.WinstonLutz.from_arrays(frames, axes, dpmm=float(SGOLD[f"{name}/dpmm"]))
+    with pytest.raises(ValueError):
+        st.results_data()
+    st.analyze()
+    np.testing.assert_allclose([[im.bb.x, im.bb.y] for im in st.images], SGOLD[f"{name}/bbs"], rtol=0, atol=POS_TOL_PX)
+    np.testing.assert_allclose([[im.field_cax.x, im.field_cax.y] for im in st.images], SGOLD[f"{name}/fields"], rtol=0, atol=POS_TOL_PX)
+    check_set(st, name, 1e-7)      # scipy L-BFGS-B on a max-of-distances objective: inputs agree to 1e-9 px
