@@ -28,9 +28,7 @@ def gpu_run(name):
     return res[0], dpmm
 
 
-@pytest.mark.parametrize("name", CASES)
-def test_pf_matches_reference_golden(name):
-    r, dpmm = gpu_run(name)
+def _compare_with_golden(r, name, GOLD):
     if f"{name}/raises" in GOLD:
         assert r.status != 0
         with pytest.raises(ValueError):
@@ -49,8 +47,11 @@ def test_pf_matches_reference_golden(name):
     assert np.array_equal(r.m["leaf_num"], g("meas_leaf"))
     assert np.array_equal(r.m["picket"], g("meas_picket"))
     assert bool(s["passed"]) == bool(g("passed"))
-    assert int(s["max_error_picket"]) == int(g("max_error_picket"))
-    assert str(r.max_error_leaf) == str(g("max_error_leaf"))
+    if float(g("max_error")) > 10 * ERR_TOL_MM:
+        # on the reference's noise-free "perfect" fixtures every error is rounding noise (~1e-13 mm): which picket / leaf holds
+        # the largest of them is decided below the fp tolerance and is not a parity property
+        assert int(s["max_error_picket"]) == int(g("max_error_picket"))
+        assert str(r.max_error_leaf) == str(g("max_error_leaf"))
     assert [str(x) for x in r.failed_leaves()] == [str(x) for x in g("failed_leaves")]
     # ---- sub-pixel quantities
     npos = g("meas_position").shape[1]
@@ -68,6 +69,31 @@ def test_pf_matches_reference_golden(name):
         np.testing.assert_allclose(float(s[key]), float(g(gk)), rtol=0, atol=ERR_TOL_MM, err_msg=key)
     pw = np.stack([s["picket_width_max"][:npk], s["picket_width_mean"][:npk], s["picket_width_median"][:npk], s["picket_width_min"][:npk]], axis=1)
     np.testing.assert_allclose(pw, g("picket_widths"), rtol=0, atol=ERR_TOL_MM)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pf_matches_reference_golden(name):
+    r, dpmm = gpu_run(name)
+    _compare_with_golden(r, name, GOLD)
+
+
+def _docs_names():
+    from tests.golden import pf_docs_cases as dc
+
+    return list(dc.DOCS)
+
+
+@pytest.mark.parametrize("name", _docs_names())
+def test_pf_matches_reference_on_docs_fixture(name):
+    """The reference's own fixtures (docs/source/files/*.dcm, 1280 x 1280) with the docs recipes' analyze() arguments."""
+    from pylinac_b200 import picketfence as pf
+    from tests.golden import pf_docs_cases as dc
+
+    if not dc.available(name):
+        pytest.skip("frame not committed (noise makes it ~2 MB) and /root/reference is absent on this box")
+    a, ps, sid, ak = dc.docs_frame(name)
+    r = pf.analyze_batch(a[None], (1 / ps) * sid / 1000.0, **ak)[0]
+    _compare_with_golden(r, name, np.load("tests/golden/pf_docs_golden.npz"))
 
 
 def test_pf_batch_matches_oracle_and_is_frame_independent():
