@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libepid.so")
+LIB_PATH = os.environ.get("EPID_LIB") or os.path.join(_HERE, "libepid.so")      # EPID_LIB: kernel-variant experiments (tools/)
 
 EPID_OK = 0
 ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NCCL = -1, -2, -3, -4, -5, -6
@@ -426,6 +426,49 @@ def pinned_empty(shape, dtype=np.uint16) -> np.ndarray:
 _PINNED_OWNERS: dict = {}
 
 
+class _PinnedPool:
+    """Page-locked result buffers, recycled between calls.  cudaHostAlloc costs milliseconds and a fresh pageable
+    ``np.zeros`` of a 30 MB result block costs thousands of first-touch page faults per call; a pooled pinned block costs
+    neither and lets the library DMA the results straight into the array the caller receives.  A block returns to the pool
+    when the last numpy view of it is garbage collected."""
+
+    MAX_FREE_PER_SIZE = 4
+
+    def __init__(self):
+        self._free: dict[int, list[int]] = {}
+        self._lock = threading.Lock()
+
+    def take(self, shape, dtype) -> np.ndarray:
+        import weakref
+
+        dtype = np.dtype(dtype)
+        nbytes = max(int(np.prod(shape)) * dtype.itemsize, 1)
+        with self._lock:
+            lst = self._free.get(nbytes)
+            ptr = lst.pop() if lst else None
+        if ptr is None:
+            p = _P()
+            check(lib().epid_host_alloc(nbytes, C.byref(p)))
+            ptr = p.value
+        buf = (C.c_char * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._give, nbytes, ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def _give(self, nbytes: int, ptr: int) -> None:
+        with self._lock:
+            lst = self._free.setdefault(nbytes, [])
+            if len(lst) < self.MAX_FREE_PER_SIZE:
+                lst.append(ptr)
+                return
+        try:
+            lib().epid_host_free(_P(ptr))
+        except Exception:
+            pass
+
+
+_RESULT_POOL = _PinnedPool()
+
+
 def frame_stats(ctx: Context, batch: Batch, view=None, percentiles=()):
     (n, h, w), _ = batch.shape_dtype
     r0, c0, vh, vw = view if view is not None else (0, 0, h, w)
@@ -483,8 +526,9 @@ def pf_analyze(ctx: Context, frames, params: PFParams, meas_cap: int = 1024, hos
         a = a[None]
     a = np.ascontiguousarray(a)
     n, h, w = a.shape
-    summ = np.zeros(n, PF_SUMMARY_DTYPE)
-    meas = np.zeros((n, meas_cap), PF_MEAS_DTYPE)
+    # every element of both blocks is overwritten by the device-to-host copy of the (zero-initialised) device result arrays
+    summ = _RESULT_POOL.take((n,), PF_SUMMARY_DTYPE)
+    meas = _RESULT_POOL.take((n, meas_cap), PF_MEAS_DTYPE)
     check(lib().epid_pf_analyze_host(ctx.handle, _ptr(a), n, h, w, C.byref(params), _ptr(summ), _ptr(meas), meas_cap))
     return summ, meas
 

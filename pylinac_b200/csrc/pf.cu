@@ -746,8 +746,9 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
     EPID_CUDA(cudaSetDevice(ctx->device));
     const int H = h - 2 * p->crop_px, W = w_ - 2 * p->crop_px;
     const size_t fbytes = sizeof(uint16_t) * (size_t)h * w_;
-    // chunk: ~256 MB of frames (one CTA per frame needs >= 148 frames in flight to fill the GPU), double buffered
-    int chunk = (int)((256u << 20) / fbytes);
+    // chunk: ~128 MB of frames, double buffered: small enough that the work left after the last H2D copy (one chunk of
+    // compute + its result copy) is short, large enough that the persistent kernels still have several work items per SM
+    int chunk = (int)((128u << 20) / fbytes);
     if (chunk < 1) chunk = 1;
     if (chunk > n) chunk = n;
     const int nchunks = (n + chunk - 1) / chunk;
@@ -775,6 +776,13 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
         h_meas[s] = (epid_pf_meas*)(r + align_up(sizeof(epid_pf_summary) * chunk, 256));
         h_cnt[s] = (int*)(r + res_bytes - 256);
     }
+    // results go straight into the caller's buffers when those are page-locked (epid_host_alloc / cudaHostRegister): no staging copy
+    auto pinned_host = [](const void* ptr) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct = pinned_host(summary) && pinned_host(meas);
     cudaEvent_t copied[2], computed[2];
     for (int s = 0; s < 2; s++) { EPID_CUDA(cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming)); EPID_CUDA(cudaEventCreateWithFlags(&computed[s], cudaEventDisableTiming)); }
     uint16_t* pools[3] = {nullptr, nullptr, nullptr};
@@ -791,7 +799,8 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
         const int s = ci & 1, cnt = count_of(ci);
         int r = pf_run(ctx, ctx->stream, bufs[s], cnt, h, w_, p, meas_cap, works[s], pools, nullptr, use_fast);
         if (r != EPID_OK) return r;
-        r = PfResultCopy::enqueue(ctx->stream, works[s], cnt, meas_cap, h_summ[s], h_meas[s], h_cnt[s]);
+        r = PfResultCopy::enqueue(ctx->stream, works[s], cnt, meas_cap, direct ? summary + (size_t)ci * chunk : h_summ[s],
+                                  direct ? meas + (size_t)ci * chunk * meas_cap : h_meas[s], h_cnt[s]);
         if (r != EPID_OK) return r;
         EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
         return EPID_OK;
@@ -805,8 +814,10 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
             if (r != EPID_OK) return r;
             EPID_CUDA(cudaEventSynchronize(computed[s]));
         }
-        memcpy(summary + (size_t)ci * chunk, h_summ[s], sizeof(epid_pf_summary) * cnt);
-        memcpy(meas + (size_t)ci * chunk * meas_cap, h_meas[s], sizeof(epid_pf_meas) * (size_t)cnt * meas_cap);
+        if (!direct) {
+            memcpy(summary + (size_t)ci * chunk, h_summ[s], sizeof(epid_pf_summary) * cnt);
+            memcpy(meas + (size_t)ci * chunk * meas_cap, h_meas[s], sizeof(epid_pf_meas) * (size_t)cnt * meas_cap);
+        }
         return EPID_OK;
     };
     rc = enqueue_copy(0);

@@ -35,7 +35,10 @@
 namespace epid {
 
 // ------------------------------------------------------------------------------------------------ shared definitions
-constexpr int ST_NCW = 12;                 // consumer warps
+#ifndef EPID_ST_NCW
+#define EPID_ST_NCW 12
+#endif
+constexpr int ST_NCW = EPID_ST_NCW;                 // consumer warps
 constexpr int ST_THREADS = (ST_NCW + 1) * 32;
 constexpr int ST_NST = 6;                  // ring stages
 constexpr int ST_KMAX = 8;                 // max row blocks (items) per frame

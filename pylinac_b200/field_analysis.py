@@ -45,6 +45,51 @@ _RESULT_KEYS = ["top_penumbra_mm", "bottom_penumbra_mm", "left_penumbra_mm", "ri
                 "top_slope_percent_mm", "bottom_slope_percent_mm"]
 
 
+# ---- protocol calculations on a SingleProfile (field_analysis.py:37-231): scalar host work on the device-computed field values
+def flatness_dose_difference(profile, in_field_ratio: float = 0.8, **kwargs) -> float:
+    """field_analysis.py:37-61"""
+    ser = kwargs.get("slope_exclusion_ratio", 0.2)
+    dmax = profile.field_calculation(in_field_ratio=in_field_ratio, calculation="max", slope_exclusion_ratio=ser)
+    dmin = profile.field_calculation(in_field_ratio=in_field_ratio, calculation="min", slope_exclusion_ratio=ser)
+    return 100 * abs(dmax - dmin) / (dmax + dmin)
+
+
+def flatness_dose_ratio(profile, in_field_ratio: float = 0.8, **kwargs) -> float:
+    """field_analysis.py:64-82"""
+    dmax = profile.field_calculation(in_field_ratio=in_field_ratio, calculation="max")
+    dmin = profile.field_calculation(in_field_ratio=in_field_ratio, calculation="min")
+    return 100 * (dmax / dmin)
+
+
+def symmetry_point_difference(profile, in_field_ratio: float, **kwargs) -> float:
+    """field_analysis.py:97-119: the point difference of largest magnitude (first one on ties), signed."""
+    field = profile.field_data(in_field_ratio=in_field_ratio, slope_exclusion_ratio=kwargs.get("slope_exclusion_ratio", 0.2))
+    fv = np.asarray(field["field values"], dtype=np.float64)
+    sym = 100 * (fv - fv[::-1]) / field["beam center value (@rounded)"]
+    return float(sym[int(np.argmax(np.abs(sym)))])
+
+
+def symmetry_pdq_iec(profile, in_field_ratio: float, **kwargs) -> float:
+    """field_analysis.py:183-207: max(|lt/rt|, |rt/lt|) with the sign of the larger ratio; first maximum on ties."""
+    field = profile.field_data(in_field_ratio=in_field_ratio, slope_exclusion_ratio=kwargs.get("slope_exclusion_ratio", 0.2))
+    fv = np.asarray(field["field values"], dtype=np.float64)
+    s1, s2 = fv / fv[::-1], fv[::-1] / fv
+    sign = np.where(np.abs(s1) > np.abs(s2), np.sign(s1), np.sign(s2))
+    sym = np.maximum(np.abs(s1), np.abs(s2)) * sign
+    return float(sym[int(np.argmax(np.abs(sym)))])
+
+
+def symmetry_area(profile, in_field_ratio: float, **kwargs) -> float:
+    """field_analysis.py:210-225"""
+    import math
+
+    fv = np.asarray(profile.field_data(in_field_ratio=in_field_ratio,
+                                       slope_exclusion_ratio=kwargs.get("slope_exclusion_ratio", 0.2))["field values"], dtype=np.float64)
+    n = len(fv)
+    left, right = np.sum(fv[: math.floor(n / 2)]), np.sum(fv[math.ceil(n / 2):])
+    return float(100 * (left - right) / (left + right))
+
+
 class FieldResult(ResultBase):
     """field_analysis.py:291-439 (without the central ROI statistics)."""
 
