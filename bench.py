@@ -208,6 +208,9 @@ def main():
     if ndev == 0:
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     ctx = nat.Context.default(local % ndev)
+    from pylinac_b200 import parallel as par
+
+    numa = par.bind_host_to_gpu(local % ndev)      # before the page-locked buffers exist: first touch puts them on the GPU's node
     params = pf.make_params(DPMM, FRAME_SHAPE)
     pinned = nat.pinned_empty(frames_np.shape, np.uint16)
     pinned[...] = frames_np
@@ -301,6 +304,7 @@ def main():
             "config": {"workload": f"PicketFence.analyze() on a batch of {n} synthetic 1024x1024 MLC picket frames per GPU "
                                    "(BASELINE.json configs[1]); 10 pickets x 50 leaf pairs = 500 kisses per frame",
                        "frames_per_gpu": n, "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "host_numa": numa,
                        "l2": f"batch = {n * FRAME_SHAPE[0] * FRAME_SHAPE[1] * 2 / 1e6:.0f} MB per GPU, larger than the 126 MB L2; no flush needed"},
             "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(n * FRAME_SHAPE[0] * FRAME_SHAPE[1] * 2),
                     "d2h_bytes_per_step": int(summ_bytes + meas_bytes), "ms_per_step": e2e_ms / args.steps,

@@ -47,6 +47,8 @@ int32_t epid_ctx_destroy(epid_ctx* ctx);
 const char* epid_last_error(void);                             /* thread-local message of the last failure */
 int32_t epid_sync(epid_ctx* ctx);
 int32_t epid_device_info(epid_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, size_t* hbm_bytes);
+/* PCI bus id ("0000:1b:00.0") of CUDA device `device`: lets a rank bind its host threads / pinned allocations to the GPU's NUMA node */
+int32_t epid_device_pci_bus_id(int32_t device, char* out, int32_t cap);
 int32_t epid_launch_count(epid_ctx* ctx, int64_t* launches);   /* kernels launched by this ctx so far */
 int32_t epid_version(void);
 /* options / diagnostic counters (no reference counterpart: the reference has a single CPU code path).

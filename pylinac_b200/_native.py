@@ -212,6 +212,7 @@ _SIGNATURES = {
     "epid_ctx_destroy": [_P],
     "epid_sync": [_P],
     "epid_device_info": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_size_t)],
+    "epid_device_pci_bus_id": [C.c_int32, C.c_char_p, C.c_int32],
     "epid_launch_count": [_P, C.POINTER(C.c_int64)],
     "epid_version": [],
     "epid_set_option": [_P, C.c_int32, C.c_int64],

@@ -128,6 +128,12 @@ int32_t epid_device_info(epid_ctx* ctx, int32_t* sm_count, int32_t* cc_major, in
     return EPID_OK;
 }
 
+int32_t epid_device_pci_bus_id(int32_t device, char* out, int32_t cap) {
+    EPID_REQUIRE(out && cap >= 16, EPID_ERR_INVALID, "output buffer too small");
+    EPID_CUDA(cudaDeviceGetPCIBusId(out, cap, device));
+    return EPID_OK;
+}
+
 int32_t epid_launch_count(epid_ctx* ctx, int64_t* launches) {
     EPID_REQUIRE(ctx && launches, EPID_ERR_INVALID, "NULL argument");
     *launches = ctx->launches;

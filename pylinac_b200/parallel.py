@@ -17,6 +17,44 @@ def world_info():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device: int, *, sysfs: str = "/sys") -> dict:
+    """Pin this process to the CPU cores of the NUMA node CUDA device `device` hangs off, so that the page-locked frame /
+    result buffers it allocates afterwards are node-local (first touch) and the H2D DMA does not cross the socket
+    interconnect.  With one process per GPU and ~54 GB/s of H2D per GPU this is what keeps 8 ranks from sharing one
+    socket's memory controllers.  Returns {"numa_node", "cpus"}; a no-op (numa_node None) when sysfs has no answer."""
+    import ctypes as C
+
+    from . import _native as nat
+
+    info = {"numa_node": None, "cpus": None}
+    try:
+        buf = C.create_string_buffer(32)
+        nat.check(nat.lib().epid_device_pci_bus_id(int(device), buf, 32))
+        bus = buf.value.decode().lower()
+        with open(os.path.join(sysfs, "bus/pci/devices", bus, "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return info
+        with open(os.path.join(sysfs, "devices/system/node", f"node{node}", "cpulist")) as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        pass
+    return info
+
+
 def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int]:
     """Contiguous block of frame indices owned by `rank`: sizes differ by at most one, earlier ranks take the remainder."""
     if not 0 <= rank < world:

@@ -216,3 +216,69 @@ def test_fast_front_kernel_is_used_for_the_benchmark_frames():
     res = pf.analyze_batch(frames, 2.56)
     assert all(int(s) == 0 for s in res.summary["status"])
     assert ctx.counter(nat.CTR_PF_FALLBACKS) == before, "the fused front kernel fell back to the exact pipeline"
+
+
+def _shape_cases():
+    """Non-square / odd-sized EPID panels: aS500 (384 x 512), aS1000 (768 x 1024), and views whose rows are not a multiple
+    of 8 pixels (unaligned pitch: the TMA front end declines them and the exact pipeline runs)."""
+    from oracle import synth
+
+    out = {}
+    fr = synth.as1000(1000.0)
+    out["as1000_768x1024"] = (synth.picketfence_frame(fr, pickets=7, picket_spacing_mm=25, picket_width_mm=3, seed=201), fr.pixel_size, 1000.0, {})
+    fr = synth.as500(1000.0)
+    out["as500_384x512"] = (synth.picketfence_frame(fr, pickets=5, picket_spacing_mm=30, picket_width_mm=4, picket_height_mm=200, seed=202),
+                            fr.pixel_size, 1000.0, {})
+    fr = synth.as1000(1000.0)
+    a = synth.picketfence_frame(fr, pickets=7, picket_spacing_mm=25, picket_width_mm=3, orientation="left_right", seed=203)
+    out["as1000_left_right"] = (a, fr.pixel_size, 1000.0, {})
+    fr = synth.epid1024()
+    a = synth.picketfence_frame(fr, seed=204)
+    out["odd_1001x1019"] = (np.ascontiguousarray(a[11:1012, 3:1022]), fr.pixel_size, 1000.0, {})
+    out["odd_1019x1001_crop0"] = (np.ascontiguousarray(a[3:1022, 11:1012]), fr.pixel_size, 1000.0, {"crop_mm": 0})
+    return out
+
+
+@pytest.mark.parametrize("name", list(_shape_cases()))
+def test_pf_ragged_shapes_match_the_oracle(name):
+    from oracle import pf_oracle
+    from pylinac_b200 import picketfence as pf
+
+    a, ps, sid, kw = _shape_cases()[name]
+    dpmm = (1 / ps) * sid / 1000.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        o = pf_oracle.pf_analyze(a, dpmm, **kw)
+    r = pf.analyze_batch(np.stack([a, a]), dpmm, **kw)[1]
+    assert r.status == 0
+    assert int(r.s["orientation"]) == int(o["orientation"])
+    assert tuple(int(v) for v in (r.s["height"], r.s["width"])) == tuple(o["shape"])
+    assert sorted(int(v) for v in r.picket_idx) == sorted(int(v) for v in o["picket_idx"])
+    assert int(r.s["n_meas"]) == o["n_meas"] and o["n_meas"] > 50
+    assert np.array_equal(r.m["leaf_num"], o["meas_leaf"]) and np.array_equal(r.m["picket"], o["meas_picket"])
+    np.testing.assert_allclose(r.m["position"][:, :1], o["meas_position"], rtol=0, atol=POS_TOL_PX)
+    np.testing.assert_allclose(r.m["error"][:, :1], o["meas_error"], rtol=0, atol=ERR_TOL_MM)
+    np.testing.assert_allclose(float(r.s["max_error_mm"]), float(o["max_error"]), rtol=0, atol=ERR_TOL_MM)
+
+
+def test_pf_degenerate_inputs_fail_like_the_reference():
+    """Flat frames and frames without pickets raise ValueError in the reference (picketfence.py:760-764, 804-807); a batch
+    keeps going and reports them per frame."""
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    good = synth.bench_pf_frame(70)
+    flat = np.full_like(good, 1234)
+    noise = np.random.default_rng(9).integers(1000, 1100, good.shape).astype(np.uint16)
+    res = pf.analyze_batch(np.stack([good, flat, noise, good]), 2.56)
+    assert res[0].status == 0 and res[3].status == 0
+    assert np.array_equal(res[0].m["position"], res[3].m["position"])
+    for k in (1, 2):
+        assert res[k].status != 0
+        with pytest.raises(ValueError):
+            res[k].raise_for_status()
+    with pytest.raises((ValueError, nat.NativeError)):
+        pf.analyze_batch(np.zeros((1, 8, 8), np.uint16), 2.56)
+    with pytest.raises(TypeError):
+        pf.analyze_batch(np.zeros((1, 1024, 1024), np.float32), 2.56)

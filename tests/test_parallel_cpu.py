@@ -69,3 +69,16 @@ def test_gather_rows_world_size_2_gloo(n_total):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, 2.0), (1, True, 2.0)]
+
+
+def test_bind_host_to_gpu_is_a_noop_without_a_device(tmp_path):
+    """No GPU here: the PCI bus id query fails and the helper must leave the affinity untouched and say so."""
+    import os
+
+    from pylinac_b200 import parallel as par
+
+    before = os.sched_getaffinity(0)
+    info = par.bind_host_to_gpu(0, sysfs=str(tmp_path))
+    assert info == {"numa_node": None, "cpus": None}
+    assert os.sched_getaffinity(0) == before
+    assert par._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
