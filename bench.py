@@ -268,6 +268,8 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
     clk = clocks.stop()
+    # ---- untimed: per-kernel device times (CUDA events between the kernels) for the roofline table
+    stage_ms = nat.pf_bench_stages(ctx, batch, params, max(2, min(args.steps, 5))) if rank == 0 else {}
     assert all(int(s) == 0 for s in res.summary["status"]), "pipeline reported a failed frame"
 
     # ---- max over ranks
@@ -297,6 +299,22 @@ def main():
         except Exception:
             pass
         frames_total = world * n * args.steps
+        # per-kernel table: algorithmic bytes = the pixels the kernel has to read once (pilot: every 32nd row; windows: the
+        # (leaf, picket) windows of PicketFence._get_mlc_window; tail / finalize: 1-D partial sums and window results)
+        m0 = int(res.summary["n_meas"][0])
+        widths = {int(params.leaf_num[i]): params.leaf_width_mm[i] * DPMM for i in range(params.n_leaves)}
+        spacing = int(float(res.summary["picket_spacing_px"][0]))
+        win_px = sum(int(widths[int(l)]) * spacing for l in res.meas["leaf_num"][0, :m0])
+        alg = {"k_pf_init + k_pf_pilot": n * ((H + 31) // 32) * W * 2, "k_pf_stream": alg_bytes, "k_pf_windows_fast": n * win_px * 2}
+        ktable = []
+        step_ms = sum(stage_ms.values()) or 1.0
+        for name, ms in stage_ms.items():
+            if ms <= 0:
+                continue
+            ab = alg.get(name)
+            ktable.append({"kernel": name, "ms": ms, "share": ms / step_ms, "algorithmic_bytes": ab,
+                           "GBps": (ab / (ms * 1e-3) / 1e9) if ab else None, "frac": (ab / (ms * 1e-3) / 1e9 / peak) if ab else None})
+        pipe_gbs = (n * args.steps / (total_ms * 1e-3)) * H * W * 2 / 1e9
         out = {
             "metric": METRIC, "value": frames_total / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -314,7 +332,12 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_pf_stream<4>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_per_launch": stats_ms / args.steps,
-                         "kernel_share_of_step": stats_ms / total_ms},
+                         "kernel_share_of_step": stats_ms / total_ms,
+                         "note": "k_pf_stream is the only kernel that reads whole frames from HBM; the (leaf, picket) window kernel is "
+                                 "the longest kernel of the step but is bound by integer issue (sorting-network medians), not by HBM",
+                         "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
+                                      "what": "device-resident frames/s per GPU x H*W*2 bytes (SURVEY.md 8(d) one-read metric) / peak"},
+                         "kernels": ktable},
             "clocks": clk,
         }
         if cpu_base is not None:

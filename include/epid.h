@@ -236,6 +236,10 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
  * device except the last), return the CUDA-event time of the whole region and of the frame-statistics kernel. */
 int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters,
                       float* total_ms, float* stats_kernel_ms, int64_t* launches);
+/* per-stage device times of `iters` passes (CUDA events between the kernels; bench.py's per-kernel roofline table):
+ * stage_ms[0..6] = init + pilot, stream, tail, windows (fast), windows (generic), finalize, exact front end (fallback only) */
+int32_t epid_pf_bench_stages(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* stage_ms,
+                             int32_t nstages);
 
 
 /* ----------------------------------------------------------------------------------------- Starshot

@@ -243,6 +243,7 @@ _SIGNATURES = {
     "epid_pf_analyze_host": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(PFParams), _P, _P, C.c_int32],
     "epid_pf_bench": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                       C.POINTER(C.c_int64)],
+    "epid_pf_bench_stages": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.c_int32],
     "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
     "epid_circle_profile": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_double,
                             C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)],
@@ -539,6 +540,17 @@ def pf_bench(ctx: Context, batch: Batch, params: PFParams, iters: int):
     launches = C.c_int64()
     check(lib().epid_pf_bench(ctx.handle, batch.handle, C.byref(params), iters, C.byref(total), C.byref(stats), C.byref(launches)))
     return total.value, stats.value, launches.value
+
+
+PF_STAGE_NAMES = ("k_pf_init + k_pf_pilot", "k_pf_stream", "k_pf_tail", "k_pf_windows_fast", "k_pf_windows (generic)", "k_pf_finalize",
+                  "exact front end (fallback)")
+
+
+def pf_bench_stages(ctx: Context, batch: Batch, params: PFParams, iters: int) -> dict:
+    """{stage name: ms per pass} from CUDA events recorded between the kernels of `iters` device-resident passes."""
+    out = (C.c_float * 8)()
+    check(lib().epid_pf_bench_stages(ctx.handle, batch.handle, C.byref(params), iters, out, 8))
+    return {name: out[k] / iters for k, name in enumerate(PF_STAGE_NAMES)}
 
 
 def gaussian_kernel_table(max_sigma: int):

@@ -514,6 +514,7 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     g.box = 10;
     g.rp = (int)(0.01 * H) > 1 ? (int)(0.01 * H) : 1;
     g.cp = (int)(0.01 * W) > 1 ? (int)(0.01 * W) : 1;
+    if (tm) { rc = tm->mark(stream, PF_STAGE_START); if (rc != EPID_OK) return rc; }
     EPID_CUDA(cudaMemcpyAsync(w.cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream));
     const int tb = 128, nb = (n + tb - 1) / tb;
     k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters);
@@ -605,17 +606,21 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
         k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
         ctx->launches++;
     }
+    if (tm) { rc = tm->mark(stream, PF_STAGE_EXACT_FRONT); if (rc != EPID_OK) return rc; }
     }   // !fast
     {
         // fast path for ordinary window sizes, then the generic kernel for whatever it left marked (valid == -1)
         rc = launch_pf_windows_fast(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
         if (rc != EPID_OK) return rc;
+        if (tm) { rc = tm->mark(stream, PF_STAGE_WINDOWS); if (rc != EPID_OK) return rc; }
         dim3 grid(p->n_leaves < 8 ? p->n_leaves : 8, n);   // exits at once unless the fast kernel left work (PfFrame.todo)
         k_pf_windows<<<grid, WIN_WARPS * 32, 0, stream>>>(w.cst, w.refs, w.fr, w.wins, 1);
         ctx->launches++;
+        if (tm) { rc = tm->mark(stream, PF_STAGE_WINDOWS_GENERIC); if (rc != EPID_OK) return rc; }
     }
     rc = launch_pf_finalize(ctx, stream, w.cst, w.fr, w.wins, w.summ, w.meas, n, meas_cap);
     if (rc != EPID_OK) return rc;
+    if (tm) { rc = tm->mark(stream, PF_STAGE_FINALIZE); if (rc != EPID_OK) return rc; }
     EPID_CUDA(cudaGetLastError());
     return EPID_OK;
 }
@@ -733,6 +738,34 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
         fast = false;
     }
     cudaEventDestroy(t0); cudaEventDestroy(t1);
+    for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+    return rc;
+}
+
+int32_t epid_pf_bench_stages(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* stage_ms, int32_t nstages) {
+    EPID_REQUIRE(ctx && frames && p && stage_ms && iters > 0 && nstages >= PF_NSTAGES, EPID_ERR_INVALID, "bad argument");
+    EPID_REQUIRE(frames->dtype == EPID_U16, EPID_ERR_UNSUPPORTED, "picket fence frames must be uint16");
+    const int meas_cap = 1024;
+    int rc = pf_validate(p, frames->h, frames->w, meas_cap);
+    if (rc != EPID_OK) return rc;
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    const int n = frames->n, H = frames->h - 2 * p->crop_px, W = frames->w - 2 * p->crop_px;
+    PfWork w;
+    carve(w, nullptr, n, H, W, meas_cap);
+    rc = ensure_scratch(ctx, w.total);
+    if (rc != EPID_OK) return rc;
+    carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
+    uint16_t* pools[3] = {nullptr, nullptr, nullptr};
+    const bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
+    PfTimers tm;
+    tm.stages = true;
+    EPID_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int it = 0; it < iters && rc == EPID_OK; it++)
+        rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm, fast);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
+    if (rc == EPID_OK) tm.stage_ms(stage_ms, PF_NSTAGES);
+    tm.destroy();
     for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
     return rc;
 }

@@ -106,8 +106,36 @@ struct PfTimers {
         for (size_t i = 0; i + 1 < ev.size(); i += 2) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); t += ms; }
         return t;
     }
-    void destroy() { for (auto e : ev) cudaEventDestroy(e); ev.clear(); }
+    // stage marks (epid_pf_bench_stages): the time between two consecutive marks is charged to the later mark's stage id
+    bool stages = false;
+    std::vector<std::pair<int, cudaEvent_t>> marks;
+    int mark(cudaStream_t s, int stage) {
+        if (!stages) return EPID_OK;
+        cudaEvent_t e;
+        EPID_CUDA(cudaEventCreate(&e));
+        EPID_CUDA(cudaEventRecord(e, s));
+        marks.push_back({stage, e});
+        return EPID_OK;
+    }
+    void stage_ms(float* out, int nstages) {   // call after the stream has been synchronised
+        for (int k = 0; k < nstages; k++) out[k] = 0.f;
+        for (size_t i = 1; i < marks.size(); i++) {
+            const int st = marks[i].first;
+            if (st < 0 || st >= nstages) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            out[st] += ms;
+        }
+    }
+    void destroy() {
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
 };
+enum { PF_STAGE_START = -1, PF_STAGE_INIT_PILOT = 0, PF_STAGE_STREAM = 1, PF_STAGE_TAIL = 2, PF_STAGE_WINDOWS = 3, PF_STAGE_WINDOWS_GENERIC = 4,
+       PF_STAGE_FINALIZE = 5, PF_STAGE_EXACT_FRONT = 6, PF_NSTAGES = 7 };
 
 // pf_windows.cu
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);

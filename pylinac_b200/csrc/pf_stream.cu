@@ -765,6 +765,7 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
     const size_t smem = 256 + (size_t)ST_NST * sg.rps * sg.row_bytes + sizeof(uint32_t) * (size_t)ST_NCW * vpl * 256;
     const int grid = nitems < ctx->sm_count ? nitems : ctx->sm_count;
     int rc = EPID_OK;
+    if (tm) { rc = tm->mark(stream, PF_STAGE_INIT_PILOT); if (rc != EPID_OK) return rc; }
     if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
     switch (vpl) {
         case 1: rc = launch_stream<1>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
@@ -775,6 +776,7 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
     if (rc != EPID_OK) return rc;
     ctx->launches++;
     if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
+    if (tm) { rc = tm->mark(stream, PF_STAGE_STREAM); if (rc != EPID_OK) return rc; }
     {
         static size_t attr = 0;
         const size_t tsm = pf_tail_smem_bytes(H, W);
@@ -784,6 +786,7 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
         }
         k_pf_tail<<<n, TAIL_THREADS, tsm, stream>>>(d_cst, g, sg, refs, pilot, items, col_raw, col_cl, row_raw, row_cl, fr, stats, counters);
         ctx->launches++;
+        if (tm) { rc = tm->mark(stream, PF_STAGE_TAIL); if (rc != EPID_OK) return rc; }
     }
     EPID_CUDA(cudaGetLastError());
     return EPID_OK;
