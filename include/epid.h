@@ -54,7 +54,7 @@ int32_t epid_version(void);
 /* options / diagnostic counters (no reference counterpart: the reference has a single CPU code path).
  * EPID_OPT_PF_EXACT_ONLY: 1 = always use the exact-histogram PicketFence pipeline (default 0: fused sample-guided front
  * kernel with automatic per-batch fallback to the exact pipeline).  EPID_CTR_PF_FALLBACKS: batches / chunks re-run exactly. */
-enum { EPID_OPT_PF_EXACT_ONLY = 1 };
+enum { EPID_OPT_PF_EXACT_ONLY = 1, EPID_OPT_PF_LEAFBAND = 2 /* 1 = experimental leaf-band window kernel (bit-identical results; default 0) */ };
 enum { EPID_CTR_PF_FALLBACKS = 1 };
 int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value);
 int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value);
@@ -237,7 +237,8 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
 int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters,
                       float* total_ms, float* stats_kernel_ms, int64_t* launches);
 /* per-stage device times of `iters` passes (CUDA events between the kernels; bench.py's per-kernel roofline table):
- * stage_ms[0..6] = init + pilot, stream, tail, windows (fast), windows (generic), finalize, exact front end (fallback only) */
+ * stage_ms[0..7] = init + pilot, stream, tail, windows (per-window kernel), windows (generic), finalize, exact front end (fallback
+ * only), windows (leaf-band kernel) */
 int32_t epid_pf_bench_stages(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* stage_ms,
                              int32_t nstages);
 

@@ -24,6 +24,7 @@ _NP2DT = {np.dtype(np.uint8): U8, np.dtype(np.uint16): U16, np.dtype(np.int32): 
 _DT2NP = {v: k for k, v in _NP2DT.items()}
 
 OPT_PF_EXACT_ONLY = 1
+OPT_PF_LEAFBAND = 2
 CTR_PF_FALLBACKS = 1
 PF_MAX_PICKETS = 32
 PF_MAX_LEAVES = 160
@@ -543,13 +544,13 @@ def pf_bench(ctx: Context, batch: Batch, params: PFParams, iters: int):
 
 
 PF_STAGE_NAMES = ("k_pf_init + k_pf_pilot", "k_pf_stream", "k_pf_tail", "k_pf_windows_fast", "k_pf_windows (generic)", "k_pf_finalize",
-                  "exact front end (fallback)")
+                  "exact front end (fallback)", "k_pf_leafband")
 
 
 def pf_bench_stages(ctx: Context, batch: Batch, params: PFParams, iters: int) -> dict:
     """{stage name: ms per pass} from CUDA events recorded between the kernels of `iters` device-resident passes."""
-    out = (C.c_float * 8)()
-    check(lib().epid_pf_bench_stages(ctx.handle, batch.handle, C.byref(params), iters, out, 8))
+    out = (C.c_float * 16)()
+    check(lib().epid_pf_bench_stages(ctx.handle, batch.handle, C.byref(params), iters, out, 16))
     return {name: out[k] / iters for k, name in enumerate(PF_STAGE_NAMES)}
 
 

@@ -59,14 +59,17 @@ struct epid_ctx {
     size_t pinned_bytes = 0;
     // options / diagnostics (epid_set_option / epid_get_counter)
     int pf_exact_only = 0;               // 1: never use the fused sample-guided front kernel
+    int pf_leafband = 0;                 // 1: experimental leaf-band window kernel for the frames it covers (default: per-window kernel)
     int64_t pf_fallbacks = 0;            // batches (or chunks) re-run by the exact pipeline
 };
 
+constexpr size_t EPID_BATCH_PAD = 256;
 struct epid_batch {
     epid_ctx* ctx = nullptr;
     int dtype = EPID_U16;
     int n = 0, h = 0, w = 0;
     void* dptr = nullptr;
+    void* base = nullptr;   // allocation start: dptr = base + EPID_BATCH_PAD (16-byte vector / TMA reads may touch a few bytes either side)
     bool owns = true;
     size_t bytes() const { return (size_t)n * h * w * epid::dtype_size(dtype); }
 };

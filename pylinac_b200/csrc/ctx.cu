@@ -144,6 +144,7 @@ int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value) {
     EPID_REQUIRE(ctx, EPID_ERR_INVALID, "ctx is NULL");
     switch (key) {
         case EPID_OPT_PF_EXACT_ONLY: ctx->pf_exact_only = value ? 1 : 0; return EPID_OK;
+        case EPID_OPT_PF_LEAFBAND: ctx->pf_leafband = value ? 1 : 0; return EPID_OK;
     }
     set_error("unknown option %d", key);
     return EPID_ERR_INVALID;
@@ -185,12 +186,13 @@ int32_t epid_batch_alloc(epid_ctx* ctx, int32_t dtype, int32_t n, int32_t h, int
     b->n = n;
     b->h = h;
     b->w = w;
-    cudaError_t e = cudaMalloc(&b->dptr, b->bytes());
+    cudaError_t e = cudaMalloc(&b->base, b->bytes() + 2 * EPID_BATCH_PAD);
     if (e != cudaSuccess) {
         set_error("cudaMalloc(%zu) failed: %s", b->bytes(), cudaGetErrorString(e));
         delete b;
         return EPID_ERR_NOMEM;
     }
+    b->dptr = (char*)b->base + EPID_BATCH_PAD;
     *out = b;
     return EPID_OK;
 }
@@ -204,7 +206,7 @@ int32_t epid_batch_upload(epid_ctx* ctx, const void* host, int32_t dtype, int32_
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         set_error("H2D copy failed: %s", cudaGetErrorString(e));
-        cudaFree(b->dptr);
+        cudaFree(b->base);
         delete b;
         *out = nullptr;
         return EPID_ERR_CUDA;
@@ -222,9 +224,9 @@ int32_t epid_batch_download(epid_batch* b, void* host) {
 
 int32_t epid_batch_free(epid_batch* b) {
     if (!b) return EPID_OK;
-    if (b->owns && b->dptr) {
+    if (b->owns && b->base) {
         cudaSetDevice(b->ctx->device);
-        cudaFree(b->dptr);
+        cudaFree(b->base);
     }
     delete b;
     return EPID_OK;

@@ -502,6 +502,7 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     hc.W = W;
     hc.meas_cap = meas_cap;
     hc.post_filter = 0;
+    hc.leafband = ctx->pf_leafband ? 1 : 0;
     const int npix = H * W;
     hc.lo = pct_plan(npix, 0.5);
     hc.hi = pct_plan(npix, 99.5);
@@ -610,6 +611,11 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     }   // !fast
     {
         // fast path for ordinary window sizes, then the generic kernel for whatever it left marked (valid == -1)
+        if (hc.leafband) {
+            rc = launch_pf_leafband(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
+            if (rc != EPID_OK) return rc;
+            if (tm) { rc = tm->mark(stream, PF_STAGE_LEAFBAND); if (rc != EPID_OK) return rc; }
+        }
         rc = launch_pf_windows_fast(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
         if (rc != EPID_OK) return rc;
         if (tm) { rc = tm->mark(stream, PF_STAGE_WINDOWS); if (rc != EPID_OK) return rc; }
@@ -789,7 +795,7 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
     carve(wk, nullptr, chunk, H, W, meas_cap);
     const size_t work_bytes = align_up(wk.total, 256);
     const size_t buf_bytes = align_up(fbytes * chunk, 256);
-    rc = ensure_scratch(ctx, 2 * work_bytes + 2 * buf_bytes);
+    rc = ensure_scratch(ctx, 2 * work_bytes + 2 * buf_bytes + 512);   // slack: 16-byte vector / TMA reads may run a few bytes past the last frame
     if (rc != EPID_OK) return rc;
     // pinned staging for the results of two chunks in flight
     const size_t res_bytes = align_up(sizeof(epid_pf_summary) * chunk, 256) + align_up(sizeof(epid_pf_meas) * (size_t)chunk * meas_cap, 256) + 256;

@@ -31,6 +31,7 @@
 // (a block of rows of one frame) and are reduced across warps through shared memory once per item.  All per-pixel work is
 // packed u16x2 arithmetic (VIMNMX.U16x2, IDP.2A), branch free: ~12 integer instructions per pixel.
 #include "pf_common.cuh"
+#include "tma.cuh"
 
 namespace epid {
 
@@ -69,31 +70,6 @@ struct StreamGeom {
     int rps;                 // rows per stage = ST_NCW / nstrips
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(ST_NCW * 32) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
@@ -355,7 +331,7 @@ k_pf_stream(const StreamGeom sg, const FrameRef* __restrict__ frames, const Pilo
         sh->mn = 0xffffu;
         sh->mx = 0;
         sh->cnt[0] = sh->cnt[1] = sh->cnt[2] = sh->cnt[3] = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_fence_init();
     }
     __syncthreads();
     const int H = sg.H, W = sg.W;

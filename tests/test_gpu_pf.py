@@ -282,3 +282,74 @@ def test_pf_degenerate_inputs_fail_like_the_reference():
         pf.analyze_batch(np.zeros((1, 8, 8), np.uint16), 2.56)
     with pytest.raises(TypeError):
         pf.analyze_batch(np.zeros((1, 1024, 1024), np.float32), 2.56)
+
+
+def _leafband_cases():
+    from oracle import synth
+    from tests.golden import pf_docs_cases as dc
+
+    out = {}
+    out["bench"] = (np.stack([synth.bench_pf_frame(i) for i in range(80, 86)]), 2.56, {})
+    a = synth.bench_pf_frame(86)
+    out["sag"] = (a[None], 2.56, {"sag_adjustment": 1.5})
+    out["separate"] = (a[None], 2.56, {"separate_leaves": True, "nominal_gap_mm": 3})
+    out["inverted"] = ((a.max() - a).astype(np.uint16)[None], 2.56, {})
+    out["crop2_misaligned"] = (a[None], 2.56, {"crop_mm": 2})
+    out["crop0"] = (a[None], 2.56, {"crop_mm": 0})
+    out["wide_windows"] = (a[None], 2.56, {"leaf_analysis_width_ratio": 0.9, "picket_spacing": 40.0})
+    for nm in ("as1200", "hdmlc", "fwxm70_edge", "tight_tol", "dead_pixel"):
+        fr, ps, sid, ck, ak = case_frame(nm)
+        ck = dict(ck)
+        if ck.get("mlc") == "HD":
+            from pylinac_b200 import picketfence as pf
+
+            ck["mlc"] = pf.MLC.HD_MILLENNIUM
+        out[nm] = (fr[None], (1 / ps) * sid / 1000.0, {**ck, **ak})
+    for nm in ("rotated_up_down", "erroneous_leaves"):
+        if dc.available(nm):
+            fr, ps, sid, ak = dc.docs_frame(nm)
+            out["docs_" + nm] = (fr[None], (1 / ps) * sid / 1000.0, ak)
+    return out
+
+
+@pytest.mark.parametrize("name", list(_leafband_cases()))
+def test_leafband_kernel_equals_per_window_kernel(name):
+    """The experimental leaf-band window kernel (one CTA per leaf, all pickets at once; opt-in) must reproduce
+    the per-window kernel bit for bit."""
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    frames, dpmm, kw = _leafband_cases()[name]
+    ctx = nat.Context.default()
+    try:
+        ctx.set_option(nat.OPT_PF_LEAFBAND, 0)
+        old = pf.analyze_batch(frames, dpmm, **kw)
+        ctx.set_option(nat.OPT_PF_LEAFBAND, 1)
+        new = pf.analyze_batch(frames, dpmm, **kw)
+    finally:
+        ctx.set_option(nat.OPT_PF_LEAFBAND, 0)
+    for k in old.summary.dtype.names:
+        np.testing.assert_array_equal(old.summary[k], new.summary[k], err_msg=k)
+    for i in range(len(frames)):
+        if int(old.summary["status"][i]) == 0:
+            m = int(old.summary["n_meas"][i])
+            assert m > 0
+            for k in old.meas.dtype.names:
+                np.testing.assert_array_equal(old.meas[k][i, :m], new.meas[k][i, :m], err_msg=k)
+
+
+def test_leafband_kernel_runs_when_enabled():
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    ctx = nat.Context.default()
+    frames = np.stack([synth.bench_pf_frame(i) for i in range(60, 76)])
+    b = nat.Batch.upload(ctx, frames)
+    try:
+        ctx.set_option(nat.OPT_PF_LEAFBAND, 1)
+        st = nat.pf_bench_stages(ctx, b, pf.make_params(2.56, frames.shape[1:]), 2)
+    finally:
+        ctx.set_option(nat.OPT_PF_LEAFBAND, 0)
+        b.free()
+    assert st["k_pf_leafband"] > 5 * st["k_pf_windows_fast"] > 0
