@@ -102,3 +102,38 @@ def gather_rows(rows: np.ndarray, n_total: int, *, dist=None, ctx=None) -> np.nd
         out[pos: pos + sizes[r]] = allbuf[r * width: r * width + sizes[r]]
         pos += sizes[r]
     return out
+
+
+def init_comm(ctx, dist) -> None:
+    """Create the NCCL communicator of `ctx` across the ranks of an initialised torch.distributed group: rank 0 makes the
+    ncclUniqueId, the 128 bytes travel through `dist.broadcast` (plumbing), every rank calls epid_comm_init."""
+    import torch
+
+    from . import _native as nat
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = np.zeros(128, np.uint8)
+        nat.check(nat.lib().epid_comm_unique_id(buf.ctypes.data))
+        uid = torch.from_numpy(buf)
+    dist.broadcast(uid, src=0)
+    nat.check(nat.lib().epid_comm_init(ctx.handle, world, rank, uid.numpy().ctypes.data))
+
+
+def analyze_sharded(analyze_rows, frames, *, dist=None, ctx=None) -> np.ndarray:
+    """Run a batched analysis on this rank's contiguous shard of ``frames`` and return ALL ranks' result rows in frame order.
+
+    analyze_rows : callable(frames_shard) -> numpy structured array, one row per frame (e.g.
+                   ``lambda f: winston_lutz.analyze_batch(f, dpmm).rows``); the frames of a batch are independent, so no
+                   data-path collective is involved -- the only exchange is the final gather of the fixed-size rows.
+    frames       : anything sliceable by frame index whose length is the total frame count (an ndarray, a memmap, a lazy loader);
+                   only ``frames[start:end]`` of this rank's shard is touched.
+    """
+    world, rank, _ = world_info() if dist is None else (dist.get_world_size(), dist.get_rank(), 0)
+    n_total = len(frames)
+    start, end = shard_range(n_total, world, rank)
+    rows = analyze_rows(frames[start:end])
+    if len(rows) != end - start:
+        raise ValueError(f"analyze_rows returned {len(rows)} rows for a shard of {end - start} frames")
+    return gather_rows(rows, n_total, dist=dist, ctx=ctx)

@@ -44,6 +44,26 @@ def _worker(rank, world, port, n_total, q):
         ok = (len(allrows) == n_total and np.array_equal(allrows["start_x"], np.arange(n_total))
               and np.array_equal(allrows["wobble_x"], np.arange(n_total) * 0.5)
               and np.array_equal(allrows["peak_idx"][:, 3], np.arange(n_total) + 7))
+        # analyze_sharded: each rank analyses only its shard (a stand-in analysis: no GPU here), everyone gets all rows
+        touched = []
+
+        class Lazy:
+            def __len__(self):
+                return n_total
+
+            def __getitem__(self, sl):
+                touched.append((sl.start, sl.stop))
+                return np.arange(sl.start, sl.stop)
+
+        def fake_analyze(shard):
+            r = np.zeros(len(shard), nat.WL_RESULT_DTYPE)
+            r["bb_x"] = shard * 2.0
+            r["n_bbs"] = shard
+            return r
+
+        allwl = parallel.analyze_sharded(fake_analyze, Lazy(), dist=dist)
+        ok = ok and touched == [(lo, hi)] and np.array_equal(allwl["bb_x"], np.arange(n_total) * 2.0) and \
+            np.array_equal(allwl["n_bbs"], np.arange(n_total))
         # max-over-ranks of a timing, as bench.py does
         import torch
 
