@@ -44,6 +44,7 @@ struct WlConst {
     epid_wl_params p;
     int H, W;
     size_t field_tile_cap;             // bytes available for the field tile in k_wl_field's dynamic shared memory
+    int win_edge;                      // largest BB window edge of this launch: the union-find forest holds win_edge^2 ints
 };
 
 struct WlFrame {
@@ -55,6 +56,7 @@ struct WlFrame {
     uint32_t mn, D;                    // ground / normalize: I = (T(v) - mn) / D
     uint32_t g_field;                  // field mask: g >= g_field  <=>  I >= (p99.9 - p5) / 2 + p5
     double field_x, field_y;
+    int by0, by1, bx0, bx1;            // bounding box of the thresholded field (k_wl_bbox)
 };
 
 __device__ __forceinline__ uint32_t wl_T(const WlFrame& f, uint32_t v) { return f.flip ? f.S - v : v; }
@@ -75,19 +77,58 @@ __device__ __forceinline__ void wl_pct_plan(uint32_t n, double q_percent, uint32
 }
 
 // ------------------------------------------------------------------------------------------------ histogram
+constexpr int WL_HSLOTS = 4096;        // direct-mapped shared-memory cache of histogram bins (slot = value mod 4096)
+constexpr int WL_HPARTS = 8;           // CTAs per frame
+
+// Exact histogram.  A CTA streams 1/8 of a frame with 16-byte loads; lanes that hold the same value are merged
+// (__match_any_sync), and the merged count goes to a shared-memory cache in which the first value that claims a slot owns it for
+// the CTA's lifetime -- EPID frames use a narrow band of values locally, so nearly every add stays in shared memory; values that
+// lose a slot go straight to the global histogram.  The cache is flushed with one global atomic per occupied slot.
 __global__ void __launch_bounds__(256)
 k_wl_hist(const uint16_t* __restrict__ base, int H, int W, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_tag[WL_HSLOTS];     // value + 1, 0 = free
+    __shared__ uint32_t s_cnt[WL_HSLOTS];
     const int fi = blockIdx.y;
     const uint16_t* f = base + (size_t)fi * H * W;
     uint32_t* h = hist + (size_t)fi * 65536;
     const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < WL_HSLOTS; i += 256) { s_tag[i] = 0; s_cnt[i] = 0; }
+    __syncthreads();
+    auto add = [&](uint32_t v, bool in) {
+        const unsigned m = __match_any_sync(0xffffffffu, in ? v : 0x10000u);
+        if (in && lane == __ffs(m) - 1) {
+            const uint32_t c = (uint32_t)__popc(m), slot = v & (WL_HSLOTS - 1);
+            const uint32_t old = atomicCAS(&s_tag[slot], 0u, v + 1u);
+            if (old == 0u || old == v + 1u) atomicAdd(&s_cnt[slot], c);
+            else atomicAdd(&h[v], c);
+        }
+    };
     const size_t npx = (size_t)H * W;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ((npx + 31) & ~(size_t)31); i += (size_t)gridDim.x * blockDim.x) {
-        const bool in = i < npx;
-        const uint32_t v = in ? f[i] : 0x10000u;
-        // lanes that hold the same value add once (clipped floors put most of a frame into one bin)
-        const unsigned m = __match_any_sync(0xffffffffu, v);
-        if (in && lane == __ffs(m) - 1) atomicAdd(&h[v], (uint32_t)__popc(m));
+    const size_t per = ((npx + WL_HPARTS - 1) / WL_HPARTS + 7) & ~(size_t)7;
+    const size_t p0 = (size_t)blockIdx.x * per, p1 = p0 + per < npx ? p0 + per : npx;
+    // head up to the first 16-byte boundary, vector body, tail
+    const size_t mis = ((reinterpret_cast<uintptr_t>(f + p0) >> 1) & 7);
+    const size_t v0 = p0 + ((8 - mis) & 7) < p1 ? p0 + ((8 - mis) & 7) : p1;
+    const size_t nvec = (p1 - v0) >> 3;
+    if (threadIdx.x < 32) add(p0 + lane < v0 ? f[p0 + lane] : 0u, p0 + lane < v0);
+    const size_t nvec32 = (nvec + 31) & ~(size_t)31;            // every lane of a warp takes the same number of trips
+    for (size_t k = threadIdx.x; k < ((nvec32 + 255) & ~(size_t)255); k += 256) {
+        const bool in = k < nvec;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (in) q = ldg_stream16(f + v0 + k * 8);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            add(w[t] & 0xffffu, in);
+            add(w[t] >> 16, in);
+        }
+    }
+    const size_t t0 = v0 + nvec * 8;
+    if (threadIdx.x < 32) add(t0 + lane < p1 ? f[t0 + lane] : 0u, t0 + lane < p1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < WL_HSLOTS; i += 256) {
+        const uint32_t tg = s_tag[i];
+        if (tg) atomicAdd(&h[tg - 1u], s_cnt[i]);
     }
 }
 
@@ -167,7 +208,7 @@ k_wl_front(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, ui
     }
     __syncthreads();
     if (s.first == s.last) {
-        if (tid == 0) { F.status = EPID_WL_FLAT_IMAGE; F.flip = 0; F.S = 0; F.crop = 0; F.h = H; F.w = W; F.mn = 0; F.D = 0; F.g_field = 0; }
+        if (tid == 0) { F.status = EPID_WL_FLAT_IMAGE; F.flip = 0; F.S = 0; F.crop = 0; F.h = H; F.w = W; F.mn = 0; F.D = 0; F.g_field = 0; F.by0 = H; F.by1 = -1; F.bx0 = W; F.bx1 = -1; }
         return;
     }
     // ---- _clean_edges(window_size=2) (winston_lutz.py:1109-1133)
@@ -256,6 +297,7 @@ k_wl_front(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, ui
         F.mn = tmin;
         F.D = D;
         F.g_field = 0;
+        F.by0 = h; F.by1 = -1; F.bx0 = w; F.bx1 = -1;
         if (D) {
             double v[4];
             for (int k = 0; k < 4; k++) {
@@ -301,10 +343,37 @@ __device__ inline void wl_flood_outside(unsigned char* tile, int th, int tw) {
     }
 }
 
+constexpr int WL_BBOX_PARTS = 16;      // CTAs per frame in the bounding-box pass
+
+// bounding box of the field mask (I >= threshold), rows dealt to warps, coalesced 2-byte loads, one atomic per warp
+__global__ void __launch_bounds__(WL_THREADS)
+k_wl_bbox(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, WlFrame* wf) {
+    const WlConst& c = *cc;
+    const int fi = blockIdx.y, lane = threadIdx.x & 31;
+    WlFrame& F = wf[fi];
+    if (F.status != EPID_WL_OK || c.p.open_field) return;
+    const int W = c.W;
+    const uint16_t* f = base + (size_t)fi * c.H * W;
+    const int h = F.h, w = F.w, crop = F.crop;
+    const uint32_t gth = F.g_field, mn = F.mn, S = F.S;
+    const int flip = F.flip;
+    int y0 = h, y1 = -1, x0 = w, x1 = -1;
+    const int nwarps = WL_BBOX_PARTS * WL_WARPS;
+    for (int y = blockIdx.x * WL_WARPS + (threadIdx.x >> 5); y < h; y += nwarps) {
+        const uint16_t* row = f + (size_t)(y + crop) * W + crop;
+        for (int x = lane; x < w; x += 32) {
+            const uint32_t v = row[x];
+            const uint32_t g = (flip ? S - v : v) - mn;
+            if (g >= gth) { y0 = min(y0, y); y1 = max(y1, y); x0 = min(x0, x); x1 = max(x1, x); }
+        }
+    }
+    y0 = warp_min(y0); y1 = warp_max(y1); x0 = warp_min(x0); x1 = warp_max(x1);
+    if (lane == 0 && y1 >= 0) { atomicMin(&F.by0, y0); atomicMax(&F.by1, y1); atomicMin(&F.bx0, x0); atomicMax(&F.bx1, x1); }
+}
+
 __global__ void __launch_bounds__(WL_THREADS)
 k_wl_field(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, WlFrame* wf) {
     extern __shared__ __align__(16) unsigned char tile[];
-    __shared__ int s_box[4];
     __shared__ unsigned long long s_sum[3];
     const WlConst& c = *cc;
     const int fi = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -318,18 +387,9 @@ k_wl_field(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, Wl
         return;
     }
     const uint32_t gth = F.g_field, mn = F.mn;
-    if (tid == 0) { s_box[0] = h; s_box[1] = -1; s_box[2] = w; s_box[3] = -1; s_sum[0] = s_sum[1] = s_sum[2] = 0; }
+    if (tid == 0) { s_sum[0] = s_sum[1] = s_sum[2] = 0; }
     __syncthreads();
-    int y0 = h, y1 = -1, x0 = w, x1 = -1;
-    for (int i = tid; i < h * w; i += WL_THREADS) {
-        const int y = i / w, x = i - y * w;
-        const uint32_t g = wl_T(F, f[(size_t)(y + crop) * W + (x + crop)]) - mn;
-        if (g >= gth) { y0 = min(y0, y); y1 = max(y1, y); x0 = min(x0, x); x1 = max(x1, x); }
-    }
-    y0 = warp_min(y0); y1 = warp_max(y1); x0 = warp_min(x0); x1 = warp_max(x1);
-    if (lane == 0) { atomicMin(&s_box[0], y0); atomicMax(&s_box[1], y1); atomicMin(&s_box[2], x0); atomicMax(&s_box[3], x1); }
-    __syncthreads();
-    y0 = s_box[0]; y1 = s_box[1]; x0 = s_box[2]; x1 = s_box[3];
+    const int y0 = F.by0, y1 = F.by1, x0 = F.bx0, x1 = F.bx1;      // k_wl_bbox
     if (y1 < 0) { if (tid == 0) F.status = EPID_WL_NO_FIELD; return; }     // center_of_mass of nothing: nan in the reference
     // tile = bounding box + 1 pixel of margin (the margin is background reachable from the image border or is outside the image)
     const int th = y1 - y0 + 3, tw = x1 - x0 + 3;
@@ -424,12 +484,12 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     const int left = max((int)floor(ex - win / 2), 0), right = min((int)ceil(ex + win / 2), w);
     const int top = max((int)floor(ey - win / 2), 0), bottom = min((int)ceil(ey + win / 2), h);
     const int wh = bottom - top, ww = right - left;
-    if (wh < 3 || ww < 3 || wh > WL_MAXWIN || ww > WL_MAXWIN) { if (tid == 0) R.status = EPID_WL_CAPACITY; return; }
+    if (wh < 3 || ww < 3 || wh > c.win_edge || ww > c.win_edge) { if (tid == 0) R.status = EPID_WL_CAPACITY; return; }
     const int npx = wh * ww;
     int* parent = reinterpret_cast<int*>(smraw);                         // npx ints (shared): union-find forest of the window
     unsigned short* cid = cid_all + (size_t)fi * WL_MAXWIN * WL_MAXWIN;  // component id of a root pixel (HBM scratch, L2 resident)
     WlComp* comp = comp_all + fi;                                        // per-component accumulators (HBM scratch)
-    unsigned char* tile = reinterpret_cast<unsigned char*>(parent + WL_MAXWIN * WL_MAXWIN);   // WL_TILE^2: candidate mask / flood states
+    unsigned char* tile = reinterpret_cast<unsigned char*>(parent + c.win_edge * c.win_edge);   // WL_TILE^2: candidate mask / flood states
     unsigned char* tile2 = tile + WL_TILE * WL_TILE;                     // border image of the perimeter
     double* smp = samples + (size_t)fi * WL_MAXWIN * WL_MAXWIN;
     // ---- sample = stretch(invert(image[window])) with the reference's fp64 operation order
@@ -761,12 +821,18 @@ extern "C" int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, co
     if (rc != EPID_OK) return rc;
     char* base = (char*)ctx->scratch;
     cudaStream_t st = ctx->stream;
+    // the BB window is (40 + bb) mm: size the shared-memory forest for it, not for the largest window the kernel supports
+    int win_edge = (int)ceil((40 + p->bb_size_mm) * p->dpmm) + 2;
+    if (win_edge > WL_MAXWIN) win_edge = WL_MAXWIN;      // larger windows report EPID_WL_CAPACITY per frame
+    if (win_edge < 8) win_edge = 8;
+    hc.win_edge = win_edge;
+    const size_t bb_smem = sizeof(int) * (size_t)win_edge * win_edge + 2 * WL_TILE * WL_TILE + 64;
+    const size_t bb_smem_max = sizeof(int) * WL_MAXWIN * WL_MAXWIN + 2 * WL_TILE * WL_TILE + 64;
     EPID_CUDA(cudaMemcpyAsync(base + o_cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
-    const size_t bb_smem = sizeof(int) * WL_MAXWIN * WL_MAXWIN + 2 * WL_TILE * WL_TILE + 64;
     static bool attr = false;
     if (!attr) {
         EPID_CUDA(cudaFuncSetAttribute(k_wl_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hc.field_tile_cap));
-        EPID_CUDA(cudaFuncSetAttribute(k_wl_bb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem));
+        EPID_CUDA(cudaFuncSetAttribute(k_wl_bb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_max));
         attr = true;
     }
     for (int c0 = 0; c0 < n; c0 += chunk) {
@@ -774,12 +840,13 @@ extern "C" int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, co
         const uint16_t* d_frames = (const uint16_t*)frames->dptr + (size_t)c0 * H * W;
         EPID_CUDA(cudaMemsetAsync(base + o_hist, 0, sizeof(uint32_t) * (size_t)cn * 65536, st));
         EPID_CUDA(cudaMemsetAsync(base + o_res, 0, sizeof(epid_wl_result) * cn, st));
-        k_wl_hist<<<dim3(64, cn), 256, 0, st>>>(d_frames, H, W, (uint32_t*)(base + o_hist));
+        k_wl_hist<<<dim3(WL_HPARTS, cn), 256, 0, st>>>(d_frames, H, W, (uint32_t*)(base + o_hist));
         k_wl_front<<<cn, WL_THREADS, 0, st>>>((const WlConst*)(base + o_cst), d_frames, (uint32_t*)(base + o_hist), (WlFrame*)(base + o_fr));
+        k_wl_bbox<<<dim3(WL_BBOX_PARTS, cn), WL_THREADS, 0, st>>>((const WlConst*)(base + o_cst), d_frames, (WlFrame*)(base + o_fr));
         k_wl_field<<<cn, WL_THREADS, hc.field_tile_cap, st>>>((const WlConst*)(base + o_cst), d_frames, (WlFrame*)(base + o_fr));
         k_wl_bb<<<cn, WL_THREADS, bb_smem, st>>>((const WlConst*)(base + o_cst), d_frames, (const WlFrame*)(base + o_fr), (double*)(base + o_smp),
                                                  (unsigned short*)(base + o_cid), (WlComp*)(base + o_cmp), (epid_wl_result*)(base + o_res));
-        ctx->launches += 4;
+        ctx->launches += 5;
         EPID_CUDA(cudaGetLastError());
         EPID_CUDA(cudaMemcpyAsync(results + c0, base + o_res, sizeof(epid_wl_result) * cn, cudaMemcpyDeviceToHost, st));
         cudaError_t e = cudaStreamSynchronize(st);

@@ -1,4 +1,4 @@
-"""Device-resident throughput of the Starshot and FieldAnalysis batch pipelines (BASELINE.json configs[3], configs[4]) next to
+"""Device-resident throughput of the Starshot, FieldAnalysis and Winston-Lutz batch pipelines (BASELINE.json configs[2..4]) next to
 the CPU oracle port on one host core.  Not the judged benchmark (that is bench.py / PicketFence); prints one JSON line each.
 
     python tools/bench_modules.py [--star 256] [--field 512] [--iters 3]
@@ -67,4 +67,24 @@ err = abs(float(rows["field_size_horizontal_mm"][0]) - o["field_size_horizontal_
 print(json.dumps({"module": "field_analysis", "frames": len(frames), "ms_per_batch": dt * 1e3, "frames_per_s": len(frames) / dt,
                   "status_ok": int((rows["status"] == 0).sum()), "gb_per_s_one_read": frames.nbytes / dt / 1e9,
                   "cpu_oracle_s_per_frame_1core": cpu, "field_size_err_mm_vs_oracle": err, "includes": "D2H of results"}))
+b.free()
+# ---- Winston-Lutz 2-D: 1024x1024 BB + field frames (gantry / couch sweep, seeded BB offsets), tiled from 16 unique frames
+from oracle import wl_oracle
+from pylinac_b200 import winston_lutz as wlm
+
+uniq = np.stack([synth.winstonlutz_frame(synth.epid1024(), offset_mm_left=rng.uniform(-1, 1), offset_mm_up=rng.uniform(-1, 1),
+                                         offset_mm_in=rng.uniform(-1, 1), gantry=22.5 * i, couch=(0, 45, 90, 270, 315)[i % 5] if i % 4 == 0 else 0,
+                                         noise_sigma=0.002, seed=300 + i) for i in range(16)])
+frames = np.concatenate([uniq] * 32)
+b = nat.Batch.upload(ctx, frames)
+wp = wlm.make_params(2.56)
+dt, rows = timed(lambda: nat.wl2d_analyze(ctx, b, wp), args.iters)
+t0 = time.perf_counter()
+o = wl_oracle.wl2d_analyze(uniq[0], 2.56)
+cpu = time.perf_counter() - t0
+err = max(abs(float(rows["bb_x"][0]) - o["bb"][0]), abs(float(rows["bb_y"][0]) - o["bb"][1]))
+print(json.dumps({"module": "winston_lutz_2d", "frames": len(frames), "ms_per_batch": dt * 1e3, "frames_per_s": len(frames) / dt,
+                  "status_ok": int((rows["status"] == 0).sum()), "threshold_passes_per_frame": float(rows["threshold_passes"].mean()),
+                  "gb_per_s_one_read": frames.nbytes / dt / 1e9, "cpu_oracle_s_per_frame_1core": cpu, "max_bb_err_px_vs_oracle": err,
+                  "includes": "D2H of results"}))
 b.free()
