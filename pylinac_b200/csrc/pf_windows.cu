@@ -29,7 +29,7 @@ namespace epid {
 constexpr int W2_WARPS = 16;
 constexpr int W2_POOL = 100 * 1024;   // shared memory per CTA, split into per-warp slots sized for the frame's largest window
 constexpr int W2_MAXNC = 256;    // travel samples per window on the fast path
-constexpr int W2_GRID_X = 32;    // CTAs per frame
+constexpr int W2_GRID_X = 8;     // CTAs per frame: a warp takes ~4 windows and prefetches the next one while it analyses the current one
 
 template <int N>
 __device__ __forceinline__ void sort_net_u16x2(uint32_t (&r)[N]) {
@@ -353,6 +353,27 @@ k_pf_windows_fast(const PfConst* __restrict__ cc, const FrameRef* __restrict__ f
             }
             for (int i = lane; i < nr; i += 32)
                 for (int jj = nc; jj < S; jj++) px[i * S + jj] = 0;
+        }
+        {
+            // the warp's next window: pull its rows towards L2 / L1 now, so that its staging loads do not wait for HBM
+            const int nwidx = widx + gridDim.x * active;
+            if (nwidx < total && orient == 0) {
+                const int nli = nwidx / np, npk = nwidx - nli * np;
+                const int nleaf = f.inview[nli];
+                const double nlw = c.p.leaf_width_mm[nleaf] * dpmm;
+                const double nlc = c.p.leaf_center_mm[nleaf] * dpmm + (double)H / 2.0;
+                const double npidx = (double)f.picket_idx[npk];
+                const int na0 = max((int)(npidx - spacing / 2.0), 0), na1 = min((int)(npidx + spacing / 2.0), W);
+                const int nb0 = max((int)(nlc - nlw / 2.0), 0), nb1 = min((int)(nlc + nlw / 2.0), H);
+                for (int i = lane; i < nb1 - nb0; i += 32) {
+                    int row = nb0 + i - sag;
+                    if (sag) { row %= H; if (row < 0) row += H; }
+                    const uint16_t* ptr = frf.origin + (size_t)row * frf.pitch + na0;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                    if (na1 - na0 > 56) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 64));
+                    if (na1 - na0 > 120) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 128));
+                }
+            }
         }
         gmax = warp_max(gmax);
         __syncwarp();
