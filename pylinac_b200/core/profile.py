@@ -360,31 +360,277 @@ def utils_negate(values) -> np.ndarray:
     return np.negative(np.asarray(values, dtype=np.float64))
 
 
-class FWXMProfile(ProfileMixin):
-    """core/profile.py:195-344, 578-611: FWXM field edges of a single-peak profile (x_values = sample indices)."""
+def _linear_spline(xk: np.ndarray, yk: np.ndarray, xq):
+    """UnivariateSpline(x, y, k=1, s=0)(xq) (core/profile.py:249-274): the interpolating linear B-spline, evaluated like FITPACK's
+    splev -- y0 * (x1 - x) / (x1 - x0) + y1 * (x - x0) / (x1 - x0) on the knot interval that holds x (extrapolating the end
+    intervals)."""
+    xq_arr = np.atleast_1d(np.asarray(xq, dtype=np.float64))
+    i = np.clip(np.searchsorted(xk, xq_arr, side="right") - 1, 0, len(xk) - 2)
+    x0, x1 = xk[i], xk[i + 1]
+    d = x1 - x0
+    out = yk[i] * ((x1 - xq_arr) / d) + yk[i + 1] * ((xq_arr - x0) / d)
+    return float(out[0]) if np.ndim(xq) == 0 else out
 
-    def __init__(self, values, x_values=None, ground: bool = False, normalization=Normalization.NONE, fwxm_height: float = 50):
-        self.values = np.asarray(values, dtype=np.float64)
-        if x_values is not None and not np.array_equal(np.asarray(x_values), np.arange(len(self.values))):
-            raise NotImplementedError("custom x_values are outside the accelerated hot path")
-        self.fwxm_height = fwxm_height
+
+def _interp1d_linear(xs: np.ndarray, ys: np.ndarray, xq: float) -> float:
+    """scipy interp1d(x, y) (kind linear, assume_sorted False) at one point: stable sort by x, then _call_linear
+    (scipy/interpolate/_interpolate.py): slope * (x_new - x_lo) + y_lo on the bracketing samples; out of range raises."""
+    order = np.argsort(xs, kind="mergesort")
+    x, y = xs[order], ys[order]
+    if xq < x[0] or xq > x[-1]:
+        raise ValueError("A value in x_new is outside the interpolation range.")
+    hi = int(np.clip(np.searchsorted(x, xq), 1, len(x) - 1))
+    lo = hi - 1
+    slope = (y[hi] - y[lo]) / (x[hi] - x[lo])
+    return float(slope * (xq - x[lo]) + y[lo])
+
+
+class ProfileBase(ProfileMixin):
+    """core/profile.py:195-575: a single-field profile with linear look-ups between samples, in-field extraction and metric
+    plug-ins.  ``field_edge_idx`` comes from the subclass; the peak search behind it runs on the GPU (``find_peaks``)."""
+
+    def __init__(self, values, x_values=None, ground: bool = False, normalization=Normalization.NONE):
+        values = np.asarray(values, dtype=np.float64)
+        if values.ndim != 1:
+            raise ValueError("Profile values must be 1-D")
+        self.metrics = []
+        self.metric_values = {}
+        if x_values is None:
+            x_values = np.arange(len(values))
+        x_values = np.asarray(x_values)
+        xd = np.diff(x_values)
+        if xd.max() > 0 > xd.min():
+            raise ValueError("X values must be monotonically increasing or decreasing")
+        order = np.argsort(x_values)
+        self.x_values = x_values[order]
+        self.values = values[order]
+        self._cache = {}
         if ground:
-            self.ground()
-        norm = Normalization(normalization) if not isinstance(normalization, Normalization) else normalization
+            self.values = utils.ground(self.values)
+        # as in the reference the argument is compared with the enum MEMBERS: a plain string ("Max") selects no normalisation
+        # (FieldProfileAnalysis hands the caller's raw argument through, field_profile_analysis.py:176-181)
+        norm = normalization
         if norm == Normalization.MAX:
-            self.normalize("max")
-        elif norm != Normalization.NONE:
-            raise NotImplementedError("only Normalization.NONE / MAX are available on FWXMProfile")
+            self.values = utils.normalize(self.values)
+        elif norm == Normalization.GEOMETRIC_CENTER:
+            self.values = utils.normalize(self.values, utils.geometric_center_value(self.values))
+        elif norm == Normalization.BEAM_CENTER:
+            self.values = utils.normalize(self.values, self.y_at_x(self.center_idx))
+            self._cache = {}
+
+    # -- look-ups (core/profile.py:249-288)
+    def x_at_x_idx(self, x):
+        return _linear_spline(np.arange(len(self.x_values), dtype=np.float64), self.x_values.astype(np.float64), x)
+
+    def x_idx_at_x(self, x: float) -> int:
+        return int(np.argmin(np.abs(self.x_values - x)))
+
+    def y_at_x(self, x):
+        return _linear_spline(self.x_values.astype(np.float64), self.values, x)
+
+    def x_at_y(self, y: float, side: str) -> float:
+        s = self.x_idx_at_x(self.center_idx)
+        if side == "left":
+            return _interp1d_linear(self.values[:s], self.x_values[:s].astype(np.float64), float(y))
+        return _interp1d_linear(self.values[s:], self.x_values[s:].astype(np.float64), float(y))
 
     def field_edge_idx(self, side: str) -> float:
-        _, props = find_peaks(self.values, fwxm_height=self.fwxm_height / 100, max_number=1)
-        return float(props["left_ips"][0] if side == "left" else props["right_ips"][0])
+        raise NotImplementedError
 
+    def _edges(self):
+        if "edges" not in self._cache:
+            self._cache["edges"] = (self.field_edge_idx("left"), self.field_edge_idx("right"))
+        return self._cache["edges"]
+
+    # -- field geometry (core/profile.py:295-344)
     @property
     def center_idx(self) -> float:
-        left, right = self.field_edge_idx("left"), self.field_edge_idx("right")
+        left, right = self._edges()
         return abs(right - left) / 2 + left
 
     @property
+    def geometric_center_idx(self) -> float:
+        return self.x_at_x_idx(utils.geometric_center_idx(self.values))
+
+    @property
+    def cax_index(self) -> float:
+        return self.x_at_x_idx((len(self.x_values) - 1) / 2)
+
+    @property
     def field_width_px(self) -> float:
-        return self.field_edge_idx("right") - self.field_edge_idx("left")
+        left, right = self._edges()
+        return max(right, left) - min(right, left)
+
+    def field_x_values(self, in_field_ratio: float) -> np.ndarray:
+        import math
+
+        left, right = self._edges()
+        width = self.field_width_px
+        f_left = left + (1 - in_field_ratio) / 2 * width
+        f_right = right - (1 - in_field_ratio) / 2 * width
+        lower, upper = math.floor(min(f_left, f_right)), math.ceil(max(f_left, f_right))
+        return self.x_values[np.nonzero((self.x_values >= lower) & (self.x_values <= upper))[0]]
+
+    def field_indices(self, in_field_ratio: float):
+        xs = self.field_x_values(in_field_ratio)
+        left, right = xs[0], xs[-1]
+        return left, right, max(right, left) - min(right, left)
+
+    def field_values(self, in_field_ratio: float = 0.8) -> np.ndarray:
+        return self.y_at_x(self.field_x_values(in_field_ratio))
+
+    # -- metric plug-ins (core/profile.py:541-575)
+    def compute(self, metrics):
+        from ..metrics.profile import ProfileMetric
+
+        values = {}
+        if isinstance(metrics, ProfileMetric):
+            metrics = [metrics]
+        key = None
+        for metric in metrics:
+            metric.inject_profile(self)
+            self.metrics.append(metric)
+            key, k = metric.full_name, 1
+            while key in values or key in self.metric_values:      # uniquify
+                key = f"{metric.full_name}-{k}"
+                k += 1
+            values[key] = metric.calculate()
+        self.metric_values |= values
+        return values[key] if len(values) == 1 else values
+
+    def __len__(self):
+        return len(self.values)
+
+
+class FWXMProfile(ProfileBase):
+    """core/profile.py:578-611: field edges = left / right interpolated positions of the largest peak at ``fwxm_height`` %."""
+
+    def __init__(self, values, x_values=None, ground: bool = False, normalization=Normalization.NONE, fwxm_height: float = 50):
+        self.fwxm_height = fwxm_height
+        super().__init__(values, x_values=x_values, ground=ground, normalization=normalization)
+
+    def field_edge_idx(self, side: str) -> float:
+        _, props = find_peaks(self.values, fwxm_height=self.fwxm_height / 100, max_number=1)
+        return float(self.x_at_x_idx(float(props["left_ips"][0] if side == "left" else props["right_ips"][0])))
+
+
+def _not_a_knot_cubic(x: np.ndarray, y: np.ndarray):
+    """Second derivatives M of the cubic spline through (x, y) with not-a-knot end conditions -- the interpolant of
+    scipy interp1d(kind="cubic") (make_interp_spline(k=3), default boundary).  The two end conditions express M[0] and M[n-1]
+    through their neighbours, which leaves a diagonally dominant tridiagonal system for M[1..n-2] (Thomas algorithm, O(n))."""
+    n = len(x)
+    h = np.diff(x).astype(np.float64)
+    r = np.zeros(n)
+    r[1:-1] = 6 * ((y[2:] - y[1:-1]) / h[1:] - (y[1:-1] - y[:-2]) / h[:-1])
+    lo = np.zeros(n)          # sub-diagonal, diagonal, super-diagonal of rows 1 .. n-2
+    di = np.zeros(n)
+    up = np.zeros(n)
+    lo[2:-1] = h[1:-1]
+    di[1:-1] = 2 * (h[:-1] + h[1:])
+    up[1:-2] = h[1:-1]
+    # not-a-knot at the left:  M0 = ((h0 + h1) M1 - h0 M2) / h1;  at the right:  M[n-1] = ((hl + hk) M[n-2] - hl M[n-3]) / hk
+    h0, h1, hk, hl = h[0], h[1], h[-2], h[-1]
+    di[1] += h0 * (h0 + h1) / h1
+    up[1] = h1 - h0 * h0 / h1
+    di[n - 2] += hl * (hl + hk) / hk
+    lo[n - 2] = hk - hl * hl / hk
+    M = np.zeros(n)
+    cp = np.zeros(n)
+    dp = np.zeros(n)
+    cp[1] = up[1] / di[1]
+    dp[1] = r[1] / di[1]
+    for i in range(2, n - 1):
+        den = di[i] - lo[i] * cp[i - 1]
+        cp[i] = up[i] / den
+        dp[i] = (r[i] - lo[i] * dp[i - 1]) / den
+    M[n - 2] = dp[n - 2]
+    for i in range(n - 3, 0, -1):
+        M[i] = dp[i] - cp[i] * M[i + 1]
+    M[0] = ((h0 + h1) * M[1] - h0 * M[2]) / h1
+    M[n - 1] = ((hl + hk) * M[n - 2] - hl * M[n - 3]) / hk
+    return M
+
+
+def _cubic_stationary_near(x: np.ndarray, y: np.ndarray, M: np.ndarray, i0: int, want_max: bool) -> float:
+    """Local extremum of the cubic spline nearest to sample i0 (where minimize(..., x0=x[i0]) of the reference ends up):
+    roots of the quadratic derivative on the intervals around i0."""
+    best, best_d = float(x[i0]), np.inf
+    for i in range(max(i0 - 2, 0), min(i0 + 2, len(x) - 1)):
+        h = x[i + 1] - x[i]
+        # S(t) on [x_i, x_i+1], t = x - x_i:  S = y_i + b t + (M_i / 2) t^2 + ((M_i+1 - M_i) / (6 h)) t^3
+        b = (y[i + 1] - y[i]) / h - h * (2 * M[i] + M[i + 1]) / 6
+        c2, c3 = M[i] / 2, (M[i + 1] - M[i]) / (6 * h)
+        roots = np.roots([3 * c3, 2 * c2, b]) if c3 != 0 else (np.array([-b / (2 * c2)]) if c2 != 0 else np.array([]))
+        for t in roots:
+            if abs(t.imag) > 0:
+                continue
+            t = float(t.real)
+            if -1e-12 <= t <= h + 1e-12:
+                curv = 2 * c2 + 6 * c3 * t
+                if (curv < 0) == want_max and abs(x[i] + t - x[i0]) < best_d:
+                    best, best_d = float(x[i] + t), abs(x[i] + t - x[i0])
+    return best
+
+
+class InflectionDerivativeProfile(ProfileBase):
+    """core/profile.py:629-684: field edges = extrema of the cubic interpolant of the gradient of the gaussian-smoothed profile.
+    The reference finds them with scipy.optimize.minimize started at the arg-max / arg-min sample; here the stationary point of
+    the same not-a-knot cubic spline next to that sample is computed in closed form (agreement ~1e-6 samples, the BFGS
+    tolerance).  The gaussian smoothing runs on the GPU."""
+
+    def __init__(self, values, x_values=None, ground: bool = False, normalization=Normalization.NONE,
+                 edge_smoothing_ratio: float = 0.003):
+        self.edge_smoothing_ratio = edge_smoothing_ratio
+        super().__init__(values, x_values=x_values, ground=ground, normalization=normalization)
+
+    def _derivative(self):
+        if "diff" not in self._cache:
+            filtered = utils.gaussian_filter(self.values, self.edge_smoothing_ratio * len(self.values))
+            diff = np.gradient(filtered)
+            xs = self.x_values.astype(np.float64)
+            self._cache["diff"] = (diff, _not_a_knot_cubic(xs, diff))
+        return self._cache["diff"]
+
+    def field_edge_idx(self, side: str) -> float:
+        diff, M = self._derivative()
+        xs = self.x_values.astype(np.float64)
+        if side == "left":
+            return _cubic_stationary_near(xs, diff, M, int(np.argmax(diff)), want_max=True)
+        return _cubic_stationary_near(xs, diff, M, int(np.argmin(diff)), want_max=False)
+
+
+class PhysicalProfileMixin:
+    """core/profile.py:742-790"""
+
+    def _init_physical(self, dpmm):
+        self.dpmm = dpmm
+        self.implicit_dpmm = float(np.mean(np.diff(self.x_values))) if dpmm is None else dpmm
+
+    @property
+    def physical_x_values(self) -> np.ndarray:
+        if self.dpmm is None:
+            return self.x_values
+        return self.x_values / self.dpmm + 0.5 / self.dpmm
+
+    @property
+    def field_width_mm(self) -> float:
+        return self.field_width_px / self.implicit_dpmm
+
+
+class FWXMProfilePhysical(PhysicalProfileMixin, FWXMProfile):
+    """core/profile.py:1016-1047"""
+
+    def __init__(self, values, dpmm: float | None = None, x_values=None, ground: bool = False, normalization=Normalization.NONE,
+                 fwxm_height: float = 50):
+        FWXMProfile.__init__(self, values, x_values=x_values, ground=ground, normalization=normalization, fwxm_height=fwxm_height)
+        self._init_physical(dpmm)
+
+
+class InflectionDerivativeProfilePhysical(PhysicalProfileMixin, InflectionDerivativeProfile):
+    """core/profile.py:1050-1083"""
+
+    def __init__(self, values, dpmm: float | None = None, x_values=None, ground: bool = False, normalization=Normalization.NONE,
+                 edge_smoothing_ratio: float = 0.003):
+        InflectionDerivativeProfile.__init__(self, values, x_values=x_values, ground=ground, normalization=normalization,
+                                             edge_smoothing_ratio=edge_smoothing_ratio)
+        self._init_physical(dpmm)
