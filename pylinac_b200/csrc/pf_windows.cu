@@ -29,7 +29,7 @@ namespace epid {
 constexpr int W2_WARPS = 16;
 constexpr int W2_POOL = 100 * 1024;   // shared memory per CTA, split into per-warp slots sized for the frame's largest window
 constexpr int W2_MAXNC = 256;    // travel samples per window on the fast path
-constexpr int W2_GRID_X = 8;     // CTAs per frame: a warp takes ~4 windows and prefetches the next one while it analyses the current one
+constexpr int W2_GRID_X = 12;    // CTAs per frame: a warp takes ~3 windows and prefetches the next one while it analyses the current one (sweep 4..24: flat, 12 best)
 
 template <int N>
 __device__ __forceinline__ void sort_net_u16x2(uint32_t (&r)[N]) {
@@ -981,7 +981,9 @@ int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cs
         EPID_CUDA(cudaFuncSetAttribute(k_pf_windows_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = true;
     }
-    dim3 grid(W2_GRID_X, n);
+    static int gx = 0;
+    if (gx == 0) { const char* e = getenv("EPID_W2_GRID"); gx = e ? atoi(e) : W2_GRID_X; if (gx < 1 || gx > 64) gx = W2_GRID_X; }
+    dim3 grid(gx, n);
     k_pf_windows_fast<<<grid, W2_WARPS * 32, smem, stream>>>(cst, refs, fr, wins);
     ctx->launches++;
     EPID_CUDA(cudaGetLastError());
