@@ -47,3 +47,31 @@ def test_no_device_is_reported_not_faked():
 
     with pytest.raises(nat.NoDeviceError):
         pf.analyze_batch(np.zeros((1, 64, 64), np.uint16), 2.56)
+
+
+def test_product_never_imports_the_oracle_and_has_one_scipy_call_site():
+    """The oracle is test infrastructure: nothing under pylinac_b200/ may import it (a product path through the oracle would void
+    every parity claim).  scipy is allowed in exactly one place: the set-level Winston-Lutz minimisation the reference itself does
+    on the host (winston_lutz.py:1614-1640)."""
+    import ast
+    import pathlib
+
+    root = pathlib.Path(__file__).resolve().parents[1] / "pylinac_b200"
+    scipy_sites = []
+    for path in root.rglob("*.py"):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.module:
+                names = [node.module]
+            for nm in names:
+                top = nm.split(".")[0]
+                assert top != "oracle", f"{path} imports the oracle"
+                # torch.distributed is rendezvous / barrier plumbing of the multi-GPU helpers only (parallel.py)
+                banned = ("triton", "cupy", "numba") + (() if path.name == "parallel.py" else ("torch",))
+                assert top not in banned, f"{path} imports {top}"
+                if top == "scipy":
+                    scipy_sites.append(path.name)
+    assert scipy_sites == ["winston_lutz.py"], scipy_sites
