@@ -353,3 +353,31 @@ def test_leafband_kernel_runs_when_enabled():
         ctx.set_option(nat.OPT_PF_LEAFBAND, 0)
         b.free()
     assert st["k_pf_leafband"] > 5 * st["k_pf_windows_fast"] > 0
+
+
+def test_pf_host_pipeline_staged_and_direct_result_paths_agree():
+    """epid_pf_analyze_host DMA's the results straight into page-locked caller buffers and goes through its pinned staging area
+    for pageable ones (a C caller's malloc'd arrays): both paths must deliver identical bytes for the used rows."""
+    import ctypes as C
+
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    frames = np.ascontiguousarray(np.stack([synth.bench_pf_frame(i) for i in range(90, 93)] * 50))     # 150 frames: 3 chunks
+    ctx = nat.Context.default()
+    params = pf.make_params(2.56, frames.shape[1:])
+    n, h, w = frames.shape
+    cap = 1024
+    s_direct, m_direct = nat.pf_analyze(ctx, frames, params, meas_cap=cap)                              # pooled pinned arrays
+    s_staged = np.zeros(n, nat.PF_SUMMARY_DTYPE)                                                        # pageable
+    m_staged = np.zeros((n, cap), nat.PF_MEAS_DTYPE)
+    nat.check(nat.lib().epid_pf_analyze_host(ctx.handle, frames.ctypes.data_as(C.c_void_p), n, h, w, C.byref(params),
+                                             s_staged.ctypes.data_as(C.c_void_p), m_staged.ctypes.data_as(C.c_void_p), cap))
+    assert (s_direct["status"] == 0).all()
+    for k in s_direct.dtype.names:
+        np.testing.assert_array_equal(s_direct[k], s_staged[k], err_msg=k)
+    for i in range(n):
+        m = int(s_direct["n_meas"][i])
+        for k in m_direct.dtype.names:
+            np.testing.assert_array_equal(m_direct[k][i, :m], m_staged[k][i, :m], err_msg=k)
