@@ -31,6 +31,13 @@ constexpr int W2_POOL = 100 * 1024;   // shared memory per CTA, split into per-w
 constexpr int W2_MAXNC = 256;    // travel samples per window on the fast path
 constexpr int W2_GRID_X = 12;    // CTAs per frame: a warp takes ~3 windows and prefetches the next one while it analyses the current one (sweep 4..24: flat, 12 best)
 
+// a * b + c with a 64-bit accumulator in ONE instruction (IMAD.WIDE.U32); the compiler emits IMAD + IADD3 + IADD3.X for the C form
+__device__ __forceinline__ unsigned long long mad_wide_u32(uint32_t a, uint32_t b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
 template <int N>
 __device__ __forceinline__ void sort_net_u16x2(uint32_t (&r)[N]) {
     // Batcher merge exchange (valid for any N), ascending in both 16-bit halves independently
@@ -106,7 +113,7 @@ __device__ __noinline__ uint2 pair_median_any(const uint16_t* __restrict__ px, i
 // sqrt(nc*S2 - S1^2) / (nc * D) with an exact integer numerator.  NSL = row slots per lane (1: nr <= 32, 2: nr <= 64).
 template <int NSL>
 __device__ __forceinline__ void row_std_stats(const uint16_t* __restrict__ px, int S, int nr, int nc, double Dd, int lane,
-                                              double& sd_max, double& sd_med) {
+                                              double& sd_max, double& sd_med, int t0, int t1) {
     double sd[NSL];
 #pragma unroll
     for (int sl = 0; sl < NSL; sl++) {
@@ -116,14 +123,13 @@ __device__ __forceinline__ void row_std_stats(const uint16_t* __restrict__ px, i
             const uint32_t* __restrict__ rowp = reinterpret_cast<const uint32_t*>(px + i * S);
             uint32_t s1 = 0;
             unsigned long long s2 = 0;
-            const int nw = S >> 1;
 #pragma unroll 4
-            for (int t = 0; t < nw; t++) {   // samples outside the window were staged as zero
+            for (int t = t0; t < t1; t++) {  // the words that hold window samples; samples outside the window were staged as zero
                 const uint32_t w = rowp[t];
                 const uint32_t lo = w & 0xffffu, hi = w >> 16;
                 s1 = __dp2a_lo(w, 0x0101u, s1);
-                s2 += (unsigned long long)lo * lo;
-                s2 += (unsigned long long)hi * hi;
+                s2 = mad_wide_u32(lo, lo, s2);
+                s2 = mad_wide_u32(hi, hi, s2);
             }
             const double num = (double)((unsigned long long)nc * s2 - (unsigned long long)s1 * s1);
             sd[sl] = sqrt(num) / ((double)nc * Dd);
@@ -379,8 +385,9 @@ k_pf_windows_fast(const PfConst* __restrict__ cc, const FrameRef* __restrict__ f
         __syncwarp();
         // ---- 2. _is_mlc_peak_in_window (picketfence.py:847-857): lanes own rows
         double sd_max, sd_med;
-        if (nr <= 32) row_std_stats<1>(px, S, nr, nc, Dd, lane, sd_max, sd_med);
-        else row_std_stats<2>(px, S, nr, nc, Dd, lane, sd_max, sd_med);
+        const int t0 = off >> 1, t1 = (off + nc + 1) >> 1;      // words that hold window samples
+        if (nr <= 32) row_std_stats<1>(px, S, nr, nc, Dd, lane, sd_max, sd_med, t0, t1);
+        else row_std_stats<2>(px, S, nr, nc, Dd, lane, sd_max, sd_med, t0, t1);
         const bool above = ((double)gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
         const bool not_edge = sd_max < c.p.edge_threshold * sd_med;
         if (!(above && not_edge)) {
@@ -389,7 +396,6 @@ k_pf_windows_fast(const PfConst* __restrict__ cc, const FrameRef* __restrict__ f
         }
         // ---- 3. np.median(window, axis) -> 2 * median per travel sample (picketfence.py:1605-1609)
         uint32_t lmin = 0xffffffffu, lmax = 0;
-        const int t0 = off >> 1, t1 = (off + nc + 1) >> 1;      // words that hold window samples
         for (int t = t0 + lane; t < t1; t += 32) {
             const uint2 mm = pair_median_any(px, S, nr, t);
             const uint32_t m_lo = mm.x, m_hi = mm.y;
