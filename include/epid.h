@@ -54,8 +54,9 @@ int32_t epid_version(void);
 /* options / diagnostic counters (no reference counterpart: the reference has a single CPU code path).
  * EPID_OPT_PF_EXACT_ONLY: 1 = always use the exact-histogram PicketFence pipeline (default 0: fused sample-guided front
  * kernel with automatic per-batch fallback to the exact pipeline).  EPID_CTR_PF_FALLBACKS: batches / chunks re-run exactly. */
-enum { EPID_OPT_PF_EXACT_ONLY = 1, EPID_OPT_PF_LEAFBAND = 2 /* 1 = experimental leaf-band window kernel (bit-identical results; default 0) */ };
-enum { EPID_CTR_PF_FALLBACKS = 1 };
+enum { EPID_OPT_PF_EXACT_ONLY = 1, EPID_OPT_PF_LEAFBAND = 2 /* 1 = experimental leaf-band window kernel (bit-identical results; default 0) */,
+       EPID_OPT_PF_WIN2 = 3 /* 1 (default) = two-kernel window path (medians + per-window analysis); 0 = single per-window kernel (bit-identical) */ };
+enum { EPID_CTR_PF_FALLBACKS = 1, EPID_CTR_PF_REDONE_FRAMES = 2 /* frames re-run individually by the exact pipeline */ };
 int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value);
 int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value);
 
@@ -237,8 +238,8 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
 int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters,
                       float* total_ms, float* stats_kernel_ms, int64_t* launches);
 /* per-stage device times of `iters` passes (CUDA events between the kernels; bench.py's per-kernel roofline table):
- * stage_ms[0..7] = init + pilot, stream, tail, windows (per-window kernel), windows (generic), finalize, exact front end (fallback
- * only), windows (leaf-band kernel) */
+ * stage_ms[0..9] = init + pilot, stream, tail, windows (per-window kernel), windows (generic), finalize, exact front end (fallback
+ * only), windows (leaf-band kernel), windows (two-kernel path: medians), windows (two-kernel path: per-window analysis) */
 int32_t epid_pf_bench_stages(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* stage_ms,
                              int32_t nstages);
 
@@ -434,6 +435,9 @@ int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_wl
 int32_t epid_comm_unique_id(void* id128);
 int32_t epid_comm_init(epid_ctx* ctx, int32_t nranks, int32_t rank, const void* id128);
 int32_t epid_comm_destroy(epid_ctx* ctx);
+/* size and rank of ctx's communicator (1, 0 until epid_comm_init succeeded): lets the host side check that the gather it is about
+ * to post matches the job's world size instead of silently taking the single-rank path */
+int32_t epid_comm_info(const epid_ctx* ctx, int32_t* nranks, int32_t* rank);
 /* all ranks contribute bytes_per_rank bytes (host); `all` (host, nranks*bytes_per_rank) is filled on every rank */
 int32_t epid_gather_results(epid_ctx* ctx, const void* local, size_t bytes_per_rank, void* all);
 int32_t epid_barrier(epid_ctx* ctx);

@@ -25,7 +25,9 @@ _DT2NP = {v: k for k, v in _NP2DT.items()}
 
 OPT_PF_EXACT_ONLY = 1
 OPT_PF_LEAFBAND = 2
+OPT_PF_WIN2 = 3
 CTR_PF_FALLBACKS = 1
+CTR_PF_REDONE_FRAMES = 2
 PF_MAX_PICKETS = 32
 PF_MAX_LEAVES = 160
 
@@ -256,6 +258,7 @@ _SIGNATURES = {
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
+    "epid_comm_info": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "epid_gather_results": [_P, _P, C.c_size_t, _P],
     "epid_barrier": [_P],
 }
@@ -348,6 +351,12 @@ class Context:
         check(lib().epid_get_counter(self.handle, key, C.byref(v)))
         return v.value
 
+    def comm_info(self) -> tuple[int, int]:
+        """(nranks, rank) of this context's NCCL communicator; (1, 0) before parallel.init_comm."""
+        n, r = C.c_int32(), C.c_int32()
+        check(lib().epid_comm_info(self.handle, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
     def launches(self) -> int:
         n = C.c_int64()
         check(lib().epid_launch_count(self.handle, C.byref(n)))
@@ -409,24 +418,19 @@ def pinned_empty(shape, dtype=np.uint16) -> np.ndarray:
     nbytes = int(np.prod(shape)) * dtype.itemsize
     p = _P()
     check(lib().epid_host_alloc(nbytes, C.byref(p)))
-    buf = (C.c_char * nbytes).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    import weakref
 
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib().epid_host_free(self.ptr)
-            except Exception:
-                pass
-
-    _PINNED_OWNERS[arr.ctypes.data] = _Owner(p)
-    return arr
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    # every numpy view keeps `buf` alive through its .base chain; when the last one dies the block is unpinned and freed
+    weakref.finalize(buf, _host_free, p.value)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
-_PINNED_OWNERS: dict = {}
+def _host_free(ptr: int) -> None:
+    try:
+        lib().epid_host_free(_P(ptr))
+    except Exception:
+        pass
 
 
 class _PinnedPool:
@@ -544,7 +548,7 @@ def pf_bench(ctx: Context, batch: Batch, params: PFParams, iters: int):
 
 
 PF_STAGE_NAMES = ("k_pf_init + k_pf_pilot", "k_pf_stream", "k_pf_tail", "k_pf_windows_fast", "k_pf_windows (generic)", "k_pf_finalize",
-                  "exact front end (fallback)", "k_pf_leafband")
+                  "exact front end (fallback)", "k_pf_leafband", "k_pf_win_medians", "k_pf_win_fwxm")
 
 
 def pf_bench_stages(ctx: Context, batch: Batch, params: PFParams, iters: int) -> dict:

@@ -31,16 +31,64 @@ def _is_dicom(path) -> bool:
         return False
 
 
+def _is_image_file(path) -> bool:
+    """core/image.py:429-435: readable by Pillow."""
+    try:
+        from PIL import Image as pImage
+
+        with pImage.open(path):
+            return True
+    except Exception:
+        return False
+
+
 def load(path, **kwargs):
-    """core/image.py:244-286.  ndarray -> ArrayImage, DICOM -> DicomImage.  (TIFF/JPG FileImage is file-format
-    plumbing outside the hot path and not provided.)"""
+    """core/image.py:244-286.  ndarray -> ArrayImage, DICOM -> DicomImage, TIFF/PNG/JPG/BMP -> FileImage."""
     if isinstance(path, BaseImage):
         return path
     if _is_array(path):
         return ArrayImage(path, **kwargs)
     if _is_dicom(path):
         return DicomImage(path, **kwargs)
+    if _is_image_file(path):
+        return FileImage(path, **kwargs)
     raise TypeError(f"The argument `{path}` was not found to be a valid DICOM file, Image file, or array")
+
+
+def frame_u16(img, what: str = "GPU") -> np.ndarray:
+    """The integer frame the device pipelines analyse, from an image object or an array.
+
+    * uint16 is passed through, uint8 is widened, any other dtype whose values are integers in [0, 65535] is cast;
+    * a float image that is still the DICOM rescale of its stored values (``stored * RescaleSlope + RescaleIntercept``, optionally
+      flipped by ``PixelIntensityRelationshipSign``; core/image.py:363-389) is analysed on the STORED integers, order-flipped when
+      the map is decreasing: every pipeline grounds / normalises / thresholds relative to the frame's own range, so a positive
+      affine map changes sub-pixel results only by fp64 rounding (~1e-12 px), integer results not at all;
+    * anything else (genuinely fractional pixel values) raises ``ValueError``.
+    """
+    a = img.array if isinstance(img, BaseImage) else np.asarray(img)
+    if a.dtype == np.uint16:
+        return a
+    if a.dtype == np.uint8:
+        return a.astype(np.uint16)
+    if a.dtype.kind not in "fiu":
+        raise TypeError(f"the {what} path takes numeric pixel data, got {a.dtype}")
+    stored = getattr(img, "_stored", None)
+    if stored is not None and stored.shape == a.shape and stored.dtype.kind == "u" and stored.dtype.itemsize <= 2:
+        slope, intercept, flipped = img._stored_map
+        if slope != 0:
+            expect = stored.astype(np.float64) * slope + intercept if (slope, intercept) != (1.0, 0.0) else stored.astype(np.float64)
+            if flipped:
+                expect = expect.max() - expect + expect.min()
+            if np.array_equal(a, expect):
+                s16 = stored.astype(np.uint16)
+                if flipped != (slope < 0):        # decreasing map of the stored values: exact modular order flip
+                    s16 = (int(s16.max()) + int(s16.min()) - s16.astype(np.int64)).astype(np.uint16)
+                return s16
+    mn, mx = a.min(), a.max()
+    if mn >= 0 and mx <= 65535 and np.array_equal(a, np.floor(a)):
+        return a.astype(np.uint16)  # integer-valued pixels stored as another dtype (e.g. DICOM rescale 1.0 / 0.0)
+    raise ValueError(f"the {what} path takes integer-valued pixel data in [0, 65535] (or a DICOM image whose array is still the "
+                     "rescale of its stored values); got fractional / out-of-range values")
 
 
 class BaseImage:
@@ -237,6 +285,14 @@ class DicomImage(BaseImage):
         self._invert_pixels = invert_pixels
         self.array = pix.astype(dtype) if dtype is not None else pix.copy()
         self.array = _rescale_dicom_values(self.array, self.metadata, raw_pixels, invert_pixels)
+        # the stored integers + the map that produced ``array`` from them (frame_u16 analyses the stored values when the
+        # array is still that map of them)
+        slope, intercept = self.metadata.get("RescaleSlope"), self.metadata.get("RescaleIntercept")
+        has = (not raw_pixels) and slope is not None and intercept is not None
+        sign = self.metadata.get("PixelIntensityRelationshipSign")
+        flipped = (not raw_pixels) and bool(invert_pixels or (invert_pixels is None and sign == -1))
+        self._stored = pix
+        self._stored_map = (float(slope) if has else 1.0, float(intercept) if has else 0.0, flipped)
 
     @property
     def sid(self) -> float:
@@ -299,6 +355,52 @@ def _rescale_dicom_values(unscaled, metadata, raw_pixels, invert_pixels):
     if invert_pixels or (invert_pixels is None and sign == -1):
         scaled = scaled.max() - scaled + scaled.min()
     return scaled
+
+
+class FileImage(BaseImage):
+    """core/image.py:1733-1812: TIFF / PNG / JPG / BMP through Pillow (host-side ingest)."""
+
+    def __init__(self, path, *, dpi: float | None = None, sid: float | None = None, dtype=None):
+        from PIL import Image as pImage
+        from PIL.TiffTags import TAGS
+
+        super().__init__(path)
+        pil_image = pImage.open(path)
+        if len(pil_image.getbands()) > 1:
+            pil_image = pil_image.convert("I")  # multi-channel -> int32 (core/image.py:1770-1774)
+        self.info = pil_image.info
+        try:
+            self.tags = {TAGS[key]: pil_image.tag_v2[key] for key in pil_image.tag_v2}
+        except AttributeError:
+            pass
+        self.array = np.array(pil_image, dtype=dtype)
+        self._dpi = dpi
+        self.sid = sid
+
+    @property
+    def dpi(self) -> float | None:  # core/image.py:1784-1803
+        dpi = None
+        for key in ("dpi", "resolution"):
+            dpi = self.info.get(key)
+            if dpi is not None:
+                dpi = float(dpi[0])
+                if dpi < 3 and not self._dpi:
+                    raise ValueError(f"The DPI setting is abnormal or nonsensical. Got resolution of {dpi}. Pass in the dpi manually.")
+                if dpi < 3:
+                    dpi = None
+                break
+        if dpi is None:
+            dpi = self._dpi
+        if self.sid is not None and dpi is not None:
+            dpi *= self.sid / 1000
+        return dpi
+
+    @property
+    def dpmm(self) -> float | None:
+        try:
+            return self.dpi / MM_PER_INCH
+        except TypeError:
+            return None
 
 
 class LinacDicomImage(DicomImage):

@@ -88,6 +88,13 @@ int32_t epid_comm_destroy(epid_ctx* ctx) {
     return EPID_OK;
 }
 
+int32_t epid_comm_info(const epid_ctx* ctx, int32_t* nranks, int32_t* rank) {
+    EPID_REQUIRE(ctx && nranks && rank, EPID_ERR_INVALID, "NULL argument");
+    *nranks = ctx->nccl_comm ? ctx->nranks : 1;
+    *rank = ctx->nccl_comm ? ctx->rank : 0;
+    return EPID_OK;
+}
+
 int32_t epid_gather_results(epid_ctx* ctx, const void* local, size_t bytes_per_rank, void* all) {
     EPID_REQUIRE(ctx && local && all, EPID_ERR_INVALID, "NULL argument");
     if (ctx->nranks == 1 || !ctx->nccl_comm) {

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/epid.h"
@@ -55,12 +56,18 @@ struct epid_ctx {
     // reusable device scratch (grown on demand, freed with the ctx)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    void* scratch2 = nullptr;            // work area of the per-frame exact re-run (pf.cu)
+    size_t scratch2_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     // options / diagnostics (epid_set_option / epid_get_counter)
     int pf_exact_only = 0;               // 1: never use the fused sample-guided front kernel
     int pf_leafband = 0;                 // 1: experimental leaf-band window kernel for the frames it covers (default: per-window kernel)
+    int pf_win2 = 1;                     // 1 (default): two-kernel window path for the frames it covers (pf_windows2.cu)
     int64_t pf_fallbacks = 0;            // batches (or chunks) re-run by the exact pipeline
+    int64_t pf_redone_frames = 0;        // frames re-run by the exact pipeline (per-frame fallback)
+    // dynamic shared memory opt-ins already made ON THIS DEVICE (cudaFuncSetAttribute is per device; one ctx per device)
+    std::unordered_map<const void*, size_t> smem_optin;
 };
 
 constexpr size_t EPID_BATCH_PAD = 256;
@@ -77,6 +84,18 @@ struct epid_batch {
 namespace epid {
 int ensure_scratch(epid_ctx* ctx, size_t bytes);   // grows ctx->scratch
 int ensure_pinned(epid_ctx* ctx, size_t bytes);
+
+// opt a kernel in to `bytes` of dynamic shared memory on ctx's device (remembered per ctx, i.e. per device)
+template <class K>
+inline int smem_opt_in(epid_ctx* ctx, K* kernel, size_t bytes) {
+    size_t& cur = ctx->smem_optin[(const void*)kernel];
+    if (bytes > cur) {
+        EPID_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return EPID_OK;
+}
+#define EPID_SMEM_OPT_IN(ctx, kernel, bytes) do { int _rc = ::epid::smem_opt_in(ctx, kernel, bytes); if (_rc != EPID_OK) return _rc; } while (0)
 
 // ------------------------------------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__

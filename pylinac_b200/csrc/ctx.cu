@@ -145,6 +145,7 @@ int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value) {
     switch (key) {
         case EPID_OPT_PF_EXACT_ONLY: ctx->pf_exact_only = value ? 1 : 0; return EPID_OK;
         case EPID_OPT_PF_LEAFBAND: ctx->pf_leafband = value ? 1 : 0; return EPID_OK;
+        case EPID_OPT_PF_WIN2: ctx->pf_win2 = value ? 1 : 0; return EPID_OK;
     }
     set_error("unknown option %d", key);
     return EPID_ERR_INVALID;
@@ -154,6 +155,7 @@ int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value) {
     EPID_REQUIRE(ctx && value, EPID_ERR_INVALID, "NULL argument");
     switch (key) {
         case EPID_CTR_PF_FALLBACKS: *value = ctx->pf_fallbacks; return EPID_OK;
+        case EPID_CTR_PF_REDONE_FRAMES: *value = ctx->pf_redone_frames; return EPID_OK;
     }
     set_error("unknown counter %d", key);
     return EPID_ERR_INVALID;

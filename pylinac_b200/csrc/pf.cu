@@ -27,11 +27,12 @@
 namespace epid {
 
 // ------------------------------------------------------------------------------------------------ init
-__global__ void k_pf_init(const uint16_t* base, int n, int H0, int W0, int crop, FrameRef* refs, PfFrame* fr, int* counters) {
+// sel: frame i of this run is frame sel[i] of the batch (per-frame re-run of deferred frames); nullptr: identity
+__global__ void k_pf_init(const uint16_t* base, int n, int H0, int W0, int crop, FrameRef* refs, PfFrame* fr, int* counters, const int* __restrict__ sel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { counters[0] = 0; counters[1] = 0; }
+    if (i == 0) { counters[0] = 0; counters[1] = 0; counters[2] = 0; }
     if (i >= n) return;
-    refs[i].origin = base + (size_t)i * H0 * W0 + (size_t)crop * W0 + crop;
+    refs[i].origin = base + (size_t)(sel ? sel[i] : i) * H0 * W0 + (size_t)crop * W0 + crop;
     refs[i].pitch = W0;
     refs[i].pad = 0;
     PfFrame& f = fr[i];
@@ -43,6 +44,7 @@ __global__ void k_pf_init(const uint16_t* base, int n, int H0, int W0, int crop,
     f.n_pickets = 0;
     f.n_inview = 0;
     f.todo = 0;
+    f.win2 = 0;
     f.orientation = 0;
 }
 
@@ -418,7 +420,9 @@ struct PfWork {   // carved out of ctx->scratch
     PfConst* cst;
     int* counters;           // [0] noisy count
     int* select;             // per-frame flags
+    int* sel_idx;            // indices of the deferred frames (k_pf_collect_deferred), count in counters[2]
     void* front;             // partial sums / thresholds of the single-pass front end (pf_stream.cu)
+    PfWinRec* winrec;        // records of the two-kernel window path (pf_windows2.cu)
     size_t total;
 };
 
@@ -442,7 +446,9 @@ static void carve(PfWork& w, char* base, int n, int H, int W, int meas_cap) {
     w.cst = (PfConst*)take(sizeof(PfConst));
     w.counters = (int*)take(sizeof(int) * 8);
     w.select = (int*)take(sizeof(int) * n);
+    w.sel_idx = (int*)take(sizeof(int) * n);
     w.front = (void*)take(pf_front_scratch_bytes(n, H, W));
+    w.winrec = (PfWinRec*)take(pf_win2_scratch_bytes(n));
     w.total = o;
 }
 
@@ -488,8 +494,45 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
 
 // fast == true: fused front kernel (sample-guided exact selection), no host round trip; frames it cannot certify
 // (counters[1]) or that _check_for_noise flags (counters[0]) make the caller re-run the batch with fast == false.
+__global__ void k_pf_collect_deferred(const PfFrame* __restrict__ fr, int n, int* __restrict__ sel_idx, int* counters) {
+    // ascending list of the deferred frames (one block; n is a few hundred)
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool d = i < n && fr[i].status == PF_STATUS_DEFERRED;
+        const unsigned b = __ballot_sync(0xffffffffu, d);
+        __shared__ int s_w[32];
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) s_w[wid] = __popc(b);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < wid; k++) off += s_w[k];
+        if (d) sel_idx[off + __popc(b & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_w[k]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counters[2] = s_base;
+}
+
+__global__ void k_pf_scatter_results(const int* __restrict__ sel_idx, int m, const epid_pf_summary* __restrict__ s_src, const epid_pf_meas* __restrict__ m_src,
+                                     epid_pf_summary* __restrict__ s_dst, epid_pf_meas* __restrict__ m_dst, int meas_cap) {
+    // rows of the re-run frames back into the batch's result arrays (word copies; both structs are multiples of 4 bytes)
+    const int j = blockIdx.x;
+    if (j >= m) return;
+    const int dst = sel_idx[j];
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(s_src + j);
+    uint32_t* b = reinterpret_cast<uint32_t*>(s_dst + dst);
+    for (int k = threadIdx.x; k < (int)(sizeof(epid_pf_summary) / 4); k += blockDim.x) b[k] = a[k];
+    const uint32_t* c = reinterpret_cast<const uint32_t*>(m_src + (size_t)j * meas_cap);
+    uint32_t* e = reinterpret_cast<uint32_t*>(m_dst + (size_t)dst * meas_cap);
+    for (int k = threadIdx.x; k < (int)(sizeof(epid_pf_meas) / 4) * meas_cap; k += blockDim.x) e[k] = c[k];
+}
+
 static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int n, int H0, int W0, const epid_pf_params* p,
-                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm, bool fast) {
+                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm, bool fast, const int* d_sel = nullptr) {
     const int crop = p->crop_px;
     const int H = H0 - 2 * crop, W = W0 - 2 * crop;
     StatsGeom g;
@@ -503,6 +546,7 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     hc.meas_cap = meas_cap;
     hc.post_filter = 0;
     hc.leafband = ctx->pf_leafband ? 1 : 0;
+    hc.win2 = (ctx->pf_win2 && !hc.leafband) ? 1 : 0;
     const int npix = H * W;
     hc.lo = pct_plan(npix, 0.5);
     hc.hi = pct_plan(npix, 99.5);
@@ -518,7 +562,7 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     if (tm) { rc = tm->mark(stream, PF_STAGE_START); if (rc != EPID_OK) return rc; }
     EPID_CUDA(cudaMemcpyAsync(w.cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, stream));
     const int tb = 128, nb = (n + tb - 1) / tb;
-    k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters);
+    k_pf_init<<<nb, tb, 0, stream>>>(d_frames, n, H0, W0, crop, w.refs, w.fr, w.counters, d_sel);
     ctx->launches++;
     // bench timers: around the frame-streaming kernel only (k_pf_stream inside launch_pf_front, k_frame_stats otherwise)
     if (fast) {
@@ -593,17 +637,15 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     }
     // ---- orientation sums
     if (p->orientation < 0) {
-        static bool attr = false;
         const size_t smem = sizeof(uint32_t) * (size_t)(STATS_THREADS * 8 + H);
-        if (!attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_clamp_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+        EPID_SMEM_OPT_IN(ctx, k_pf_clamp_sums, 64 * 1024);
         const int grid = n < ctx->sm_count ? n : ctx->sm_count;
         k_pf_clamp_sums<<<grid, STATS_THREADS, smem, stream>>>(g, w.refs, w.fr, n, w.rowsum2, w.colsum2);
         ctx->launches++;
     }
     {
-        static size_t attr = 0;
         const size_t smem = pf_profile_smem_bytes(PROF_THREADS, H, W);
-        if (smem > attr) { EPID_CUDA(cudaFuncSetAttribute(k_pf_profile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+        EPID_SMEM_OPT_IN(ctx, k_pf_profile, smem);
         k_pf_profile<<<n, PROF_THREADS, smem, stream>>>(w.cst, w.fr, w.rowsum, w.colsum, w.rowsum2, w.colsum2);
         ctx->launches++;
     }
@@ -616,6 +658,10 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
             if (rc != EPID_OK) return rc;
             if (tm) { rc = tm->mark(stream, PF_STAGE_LEAFBAND); if (rc != EPID_OK) return rc; }
         }
+        if (hc.win2) {
+            rc = launch_pf_windows2(ctx, stream, w.cst, w.refs, w.fr, w.winrec, w.wins, n, tm);
+            if (rc != EPID_OK) return rc;
+        }
         rc = launch_pf_windows_fast(ctx, stream, w.cst, w.refs, w.fr, w.wins, n);
         if (rc != EPID_OK) return rc;
         if (tm) { rc = tm->mark(stream, PF_STAGE_WINDOWS); if (rc != EPID_OK) return rc; }
@@ -626,7 +672,45 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     }
     rc = launch_pf_finalize(ctx, stream, w.cst, w.fr, w.wins, w.summ, w.meas, n, meas_cap);
     if (rc != EPID_OK) return rc;
+    if (fast) {      // which frames were deferred (none on ordinary batches): list + count for the per-frame re-run
+        k_pf_collect_deferred<<<1, 256, 0, stream>>>(w.fr, n, w.sel_idx, w.counters);
+        ctx->launches++;
+    }
     if (tm) { rc = tm->mark(stream, PF_STAGE_FINALIZE); if (rc != EPID_OK) return rc; }
+    EPID_CUDA(cudaGetLastError());
+    return EPID_OK;
+}
+
+// Per-frame fallback: the m frames the fast pipeline deferred (w.sel_idx, ascending) are re-run by the exact-histogram pipeline in
+// sub-batches whose work area lives in ctx->scratch2, and their result rows are scattered into the batch's device result arrays.
+static int ensure_scratch2(epid_ctx* ctx, size_t bytes) {
+    if (ctx->scratch2_bytes >= bytes) return EPID_OK;
+    if (ctx->scratch2) { EPID_CUDA(cudaStreamSynchronize(ctx->stream)); EPID_CUDA(cudaFree(ctx->scratch2)); ctx->scratch2 = nullptr; ctx->scratch2_bytes = 0; }
+    cudaError_t e = cudaMalloc(&ctx->scratch2, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return EPID_ERR_NOMEM; }
+    ctx->scratch2_bytes = bytes;
+    return EPID_OK;
+}
+
+constexpr int PF_REDO_CHUNK = 64;
+
+static int pf_redo_deferred(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int m, int H0, int W0, const epid_pf_params* p,
+                            int meas_cap, PfWork& w, uint16_t** pools) {
+    const int H = H0 - 2 * p->crop_px, W = W0 - 2 * p->crop_px;
+    const int chunk = m < PF_REDO_CHUNK ? m : PF_REDO_CHUNK;
+    PfWork rw;
+    carve(rw, nullptr, chunk, H, W, meas_cap);
+    int rc = ensure_scratch2(ctx, rw.total);
+    if (rc != EPID_OK) return rc;
+    carve(rw, (char*)ctx->scratch2, chunk, H, W, meas_cap);
+    for (int c0 = 0; c0 < m; c0 += chunk) {
+        const int cn = m - c0 < chunk ? m - c0 : chunk;
+        rc = pf_run(ctx, stream, d_frames, cn, H0, W0, p, meas_cap, rw, pools, nullptr, false, w.sel_idx + c0);
+        if (rc != EPID_OK) return rc;
+        k_pf_scatter_results<<<cn, 256, 0, stream>>>(w.sel_idx + c0, cn, rw.summ, rw.meas, w.summ, w.meas, meas_cap);
+        ctx->launches++;
+    }
+    ctx->pf_redone_frames += m;
     EPID_CUDA(cudaGetLastError());
     return EPID_OK;
 }
@@ -651,11 +735,11 @@ using namespace epid;
 
 namespace {
 
-struct PfResultCopy {   // async D2H of one chunk's results + the two fallback counters
+struct PfResultCopy {   // async D2H of one chunk's results + the counters ([2] = number of deferred frames)
     static int enqueue(cudaStream_t st, const PfWork& w, int cnt, int meas_cap, epid_pf_summary* summ, epid_pf_meas* meas, int* counters2) {
         EPID_CUDA(cudaMemcpyAsync(summ, w.summ, sizeof(epid_pf_summary) * cnt, cudaMemcpyDeviceToHost, st));
         EPID_CUDA(cudaMemcpyAsync(meas, w.meas, sizeof(epid_pf_meas) * (size_t)cnt * meas_cap, cudaMemcpyDeviceToHost, st));
-        EPID_CUDA(cudaMemcpyAsync(counters2, w.counters, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+        EPID_CUDA(cudaMemcpyAsync(counters2, w.counters, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
         return EPID_OK;
     }
 };
@@ -683,20 +767,22 @@ int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_p
     if (rc != EPID_OK) return rc;
     carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
     uint16_t* pools[3] = {nullptr, nullptr, nullptr};
-    bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
-    for (int attempt = 0; attempt < 2; attempt++) {
-        rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr, fast);
-        int cnt2[2] = {0, 0};
-        if (rc == EPID_OK) {
-            rc = PfResultCopy::enqueue(ctx->stream, w, n, meas_cap, summary, meas, cnt2);
-            cudaError_t e = cudaStreamSynchronize(ctx->stream);
-            if (rc == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
-        } else {
-            cudaStreamSynchronize(ctx->stream);
-        }
-        if (rc != EPID_OK || !fast || (cnt2[0] == 0 && cnt2[1] == 0)) break;
+    const bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
+    auto copy_and_wait = [&](int* cnt3) -> int {
+        int r = PfResultCopy::enqueue(ctx->stream, w, n, meas_cap, summary, meas, cnt3);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (r == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); r = EPID_ERR_CUDA; }
+        return r;
+    };
+    int cnt3[3] = {0, 0, 0};
+    rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr, fast);
+    if (rc == EPID_OK) rc = copy_and_wait(cnt3); else cudaStreamSynchronize(ctx->stream);
+    if (rc == EPID_OK && fast && cnt3[2] > 0) {
+        // frames the certified front end deferred (noise candidates, undecidable orientation): exactly those are re-run
         ctx->pf_fallbacks++;
-        fast = false;   // a frame was flagged noisy or could not be certified: exact pipeline for the whole batch
+        int dummy[3];
+        rc = pf_redo_deferred(ctx, ctx->stream, (const uint16_t*)frames->dptr, cnt3[2], frames->h, frames->w, p, meas_cap, w, pools);
+        if (rc == EPID_OK) rc = copy_and_wait(dummy); else cudaStreamSynchronize(ctx->stream);
     }
     for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
     return rc;
@@ -717,21 +803,29 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
     if (rc != EPID_OK) return rc;
     carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
     uint16_t* pools[3] = {nullptr, nullptr, nullptr};
-    bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
+    const bool fast = pf_fast_ok(ctx, p, frames->h, frames->w);
     cudaEvent_t t0, t1;
     EPID_CUDA(cudaEventCreate(&t0));
     EPID_CUDA(cudaEventCreate(&t1));
-    for (int attempt = 0; attempt < 2; attempt++) {
+    // pass 0: back-to-back passes, no host round trip (what an ordinary batch costs).  If that left deferred frames, pass 1 times
+    // the real control flow: after every fast pass the host reads the deferred count and enqueues the per-frame exact re-run.
+    for (int mode = 0; mode < 2; mode++) {
         PfTimers tm;
         tm.on = true;
         const int64_t l0 = ctx->launches;
+        int cnt3[3] = {0, 0, 0};
         EPID_CUDA(cudaStreamSynchronize(ctx->stream));
         EPID_CUDA(cudaEventRecord(t0, ctx->stream));
-        for (int it = 0; it < iters && rc == EPID_OK; it++)
+        for (int it = 0; it < iters && rc == EPID_OK; it++) {
             rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm, fast);
+            if (mode == 1 && rc == EPID_OK) {
+                cudaMemcpyAsync(cnt3, w.counters, sizeof(cnt3), cudaMemcpyDeviceToHost, ctx->stream);
+                cudaStreamSynchronize(ctx->stream);
+                if (cnt3[2] > 0) rc = pf_redo_deferred(ctx, ctx->stream, (const uint16_t*)frames->dptr, cnt3[2], frames->h, frames->w, p, meas_cap, w, pools);
+            }
+        }
         cudaEventRecord(t1, ctx->stream);
-        int cnt2[2] = {0, 0};
-        cudaMemcpyAsync(cnt2, w.counters, sizeof(cnt2), cudaMemcpyDeviceToHost, ctx->stream);
+        if (mode == 0) cudaMemcpyAsync(cnt3, w.counters, sizeof(cnt3), cudaMemcpyDeviceToHost, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
         float ms = 0;
         cudaEventElapsedTime(&ms, t0, t1);
@@ -739,9 +833,8 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
         if (stats_kernel_ms) *stats_kernel_ms = tm.total_ms();
         if (launches) *launches = ctx->launches - l0;
         tm.destroy();
-        if (rc != EPID_OK || !fast || (cnt2[0] == 0 && cnt2[1] == 0)) break;
+        if (rc != EPID_OK || !fast || mode == 1 || cnt3[2] == 0) break;
         ctx->pf_fallbacks++;
-        fast = false;
     }
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
@@ -844,13 +937,17 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
         EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
         return EPID_OK;
     };
-    auto finish = [&](int ci) -> int {   // wait for chunk ci, redo it exactly if flagged, hand the results to the caller
+    auto finish = [&](int ci) -> int {   // wait for chunk ci, re-run its deferred frames exactly, hand the results to the caller
         const int s = ci & 1, cnt = count_of(ci);
         EPID_CUDA(cudaEventSynchronize(computed[s]));
-        if (fast && (h_cnt[s][0] != 0 || h_cnt[s][1] != 0)) {
+        if (fast && h_cnt[s][2] > 0) {     // re-run exactly the frames the front end deferred, then fetch the chunk's rows again
             ctx->pf_fallbacks++;
-            int r = enqueue_run(ci, false);
+            int r = pf_redo_deferred(ctx, ctx->stream, bufs[s], h_cnt[s][2], h, w_, p, meas_cap, works[s], pools);
             if (r != EPID_OK) return r;
+            r = PfResultCopy::enqueue(ctx->stream, works[s], cnt, meas_cap, direct ? summary + (size_t)ci * chunk : h_summ[s],
+                                      direct ? meas + (size_t)ci * chunk * meas_cap : h_meas[s], h_cnt[s] + 4);
+            if (r != EPID_OK) return r;
+            EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
             EPID_CUDA(cudaEventSynchronize(computed[s]));
         }
         if (!direct) {

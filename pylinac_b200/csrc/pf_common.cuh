@@ -21,12 +21,17 @@ constexpr int FIN_THREADS = 256;
 
 struct PctPlan { int prev, next; double gamma; };
 
+// internal status of a frame whose decisions the single-pass front end could not certify (or that _check_for_noise may flag): the
+// fast pipeline skips it and the caller re-runs exactly that frame through the exact-histogram pipeline (never visible to callers)
+constexpr int PF_STATUS_DEFERRED = 90;
+
 struct PfConst {
     epid_pf_params p;
     int H, W;
     int meas_cap;
     int post_filter;       // stats were taken on an already inverted+filtered copy
     int leafband;          // 1: frames the leaf-band window kernel covers are processed by it (pf_windows.cu)
+    int win2;              // 1: frames the two-kernel window path covers are processed by it (pf_windows2.cu)
     PctPlan lo, hi;        // p0.5 / p99.5 of the frame (ranks live in StatsGeom slots 0..3)
     PctPlan p85[2], p99[2];  // [0]: arrays of length W (np.sum(axis 0)), [1]: length H
 };
@@ -43,6 +48,7 @@ struct PfFrame {
     int n_pickets;
     int n_inview;
     int todo;              // windows left to the generic kernel (set by k_pf_windows_fast)
+    int win2;              // the frame's windows are processed by k_pf_win_medians / k_pf_win_fwxm (set by the former)
     int picket_idx[PF_P];
     double picket_val[PF_P];
     double spacing;
@@ -50,6 +56,18 @@ struct PfFrame {
 };
 
 struct PfWin { int valid; double l, r; };  // per (in-view leaf, picket)
+
+// two-kernel window path (pf_windows2.cu): what k_pf_win_medians hands to k_pf_win_fwxm for one window
+constexpr int PF_W2_NCW = 64;      // travel samples per window
+constexpr int PF_W2_NRW = 32;      // rows per window
+constexpr int PF_W2_WCAP = 1024;   // windows per frame (in-view leaves x pickets)
+struct PfWinRec {
+    uint32_t hdr;                          // nc | nr << 16 (signed 16-bit each)
+    uint32_t pad;
+    uint32_t m2[PF_W2_NCW];                // 2 * median over the rows, g units
+    unsigned long long num[PF_W2_NRW];     // nc * S2 - S1^2 per row (variance numerator along travel)
+    uint32_t ext[PF_W2_NRW];               // raw row maximum << 16 | raw row minimum, inside the window
+};
 
 // numpy _lerp (numpy/lib/_function_base_impl.py): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
 __device__ __forceinline__ double np_lerp(double a, double b, double t) {
@@ -136,11 +154,15 @@ struct PfTimers {
     }
 };
 enum { PF_STAGE_START = -1, PF_STAGE_INIT_PILOT = 0, PF_STAGE_STREAM = 1, PF_STAGE_TAIL = 2, PF_STAGE_WINDOWS = 3, PF_STAGE_WINDOWS_GENERIC = 4,
-       PF_STAGE_FINALIZE = 5, PF_STAGE_EXACT_FRONT = 6, PF_STAGE_LEAFBAND = 7, PF_NSTAGES = 8 };
+       PF_STAGE_FINALIZE = 5, PF_STAGE_EXACT_FRONT = 6, PF_STAGE_LEAFBAND = 7, PF_STAGE_WIN_MEDIANS = 8, PF_STAGE_WIN_FWXM = 9, PF_NSTAGES = 10 };
 
 // pf_windows.cu
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
 int launch_pf_leafband(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
+// pf_windows2.cu
+size_t pf_win2_scratch_bytes(int n);
+int launch_pf_windows2(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWinRec* recs, PfWin* wins,
+                       int n, PfTimers* tm);
 // pf_stream.cu
 size_t pf_front_scratch_bytes(int n, int H, int W);
 // pf_finalize.cu
@@ -229,7 +251,10 @@ __device__ inline void pf_profile_block(const PfConst& c, PfFrame& f, const uint
             // every percentile of a sum vector moves by at most its d, so each range moves by at most d (+1: lerp rounding)
             const bool sure_lr = row_range + d_colsum2 + 1.0 < col_range - d_rowsum2;
             const bool sure_ud = row_range - d_colsum2 >= col_range + d_rowsum2 + 1.0;
-            if (!sure_lr && !sure_ud && threadIdx.x == 0) atomicAdd(&counters[1], 1);
+            if (!sure_lr && !sure_ud) {      // the same in every thread: the frame is re-run by the exact pipeline
+                if (threadIdx.x == 0) { atomicAdd(&counters[1], 1); f.status = PF_STATUS_DEFERRED; }
+                return;
+            }
         }
     }
     // ---- leaf profile: np.mean(image, axis) then / max   (picketfence.py:747-752)

@@ -347,11 +347,7 @@ int launch_pf_finalize(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, P
     int m2 = 1;
     while (m2 < 2 * meas_cap) m2 <<= 1;
     const size_t smem = sizeof(double) * m2;
-    static size_t attr_set = 0;
-    if (smem > attr_set && smem > 16 * 1024) {
-        EPID_CUDA(cudaFuncSetAttribute(k_pf_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = smem;
-    }
+    if (smem > 16 * 1024) EPID_SMEM_OPT_IN(ctx, k_pf_finalize, smem);
     k_pf_finalize<<<n, FIN_THREADS, smem, stream>>>(cst, fr, wins, summ, meas);
     ctx->launches++;
     EPID_CUDA(cudaGetLastError());

@@ -605,6 +605,7 @@ k_pf_tail(const PfConst* __restrict__ cc, const StatsGeom g, const StreamGeom sg
         f.n_pickets = 0;
         f.n_inview = 0;
         f.todo = 0;
+        f.win2 = 0;
         f.orientation = 0;
         f.mn = mn;
         f.mx = mx;
@@ -643,7 +644,7 @@ k_pf_tail(const PfConst* __restrict__ cc, const StatsGeom g, const StreamGeom sg
         for (int i = 0; i < STATS_MAX_RANKS; i++) st.ostat[i] = 0;
         st.ostat[0] = mn; st.ostat[1] = po.u_lo; st.ostat[2] = po.l_hi; st.ostat[3] = mx; st.ostat[4] = po.a1; st.ostat[5] = po.b1;
         stats[fi] = st;
-        if (bad) { atomicAdd(&counters[1], 1); s_flag = 1; }
+        if (bad) { atomicAdd(&counters[1], 1); s_flag = 1; f.status = PF_STATUS_DEFERRED; }
     }
     __syncthreads();
     if (s_flag || f.status != EPID_PF_OK) return;
@@ -697,13 +698,9 @@ size_t pf_front_scratch_bytes(int n, int H, int W) {
 }
 
 template <int VPL>
-static int launch_stream(cudaStream_t stream, int grid, size_t smem, const StreamGeom& sg, const FrameRef* refs, const PilotOut* pilot,
+static int launch_stream(epid_ctx* ctx, cudaStream_t stream, int grid, size_t smem, const StreamGeom& sg, const FrameRef* refs, const PilotOut* pilot,
                          int nitems, ItemOut* items, uint32_t* col_raw, uint32_t* col_cl, uint32_t* row_raw, uint32_t* row_cl) {
-    static size_t attr = 0;
-    if (smem > attr) {
-        EPID_CUDA(cudaFuncSetAttribute(k_pf_stream<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    EPID_SMEM_OPT_IN(ctx, k_pf_stream<VPL>, smem);
     k_pf_stream<VPL><<<grid, ST_THREADS, smem, stream>>>(sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl);
     return EPID_OK;
 }
@@ -744,22 +741,18 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
     if (tm) { rc = tm->mark(stream, PF_STAGE_INIT_PILOT); if (rc != EPID_OK) return rc; }
     if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
     switch (vpl) {
-        case 1: rc = launch_stream<1>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
-        case 2: rc = launch_stream<2>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
-        case 3: rc = launch_stream<3>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
-        default: rc = launch_stream<4>(stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
+        case 1: rc = launch_stream<1>(ctx, stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
+        case 2: rc = launch_stream<2>(ctx, stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
+        case 3: rc = launch_stream<3>(ctx, stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
+        default: rc = launch_stream<4>(ctx, stream, grid, smem, sg, refs, pilot, nitems, items, col_raw, col_cl, row_raw, row_cl); break;
     }
     if (rc != EPID_OK) return rc;
     ctx->launches++;
     if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
     if (tm) { rc = tm->mark(stream, PF_STAGE_STREAM); if (rc != EPID_OK) return rc; }
     {
-        static size_t attr = 0;
         const size_t tsm = pf_tail_smem_bytes(H, W);
-        if (tsm > attr) {
-            EPID_CUDA(cudaFuncSetAttribute(k_pf_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-            attr = tsm;
-        }
+        EPID_SMEM_OPT_IN(ctx, k_pf_tail, tsm);
         k_pf_tail<<<n, TAIL_THREADS, tsm, stream>>>(d_cst, g, sg, refs, pilot, items, col_raw, col_cl, row_raw, row_cl, fr, stats, counters);
         ctx->launches++;
         if (tm) { rc = tm->mark(stream, PF_STAGE_TAIL); if (rc != EPID_OK) return rc; }

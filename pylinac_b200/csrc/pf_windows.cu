@@ -23,6 +23,7 @@
 
 #include "pf_common.cuh"
 #include "tma.cuh"
+#include "pf_win_common.cuh"
 
 namespace epid {
 
@@ -30,84 +31,6 @@ constexpr int W2_WARPS = 16;
 constexpr int W2_POOL = 100 * 1024;   // shared memory per CTA, split into per-warp slots sized for the frame's largest window
 constexpr int W2_MAXNC = 256;    // travel samples per window on the fast path
 constexpr int W2_GRID_X = 12;    // CTAs per frame: a warp takes ~3 windows and prefetches the next one while it analyses the current one (sweep 4..24: flat, 12 best)
-
-// a * b + c with a 64-bit accumulator in ONE instruction (IMAD.WIDE.U32); the compiler emits IMAD + IADD3 + IADD3.X for the C form
-__device__ __forceinline__ unsigned long long mad_wide_u32(uint32_t a, uint32_t b, unsigned long long c) {
-    unsigned long long d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-
-template <int N>
-__device__ __forceinline__ void sort_net_u16x2(uint32_t (&r)[N]) {
-    // Batcher merge exchange (valid for any N), ascending in both 16-bit halves independently
-#pragma unroll
-    for (int p = 1; p < N; p <<= 1) {
-#pragma unroll
-        for (int k = p; k >= 1; k >>= 1) {
-#pragma unroll
-            for (int j = k % p; j <= N - 1 - k; j += 2 * k) {
-#pragma unroll
-                for (int i = 0; i < k; i++) {
-                    if (i <= N - j - k - 1 && (i + j) / (2 * p) == (i + j + k) / (2 * p)) {
-                        const uint32_t a = r[i + j], b = r[i + j + k];
-                        r[i + j] = __vminu2(a, b);
-                        r[i + j + k] = __vmaxu2(a, b);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// 2 * median over exactly N rows of the travel-sample pair in word `t`: (va + vb) per half
-template <int N>
-__device__ __forceinline__ void pair_median_exact(const uint16_t* __restrict__ px, int S, int t, uint32_t& m_lo, uint32_t& m_hi) {
-    uint32_t r[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) r[i] = *reinterpret_cast<const uint32_t*>(px + i * S + 2 * t);
-    sort_net_u16x2<N>(r);
-    const uint32_t va = r[(N - 1) / 2], vb = r[N / 2];
-    m_lo = (va & 0xffffu) + (vb & 0xffffu);
-    m_hi = (va >> 16) + (vb >> 16);
-}
-
-// padded variant for row counts without an exact instantiation
-template <int NRP>
-__device__ __forceinline__ void pair_median_padded(const uint16_t* __restrict__ px, int S, int nr, int t, uint32_t& m_lo, uint32_t& m_hi) {
-    uint32_t r[NRP];
-#pragma unroll
-    for (int i = 0; i < NRP; i++)
-        r[i] = i < nr ? *reinterpret_cast<const uint32_t*>(px + i * S + 2 * t) : 0xffffffffu;
-    sort_net_u16x2<NRP>(r);
-    const int k1 = (nr - 1) / 2, k2 = nr / 2;
-    uint32_t va = 0, vb = 0;
-#pragma unroll
-    for (int i = 0; i < NRP; i++) {
-        if (i == k1) va = r[i];
-        if (i == k2) vb = r[i];
-    }
-    m_lo = (va & 0xffffu) + (vb & 0xffffu);
-    m_hi = (va >> 16) + (vb >> 16);
-}
-
-__device__ __noinline__ uint2 pair_median_any(const uint16_t* __restrict__ px, int S, int nr, int t) {
-    uint32_t m_lo = 0, m_hi = 0;
-    switch (nr) {
-#define EPID_MED_CASE(N) case N: pair_median_exact<N>(px, S, t, m_lo, m_hi); break;
-        EPID_MED_CASE(6) EPID_MED_CASE(7) EPID_MED_CASE(8) EPID_MED_CASE(9) EPID_MED_CASE(10) EPID_MED_CASE(11)
-        EPID_MED_CASE(12) EPID_MED_CASE(13) EPID_MED_CASE(14) EPID_MED_CASE(15) EPID_MED_CASE(16) EPID_MED_CASE(17)
-        EPID_MED_CASE(18) EPID_MED_CASE(19) EPID_MED_CASE(20) EPID_MED_CASE(21) EPID_MED_CASE(22) EPID_MED_CASE(23)
-        EPID_MED_CASE(24) EPID_MED_CASE(25) EPID_MED_CASE(26) EPID_MED_CASE(27) EPID_MED_CASE(28) EPID_MED_CASE(29)
-        EPID_MED_CASE(30) EPID_MED_CASE(31) EPID_MED_CASE(32)
-#undef EPID_MED_CASE
-        default:
-            if (nr < 6) pair_median_padded<8>(px, S, nr, t, m_lo, m_hi);
-            else if (nr <= 48) pair_median_padded<48>(px, S, nr, t, m_lo, m_hi);
-            else pair_median_padded<64>(px, S, nr, t, m_lo, m_hi);
-    }
-    return make_uint2(m_lo, m_hi);
-}
 
 // Row statistics of _is_mlc_peak_in_window: max(std) and median(std) over the nr rows, std along travel as
 // sqrt(nc*S2 - S1^2) / (nc * D) with an exact integer numerator.  NSL = row slots per lane (1: nr <= 32, 2: nr <= 64).
@@ -194,7 +117,7 @@ k_pf_windows_fast(const PfConst* __restrict__ cc, const FrameRef* __restrict__ f
             int stage_b = max(nr_max * s_max * 2, nc_max * 8);
             stage_b = (stage_b + 15) & ~15;
             const int slot = stage_b + ((nc_max * 4 + 15) & ~15);
-            s_geo[0] = leafband ? -1 : st;
+            s_geo[0] = (leafband || f.win2) ? -1 : st;     // another window kernel owns this frame
             s_geo[1] = slot;
             s_geo[2] = stage_b;
             s_geo[3] = nc_max > W2_MAXNC + 2 ? 0 : min(W2_WARPS, W2_POOL / slot);
@@ -639,98 +562,6 @@ __device__ __forceinline__ void lb_leaf_rows(const PfConst& c, const PfFrame& f,
     nr = min((int)(lc_px + lw_px / 2.0), c.H) - b0;
 }
 
-// serial FWXM analysis of one window's median profile m[0..nc) (2 * median in g units), lane-private.
-// Mirrors find_peaks(values, fwxm_height=0.5, max_number=1) on xs = (m - min) / (max - min) and scipy's _peak_widths.
-// returns valid (1), 0 = no peak / flat (the caller raises EPID_PF_WINDOW_NO_PEAK)
-__device__ inline int lb_window_fwxm(const uint32_t* __restrict__ m, int nc, double& out_l, double& out_r) {
-    // one branch-light pass (the lanes of the warp -- one window each -- stay in lockstep): min, max and the two highest local
-    // maxima (scipy _local_maxima_1d: rise, plateau, fall; midpoint of the plateau), key = height << 8 | position
-    uint32_t lmin, lmax, best1 = 0, best2 = 0;
-    {
-        int start = -1;
-        uint32_t prev = m[0];
-        lmin = lmax = prev;
-        for (int i = 1; i < nc; i++) {
-            const uint32_t v = m[i];
-            lmin = min(lmin, v);
-            lmax = max(lmax, v);
-            if (v < prev && start >= 0) {
-                const uint32_t key = (prev << 8) | (uint32_t)((start + i - 1) >> 1);
-                if (key > best1) { best2 = best1; best1 = key; }
-                else if (key > best2) best2 = key;
-            }
-            start = v > prev ? i : (v < prev ? -1 : start);
-            prev = v;
-        }
-    }
-    if (lmax == lmin || best1 == 0) return 0;
-    const double den = (double)(lmax - lmin);
-    auto xs = [&](int j) { return (double)(m[j] - lmin) / den; };
-    double best_prom = -1.0;
-    int best_idx = -1, best_lb = 0, best_rb = 0, best_int = -1;
-    auto evaluate = [&](uint32_t key) {
-        const uint32_t hp = key >> 8;
-        const int p = (int)(key & 255u);
-        int k = p, lb = p, rb = p;
-        uint32_t lm = hp, rm = hp;
-        while (k >= 0 && m[k] <= hp) { if (m[k] < lm) { lm = m[k]; lb = k; } k--; }
-        k = p;
-        while (k <= nc - 1 && m[k] <= hp) { if (m[k] < rm) { rm = m[k]; rb = k; } k++; }
-        const double prom = xs(p) - xs(lm > rm ? lb : rb);      // fmax(xs[lb], xs[rb]): xs is monotone in m
-        if (prom > best_prom || (prom == best_prom && p > best_idx)) { best_prom = prom; best_idx = p; best_lb = lb; best_rb = rb; }
-        best_int = max(best_int, (int)(hp - max(lm, rm)));
-    };
-    // candidates from the highest down: one of height hp cannot have a prominence above hp - min(profile)
-    evaluate(best1);
-    if (best2 != 0 && (int)((best2 >> 8) - lmin) >= best_int) {      // rare: the runner-up could still win
-        uint32_t bound = best1;
-        while (true) {
-            uint32_t key = 0;
-            int start = -1;
-            uint32_t prev = m[0];
-            for (int i = 1; i < nc; i++) {
-                const uint32_t v = m[i];
-                if (v < prev && start >= 0) {
-                    const uint32_t kk = (prev << 8) | (uint32_t)((start + i - 1) >> 1);
-                    if (kk < bound && kk > key) key = kk;
-                }
-                start = v > prev ? i : (v < prev ? -1 : start);
-                prev = v;
-            }
-            if (key == 0 || (int)((key >> 8) - lmin) < best_int) break;
-            bound = key;
-            evaluate(key);
-        }
-    }
-    const int p = best_idx;
-    const double h = xs(p) - best_prom * 0.5;
-    // integer pre-filter for "h < xs[k]": xs is a monotone map of m, T = h * den + min is h in integer units up to ~1e-10
-    const double T = h * den + (double)lmin;
-    auto above = [&](int k) {
-        const double mk = (double)m[k];
-        if (mk > T + 0.5) return true;
-        if (mk < T - 0.5) return false;
-        return h < xs(k);
-    };
-    int kl = p;
-    while (kl > best_lb && above(kl)) kl--;
-    double l = (double)kl;
-    {
-        const double xk = xs(kl);
-        if (xk < h) l += (h - xk) / (xs(kl + 1) - xk);
-    }
-    int kr = p;
-    while (kr < best_rb && above(kr)) kr++;
-    double r = (double)kr;
-    {
-        const double xk = xs(kr);
-        if (xk < h) r -= (h - xk) / (xs(kr - 1) - xk);
-    }
-    out_l = l;
-    out_r = r;
-    return 1;
-}
-
 __device__ __forceinline__ void lb_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 __global__ void __launch_bounds__(LB_THREADS, 4)
@@ -959,18 +790,16 @@ k_pf_leafband(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frame
 }
 
 int launch_pf_leafband(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n) {
-    static bool attr = false;
     const size_t smem = LB_BAND_BYTES + sizeof(uint32_t) * LB_RING * LB_MAXJ + sizeof(unsigned long long) * LB_MAXP * 32 +
                         sizeof(uint32_t) * LB_MAXP * 32 + sizeof(int) * LB_RING * LB_MAXP + 64;
-    if (!attr) {
-        EPID_CUDA(cudaFuncSetAttribute(k_pf_leafband, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (ctx->smem_optin.find((const void*)k_pf_leafband) == ctx->smem_optin.end()) {
+        EPID_SMEM_OPT_IN(ctx, k_pf_leafband, smem);
         EPID_CUDA(cudaFuncSetAttribute(k_pf_leafband, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         if (getenv("EPID_DEBUG")) {
             int nb = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pf_leafband, LB_THREADS, smem);
             fprintf(stderr, "[epid] k_pf_leafband: %zu B dynamic shared memory, %d CTAs / SM\n", smem, nb);
         }
-        attr = true;
     }
     const int nitems = n * LB_CHUNKS;
     const int grid = nitems < 4 * ctx->sm_count ? nitems : 4 * ctx->sm_count;
@@ -981,12 +810,8 @@ int launch_pf_leafband(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, c
 }
 
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n) {
-    static bool attr = false;
     const size_t smem = W2_POOL;
-    if (!attr) {
-        EPID_CUDA(cudaFuncSetAttribute(k_pf_windows_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    EPID_SMEM_OPT_IN(ctx, k_pf_windows_fast, smem);
     static int gx = 0;
     if (gx == 0) { const char* e = getenv("EPID_W2_GRID"); gx = e ? atoi(e) : W2_GRID_X; if (gx < 1 || gx > 64) gx = W2_GRID_X; }
     dim3 grid(gx, n);

@@ -647,11 +647,7 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
         const int n_max = hc.cw > hc.ch ? hc.cw : hc.ch;
         const int n_al = (n_max + 3) & ~3;
         const size_t smem = sizeof(double) * (size_t)(2 * n_al + 5 * SS_PEAK_CAP) + sizeof(int) * (size_t)(5 * SS_PEAK_CAP + SS_THREADS + 8);
-        static size_t attr = 0;
-        if (smem > attr) {
-            EPID_CUDA(cudaFuncSetAttribute(k_star_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr = smem;
-        }
+        EPID_SMEM_OPT_IN(ctx, k_star_front, smem);
         k_star_front<<<n, SS_THREADS, smem, st>>>(d_cst, d_rf, d_sf, d_sc, d_fr, d_res);
         ctx->launches++;
     }

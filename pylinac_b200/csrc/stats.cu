@@ -303,13 +303,9 @@ static size_t stats_smem_bytes(const StatsGeom& g) {
 
 int launch_frame_stats(epid_ctx* ctx, cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames,
                        const int* d_out_index, int n, FrameStats* d_stats, uint32_t* d_rowsum, uint32_t* d_colsum) {
-    static bool attr_set = false;
     const size_t smem = stats_smem_bytes(g);
-    if (!attr_set) {
-        EPID_CUDA(cudaFuncSetAttribute(k_frame_stats<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        EPID_CUDA(cudaFuncSetAttribute(k_frame_stats<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
-    }
+    EPID_SMEM_OPT_IN(ctx, k_frame_stats<0>, 220 * 1024);
+    EPID_SMEM_OPT_IN(ctx, k_frame_stats<1>, 220 * 1024);
     const int grid = n < ctx->sm_count ? n : ctx->sm_count;
     k_frame_stats<0><<<grid, STATS_THREADS, smem, stream>>>(g, d_frames, d_out_index, n, d_stats, d_rowsum, d_colsum);
     // exact fallback for frames whose packed counters overflowed (CTAs of other frames exit at once)

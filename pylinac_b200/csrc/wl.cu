@@ -829,12 +829,8 @@ extern "C" int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, co
     const size_t bb_smem = sizeof(int) * (size_t)win_edge * win_edge + 2 * WL_TILE * WL_TILE + 64;
     const size_t bb_smem_max = sizeof(int) * WL_MAXWIN * WL_MAXWIN + 2 * WL_TILE * WL_TILE + 64;
     EPID_CUDA(cudaMemcpyAsync(base + o_cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
-    static bool attr = false;
-    if (!attr) {
-        EPID_CUDA(cudaFuncSetAttribute(k_wl_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hc.field_tile_cap));
-        EPID_CUDA(cudaFuncSetAttribute(k_wl_bb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb_smem_max));
-        attr = true;
-    }
+    EPID_SMEM_OPT_IN(ctx, k_wl_field, (size_t)hc.field_tile_cap);
+    EPID_SMEM_OPT_IN(ctx, k_wl_bb, bb_smem_max);
     for (int c0 = 0; c0 < n; c0 += chunk) {
         const int cn = n - c0 < chunk ? n - c0 : chunk;
         const uint16_t* d_frames = (const uint16_t*)frames->dptr + (size_t)c0 * H * W;

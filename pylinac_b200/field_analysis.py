@@ -251,14 +251,7 @@ class FieldAnalysis(ResultsDataMixin[FieldResult]):
         self._is_analyzed = False
 
     def _frame_u16(self) -> np.ndarray:
-        a = np.asarray(self.image.array)
-        if a.dtype == np.uint16:
-            return a
-        if a.dtype == np.uint8:
-            return a.astype(np.uint16)
-        if a.dtype.kind in "fiu" and a.min() >= 0 and a.max() <= 65535 and np.array_equal(a, np.floor(a)):
-            return a.astype(np.uint16)
-        raise NotImplementedError("the GPU field-analysis path takes integer-valued pixel data in [0, 65535]")
+        return image.frame_u16(self.image, "GPU field-analysis")
 
     def analyze(self, protocol=Protocol.VARIAN, centering=Centering.BEAM_CENTER, vert_position: float = 0.5, horiz_position: float = 0.5,
                 vert_width: float = 0, horiz_width: float = 0, in_field_ratio: float = 0.8, slope_exclusion_ratio: float = 0.2,

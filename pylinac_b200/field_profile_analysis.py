@@ -63,14 +63,7 @@ class FieldProfileAnalysis(ResultsDataMixin[FieldProfileResult]):
 
     # ---- device helpers: exact integer sums of frame strips
     def _frame_u16(self) -> np.ndarray:
-        a = np.asarray(self.image.array)
-        if a.dtype == np.uint16:
-            return a
-        if a.dtype == np.uint8:
-            return a.astype(np.uint16)
-        if a.dtype.kind in "fiu" and a.min() >= 0 and a.max() <= 65535 and np.array_equal(a, np.floor(a)):
-            return a.astype(np.uint16)
-        raise NotImplementedError("the GPU path takes integer-valued pixel data in [0, 65535]")
+        return image.frame_u16(self.image, "GPU field-profile")
 
     def analyze(self, centering=Centering.BEAM_CENTER, position: tuple[float, float] = (0.5, 0.5), x_width: float = 0.0,
                 y_width: float = 0.0, normalization=Normalization.NONE, edge_type=Edge.INFLECTION_DERIVATIVE, invert: bool = False,

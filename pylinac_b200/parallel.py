@@ -78,6 +78,8 @@ def gather_rows(rows: np.ndarray, n_total: int, *, dist=None, ctx=None) -> np.nd
     world, rank, _ = world_info() if dist is None else (dist.get_world_size(), dist.get_rank(), 0)
     if world == 1:
         return rows
+    if ctx is None and dist is None:
+        raise ValueError(f"world size is {world}: pass ctx= (NCCL communicator initialised with init_comm) or dist= (torch.distributed)")
     sizes = shard_sizes(n_total, world)
     if len(rows) != sizes[rank]:
         raise ValueError(f"rank {rank} holds {len(rows)} rows, its shard has {sizes[rank]}")
@@ -87,7 +89,11 @@ def gather_rows(rows: np.ndarray, n_total: int, *, dist=None, ctx=None) -> np.nd
     if ctx is not None:
         from . import _native as nat
 
-        allbuf = np.empty(world * width, rows.dtype)
+        nranks, crank = ctx.comm_info()
+        if (nranks, crank) != (world, rank):
+            raise RuntimeError(f"the context's communicator has {nranks} rank(s) (this one is {crank}) but the job has {world} "
+                               f"(this one is {rank}): call parallel.init_comm(ctx, dist) on every rank first")
+        allbuf = np.zeros(world * width, rows.dtype)
         nat.check(nat.lib().epid_gather_results(ctx.handle, padded.ctypes.data, padded.nbytes, allbuf.ctypes.data))
     else:
         import torch

@@ -273,7 +273,7 @@ class PFBatchResult(Sequence):
         return PFFrameResult(self.summary[i], self.meas[i], self.params, *self._args)
 
 
-def analyze_batch(frames, dpmm: float, *, device: int | None = None, meas_cap: int = 1024, crop_mm=3, filter=None,
+def analyze_batch(frames, dpmm: float, *, device: int | None = None, meas_cap: int | None = None, crop_mm=3, filter=None,
                   mlc=MLC.MILLENNIUM, **analyze_kwargs) -> PFBatchResult:
     """Batched ``PicketFence(frame, filter=, mlc=, crop_mm=).analyze(**analyze_kwargs)`` over frames[n, h, w] uint16.
 
@@ -289,7 +289,13 @@ def analyze_batch(frames, dpmm: float, *, device: int | None = None, meas_cap: i
             frames = frames[None]
         n, h, w = frames.shape
     params = make_params(dpmm, (h, w), crop_mm=crop_mm, filter=filter, mlc=mlc, **analyze_kwargs)
-    summ, meas = nat.pf_analyze(ctx, frames, params, meas_cap=meas_cap)
+    # measurement-table rows per frame: 1024 covers the usual 60 leaf pairs x <= 17 pickets; a frame that needs more reports
+    # status 5 and the batch is re-run once with the largest table the arrangement can fill (the reference has no such limit)
+    cap = 1024 if meas_cap is None else int(meas_cap)
+    summ, meas = nat.pf_analyze(ctx, frames, params, meas_cap=cap)
+    cap_max = min(8192, params.n_leaves * nat.PF_MAX_PICKETS)
+    if meas_cap is None and cap < cap_max and (summ["status"] == 5).any():
+        summ, meas = nat.pf_analyze(ctx, frames, params, meas_cap=cap_max)
     return PFBatchResult(summ, meas, params, analyze_kwargs.get("tolerance", 0.5), analyze_kwargs.get("action_tolerance"),
                          analyze_kwargs.get("separate_leaves", False))
 
@@ -390,15 +396,7 @@ class PicketFence(ResultsDataMixin[PFResult]):
 
     # the frame the GPU analyses: uint16, un-cropped (the crop is a device-side view)
     def _frame_u16(self) -> np.ndarray:
-        a = self._raw.array
-        if a.dtype == np.uint16:
-            return a
-        if a.dtype == np.uint8:
-            return a.astype(np.uint16)
-        af = np.asarray(a)
-        if af.dtype.kind in "fiu" and af.min() >= 0 and af.max() <= 65535 and np.array_equal(af, np.floor(af)):
-            return af.astype(np.uint16)  # integer-valued pixels stored as another dtype (e.g. DICOM rescale 1.0/0.0)
-        raise NotImplementedError("the GPU picket-fence path takes integer-valued pixel data in [0, 65535]")
+        return image.frame_u16(self._raw, "GPU picket-fence")
 
     def analyze(self, tolerance: float = 0.5, action_tolerance: float | None = None, num_pickets: int | None = None,
                 sag_adjustment: float | int = 0, orientation=None, invert: bool = False,

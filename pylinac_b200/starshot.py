@@ -174,14 +174,7 @@ class Starshot(ResultsDataMixin[StarshotResults]):
         raise NotImplementedError("load_multiples is an ingest feature outside the accelerated hot path (SURVEY.md 8f)")
 
     def _frame_u16(self) -> np.ndarray:
-        a = np.asarray(self.image.array)
-        if a.dtype == np.uint16:
-            return a
-        if a.dtype == np.uint8:
-            return a.astype(np.uint16)
-        if a.dtype.kind in "fiu" and a.min() >= 0 and a.max() <= 65535 and np.array_equal(a, np.floor(a)):
-            return a.astype(np.uint16)
-        raise NotImplementedError("the GPU starshot path takes integer-valued pixel data in [0, 65535]")
+        return image.frame_u16(self.image, "GPU starshot")
 
     def analyze(self, radius: float = 0.85, min_peak_height: float = 0.25, max_wobble_diameter: float = 2.0,
                 tolerance: float = 1.0, start_point=None, fwhm: bool = True, recursive: bool = True, invert: bool = False):

@@ -191,11 +191,15 @@ class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
             self.image = image.ArrayImage(file, **{k: v for k, v in kwargs.items() if k in ("dpi", "sid", "dtype")})
         elif isinstance(file, image.BaseImage):
             self.image = file
+        elif image._is_dicom(file):
+            # the reference's WinstonLutz2D IS a LinacDicomImage (winston_lutz.py:629, 1137): axis angles come from the tags,
+            # gantry= / coll= / couch= override them
+            self.image = image.LinacDicomImage(file, **kwargs)
         else:
-            self.image = image.load(file, **kwargs)
-        self.gantry_angle = float(kwargs.get("gantry", getattr(self.image, "gantry_angle", 0.0) or 0.0))
-        self.collimator_angle = float(kwargs.get("coll", getattr(self.image, "collimator_angle", 0.0) or 0.0))
-        self.couch_angle = float(kwargs.get("couch", getattr(self.image, "couch_angle", 0.0) or 0.0))
+            self.image = image.load(file, **{k: v for k, v in kwargs.items() if k in ("dpi", "sid", "dtype")})
+        self.gantry_angle = float(kwargs["gantry"] if kwargs.get("gantry") is not None else getattr(self.image, "gantry_angle", 0.0) or 0.0)
+        self.collimator_angle = float(kwargs["coll"] if kwargs.get("coll") is not None else getattr(self.image, "collimator_angle", 0.0) or 0.0)
+        self.couch_angle = float(kwargs["couch"] if kwargs.get("couch") is not None else getattr(self.image, "couch_angle", 0.0) or 0.0)
         if self.image.dpmm is None:
             raise ValueError("DPI was not a tag in the image nor was it passed in. Please pass a DPI value")
         self._is_analyzed = False
@@ -204,14 +208,7 @@ class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
         self._gantry_reference = self._collimator_reference = self._couch_reference = 0.0
 
     def _frame_u16(self) -> np.ndarray:
-        a = np.asarray(self.image.array)
-        if a.dtype == np.uint16:
-            return a
-        if a.dtype == np.uint8:
-            return a.astype(np.uint16)
-        if a.dtype.kind in "fiu" and a.min() >= 0 and a.max() <= 65535 and np.array_equal(a, np.floor(a)):
-            return a.astype(np.uint16)
-        raise NotImplementedError("the GPU Winston-Lutz path takes integer-valued pixel data in [0, 65535]")
+        return image.frame_u16(self.image, "GPU Winston-Lutz")
 
     @property
     def dpmm(self) -> float:
@@ -464,7 +461,7 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
                 axes.append(tuple(float(v) for v in axis_mapping[key]))
             else:
                 axes.append((float(img.gantry_angle), float(img.collimator_angle), float(img.couch_angle)))
-            frames.append(np.asarray(img.array))
+            frames.append(image.frame_u16(img, "GPU Winston-Lutz"))
             dpmm = img.dpmm if dpmm is None else dpmm
         self._setup(np.stack(frames), axes, dpmm)
 
@@ -478,10 +475,7 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
         if frames.ndim != 3 or len(axes) != frames.shape[0]:
             raise ValueError("frames must be [n,h,w] with one (gantry, collimator, couch) triple per frame")
         if frames.dtype != np.uint16:
-            if frames.dtype.kind in "iu" and frames.min() >= 0 and frames.max() <= 65535:
-                frames = frames.astype(np.uint16)
-            else:
-                raise NotImplementedError("the GPU Winston-Lutz path takes integer-valued pixel data in [0, 65535]")
+            frames = image.frame_u16(frames, "GPU Winston-Lutz")
         self._frames, self._axes, self.dpmm = frames, axes, dpmm
         self.images: list[_SetImage] = []
         self._is_analyzed = False

@@ -1,4 +1,4 @@
-"""Generate tests/golden/pf_docs_golden.npz (+ pf_docs_frames.npz): the UNMODIFIED reference PicketFence on the reference's own
+"""Generate tests/golden/pf_docs_golden.npz (+ pf_docs_dcm.npz): the UNMODIFIED reference PicketFence on the reference's own
 docs fixtures (docs/source/files/*.dcm) with the analyze() arguments of their recipes (docs/source/picketfence.rst:455-730).
 
 Run here (the container that has /root/reference):  python -m tests.golden.make_pf_docs_golden
@@ -21,8 +21,8 @@ from tests.golden.refrun import reference_pf
 def main():
     store, frames = {}, {}
     warnings.simplefilter("ignore")
-    if os.path.exists(dc.FRAMES_NPZ):
-        os.remove(dc.FRAMES_NPZ)          # read every frame from the reference tree
+    if os.path.exists(dc.DCM_NPZ):
+        os.remove(dc.DCM_NPZ)          # read every file from the reference tree
     for name, ak in dc.DOCS.items():
         a, ps, sid, ak = dc.docs_frame(name)
         store[f"{name}/input_sha1"] = np.frombuffer(hashlib.sha1(a.tobytes()).digest(), dtype=np.uint8)
@@ -33,10 +33,9 @@ def main():
         store[f"{name}/failed_leaves"] = np.array([str(x) for x in ref["failed_leaves"]])
         print(name, "pickets", ref["number_of_pickets"], "kisses", ref["n_meas"], "max err", ref["max_error"], "offsets",
               np.round(ref["offsets_from_cax_mm"], 1).tolist(), "skew", round(float(ref["mlc_skew"]), 3), "passed", ref["passed"])
-        if name in dc.COMMITTED:
-            frames[name] = np.frombuffer(lzma.compress(a.tobytes(), preset=9), dtype=np.uint8)
+        frames[name] = np.frombuffer(lzma.compress(dc.docs_dcm_bytes(name), preset=6), dtype=np.uint8)
     np.savez_compressed("tests/golden/pf_docs_golden.npz", **store)
-    np.savez(dc.FRAMES_NPZ, **frames)
+    np.savez(dc.DCM_NPZ, **frames)
 
 
 if __name__ == "__main__":

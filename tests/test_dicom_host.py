@@ -1,0 +1,116 @@
+"""Host-side ingest: pylinac_b200.dicom + DicomImage / LinacDicomImage / FileImage / load().
+
+The reference reads files with pydicom (core/io.py:73-84) and then touches a handful of tags (core/image.py:363-389, 1383-1444,
+1509-1580, 1612-1730).  These tests read the reference's OWN DICOM fixtures (docs/source/files/*.dcm, committed lzma-compressed)
+through this repo's parser, and synthetic files with the tags clinical EPID images carry (rescale, sign flip, axis angles)."""
+import io
+
+import numpy as np
+import pytest
+
+from pylinac_b200 import dicom
+from pylinac_b200.core import image
+from tests.dicom_writer import write_dicom
+from tests.golden import pf_docs_cases as dc
+
+
+@pytest.mark.parametrize("name", list(dc.DOCS))
+def test_reference_docs_files_parse(name, tmp_path):
+    data = dc.docs_dcm_bytes(name)
+    tail, ps, sid, _ = dc.docs_frame(name)
+    ds = dicom.dcmread(data)
+    assert (ds.Rows, ds.Columns, ds.BitsAllocated) == (1280, 1280, 16)
+    assert ds.pixel_array.dtype == np.uint16 and np.array_equal(ds.pixel_array, tail)
+    assert ds.ImagePlanePixelSpacing == [ps, ps] and ds.RTImageSID == sid and ds.RadiationMachineSAD == 1000.0
+    assert ds.Modality == "RTIMAGE" and ds.TransferSyntaxUID == "1.2.840.10008.1.2"
+    # file path, stream and bytes are all accepted (core/image.py:244-286, io.py:73-84)
+    p = tmp_path / (name + ".dcm")
+    p.write_bytes(data)
+    img = image.load(str(p))
+    assert isinstance(img, image.DicomImage)
+    assert np.array_equal(image.load(io.BytesIO(data)).array, img.array)
+    # RescaleSlope 1 / RescaleIntercept 0 are present: pydicom's apply_rescale yields float64 (core/image.py:374)
+    assert img.array.dtype == np.float64 and np.array_equal(img.array, tail.astype(np.float64))
+    assert img.dpmm == pytest.approx(1 / ps * sid / 1000.0) and img.sid == sid and img.sad == 1000.0
+    assert (img.cax.x, img.cax.y) == (639.5, 639.5)
+    lin = image.LinacDicomImage(str(p))
+    assert (lin.gantry_angle, lin.collimator_angle, lin.couch_angle) == (0.0, 0.0, 0.0)
+    f16 = image.frame_u16(img)
+    assert f16.dtype == np.uint16 and np.array_equal(f16, tail)
+
+
+@pytest.mark.parametrize("explicit,preamble", [(True, True), (False, True), (False, False)])
+def test_synthetic_dicom_tags(tmp_path, explicit, preamble):
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 60000, (48, 64)).astype(np.uint16)
+    p = write_dicom(tmp_path / "x.dcm", a, pixel_spacing_mm=0.392, sid=1500.0, gantry=270.04, coll=12.0, couch=359.96, slope=2.5,
+                    intercept=-100.0, explicit=explicit, preamble=preamble, translation=[1.0, -2.0, -500.0])
+    assert dicom.is_dicom(p)
+    img = image.LinacDicomImage(p, axes_precision=1)
+    assert img.shape == (48, 64)
+    np.testing.assert_array_equal(img.array, a.astype(np.float64) * 2.5 - 100.0)      # pydicom apply_rescale
+    assert img.dpmm == pytest.approx(1 / 0.392 * 1.5)
+    assert (img.gantry_angle, img.collimator_angle, img.couch_angle) == (270.0, 12.0, 0.0)   # 359.96 -> 360.0 -> 0 (core/image.py:1700-1730)
+    assert img.cax.x == pytest.approx(img.center.x - 1.0 * img.dpmm / 1.5) and img.cax.y == pytest.approx(img.center.y - 2.0 * img.dpmm / 1.5)
+    # overrides win over tags
+    assert image.LinacDicomImage(p, gantry=10.0).gantry_angle == 10.0
+    # raw pixels: no rescale
+    raw = image.DicomImage(p, raw_pixels=True)
+    assert raw.array.dtype == np.uint16 and np.array_equal(raw.array, a)
+    # the device pipelines take the stored integers of an untouched rescaled image
+    assert np.array_equal(image.frame_u16(img), a)
+    img.array = img.array * 1.0001   # no longer the rescale of the stored values and not integer valued
+    with pytest.raises(ValueError):
+        image.frame_u16(img)
+
+
+def test_sign_flip_and_forced_inversion(tmp_path):
+    a = np.arange(30 * 40, dtype=np.uint16).reshape(30, 40) * 7 + 11
+    p = write_dicom(tmp_path / "neg.dcm", a, sign=-1, slope=1.0, intercept=0.0)
+    img = image.DicomImage(p)
+    exp = a.astype(np.float64)
+    exp = exp.max() - exp + exp.min()
+    np.testing.assert_array_equal(img.array, exp)                   # core/image.py:381-388
+    np.testing.assert_array_equal(image.DicomImage(p, invert_pixels=False).array, a.astype(np.float64))
+    f = image.frame_u16(img)
+    assert f.dtype == np.uint16 and np.array_equal(f, (int(a.max()) + int(a.min()) - a.astype(np.int64)).astype(np.uint16))
+    # without rescale tags the dtype is preserved
+    p2 = write_dicom(tmp_path / "plain.dcm", a)
+    assert image.DicomImage(p2).array.dtype == np.uint16
+
+
+def test_load_dispatch_and_errors(tmp_path):
+    a = (np.random.default_rng(1).random((20, 30)) * 1000).astype(np.uint16)
+    assert isinstance(image.load(a, dpi=100), image.ArrayImage)
+    with pytest.raises(TypeError):
+        image.load(str(tmp_path))                                    # a directory: neither DICOM, image nor array
+    with pytest.raises(FileExistsError):
+        image.DicomImage(str(tmp_path / "missing.dcm"))              # core/image.py:483
+    bad = tmp_path / "bad.dcm"
+    bad.write_bytes(b"\x00" * 256)
+    assert not dicom.is_dicom(str(bad))
+    # TIFF / PNG through Pillow -> FileImage (core/image.py:1733-1812)
+    from PIL import Image as pImage
+
+    tif = tmp_path / "f.tif"
+    pImage.fromarray(a).save(tif, dpi=(72, 72))
+    img = image.load(str(tif), sid=1500)
+    assert isinstance(img, image.FileImage) and np.array_equal(img.array, a)
+    assert img.dpi == pytest.approx(72 * 1.5) and img.dpmm == pytest.approx(72 * 1.5 / 25.4)
+    png = tmp_path / "f.png"
+    pImage.fromarray(np.stack([a >> 8] * 3, axis=-1).astype(np.uint8)).save(png)
+    rgb = image.load(str(png), dpi=50)
+    assert rgb.array.ndim == 2 and rgb.dpi == 50
+
+
+def test_winston_lutz_2d_reads_axis_tags(tmp_path):
+    """WinstonLutz2D(path) must be a LinacDicomImage like the reference's (winston_lutz.py:629, 1137)."""
+    from pylinac_b200 import winston_lutz as wl
+
+    a = np.zeros((64, 64), np.uint16)
+    p = write_dicom(tmp_path / "wl.dcm", a, gantry=90.0, coll=0.0, couch=45.0, slope=1.0, intercept=0.0)
+    w = wl.WinstonLutz2D(p)
+    assert (w.gantry_angle, w.collimator_angle, w.couch_angle) == (90.0, 0.0, 45.0)
+    w = wl.WinstonLutz2D(p, gantry=180.0)
+    assert (w.gantry_angle, w.couch_angle) == (180.0, 45.0)
+    assert w._frame_u16().dtype == np.uint16          # identity rescale -> float64 array -> stored integers

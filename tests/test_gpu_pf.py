@@ -381,3 +381,104 @@ def test_pf_host_pipeline_staged_and_direct_result_paths_agree():
         m = int(s_direct["n_meas"][i])
         for k in m_direct.dtype.names:
             np.testing.assert_array_equal(m_direct[k][i, :m], m_staged[k][i, :m], err_msg=k)
+
+
+@pytest.mark.parametrize("name", list(_leafband_cases()))
+def test_two_kernel_window_path_equals_per_window_kernel(name):
+    """The default window path (k_pf_win_medians + k_pf_win_fwxm, pf_windows2.cu) must reproduce the single per-window kernel
+    (k_pf_windows_fast, pinned to the reference by the golden tests) bit for bit, on frames it covers and on frames it declines."""
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    frames, dpmm, kw = _leafband_cases()[name]
+    ctx = nat.Context.default()
+    try:
+        ctx.set_option(nat.OPT_PF_WIN2, 0)
+        old = pf.analyze_batch(frames, dpmm, **kw)
+        ctx.set_option(nat.OPT_PF_WIN2, 1)
+        new = pf.analyze_batch(frames, dpmm, **kw)
+    finally:
+        ctx.set_option(nat.OPT_PF_WIN2, 1)
+    for k in old.summary.dtype.names:
+        np.testing.assert_array_equal(old.summary[k], new.summary[k], err_msg=k)
+    for i in range(len(frames)):
+        if int(old.summary["status"][i]) == 0:
+            m = int(old.summary["n_meas"][i])
+            assert m > 0
+            for k in old.meas.dtype.names:
+                np.testing.assert_array_equal(old.meas[k][i, :m], new.meas[k][i, :m], err_msg=k)
+
+
+def test_two_kernel_window_path_runs_for_the_benchmark_frames():
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    ctx = nat.Context.default()
+    frames = np.stack([synth.bench_pf_frame(i) for i in range(60, 76)])
+    b = nat.Batch.upload(ctx, frames)
+    try:
+        st = nat.pf_bench_stages(ctx, b, pf.make_params(2.56, frames.shape[1:]), 2)
+    finally:
+        b.free()
+    assert st["k_pf_win_medians"] > 5 * st["k_pf_windows_fast"] > 0, st
+
+
+def test_pf_mixed_batch_matches_the_oracle_frame_by_frame():
+    """Certifiable, noisy (salt-and-pepper -> _check_for_noise median passes), inverted, left-right, flat and pattern-free frames
+    interleaved in ONE batch: every frame must equal the oracle's result for that frame alone, whichever front end (certified
+    stream kernel or exact per-frame re-run) and whichever window kernel ended up processing it."""
+    from oracle import pf_oracle, synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    rng = np.random.default_rng(77)
+    base = [synth.bench_pf_frame(i) for i in range(300, 312)]
+    frames, kinds = [], []
+    for i, a in enumerate(base):
+        kind = ("clean", "noisy", "inverted", "clean", "noisy2", "left_right", "flat", "clean", "noise_only", "noisy", "clean", "inverted")[i]
+        if kind == "noisy":          # hot pixels: max > 1.25 p99.5 -> one median pass (picketfence.py:221-238)
+            a = (a // 2).copy()
+            idx = rng.integers(0, a.size, 40)
+            a.ravel()[idx] = 65535
+        elif kind == "noisy2":       # a 3 x 3 block of hot pixels survives two 3x3 median passes: three passes in the reference
+            a = (a // 2).copy()
+            a[500:503, 100:103] = 65535
+            a[40, 40] = 65535
+        elif kind == "inverted":
+            a = (int(a.max()) - a.astype(np.int64)).astype(np.uint16)
+        elif kind == "left_right":
+            a = np.ascontiguousarray(a.T)
+        elif kind == "flat":
+            a = np.full_like(a, 777)
+        elif kind == "noise_only":
+            a = rng.integers(1000, 1100, a.shape).astype(np.uint16)
+        frames.append(a)
+        kinds.append(kind)
+    frames = np.stack(frames)
+    ctx = nat.Context.default()
+    redone0 = ctx.counter(nat.CTR_PF_REDONE_FRAMES)
+    res = pf.analyze_batch(frames, 2.56)
+    redone = ctx.counter(nat.CTR_PF_REDONE_FRAMES) - redone0
+    assert 0 < redone < len(frames), f"per-frame fallback expected for the noisy frames only, {redone} frames were re-run"
+    n_noise = 0
+    for i, kind in enumerate(kinds):
+        r = res[i]
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                o = pf_oracle.pf_analyze(frames[i], 2.56)
+        except (ValueError, IndexError):
+            assert r.status != 0, (i, kind)
+            continue
+        assert r.status == 0, (i, kind, r.status)
+        n_noise += int(o["noise_median_passes"] > 0)
+        assert int(r.s["noise_median_passes"]) == o["noise_median_passes"], (i, kind)
+        assert int(r.s["orientation"]) == int(o["orientation"])
+        assert sorted(int(v) for v in r.picket_idx) == sorted(int(v) for v in o["picket_idx"]), (i, kind)
+        assert int(r.s["n_meas"]) == o["n_meas"], (i, kind)
+        assert np.array_equal(r.m["leaf_num"], o["meas_leaf"]) and np.array_equal(r.m["picket"], o["meas_picket"])
+        np.testing.assert_allclose(r.m["position"][:, :1], o["meas_position"], rtol=0, atol=POS_TOL_PX, err_msg=f"{i} {kind}")
+        np.testing.assert_allclose(r.m["error"][:, :1], o["meas_error"], rtol=0, atol=ERR_TOL_MM, err_msg=f"{i} {kind}")
+        np.testing.assert_allclose(float(r.s["max_error_mm"]), float(o["max_error"]), rtol=0, atol=ERR_TOL_MM)
+    assert n_noise >= 2, "the mixed batch should contain frames that trigger the reference's noise filter"
