@@ -429,6 +429,37 @@ typedef struct { /* one per frame */
 
 int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_wl_params* p, epid_wl_result* results);
 
+/* ----------------------------------------------------------------------------------------- SizedDiskRegion / SizedDiskLocator
+ * img.compute(SizedDiskLocator(...)) (metrics/image.py:402-667): sample = image[window] around the expected position, inverted,
+ * stretched to [0, 1]; find_features (metrics/utils.py:66-190): <= 50 thresholds { label (4-connectivity), clear_border, regionprops,
+ * is_right_size_bb / is_round / is_right_circumference / is_symmetric / is_solid } -> weighted centroids, de-duplicated by the
+ * minimum separation, until max_number points are found.  One result per uint16 frame; status values are EPID_WL_*. */
+#define EPID_DISK_MAX 8
+typedef struct {
+    double dpmm;
+    double expected_x, expected_y;     /* pixels, image coordinates (the caller has applied from_center / the physical-units quirks) */
+    double window_w, window_h;         /* search window, pixels */
+    double radius_mm, tolerance_mm;
+    double min_separation_px;
+    int32_t invert;
+    int32_t max_number;
+} epid_disk_params;
+
+typedef struct {
+    int32_t status;
+    int32_t n_points;                  /* detected disks (image coordinates x[], y[]) */
+    int32_t n_regions;                 /* regions that passed every condition at the LAST threshold visited (what find_features returns) */
+    int32_t passes;
+    int32_t left, top;                 /* offsets of the sample window */
+    double x[EPID_DISK_MAX], y[EPID_DISK_MAX];
+    /* regionprops of those regions, sample (window) coordinates */
+    double r_area[EPID_DISK_MAX], r_filled_area[EPID_DISK_MAX], r_perimeter[EPID_DISK_MAX], r_convex_area[EPID_DISK_MAX];
+    double r_centroid_y[EPID_DISK_MAX], r_centroid_x[EPID_DISK_MAX], r_wcentroid_y[EPID_DISK_MAX], r_wcentroid_x[EPID_DISK_MAX];
+    int32_t r_bbox[EPID_DISK_MAX][4];  /* min_row, min_col, max_row, max_col (half-open) */
+} epid_disk_result;
+
+int32_t epid_disk_locate(epid_ctx* ctx, const epid_batch* frames, const epid_disk_params* p, epid_disk_result* results);
+
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
  * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */

@@ -170,6 +170,22 @@ def stretch(array: np.ndarray, min: int = 0, max: int = 1) -> np.ndarray:  # :14
     return ground(scaled, value=min)
 
 
+def convert_to_dtype(array: np.ndarray, dtype) -> np.ndarray:  # :172-198
+    """Relative-range dtype conversion: float input is stretched to [0, 1] (native ground / normalize), integer input is divided by
+    its dtype's maximum; the result is ``relative * (max - min) - max - 1`` of the new dtype, cast (the reference's formula,
+    including its offset).  The affine map and the cast are one elementwise host pass over the already host-resident array."""
+    a = np.asarray(array)
+    if a.size == 0:
+        raise ValueError("Array must not be empty")
+    old = get_dtype_info(a.dtype)
+    if isinstance(old, np.finfo):
+        relative = stretch(a, min=0, max=1)
+    else:
+        relative = a.astype(float) / old.max
+    new = get_dtype_info(dtype)
+    return np.array(relative * (new.max - new.min) - new.max - 1, dtype=dtype)
+
+
 def get_dtype_info(dtype):  # :201-207
     try:
         return np.iinfo(dtype)

@@ -122,3 +122,70 @@ class Line:
         numerator = np.sqrt(np.sum(np.power(np.cross((lp2 - lp1), (lp1 - point)), 2)))
         denominator = np.sqrt(np.sum(np.power(lp2 - lp1, 2)))
         return numerator / denominator
+
+
+class Circle:
+    """core/geometry.py:213-405 (centre, radius, area, diameter, as_dict; plotting is out of scope)."""
+
+    def __init__(self, center_point=None, radius: float | None = None):
+        if center_point is None:
+            center_point = Point()
+        elif isinstance(center_point, Point) or (isinstance(center_point, Iterable) and not isinstance(center_point, (str, bytes))):
+            center_point = Point(center_point)
+        else:
+            raise TypeError("Circle center must be of type Point or iterable")
+        self.center = center_point
+        self.radius = radius
+
+    @property
+    def area(self) -> float:
+        return math.pi * self.radius**2
+
+    @property
+    def diameter(self) -> float:
+        return self.radius * 2
+
+    def as_dict(self) -> dict:
+        return {"center_x": self.center.x, "center_y": self.center.y, "diameter": self.diameter}
+
+
+class Rectangle:
+    """core/geometry.py:632-723.  Image coordinates (+x right, +y down); ``rotation`` in degrees, positive = clockwise on screen.
+    ``vertices`` = [TL, TR, BR, BL] of the UNROTATED rectangle, rotated about the origin and then translated to ``center`` (the
+    reference composes skimage's ``EuclideanTransform(rotation, translation)``: x' = x cos - y sin + tx, y' = x sin + y cos + ty)."""
+
+    def __init__(self, width: float, height: float, center, rotation: float = 0.0):
+        if not width > 0 or not height > 0:
+            raise ValueError("Rectangle width and height must be positive")
+        self.width = width
+        self.height = height
+        self.center = Point(center)
+        self.rotation = rotation
+
+    @property
+    def area(self) -> float:
+        return self.width * self.height
+
+    @property
+    def vertices(self) -> list[Point]:
+        half = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]]) @ np.diag((self.width, self.height)) / 2
+        a = np.deg2rad(self.rotation)
+        rot = np.array([[math.cos(a), -math.sin(a)], [math.sin(a), math.cos(a)]])
+        pts = half @ rot.T + self.center.as_array(("x", "y"))
+        return [Point(p) for p in pts]
+
+    @property
+    def tl_corner(self) -> Point:
+        return self.vertices[0]
+
+    @property
+    def tr_corner(self) -> Point:
+        return self.vertices[1]
+
+    @property
+    def br_corner(self) -> Point:
+        return self.vertices[2]
+
+    @property
+    def bl_corner(self) -> Point:
+        return self.vertices[3]

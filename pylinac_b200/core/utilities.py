@@ -10,6 +10,7 @@ from typing import Generic, TypeVar
 from pydantic import BaseModel, ConfigDict, Field
 
 from ..version import __version__
+from .warnings import WarningCollectorMixin
 
 
 def convert_to_enum(value, enum: type[Enum]) -> Enum:
@@ -31,7 +32,7 @@ class ResultBase(BaseModel):
 T = TypeVar("T")
 
 
-class ResultsDataMixin(Generic[T]):
+class ResultsDataMixin(Generic[T], WarningCollectorMixin):
     """core/utilities.py:72-110"""
 
     @abstractmethod

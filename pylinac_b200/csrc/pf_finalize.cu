@@ -50,6 +50,9 @@ k_pf_finalize(const PfConst* __restrict__ cc, PfFrame* fr, const PfWin* __restri
     epid_pf_summary& S = summ[fi];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int H = c.H, W = c.W;
+    // every word of the row is defined, whatever the frame's fate: rows of different runs / pipelines compare equal byte for byte
+    for (int k = tid; k < (int)(sizeof(epid_pf_summary) / 4); k += FIN_THREADS) reinterpret_cast<uint32_t*>(&S)[k] = 0u;
+    __syncthreads();
     if (tid == 0) {
         S.status = f.status;
         S.orientation = f.orientation;

@@ -99,6 +99,7 @@ k_pf_windows_fast(const PfConst* __restrict__ cc, const FrameRef* __restrict__ f
     const int fi = blockIdx.y;
     const PfConst& c = *cc;
     PfFrame& f = fr[fi];
+    if (f.win2) return;          // the two-kernel window path owns this frame (pf_windows2.cu)
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = c.H, W = c.W;
     const double dpmm = c.p.dpmm;

@@ -44,6 +44,9 @@ struct W2Geo {
     int nvmax[WA_GMAX + 1];     // widest band (16-byte vectors per row) when pickets are taken g at a time
 };
 
+// LDGSTS = false: one cp.async.bulk (TMA) per band row, completion on an mbarrier.  LDGSTS = true: 16-byte cp.async per lane
+// (LDGSTS), completion by cp.async.wait_group -- kept for comparison (EPID_WA_LOADER=1).
+template <bool LDGSTS>
 __global__ void __launch_bounds__(WA_WARPS * 32, 2)
 k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWinRec* __restrict__ recs) {
     extern __shared__ __align__(128) unsigned char smraw[];          // WA_WARPS x 2 slots
@@ -165,6 +168,19 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
         const int nvec = s_gnv[G][g], cs = s_gcs[G][g];
         if (nr <= 0) return;                         // nothing to copy: the consumer does not wait either
         const int RS = wa_row_stride_bytes(nvec);
+        if (LDGSTS) {
+            const int nv_tot = nr * nvec;
+            const float inv_nvec = 1.0f / (float)nvec;
+            for (int idx = lane; idx < nv_tot; idx += 32) {
+                const int r = (int)(((float)idx + 0.5f) * inv_nvec), v = idx - r * nvec;
+                int row = b0 + r - sag;
+                if (sag) { row %= H; if (row < 0) row += H; }
+                const uint32_t dst = smem_u32(slot0 + (size_t)sl * WA_SLOT + (size_t)r * RS + (size_t)v * 16);
+                const void* src = frf.origin + ((ptrdiff_t)row * frf.pitch + cs + v * 8);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            }
+            return;
+        }
         const uint32_t bar = sl ? bar1 : bar0;
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)nr * (uint32_t)nvec * 16u);
         __syncwarp();
@@ -181,11 +197,13 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
     uint32_t ph0 = 0, ph1 = 0;
     int cur = 0, li = 0, li_next = 0;
     if (task < ntasks) { li = leaf_of(task, 0); issue(task, li, 0); }
+    if (LDGSTS) asm volatile("cp.async.commit_group;" ::: "memory");
     for (; task < ntasks; task += tstride, cur ^= 1, li = li_next) {
         if (task + tstride < ntasks) {
             li_next = leaf_of(task + tstride, li);
             issue(task + tstride, li_next, cur ^ 1);     // that slot was released by the __syncwarp at the end of the previous iteration
         }
+        if (LDGSTS) asm volatile("cp.async.commit_group;" ::: "memory");      // (possibly empty) group of the next task
         const int G = s_lg[li], g = task - s_toff[li];
         const int nr = s_nr[li];
         const int nvec = s_gnv[G][g], cs = s_gcs[G][g];
@@ -197,7 +215,8 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
             lrec[lane].hdr = ((uint32_t)(uint16_t)(short)max(min(a1 - a0, 32767), -32768)) | ((uint32_t)(uint16_t)(short)nr << 16);
         }
         if (nr <= 0) { __syncwarp(); continue; }
-        if (cur) { mbar_wait(bar1, ph1); ph1 ^= 1u; } else { mbar_wait(bar0, ph0); ph0 ^= 1u; }
+        if (LDGSTS) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); }      // everything but the newest group has landed
+        else if (cur) { mbar_wait(bar1, ph1); ph1 ^= 1u; } else { mbar_wait(bar0, ph0); ph0 ^= 1u; }
         const unsigned char* band = slot0 + (size_t)cur * WA_SLOT;
         // ---- P1: (row, picket) sums on the raw pixels
         const int ntk = nr * Gn;
@@ -319,24 +338,11 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     uint32_t* buf = s_buf[wid];
     const int w = wbase + lane;
     const bool active = w < total;
-    // ---- numerators of the warp's 32 windows -> [row word][window]; row extremes reduced on the way
-    int my_nc = 0, my_nr = 0;
-    uint32_t my_vmx = 0, my_vmn = 0xffffu;
-    int nr_all = 0;
-    for (int k = 0; k < 32 && wbase + k < total; k++) {
-        const PfWinRec& rc = frecs[wbase + k];
-        const uint32_t hdr = rc.hdr;
-        const int nc_k = (int)(short)(hdr & 0xffffu), nr_k = (int)(short)(hdr >> 16);
-        unsigned long long nv = 0;
-        uint32_t e = 0x0000ffffu;
-        if (nc_k > 0 && lane < nr_k) { nv = rc.num[lane]; e = rc.ext[lane]; }
-        buf[(2 * lane) * WB_ST + k] = (uint32_t)nv;
-        buf[(2 * lane + 1) * WB_ST + k] = (uint32_t)(nv >> 32);
-        const uint32_t vmx = __reduce_max_sync(0xffffffffu, e >> 16), vmn = __reduce_min_sync(0xffffffffu, e & 0xffffu);
-        if (lane == k) { my_nc = nc_k; my_nr = nr_k; my_vmx = vmx; my_vmn = vmn; }
-        nr_all = max(nr_all, nr_k);
-    }
-    __syncwarp();
+    // ---- this thread's window: header, row extremes and variance numerators straight into registers (independent loads, all
+    //      in flight at once; lanes read records 648 bytes apart)
+    const PfWinRec& rec = frecs[active ? w : total - 1];
+    const uint32_t hdr = rec.hdr;
+    const int my_nc = (int)(short)(hdr & 0xffffu), my_nr = (int)(short)(hdr >> 16);
     int li = 0, pk = 0;
     if (active) { li = w / np; pk = w - li * np; }
     PfWin& out = wins[((size_t)fi * PF_L + li) * PF_P + pk];
@@ -348,13 +354,23 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
             run = true;
         }
     }
+    const int nrr = run ? my_nr : 0;
+    const int nr_all = __reduce_max_sync(0xffffffffu, nrr);
     // ---- _is_mlc_peak_in_window (picketfence.py:847-857): std along travel per row = sqrt(num) / (nc * D)
     unsigned long long kmax = 0, ka = 0, kb = 0;
+    uint32_t my_vmx = 0, my_vmn = 0xffffu;
     {
-        auto key = [&](int i) { return (unsigned long long)buf[(2 * i) * WB_ST + lane] | ((unsigned long long)buf[(2 * i + 1) * WB_ST + lane] << 32); };
-        const int nrr = run ? my_nr : 0;
+        auto key = [&](int i) { return rec.num[i]; };
         if (nr_all <= 16) rank_keys<16>(key, nrr, kmax, ka, kb);       // warp-uniform choice
         else rank_keys<32>(key, nrr, kmax, ka, kb);
+#pragma unroll
+        for (int i = 0; i < PF_W2_NRW; i++) {
+            if (i < nrr) {
+                const uint32_t e = rec.ext[i];
+                my_vmx = max(my_vmx, e >> 16);
+                my_vmn = min(my_vmn, e & 0xffffu);
+            }
+        }
     }
     if (run) {
         const double Dd = (double)f.D;
@@ -372,10 +388,16 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     }
     __syncwarp();
     // ---- median profiles of the 32 windows -> [sample][window]
-    for (int k = 0; k < 32 && wbase + k < total; k++) {
-        const PfWinRec& rc = frecs[wbase + k];
-        const int nc_k = __shfl_sync(0xffffffffu, my_nc, k);
-        for (int j = lane; j < nc_k; j += 32) buf[j * WB_ST + k] = rc.m2[j];
+    {
+        const int nc_all = __reduce_max_sync(0xffffffffu, run ? my_nc : 0);     // samples beyond a window's own nc are never read
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) {
+            const PfWinRec& rc = frecs[min(wbase + k, total - 1)];
+            const uint32_t v0 = rc.m2[lane];
+            const uint32_t v1 = nc_all > 32 ? rc.m2[lane + 32] : 0u;
+            buf[lane * WB_ST + k] = v0;
+            if (nc_all > 32) buf[(lane + 32) * WB_ST + k] = v1;
+        }
     }
     __syncwarp();
     if (run) {
@@ -392,10 +414,17 @@ size_t pf_win2_scratch_bytes(int n) { return sizeof(PfWinRec) * (size_t)n * PF_W
 int launch_pf_windows2(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWinRec* recs, PfWin* wins,
                        int n, PfTimers* tm) {
     const size_t smem = (size_t)WA_WARPS * 2 * WA_SLOT;
-    EPID_SMEM_OPT_IN(ctx, k_pf_win_medians, smem);
+    EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<false>, smem);
     static int gx = 0;
     if (gx == 0) { const char* e = getenv("EPID_WA_GRID"); gx = e ? atoi(e) : WA_GRID_X; if (gx < 1 || gx > 64) gx = WA_GRID_X; }
-    k_pf_win_medians<<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs);
+    static int loader = -1;
+    if (loader < 0) { const char* e = getenv("EPID_WA_LOADER"); loader = e ? atoi(e) : 0; }
+    if (loader == 1) {
+        EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<true>, smem);
+        k_pf_win_medians<true><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs);
+    } else {
+        k_pf_win_medians<false><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs);
+    }
     ctx->launches++;
     if (tm) { int rc = tm->mark(stream, PF_STAGE_WIN_MEDIANS); if (rc != EPID_OK) return rc; }
     k_pf_win_fwxm<<<dim3(PF_W2_WCAP / WB_THREADS, n), WB_THREADS, 0, stream>>>(cst, fr, recs, wins);

@@ -45,6 +45,9 @@ struct WlConst {
     int H, W;
     size_t field_tile_cap;             // bytes available for the field tile in k_wl_field's dynamic shared memory
     int win_edge;                      // largest BB window edge of this launch: the union-find forest holds win_edge^2 ints
+    // stand-alone disk locator (SizedDiskRegion / SizedDiskLocator, metrics/image.py:402-667): the BB search of k_wl_bb on a raw frame
+    int loc_mode;                      // 0: Winston-Lutz flow, 1: epid_disk_locate
+    epid_disk_params loc;
 };
 
 struct WlFrame {
@@ -452,9 +455,11 @@ __device__ __forceinline__ void wl_union(int* parent, int a, int b) {
 
 __global__ void __launch_bounds__(WL_THREADS)
 k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const WlFrame* __restrict__ wf, double* __restrict__ samples,
-        unsigned short* __restrict__ cid_all, WlComp* __restrict__ comp_all, epid_wl_result* __restrict__ res) {
+        unsigned short* __restrict__ cid_all, WlComp* __restrict__ comp_all, epid_wl_result* __restrict__ res,
+        epid_disk_result* __restrict__ dres) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int s_i[16];
+    __shared__ int s_added;
     __shared__ double s_d[8 + 2 * WL_WARPS];
     __shared__ double s_pts[2 * WL_MAXPTS];
     __shared__ int s_hist50[50];
@@ -462,7 +467,10 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     const WlConst& c = *cc;
     const int fi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const WlFrame F = wf[fi];
-    epid_wl_result& R = res[fi];
+    const bool loc = c.loc_mode != 0;
+    epid_wl_result r_unused;
+    epid_wl_result& R = loc ? r_unused : res[fi];      // the locator reports through dres
+    if (loc && tid == 0) { dres[fi].status = F.status; dres[fi].n_points = 0; dres[fi].n_regions = 0; dres[fi].passes = 0; }
     if (tid == 0) {
         R.status = F.status;
         R.inverted = F.flip;
@@ -478,13 +486,19 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     const int h = F.h, w = F.w, crop = F.crop;
     const double dpmm = c.p.dpmm, Dd = (double)F.D;
     // ---- SizedDiskLocator.from_center_physical((0, 0), window 40 + bb) (metrics/image.py:564-612)
-    const double bb_d = c.p.bb_size_mm;
-    const double win = (40 + bb_d) * dpmm;
-    const double ex = (double)w / 2, ey = (double)h / 2;
-    const int left = max((int)floor(ex - win / 2), 0), right = min((int)ceil(ex + win / 2), w);
-    const int top = max((int)floor(ey - win / 2), 0), bottom = min((int)ceil(ey + win / 2), h);
+    const double bb_d = loc ? 2 * c.loc.radius_mm : c.p.bb_size_mm;
+    const double winx = loc ? c.loc.window_w : (40 + bb_d) * dpmm, winy = loc ? c.loc.window_h : (40 + bb_d) * dpmm;
+    const double ex = loc ? c.loc.expected_x : (double)w / 2, ey = loc ? c.loc.expected_y : (double)h / 2;
+    // metrics/image.py:583-591: floor / ceil bounds, the slice clips at the image edge
+    const int left = min(max((int)floor(ex - winx / 2), 0), w), right = max(min((int)ceil(ex + winx / 2), w), 0);
+    const int top = min(max((int)floor(ey - winy / 2), 0), h), bottom = max(min((int)ceil(ey + winy / 2), h), 0);
     const int wh = bottom - top, ww = right - left;
-    if (wh < 3 || ww < 3 || wh > c.win_edge || ww > c.win_edge) { if (tid == 0) R.status = EPID_WL_CAPACITY; return; }
+    if (loc && tid == 0) { dres[fi].left = left; dres[fi].top = top; }
+    if (loc && (wh <= 0 || ww <= 0)) { if (tid == 0) dres[fi].status = EPID_WL_NO_BB; return; }      // empty sample
+    if (wh < 3 || ww < 3 || wh > c.win_edge || ww > c.win_edge) {
+        if (tid == 0) { R.status = EPID_WL_CAPACITY; if (loc) dres[fi].status = (wh < 3 || ww < 3) ? EPID_WL_NO_BB : EPID_WL_CAPACITY; }
+        return;
+    }
     const int npx = wh * ww;
     int* parent = reinterpret_cast<int*>(smraw);                         // npx ints (shared): union-find forest of the window
     unsigned short* cid = cid_all + (size_t)fi * WL_MAXWIN * WL_MAXWIN;  // component id of a root pixel (HBM scratch, L2 resident)
@@ -507,9 +521,9 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     gmin = (uint32_t)s_i[0]; gmax = (uint32_t)s_i[8];
     for (int k = 1; k < WL_WARPS; k++) { gmin = min(gmin, (uint32_t)s_i[k]); gmax = max(gmax, (uint32_t)s_i[8 + k]); }
     __syncthreads();
-    if (gmin == gmax) { if (tid == 0) R.status = EPID_WL_NO_BB; return; }     // stretch divides by zero, nothing is found
+    if (gmin == gmax) { if (tid == 0) { R.status = EPID_WL_NO_BB; if (loc) dres[fi].status = EPID_WL_NO_BB; } return; }     // stretch divides by zero, nothing is found
     const double amin = (double)gmin / Dd, amax = (double)gmax / Dd;
-    const bool inv = !c.p.low_density_bb;
+    const bool inv = loc ? (c.loc.invert != 0) : !c.p.low_density_bb;
     // invert: b = -a + max + min (decreasing); stretch: (b - bmin) / (bmax - bmin) * 1, then ground with value 0
     const double bmin = inv ? (-amax + amax) + amin : amin, bmax = inv ? (-amin + amax) + amin : amax;
     const double cmax = bmax - bmin;
@@ -527,18 +541,22 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     const double radius_mm = bb_d / 2;
     // _calculate_bb_tolerance: np.interp(bb_diameter, (1.5, 30), (2, 4)) (winston_lutz.py:1062-1067)
     double tol;
-    if (bb_d <= 1.5) tol = 2.0;
+    if (loc) tol = c.loc.tolerance_mm;
+    else if (bb_d <= 1.5) tol = 2.0;
     else if (bb_d >= 30.0) tol = 4.0;
     else { const double slope = (4.0 - 2.0) / (30.0 - 1.5); tol = slope * (bb_d - 1.5) + 2.0; }
+    const int max_number = loc ? min(max(c.loc.max_number, 1), WL_MAXPTS) : 1;
+    const double min_sep = loc ? c.loc.min_separation_px : 5.0 * dpmm;      // deduplicate_points_and_boundaries (metrics/utils.py:14-37)
     const double PI = 3.141592653589793;
     const double larger_area = PI * ((radius_mm + tol) * (radius_mm + tol));
     const double smaller_area = fmax(PI * ((radius_mm - tol) * (radius_mm - tol)), 2.0);
     const double imin = 0.0, imax = 1.0;
     const double step = (imax - imin) / 50;
     double cutoff = imin + step;
-    int npts = 0, passes = 0, fatal = 0;
-    while (cutoff <= imax && npts < 1) {      // max_number = 1
+    int npts = 0, passes = 0, fatal = 0, nreg = 0;
+    while (cutoff <= imax && npts < max_number) {
         passes++;
+        nreg = 0;                              // find_features returns the regions of the LAST threshold visited
         // -- measure.label(sample > cutoff, connectivity=1): union-find, roots = first pixel in raster order
         for (int i = tid; i < npx; i += WL_THREADS) parent[i] = smp[i] > cutoff ? i : -1;
         __syncthreads();
@@ -592,7 +610,7 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
         }
         __syncthreads();
         // -- regions in label order through the detection conditions (metrics/features.py:7-68)
-        for (int id = 0; id < ncomp && npts < WL_MAXPTS; id++) {
+        for (int id = 0; id < ncomp; id++) {
             if (comp->border[id]) continue;
             const int by0 = comp->y0[id], by1 = comp->y1[id] + 1, bx0 = comp->x0[id], bx1 = comp->x1[id] + 1;
             const int bh = by1 - by0, bw = bx1 - bx0;
@@ -719,7 +737,10 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             __syncthreads();
             if (!((double)comp->area[id] / (double)convex > 0.9)) continue;
             // -- accepted: centroid_weighted (local moments of the stretched sample over the region, + bbox origin)
+            if (tid < 4) s_lvl[tid] = 0;      // (the hull levels are no longer needed) 64-bit accumulators of the unweighted moments
+            __syncthreads();
             double sw = 0, swr = 0, swc = 0;
+            unsigned long long sr_i = 0, sc_i = 0;      // unweighted first moments (regionprops.centroid)
             for (int i = tid; i < bh * bw; i += WL_THREADS) {
                 const int r = i / bw, cidx = i - r * bw;
                 if (tile2[(r + 1) * tw + (cidx + 1)] != 1) continue;
@@ -727,7 +748,11 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
                 sw += wv;
                 swr += (double)r * wv;
                 swc += (double)cidx * wv;
+                sr_i += (unsigned long long)r;
+                sc_i += (unsigned long long)cidx;
             }
+            sr_i = warp_sum(sr_i); sc_i = warp_sum(sc_i);
+            if (loc && lane == 0) { atomicAdd(reinterpret_cast<unsigned long long*>(&s_lvl[0]), sr_i); atomicAdd(reinterpret_cast<unsigned long long*>(&s_lvl[2]), sc_i); }
             sw = warp_sum(sw); swr = warp_sum(swr); swc = warp_sum(swc);
             if (lane == 0) { s_d[8 + wid] = sw; s_d[8 + WL_WARPS + wid] = swr; }
             __syncthreads();
@@ -740,14 +765,47 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             for (int k = 0; k < WL_WARPS; k++) tc_ += s_d[8 + k];
             __syncthreads();
             if (tid == 0) {
-                s_pts[2 * npts] = tc_ / tw_ + (double)bx0;       // Point(x = weighted_centroid[1], y = weighted_centroid[0])
-                s_pts[2 * npts + 1] = tr_ / tw_ + (double)by0;
+                const double px = tc_ / tw_ + (double)bx0;       // Point(x = weighted_centroid[1], y = weighted_centroid[0])
+                const double py = tr_ / tw_ + (double)by0;
+                bool keep = npts < WL_MAXPTS;
+                for (int k = 0; k < npts && keep; k++) {
+                    const double dx = px - s_pts[2 * k], dy = py - s_pts[2 * k + 1];
+                    if (sqrt(dx * dx + dy * dy + 0.0) < min_sep) keep = false;
+                }
+                if (keep) { s_pts[2 * npts] = px; s_pts[2 * npts + 1] = py; }
+                s_added = keep ? 1 : 0;
+                if (loc && nreg < EPID_DISK_MAX) {
+                    epid_disk_result& D = dres[fi];
+                    const double area = (double)comp->area[id];
+                    D.r_area[nreg] = area;
+                    D.r_filled_area[nreg] = (double)filled;
+                    D.r_perimeter[nreg] = perim;
+                    D.r_convex_area[nreg] = (double)convex;
+                    D.r_bbox[nreg][0] = by0; D.r_bbox[nreg][1] = bx0; D.r_bbox[nreg][2] = by1; D.r_bbox[nreg][3] = bx1;
+                    D.r_centroid_y[nreg] = (double)*reinterpret_cast<unsigned long long*>(&s_lvl[0]) / area + (double)by0;
+                    D.r_centroid_x[nreg] = (double)*reinterpret_cast<unsigned long long*>(&s_lvl[2]) / area + (double)bx0;
+                    D.r_wcentroid_y[nreg] = py;
+                    D.r_wcentroid_x[nreg] = px;
+                }
             }
-            npts++;
+            nreg++;
+            __syncthreads();
+            npts += s_added;
             __syncthreads();
         }
         if (fatal) break;
         cutoff += step;
+    }
+    if (loc) {      // stand-alone locator: points in image coordinates + the regions of the last threshold
+        if (tid == 0) {
+            epid_disk_result& D = dres[fi];
+            D.passes = passes;
+            D.status = fatal ? EPID_WL_CAPACITY : EPID_WL_OK;
+            D.n_points = npts;
+            D.n_regions = min(nreg, EPID_DISK_MAX);
+            for (int k = 0; k < npts; k++) { D.x[k] = s_pts[2 * k] + (double)left; D.y[k] = s_pts[2 * k + 1] + (double)top; }
+        }
+        return;
     }
     // ---- matching and results (thread 0)
     if (tid == 0) {
@@ -841,12 +899,73 @@ extern "C" int32_t epid_wl2d_analyze(epid_ctx* ctx, const epid_batch* frames, co
         k_wl_bbox<<<dim3(WL_BBOX_PARTS, cn), WL_THREADS, 0, st>>>((const WlConst*)(base + o_cst), d_frames, (WlFrame*)(base + o_fr));
         k_wl_field<<<cn, WL_THREADS, hc.field_tile_cap, st>>>((const WlConst*)(base + o_cst), d_frames, (WlFrame*)(base + o_fr));
         k_wl_bb<<<cn, WL_THREADS, bb_smem, st>>>((const WlConst*)(base + o_cst), d_frames, (const WlFrame*)(base + o_fr), (double*)(base + o_smp),
-                                                 (unsigned short*)(base + o_cid), (WlComp*)(base + o_cmp), (epid_wl_result*)(base + o_res));
+                                                 (unsigned short*)(base + o_cid), (WlComp*)(base + o_cmp), (epid_wl_result*)(base + o_res), nullptr);
         ctx->launches += 5;
         EPID_CUDA(cudaGetLastError());
         EPID_CUDA(cudaMemcpyAsync(results + c0, base + o_res, sizeof(epid_wl_result) * cn, cudaMemcpyDeviceToHost, st));
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { set_error("Winston-Lutz pipeline failed: %s", cudaGetErrorString(e)); return EPID_ERR_CUDA; }
+    }
+    return EPID_OK;
+}
+
+namespace epid {
+__global__ void k_loc_init(WlFrame* wf, int n, int H, int W) {
+    // identity pixel map: the locator's sample is stretch(invert(image[window])) of the RAW frame (metrics/image.py:592-596)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    WlFrame f;
+    memset(&f, 0, sizeof(f));
+    f.status = EPID_WL_OK;
+    f.h = H; f.w = W;
+    f.mn = 0; f.D = 1;
+    wf[i] = f;
+}
+}  // namespace epid
+
+extern "C" int32_t epid_disk_locate(epid_ctx* ctx, const epid_batch* frames, const epid_disk_params* p, epid_disk_result* results) {
+    EPID_REQUIRE(ctx && frames && p && results, EPID_ERR_INVALID, "NULL argument");
+    EPID_REQUIRE(frames->dtype == EPID_U16, EPID_ERR_UNSUPPORTED, "disk locator frames must be uint16");
+    EPID_REQUIRE(p->dpmm > 0 && p->radius_mm > 0 && p->window_w > 0 && p->window_h > 0, EPID_ERR_INVALID, "dpmm, radius and window must be positive");
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    const int n = frames->n, H = frames->h, W = frames->w;
+    WlConst hc;
+    memset(&hc, 0, sizeof(hc));
+    hc.p.dpmm = p->dpmm;
+    hc.p.bb_size_mm = 2 * p->radius_mm;
+    hc.H = H;
+    hc.W = W;
+    hc.loc_mode = 1;
+    hc.loc = *p;
+    int win_edge = (int)ceil(p->window_w > p->window_h ? p->window_w : p->window_h) + 2;
+    if (win_edge > WL_MAXWIN) win_edge = WL_MAXWIN;      // larger windows report EPID_WL_CAPACITY per frame
+    if (win_edge < 8) win_edge = 8;
+    hc.win_edge = win_edge;
+    const int chunk = n < 256 ? n : 256;
+    size_t o = 0;
+    auto sz = [&](size_t b) { const size_t r = o; o += (b + 255) / 256 * 256; return r; };
+    const size_t o_cst = sz(sizeof(WlConst)), o_fr = sz(sizeof(WlFrame) * chunk), o_res = sz(sizeof(epid_disk_result) * chunk);
+    const size_t o_smp = sz(sizeof(double) * (size_t)chunk * WL_MAXWIN * WL_MAXWIN);
+    const size_t o_cid = sz(sizeof(unsigned short) * (size_t)chunk * WL_MAXWIN * WL_MAXWIN), o_cmp = sz(sizeof(WlComp) * (size_t)chunk);
+    int rc = ensure_scratch(ctx, o);
+    if (rc != EPID_OK) return rc;
+    char* base = (char*)ctx->scratch;
+    cudaStream_t st = ctx->stream;
+    const size_t bb_smem = sizeof(int) * (size_t)win_edge * win_edge + 2 * WL_TILE * WL_TILE + 64;
+    EPID_CUDA(cudaMemcpyAsync(base + o_cst, &hc, sizeof(hc), cudaMemcpyHostToDevice, st));
+    EPID_SMEM_OPT_IN(ctx, k_wl_bb, sizeof(int) * WL_MAXWIN * WL_MAXWIN + 2 * WL_TILE * WL_TILE + 64);
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int cn = n - c0 < chunk ? n - c0 : chunk;
+        const uint16_t* d_frames = (const uint16_t*)frames->dptr + (size_t)c0 * H * W;
+        EPID_CUDA(cudaMemsetAsync(base + o_res, 0, sizeof(epid_disk_result) * cn, st));
+        k_loc_init<<<(cn + 127) / 128, 128, 0, st>>>((WlFrame*)(base + o_fr), cn, H, W);
+        k_wl_bb<<<cn, WL_THREADS, bb_smem, st>>>((const WlConst*)(base + o_cst), d_frames, (const WlFrame*)(base + o_fr), (double*)(base + o_smp),
+                                                 (unsigned short*)(base + o_cid), (WlComp*)(base + o_cmp), nullptr, (epid_disk_result*)(base + o_res));
+        ctx->launches += 2;
+        EPID_CUDA(cudaGetLastError());
+        EPID_CUDA(cudaMemcpyAsync(results + c0, base + o_res, sizeof(epid_disk_result) * cn, cudaMemcpyDeviceToHost, st));
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("disk locator failed: %s", cudaGetErrorString(e)); return EPID_ERR_CUDA; }
     }
     return EPID_OK;
 }

@@ -20,6 +20,7 @@ import numpy as np
 from . import _native as nat
 from .core import image
 from .core.profile import Centering, Edge, FWXMProfilePhysical, InflectionDerivativeProfilePhysical, Normalization
+from .core.warnings import capture_warnings
 from .core.utilities import ResultBase, ResultsDataMixin, convert_to_enum
 from .metrics.profile import (CAXToLeftEdgeMetric, CAXToRightEdgeMetric, FlatnessDifferenceMetric, PenumbraLeftMetric,
                               PenumbraRightMetric, ProfileMetric, SymmetryPointDifferenceMetric)
@@ -48,6 +49,7 @@ class NotAnalyzed(Exception):
     pass
 
 
+@capture_warnings
 class FieldProfileAnalysis(ResultsDataMixin[FieldProfileResult]):
     """field_profile_analysis.py:90-368 -- same constructor / analyze() keywords."""
 

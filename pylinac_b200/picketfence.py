@@ -19,6 +19,7 @@ import numpy as np
 from . import _native as nat
 from .core import image
 from .core.geometry import Line, Point
+from .core.warnings import capture_warnings
 from .core.utilities import ResultBase, ResultsDataMixin, convert_to_enum
 
 LEFT_MLC_PREFIX = "A"
@@ -365,6 +366,7 @@ class _MLCValueView:
         return f"Leaf: {self.leaf_num}, Picket: {self.picket_num}"
 
 
+@capture_warnings
 class PicketFence(ResultsDataMixin[PFResult]):
     """picketfence.py:263-329, 439-562, 636-845, 1292-1363 -- same constructor / analyze() signature."""
 

@@ -16,6 +16,7 @@ import numpy as np
 from . import _native as nat
 from .core import image
 from .core.geometry import Line, Point
+from .core.warnings import capture_warnings
 from .core.utilities import ResultBase, ResultsDataMixin
 
 _STATUS_ERRORS = {
@@ -151,6 +152,7 @@ def analyze_batch(frames, dpmm: float, *, device: int | None = None, radius: flo
     return StarBatchResult(rows, tolerance)
 
 
+@capture_warnings
 class Starshot(ResultsDataMixin[StarshotResults]):
     """starshot.py:77-125, 230-304, 403-447 -- same constructor / analyze() signature."""
 

@@ -24,6 +24,7 @@ import numpy as np
 from . import _native as nat
 from .core import image
 from .core.geometry import Point, Vector
+from .core.warnings import capture_warnings
 from .core.utilities import ResultBase, ResultsDataMixin
 
 BB_ERROR_MESSAGE = (
@@ -181,6 +182,7 @@ def analyze_batch(frames, dpmm: float, *, device: int | None = None, bb_size_mm:
     return WLBatchResult(nat.wl2d_analyze(ctx, frames, params))
 
 
+@capture_warnings
 class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
     """winston_lutz.py:629-1231 -- same constructor keywords / analyze() signature for the single-image case."""
 
@@ -433,6 +435,7 @@ class _SetImage:
                                    field_cax=ser(self.field_cax))
 
 
+@capture_warnings
 class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
     """winston_lutz.py:1234-1611, 1614-1850, 2548-2609 -- a set of EPID images analysed as one batch on the GPU; the set-level
     quantities (3-D gantry isocentre, 2-D collimator / couch isocentres, BB shift vector, distance statistics) are scalar
