@@ -443,6 +443,9 @@ typedef struct {
     double min_separation_px;
     int32_t invert;
     int32_t max_number;
+    int32_t conditions;                /* bit mask of the detection conditions: 1 is_right_size_bb, 2 is_round, 4 is_right_circumference,
+                                          8 is_symmetric, 16 is_solid (metrics/features.py:7-68) */
+    int32_t pad;
 } epid_disk_params;
 
 typedef struct {
@@ -459,6 +462,15 @@ typedef struct {
 } epid_disk_result;
 
 int32_t epid_disk_locate(epid_ctx* ctx, const epid_batch* frames, const epid_disk_params* p, epid_disk_result* results);
+
+/* ----------------------------------------------------------------------------------------- ROI statistics / weighted centroid
+ * RectangleROI.mean / std / min / max (core/roi.py:533-706): pixels of a rectangle given by its corners verts_xy[nroi][4][(x, y)]
+ * (any rotation), selected like skimage.draw.polygon (pixel centres inside or on the boundary, clipped to the image).  Every ROI is
+ * evaluated on every frame of the batch: outputs [n][nroi] (may be NULL).  std is the population standard deviation (np.std). */
+int32_t epid_roi_stats(epid_ctx* ctx, const epid_batch* b, int32_t nroi, const double* verts_xy, double* count, double* mean,
+                       double* std, double* mn, double* mx);
+/* WeightedCentroid.calculate (metrics/image.py:959-983): cx = sum(x * a) / sum(a), cy likewise; total = sum(a) (may be NULL). */
+int32_t epid_weighted_centroid(epid_ctx* ctx, const epid_batch* b, double* cx, double* cy, double* total);
 
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the

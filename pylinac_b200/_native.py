@@ -195,6 +195,25 @@ _WL_LAYOUT = [
     ("cax2epid_x", "<f8"), ("cax2epid_y", "<f8"), ("cax2epid_distance", "<f8")]
 WL_RESULT_DTYPE = np.dtype(_WL_LAYOUT, align=True)
 assert WL_RESULT_DTYPE.itemsize == 128
+DISK_MAX = 8
+
+
+class DiskParams(C.Structure):
+    """epid_disk_params (include/epid.h)"""
+
+    _fields_ = [("dpmm", C.c_double), ("expected_x", C.c_double), ("expected_y", C.c_double), ("window_w", C.c_double),
+                ("window_h", C.c_double), ("radius_mm", C.c_double), ("tolerance_mm", C.c_double), ("min_separation_px", C.c_double),
+                ("invert", C.c_int32), ("max_number", C.c_int32), ("conditions", C.c_int32), ("pad", C.c_int32)]
+
+
+DISK_RESULT_DTYPE = np.dtype([("status", np.int32), ("n_points", np.int32), ("n_regions", np.int32), ("passes", np.int32),
+                              ("left", np.int32), ("top", np.int32), ("x", np.float64, DISK_MAX), ("y", np.float64, DISK_MAX),
+                              ("r_area", np.float64, DISK_MAX), ("r_filled_area", np.float64, DISK_MAX),
+                              ("r_perimeter", np.float64, DISK_MAX), ("r_convex_area", np.float64, DISK_MAX),
+                              ("r_centroid_y", np.float64, DISK_MAX), ("r_centroid_x", np.float64, DISK_MAX),
+                              ("r_wcentroid_y", np.float64, DISK_MAX), ("r_wcentroid_x", np.float64, DISK_MAX),
+                              ("r_bbox", np.int32, (DISK_MAX, 4))], align=True)
+assert DISK_RESULT_DTYPE.itemsize == 24 + 8 * DISK_MAX * 10 + 4 * DISK_MAX * 4
 _lib = None
 _lock = threading.Lock()
 
@@ -255,6 +274,9 @@ _SIGNATURES = {
     "epid_field_profile_len": [C.c_int32, C.c_double, C.c_int32, C.c_double],
     "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
     "epid_wl2d_analyze": [_P, _P, C.POINTER(WlParams), _P],
+    "epid_disk_locate": [_P, _P, _P, _P],
+    "epid_roi_stats": [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P],
+    "epid_weighted_centroid": [_P, _P, _P, _P, _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -648,6 +670,59 @@ def wl2d_analyze(ctx: Context, frames, params: WlParams) -> np.ndarray:
         if own is not None:
             own.free()
     return res
+
+
+def _as_batch(ctx: Context, frames, dtypes=None):
+    """-> (Batch, owned?) for a Batch or an ndarray [h,w] / [n,h,w]."""
+    if isinstance(frames, Batch):
+        return frames, False
+    a = np.ascontiguousarray(frames)
+    if a.ndim == 2:
+        a = a[None]
+    if dtypes is not None and a.dtype not in dtypes:
+        raise TypeError(f"dtype {a.dtype} is not supported here")
+    return Batch.upload(ctx, a), True
+
+
+def disk_locate(ctx: Context, frames, params: DiskParams) -> np.ndarray:
+    """SizedDiskRegion / SizedDiskLocator on uint16 frames: one DISK_RESULT_DTYPE row per frame."""
+    b, own = _as_batch(ctx, frames, (np.dtype(np.uint16),))
+    (n, _, _), _ = b.shape_dtype
+    res = np.zeros(n, DISK_RESULT_DTYPE)
+    try:
+        check(lib().epid_disk_locate(ctx.handle, b.handle, C.byref(params), _ptr(res)))
+    finally:
+        if own:
+            b.free()
+    return res
+
+
+def roi_stats(ctx: Context, frames, verts_xy) -> dict:
+    """RectangleROI statistics: verts_xy [nroi, 4, 2] corner (x, y) -> dict of [n, nroi] arrays (count, mean, std, min, max)."""
+    v = np.ascontiguousarray(verts_xy, dtype=np.float64).reshape(-1, 4, 2)
+    b, own = _as_batch(ctx, frames)
+    (n, _, _), _ = b.shape_dtype
+    out = {k: np.empty((n, len(v))) for k in ("count", "mean", "std", "min", "max")}
+    try:
+        check(lib().epid_roi_stats(ctx.handle, b.handle, len(v), _ptr(v), _ptr(out["count"]), _ptr(out["mean"]), _ptr(out["std"]),
+                                   _ptr(out["min"]), _ptr(out["max"])))
+    finally:
+        if own:
+            b.free()
+    return out
+
+
+def weighted_centroid(ctx: Context, frames):
+    """(cx, cy, total) arrays of length n: sum(x * a) / sum(a), sum(y * a) / sum(a), sum(a)."""
+    b, own = _as_batch(ctx, frames)
+    (n, _, _), _ = b.shape_dtype
+    cx, cy, tot = np.empty(n), np.empty(n), np.empty(n)
+    try:
+        check(lib().epid_weighted_centroid(ctx.handle, b.handle, _ptr(cx), _ptr(cy), _ptr(tot)))
+    finally:
+        if own:
+            b.free()
+    return cx, cy, tot
 
 
 def circle_profile(ctx: Context, image: np.ndarray, center, radius: float, start_angle: float = 0.0, ccw: bool = True,

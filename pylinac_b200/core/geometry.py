@@ -42,6 +42,25 @@ class Point:
         o = Point(other)
         return self.x == o.x and self.y == o.y and self.z == o.z
 
+    _attr_list = ("x", "y", "z", "idx", "value")
+
+    def __mul__(self, other):
+        """IN PLACE, like the reference (core/geometry.py:190-196): every attribute that can be multiplied is, self is returned."""
+        for attr in self._attr_list:
+            try:
+                setattr(self, attr, getattr(self, attr) * other)
+            except TypeError:
+                pass
+        return self
+
+    def __truediv__(self, other):
+        """IN PLACE (core/geometry.py:198-204)"""
+        for attr in self._attr_list:
+            val = getattr(self, attr)
+            if val is not None:
+                setattr(self, attr, val / other)
+        return self
+
     def __repr__(self):
         return f"Point(x={self.x:3.2f}, y={self.y:3.2f}, z={self.z:3.2f})"
 

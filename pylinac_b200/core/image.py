@@ -31,6 +31,16 @@ def _is_dicom(path) -> bool:
         return False
 
 
+def _uniquify(seq, value: str) -> str:
+    """core/utilities.py:368-377: value, value-1, value-2, ... until it is not in seq."""
+    if value not in seq:
+        return value
+    i = 1
+    while f"{value}-{i}" in seq:
+        i += 1
+    return f"{value}-{i}"
+
+
 def _is_image_file(path) -> bool:
     """core/image.py:429-435: readable by Pillow."""
     try:
@@ -154,6 +164,27 @@ class BaseImage:
 
     def as_type(self, dtype):
         return self.array.astype(dtype)
+
+    def compute(self, metrics):
+        """core/image.py:1022-1054: inject this image into the metric(s), calculate, store under a unique name."""
+        from ..metrics.image import MetricBase
+
+        if not hasattr(self, "metrics"):
+            self.metrics, self.metric_values = [], {}
+        metric_data = {}
+        if isinstance(metrics, MetricBase):
+            metrics = [metrics]
+        key = None
+        for metric in metrics:
+            metric.inject_image(self)
+            value = metric.context_calculate()
+            self.metrics.append(metric)
+            key = _uniquify(list(metric_data.keys()) + list(self.metric_values.keys()), metric.name)
+            metric_data[key] = value
+        self.metric_values |= metric_data
+        if len(metrics) == 1:
+            return metric_data[key]
+        return metric_data
 
     # ------------------------------------------------------------------ operators
     def filter(self, size=0.05, kind: str = "median") -> None:  # core/image.py:695-712

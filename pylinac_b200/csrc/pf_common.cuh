@@ -57,17 +57,20 @@ struct PfFrame {
 
 struct PfWin { int valid; double l, r; };  // per (in-view leaf, picket)
 
-// two-kernel window path (pf_windows2.cu): what k_pf_win_medians hands to k_pf_win_fwxm for one window
+// two-kernel window path (pf_windows2.cu): what k_pf_win_medians hands to k_pf_win_fwxm
 constexpr int PF_W2_NCW = 64;      // travel samples per window
 constexpr int PF_W2_NRW = 32;      // rows per window
 constexpr int PF_W2_WCAP = 1024;   // windows per frame (in-view leaves x pickets)
-struct PfWinRec {
+constexpr int PF_W2_POOL = PF_W2_WCAP * PF_W2_NCW;     // median samples per frame (bands of neighbouring windows share columns)
+struct alignas(16) PfWinRec {              // one per window, 48 bytes (read with 16-byte loads)
     uint32_t hdr;                          // nc | nr << 16 (signed 16-bit each)
+    uint32_t moff;                         // first sample of the window in the frame's median pool
+    uint32_t gmax;                         // largest g inside the window
     uint32_t pad;
-    uint32_t m2[PF_W2_NCW];                // 2 * median over the rows, g units
-    unsigned long long num[PF_W2_NRW];     // nc * S2 - S1^2 per row (variance numerator along travel)
-    uint32_t ext[PF_W2_NRW];               // raw row maximum << 16 | raw row minimum, inside the window
+    unsigned long long kmax, ka, kb;       // variance numerators nc * S2 - S1^2 of the rows: largest, and the two middle order statistics
+    unsigned long long pad2;
 };
+static_assert(sizeof(PfWinRec) == 48, "PfWinRec layout");
 
 // numpy _lerp (numpy/lib/_function_base_impl.py): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
 __device__ __forceinline__ double np_lerp(double a, double b, double t) {
@@ -160,7 +163,7 @@ enum { PF_STAGE_START = -1, PF_STAGE_INIT_PILOT = 0, PF_STAGE_STREAM = 1, PF_STA
 int launch_pf_windows_fast(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
 int launch_pf_leafband(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWin* wins, int n);
 // pf_windows2.cu
-size_t pf_win2_scratch_bytes(int n);
+size_t pf_win2_scratch_bytes(int n);       // records followed by the median pools
 int launch_pf_windows2(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWinRec* recs, PfWin* wins,
                        int n, PfTimers* tm);
 // pf_stream.cu

@@ -5,18 +5,22 @@
 // MLCValue.get_peak_positions (picketfence.py:1605-1628) -> FWXMProfilePhysical.field_edge_idx (core/profile.py:602-611).
 //
 //   k_pf_win_medians   warp-autonomous.  A task = one leaf x a group of G neighbouring pickets (their windows are column ranges of
-//       the same band of rows).  The band is copied RAW into a per-warp shared-memory slot by one cp.async.bulk (TMA, UBLKCP) per
-//       row, completion on an mbarrier; two slots per warp, so the copy of the warp's next task is in flight while it works on the
-//       current one.  P1: lanes own (row, picket) pairs -> sum / sum of squares / min / max of the row inside the picket's window;
-//       the variance numerator nc * S2 - S1^2 is an exact integer and invariant under the frame's ground / inversion map, so raw
-//       pixels do.  P2: lanes own pairs of band columns -> median over the rows by register sorting networks on packed u16x2
-//       (VIMNMX.U16x2); the median commutes with the monotone ground / inversion map, which is applied to the result.  Output per
-//       window (PfWinRec, HBM / L2): the median profile (2 * median in g units), the nr variance numerators and row extremes.
-//   k_pf_win_fwxm      thread per window, 32 windows of a warp in lock step.  The numerators are ranked by a branch-free sorting
-//       network (max and median of the row standard deviations -> _is_mlc_peak_in_window), then the serial integer FWXM analysis
-//       of the median profile (lb_window_fwxm: fp64 only for the prominence, the half-height level and the two interpolations).
-//       Records are transposed through shared memory ([sample][window], stride 33) so both the coalesced record reads and the
-//       per-thread walks are bank-conflict free.
+//       the same band of rows; G is the largest group whose band fits a staging slot with the leaf's row count).  The band is
+//       copied RAW into a per-warp shared-memory slot by one cp.async.bulk (TMA, UBLKCP) per row, issued from warp-uniform
+//       operands, completion on an mbarrier; two slots per warp, so the copy of the warp's next task is in flight while it works
+//       on the current one.
+//       P1  lanes own (picket of the group, row): sum and sum of squares of the row inside the picket's window (IDP.2A on packed
+//           pixels, 32-bit partial sums), i.e. the exact integer variance numerator nc * S2 - S1^2 -- invariant under the frame's
+//           ground / inversion map, so raw pixels do.  The numerators of a window are then ranked across its lanes (shuffles): only
+//           the largest and the two middle ones leave the kernel (max / median of the row standard deviations).
+//       P2  lanes own pairs of band columns: median over the rows by register sorting networks on packed u16x2 (VIMNMX.U16x2,
+//           comparator lists generated at compile time); the median commutes with the monotone ground / inversion map, which is
+//           applied to the result.  The column extremes give the window maximum.  The medians of a band go to the frame's median
+//           pool contiguously (columns shared by overlapping windows are computed once).
+//   k_pf_win_fwxm      thread per window, 32 windows of a warp in lock step: _is_mlc_peak_in_window from the three numerators and
+//       the window maximum (same fp64 expressions as the reference), then the serial integer FWXM analysis of the median profile
+//       (lb_window_fwxm: fp64 only for the prominence, the half-height level and the two interpolations).  The profiles are
+//       transposed through shared memory ([sample][window], stride 33): coalesced pool reads, conflict-free per-thread walks.
 //
 // Results are bit-identical to k_pf_windows_fast (same integer quantities, same fp64 expressions; tests/test_gpu_pf.py compares
 // them).  Frames this path does not cover (Left-Right orientation, unaligned pitch, windows wider than 64 samples or taller than
@@ -34,33 +38,39 @@ constexpr int WA_WARPS = 8;
 constexpr int WA_SLOT = 6656;          // bytes per staging slot (26 rows x 256 B: two 51-sample windows of a 10 mm leaf at 2.56 px/mm)
 constexpr int WA_GRID_X = 4;           // CTAs per frame
 constexpr int WA_GMAX = 4;             // pickets per task
+constexpr int WA_KMAX = 4;             // rows per lane in P1: ceil(32 rows / (32 lanes / 4 pickets))
 constexpr int WB_THREADS = 128;
-constexpr int WB_ST = 33;              // transposed record stride (words): [sample][window of the warp]
+constexpr int WB_ST = 33;              // transposed profile stride (words): [sample][window of the warp]
 
 __device__ __forceinline__ int wa_row_stride_bytes(int nvec) { return (nvec | 1) * 16; }   // odd vector count: rows start 4 banks apart
 
 struct W2Geo {
-    int ok, np, ninview, ntasks;
+    int ok, ntasks;
     int nvmax[WA_GMAX + 1];     // widest band (16-byte vectors per row) when pickets are taken g at a time
+    int gtot[WA_GMAX + 1];      // median-pool samples of one leaf when pickets are taken g at a time
 };
 
-// LDGSTS = false: one cp.async.bulk (TMA) per band row, completion on an mbarrier.  LDGSTS = true: 16-byte cp.async per lane
-// (LDGSTS), completion by cp.async.wait_group -- kept for comparison (EPID_WA_LOADER=1).
 template <bool LDGSTS>
 __global__ void __launch_bounds__(WA_WARPS * 32, 2)
-k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWinRec* __restrict__ recs) {
+k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWinRec* __restrict__ recs,
+                 uint32_t* __restrict__ pools) {
     extern __shared__ __align__(128) unsigned char smraw[];          // WA_WARPS x 2 slots
     __shared__ __align__(8) unsigned long long s_bar[WA_WARPS][2];
     __shared__ W2Geo s_geo;
     __shared__ int s_a0[PF_P], s_a1[PF_P];
-    __shared__ short s_gcs[WA_GMAX + 1][PF_P], s_gnv[WA_GMAX + 1][PF_P];   // per group size / group: first band column (view coordinates), vectors per row
+    // per group size / group: first band column (view coordinates), vectors per row, first / one-past-last band word that belongs to
+    // a window, offset of the band inside the leaf's part of the median pool
+    __shared__ short s_gcs[WA_GMAX + 1][PF_P], s_gnv[WA_GMAX + 1][PF_P], s_gt0[WA_GMAX + 1][PF_P], s_gt1[WA_GMAX + 1][PF_P];
+    __shared__ int s_gofs[WA_GMAX + 1][PF_P];
     __shared__ short s_b0[PF_L], s_nr[PF_L];
     __shared__ unsigned char s_lg[PF_L];                              // pickets per task of this leaf
     __shared__ int s_toff[PF_L + 1];                                  // tasks before leaf li
+    __shared__ int s_moff[PF_L + 1];                                  // median-pool samples before leaf li
     const int fi = blockIdx.y;
     const PfConst& c = *cc;
     PfFrame& f = fr[fi];
-    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);           // warp-uniform for the compiler: task geometry lives in uniform registers
     const int H = c.H, W = c.W;
     const FrameRef frf = frames[fi];
     const int mis = (int)((reinterpret_cast<uintptr_t>(frf.origin) >> 1) & 7);
@@ -100,52 +110,70 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
         __syncwarp();
         for (int g = 1; g <= WA_GMAX; g++) {       // band of every group of g neighbouring pickets
             const int ng = (np + g - 1) / g;
-            int nvec = 0, cs = 0;
+            int nvec = 0, nsamp = 0;
             if (lane < ng) {
                 int lo = W, hi = 0;
                 for (int q = 0; q < g && lane * g + q < np; q++) {
                     const int x0 = s_a0[lane * g + q], x1 = s_a1[lane * g + q];
                     if (x1 > x0) { lo = min(lo, x0); hi = max(hi, x1); }
                 }
-                if (hi <= lo) { lo = 0; hi = 8; }
-                cs = lo - ((lo + mis) & 7);
+                const bool empty = hi <= lo;
+                if (empty) { lo = 0; hi = 8; }
+                const int cs = lo - ((lo + mis) & 7);
                 const int ce = hi + ((8 - ((hi + mis) & 7)) & 7);
                 nvec = (ce - cs) >> 3;
+                const int t0 = (lo - cs) >> 1, t1 = empty ? t0 : (hi - cs + 1) >> 1;
                 s_gcs[g][lane] = (short)cs;
                 s_gnv[g][lane] = (short)nvec;
+                s_gt0[g][lane] = (short)t0;
+                s_gt1[g][lane] = (short)t1;
+                nsamp = 2 * (t1 - t0);
             }
+            int inc = nsamp;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane < ng) s_gofs[g][lane] = inc - nsamp;
             const int nvmax = warp_max(nvec);
-            if (lane == 0) s_geo.nvmax[g] = nvmax;
+            const int tot = __shfl_sync(0xffffffffu, inc, 31);
+            if (lane == 0) { s_geo.nvmax[g] = nvmax; s_geo.gtot[g] = tot; }
         }
     }
     bad = __syncthreads_or(bad);
     if (wid == 0) {
-        // pickets per task of every leaf: as many as fit a slot with the leaf's row count; running task offsets
-        int run = 0;
+        // pickets per task of every leaf: as many as fit a slot with the leaf's row count; running task / pool offsets
+        int run = 0, mrun = 0;
         for (int base = 0; base < ninview; base += 32) {
             const int i = base + lane;
-            int cnt = 0;
+            int cnt = 0, msz = 0;
             if (i < ninview) {
                 const int nr = s_nr[i];
                 int G = 0;
                 for (int g = WA_GMAX; g >= 1 && G == 0; g--)
                     if (max(nr, 1) * wa_row_stride_bytes(s_geo.nvmax[g]) <= WA_SLOT) G = g;
                 if (G == 0) bad = 1;
-                s_lg[i] = (unsigned char)max(G, 1);
-                cnt = (np + max(G, 1) - 1) / max(G, 1);
+                G = max(G, 1);
+                s_lg[i] = (unsigned char)G;
+                cnt = (np + G - 1) / G;
+                msz = s_geo.gtot[G];
             }
-            int inc = cnt;
+            int inc = cnt, minc = msz;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
+                const int t = __shfl_up_sync(0xffffffffu, inc, o), u = __shfl_up_sync(0xffffffffu, minc, o);
+                if (lane >= o) { inc += t; minc += u; }
             }
-            if (i < ninview) s_toff[i] = run + inc - cnt;
+            if (i < ninview) { s_toff[i] = run + inc - cnt; s_moff[i] = mrun + minc - msz; }
             run += __shfl_sync(0xffffffffu, inc, 31);
+            mrun += __shfl_sync(0xffffffffu, minc, 31);
         }
+        if (mrun > PF_W2_POOL) bad = 1;
         bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) {
             s_toff[ninview] = run;
+            s_moff[ninview] = mrun;
             s_geo.ntasks = run;
             s_geo.ok = bad ? 0 : 1;
             if (!bad && blockIdx.x == 0) f.win2 = 1;
@@ -160,6 +188,7 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
     unsigned char* slot0 = smraw + (size_t)wid * 2 * WA_SLOT;
     const uint32_t bar0 = smem_u32(&s_bar[wid][0]), bar1 = smem_u32(&s_bar[wid][1]);
     PfWinRec* frecs = recs + (size_t)fi * PF_W2_WCAP;
+    uint32_t* pool = pools + (size_t)fi * PF_W2_POOL;
 
     auto leaf_of = [&](int task, int li) { while (s_toff[li + 1] <= task) li++; return li; };     // tasks are visited in ascending order
     auto issue = [&](int task, int li, int sl) {
@@ -182,13 +211,13 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
             return;
         }
         const uint32_t bar = sl ? bar1 : bar0;
-        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nr * (uint32_t)nvec * 16u);
-        __syncwarp();
-        if (lane < nr) {
-            int row = b0 + lane - sag;               // np.roll(sag) folded into the source row
+        const uint32_t bytes = (uint32_t)nvec * 16u;
+        if (lane == 0) mbar_expect_tx(bar, (uint32_t)nr * bytes);
+        const uint32_t dst0 = smem_u32(slot0 + (size_t)sl * WA_SLOT);
+        for (int r = 0; r < nr; r++) {               // warp-uniform loop: one lane issues, every operand is uniform
+            int row = b0 + r - sag;                  // np.roll(sag) folded into the source row
             if (sag) { row %= H; if (row < 0) row += H; }
-            tma_load_1d(smem_u32(slot0 + (size_t)sl * WA_SLOT + (size_t)lane * RS), frf.origin + ((ptrdiff_t)row * frf.pitch + cs),
-                        (uint32_t)nvec * 16u, bar);
+            if (lane == 0) tma_load_1d(dst0 + (uint32_t)(r * RS), frf.origin + ((ptrdiff_t)row * frf.pitch + cs), bytes, bar);
         }
     };
 
@@ -209,121 +238,136 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
         const int nvec = s_gnv[G][g], cs = s_gcs[G][g];
         const int RS = wa_row_stride_bytes(nvec);
         const int Gn = min(G, np - g * G);
+        const int t_lo = s_gt0[G][g], t_hi = s_gt1[G][g];
+        const int boff = s_moff[li] + s_gofs[G][g];                   // the band's first sample in the median pool (even)
         PfWinRec* lrec = frecs + (size_t)li * np + (size_t)g * G;
-        if (lane < Gn) {       // header: the shape of the window (empty windows are reported by the analysis kernel)
+        if (lane < Gn) {       // header: the shape of the window (empty windows are reported by the analysis kernel) and its samples
             const int a0 = s_a0[g * G + lane], a1 = s_a1[g * G + lane];
             lrec[lane].hdr = ((uint32_t)(uint16_t)(short)max(min(a1 - a0, 32767), -32768)) | ((uint32_t)(uint16_t)(short)nr << 16);
+            lrec[lane].moff = (uint32_t)(boff + (a0 - (cs + 2 * t_lo)));
         }
         if (nr <= 0) { __syncwarp(); continue; }
         if (LDGSTS) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); }      // everything but the newest group has landed
         else if (cur) { mbar_wait(bar1, ph1); ph1 ^= 1u; } else { mbar_wait(bar0, ph0); ph0 ^= 1u; }
         const unsigned char* band = slot0 + (size_t)cur * WA_SLOT;
-        // ---- P1: (row, picket) sums on the raw pixels
-        const int ntk = nr * Gn;
-        for (int tt = lane; tt < ntk; tt += 32) {
-            int r, q;
-            if (Gn == 1) { r = tt; q = 0; }
-            else if (Gn == 2) { r = tt >> 1; q = tt & 1; }
-            else if (Gn == 4) { r = tt >> 2; q = tt & 3; }
-            else { r = tt / 3; q = tt - 3 * r; }
-            const int a0 = s_a0[g * G + q], a1 = s_a1[g * G + q];
-            unsigned long long numv = 0;
-            uint32_t e = 0x0000ffffu;
-            if (a1 > a0) {
-                const unsigned char* rowp = band + (size_t)r * RS;
-                int j0 = a0 - cs, j1 = a1 - cs;
-                uint32_t s1 = 0, vmx = 0, vmn = 0xffffu;
-                unsigned long long s2 = 0;
-                if (j0 & 1) {
-                    const uint32_t v = *reinterpret_cast<const uint16_t*>(rowp + 2 * j0);
-                    s1 += v; s2 = mad_wide_u32(v, v, s2); vmx = max(vmx, v); vmn = min(vmn, v);
-                    j0++;
+        // ---- P1: lanes = (picket of the group, row): rows [k * RPI, (k + 1) * RPI) in pass k
+        {
+            const int RPI = Gn == 1 ? 32 : (Gn == 2 ? 16 : (Gn == 3 ? 10 : 8));
+            const int q = Gn == 1 ? 0 : (Gn == 2 ? lane >> 4 : (Gn == 3 ? lane / 10 : lane >> 3));
+            const int rr = lane - q * RPI;
+            const bool lane_on = q < Gn;
+            const int a0 = lane_on ? s_a0[g * G + q] : 0, a1 = lane_on ? s_a1[g * G + q] : 0;
+            const bool win_on = lane_on && a1 > a0;
+            const int j0 = a0 - cs, j1 = a1 - cs;
+            const int wlo = j0 >> 1, whi = (j1 - 1) >> 1;              // first / last word that holds window samples
+            uint32_t mfirst = (j0 & 1) ? 0xffff0000u : 0xffffffffu;    // samples outside the window read as zero: sums unchanged
+            uint32_t mlast = (j1 & 1) ? 0x0000ffffu : 0xffffffffu;
+            if (wlo == whi) { mfirst &= mlast; }
+            const unsigned long long ncl = (unsigned long long)(a1 - a0);
+            const int nk = (nr + RPI - 1) / RPI;                       // <= WA_KMAX
+            unsigned long long num[WA_KMAX];
+#pragma unroll
+            for (int k = 0; k < WA_KMAX; k++) {
+                num[k] = 0;
+                if (k < nk) {
+                    const int r = k * RPI + rr;
+                    if (win_on && r < nr) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(band + (size_t)r * RS);
+                        uint32_t s1 = 0, sA = 0, sB = 0;
+                        auto acc = [&](uint32_t x) {
+                            // lo^2 + hi^2 = 256 * (lo * (lo >> 8) + hi * (hi >> 8)) + (lo * (lo & 255) + hi * (hi & 255)): two IDP.2A
+                            s1 = __dp2a_lo(x, 0x0101u, s1);
+                            sA = __dp2a_lo(x, __byte_perm(x, 0u, 0x4431), sA);
+                            sB = __dp2a_lo(x, __byte_perm(x, 0u, 0x4420), sB);
+                        };
+                        acc(wp[wlo] & mfirst);
+#pragma unroll 8
+                        for (int w = wlo + 1; w < whi; w++) acc(wp[w]);
+                        if (whi > wlo) acc(wp[whi] & mlast);
+                        const unsigned long long s2 = ((unsigned long long)sA << 8) + (unsigned long long)sB;
+                        num[k] = ncl * s2 - (unsigned long long)s1 * s1;
+                    }
                 }
-                if (j1 & 1) {
-                    const uint32_t v = *reinterpret_cast<const uint16_t*>(rowp + 2 * (j1 - 1));
-                    s1 += v; s2 = mad_wide_u32(v, v, s2); vmx = max(vmx, v); vmn = min(vmn, v);
-                    j1--;
-                }
-                uint32_t mx2 = 0, mn2 = 0xffffffffu;
-                const uint32_t* wp = reinterpret_cast<const uint32_t*>(rowp);
-                const int w0 = j0 >> 1, w1 = j1 >> 1;
-                // rows r and r + 8 start in the same bank (the row stride is an odd number of 16-byte vectors): lanes start (r >> 3)
-                // words into their window and wrap, so that no two lanes of the warp read the same bank
-                const int rot = min(r >> 3, max(w1 - w0 - 1, 0));
-                auto acc = [&](uint32_t x) {
-                    const uint32_t lo = x & 0xffffu, hi = x >> 16;
-                    s1 = __dp2a_lo(x, 0x0101u, s1);
-                    s2 = mad_wide_u32(lo, lo, s2);
-                    s2 = mad_wide_u32(hi, hi, s2);
-                    mx2 = __vmaxu2(mx2, x);
-                    mn2 = __vminu2(mn2, x);
-                };
-                const int cnt = w1 - w0;
-#pragma unroll 4
-                for (int t = 0; t < cnt; t++) {
-                    int w = w0 + rot + t;
-                    if (w >= w1) w -= cnt;
-                    acc(wp[w]);
-                }
-                if (w1 > w0) {
-                    vmx = max(vmx, max(mx2 & 0xffffu, mx2 >> 16));
-                    vmn = min(vmn, min(mn2 & 0xffffu, mn2 >> 16));
-                }
-                const unsigned long long ncl = (unsigned long long)(a1 - a0);
-                numv = ncl * s2 - (unsigned long long)s1 * s1;
-                e = (vmx << 16) | vmn;
             }
-            lrec[q].num[r] = numv;
-            lrec[q].ext[r] = e;
+            // ---- rank the numerators of every window across its lanes: largest, and the two middle order statistics
+            int rank[WA_KMAX];
+#pragma unroll
+            for (int k = 0; k < WA_KMAX; k++) rank[k] = 0;
+            unsigned long long kmx = 0;
+            for (int s = 0; s < RPI; s++) {
+                const int src = q * RPI + s;
+#pragma unroll
+                for (int k2 = 0; k2 < WA_KMAX; k2++) {
+                    if (k2 < nk) {
+                        const unsigned long long o = __shfl_sync(0xffffffffu, num[k2], src & 31);
+                        const int orow = k2 * RPI + s;
+                        if (orow < nr) {
+                            kmx = o > kmx ? o : kmx;
+#pragma unroll
+                            for (int k = 0; k < WA_KMAX; k++) {
+                                const int myrow = k * RPI + rr;
+                                if (o < num[k] || (o == num[k] && orow < myrow)) rank[k]++;
+                            }
+                        }
+                    }
+                }
+            }
+            if (win_on) {
+                const int k1 = (nr - 1) / 2, k2m = nr / 2;
+#pragma unroll
+                for (int k = 0; k < WA_KMAX; k++) {
+                    const int myrow = k * RPI + rr;
+                    if (k < nk && myrow < nr) {
+                        if (rank[k] == k1) lrec[q].ka = num[k];
+                        if (rank[k] == k2m) lrec[q].kb = num[k];
+                    }
+                }
+                if (rr == 0) lrec[q].kmax = kmx;
+            }
         }
-        // ---- P2: 2 * median over the rows for every pair of band columns between the group's first and last window
+        // ---- P2: 2 * median over the rows for every pair of band columns between the group's first and last window; column
+        //      extremes -> the largest g of every window (lane q keeps window q's)
         {
             const uint16_t* px = reinterpret_cast<const uint16_t*>(band);
             const int S = RS >> 1;
-            int lo = W, hi = 0;
-            for (int q = 0; q < Gn; q++) {
-                const int x0 = s_a0[g * G + q], x1 = s_a1[g * G + q];
-                if (x1 > x0) { lo = min(lo, x0); hi = max(hi, x1); }
-            }
-            const int t_lo = (lo - cs) >> 1, t_hi = (hi - cs + 1) >> 1;
-            for (int t = t_lo + lane; t < t_hi; t += 32) {
-                const uint2 mm = pair_median_any(px, S, nr, t);
-                const uint32_t g0 = inv ? 2u * mx - mm.x : mm.x - 2u * mn;
-                const uint32_t g1 = inv ? 2u * mx - mm.y : mm.y - 2u * mn;
+            uint32_t wext = inv ? 0xffffu : 0u;        // raw extreme of window `lane` (minimum when inverted)
+            const int qa0 = lane < Gn ? s_a0[g * G + lane] : 0, qa1 = lane < Gn ? s_a1[g * G + lane] : 0;
+            for (int tb = t_lo; tb < t_hi; tb += 32) {
+                const int t = tb + lane;
+                uint32_t elo = inv ? 0xffffu : 0u, ehi = elo;
+                if (t < t_hi) {
+                    const uint3 mm = pair_median_ext_any(px, S, nr, t, inv != 0);
+                    const uint32_t g0 = inv ? 2u * mx - mm.x : mm.x - 2u * mn;
+                    const uint32_t g1 = inv ? 2u * mx - mm.y : mm.y - 2u * mn;
+                    *reinterpret_cast<uint2*>(pool + boff + 2 * (t - t_lo)) = make_uint2(g0, g1);
+                    elo = mm.z & 0xffffu;
+                    ehi = mm.z >> 16;
+                }
                 const int c0 = 2 * t + cs;                 // view column of the low half
                 for (int q = 0; q < Gn; q++) {
-                    const int x0 = s_a0[g * G + q], x1 = s_a1[g * G + q];
-                    if (c0 >= x0 && c0 < x1) lrec[q].m2[c0 - x0] = g0;
-                    if (c0 + 1 >= x0 && c0 + 1 < x1) lrec[q].m2[c0 + 1 - x0] = g1;
+                    const int x0 = __shfl_sync(0xffffffffu, qa0, q), x1 = __shfl_sync(0xffffffffu, qa1, q);
+                    const bool in0 = c0 >= x0 && c0 < x1, in1 = c0 + 1 >= x0 && c0 + 1 < x1;
+                    uint32_t v;
+                    if (inv) {
+                        v = min(in0 ? elo : 0xffffu, in1 ? ehi : 0xffffu);
+                        v = __reduce_min_sync(0xffffffffu, v);
+                        if (lane == q) wext = min(wext, v);
+                    } else {
+                        v = max(in0 ? elo : 0u, in1 ? ehi : 0u);
+                        v = __reduce_max_sync(0xffffffffu, v);
+                        if (lane == q) wext = max(wext, v);
+                    }
                 }
             }
+            if (lane < Gn && qa1 > qa0) lrec[lane].gmax = inv ? mx - wext : wext - mn;
         }
         __syncwarp();       // every lane is done with the slot: the next iteration may overwrite the other one... and this one after it
     }
 }
 
-// max, and the two middle order statistics of the nr keys a thread reads through key(i) (i < N slots, slots >= nr padded)
-template <int N, class F>
-__device__ __forceinline__ void rank_keys(F key, int nr, unsigned long long& kmax, unsigned long long& ka, unsigned long long& kb) {
-    unsigned long long r[N];
-    kmax = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        r[i] = i < nr ? key(i) : ~0ull;
-        if (i < nr && r[i] > kmax) kmax = r[i];
-    }
-    sort_net_u64<N>(r);
-    const int k1 = (nr - 1) / 2, k2 = nr / 2;
-    ka = 0; kb = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        if (i == k1) ka = r[i];
-        if (i == k2) kb = r[i];
-    }
-}
-
-__global__ void __launch_bounds__(WB_THREADS)
-k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __restrict__ recs, PfWin* __restrict__ wins) {
+__global__ void __launch_bounds__(WB_THREADS, 6)
+k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __restrict__ recs, const uint32_t* __restrict__ pools,
+              PfWin* __restrict__ wins) {
     __shared__ uint32_t s_buf[WB_THREADS / 32][PF_W2_NCW * WB_ST];
     const int fi = blockIdx.y;
     PfFrame& f = fr[fi];
@@ -335,14 +379,18 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     const int wbase = blockIdx.x * WB_THREADS + wid * 32;
     if (wbase >= total) return;
     const PfWinRec* frecs = recs + (size_t)fi * PF_W2_WCAP;
+    const uint32_t* pool = pools + (size_t)fi * PF_W2_POOL;
     uint32_t* buf = s_buf[wid];
     const int w = wbase + lane;
     const bool active = w < total;
-    // ---- this thread's window: header, row extremes and variance numerators straight into registers (independent loads, all
-    //      in flight at once; lanes read records 648 bytes apart)
-    const PfWinRec& rec = frecs[active ? w : total - 1];
-    const uint32_t hdr = rec.hdr;
-    const int my_nc = (int)(short)(hdr & 0xffffu), my_nr = (int)(short)(hdr >> 16);
+    // ---- this thread's window record (40 bytes: two 16-byte loads and one 8-byte load, independent)
+    const PfWinRec* rp = frecs + (active ? w : total - 1);
+    const uint4 h4 = *reinterpret_cast<const uint4*>(rp);
+    const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(&rp->kmax);
+    const unsigned long long kb = rp->kb;
+    const int my_nc = (int)(short)(h4.x & 0xffffu), my_nr = (int)(short)(h4.x >> 16);
+    const uint32_t my_moff = h4.y, my_gmax = h4.z;
+    const unsigned long long kmax = k2.x, ka = k2.y;
     int li = 0, pk = 0;
     if (active) { li = w / np; pk = w - li * np; }
     PfWin& out = wins[((size_t)fi * PF_L + li) * PF_P + pk];
@@ -354,49 +402,32 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
             run = true;
         }
     }
-    const int nrr = run ? my_nr : 0;
-    const int nr_all = __reduce_max_sync(0xffffffffu, nrr);
     // ---- _is_mlc_peak_in_window (picketfence.py:847-857): std along travel per row = sqrt(num) / (nc * D)
-    unsigned long long kmax = 0, ka = 0, kb = 0;
-    uint32_t my_vmx = 0, my_vmn = 0xffffu;
-    {
-        auto key = [&](int i) { return rec.num[i]; };
-        if (nr_all <= 16) rank_keys<16>(key, nrr, kmax, ka, kb);       // warp-uniform choice
-        else rank_keys<32>(key, nrr, kmax, ka, kb);
-#pragma unroll
-        for (int i = 0; i < PF_W2_NRW; i++) {
-            if (i < nrr) {
-                const uint32_t e = rec.ext[i];
-                my_vmx = max(my_vmx, e >> 16);
-                my_vmn = min(my_vmn, e & 0xffffu);
-            }
-        }
-    }
     if (run) {
         const double Dd = (double)f.D;
         const double dn = (double)my_nc * Dd;
         const double sd_max = sqrt((double)kmax) / dn;
         const double sa = sqrt((double)ka) / dn, sb = sqrt((double)kb) / dn;
         const double sd_med = (my_nr & 1) ? sa : (sa + sb) / 2.0;
-        const uint32_t gmax = f.inv ? f.mx - my_vmn : my_vmx - f.mn;
-        const bool above = ((double)gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
+        const bool above = ((double)my_gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
         const bool not_edge = sd_max < c.p.edge_threshold * sd_med;
         if (!(above && not_edge)) {
             out.valid = 0; out.l = 0; out.r = 0;
             run = false;
         }
     }
-    __syncwarp();
     // ---- median profiles of the 32 windows -> [sample][window]
     {
         const int nc_all = __reduce_max_sync(0xffffffffu, run ? my_nc : 0);     // samples beyond a window's own nc are never read
+        if (nc_all > 0) {
 #pragma unroll 8
-        for (int k = 0; k < 32; k++) {
-            const PfWinRec& rc = frecs[min(wbase + k, total - 1)];
-            const uint32_t v0 = rc.m2[lane];
-            const uint32_t v1 = nc_all > 32 ? rc.m2[lane + 32] : 0u;
-            buf[lane * WB_ST + k] = v0;
-            if (nc_all > 32) buf[(lane + 32) * WB_ST + k] = v1;
+            for (int k = 0; k < 32; k++) {
+                const uint32_t mo = __shfl_sync(0xffffffffu, my_moff, k);
+                const uint32_t v0 = pool[mo + lane];                  // stays inside the frame's pool: moff + 64 <= pool size + slack
+                const uint32_t v1 = nc_all > 32 ? pool[mo + lane + 32] : 0u;
+                buf[lane * WB_ST + k] = v0;
+                if (nc_all > 32) buf[(lane + 32) * WB_ST + k] = v1;
+            }
         }
     }
     __syncwarp();
@@ -409,25 +440,29 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     }
 }
 
-size_t pf_win2_scratch_bytes(int n) { return sizeof(PfWinRec) * (size_t)n * PF_W2_WCAP; }
+// records of every window + median pools (64 samples of slack behind the last pool: the profile staging reads 64 samples per window)
+size_t pf_win2_scratch_bytes(int n) {
+    return sizeof(PfWinRec) * (size_t)n * PF_W2_WCAP + 256 + sizeof(uint32_t) * ((size_t)n * PF_W2_POOL + 256);
+}
 
 int launch_pf_windows2(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWinRec* recs, PfWin* wins,
                        int n, PfTimers* tm) {
     const size_t smem = (size_t)WA_WARPS * 2 * WA_SLOT;
-    EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<false>, smem);
+    uint32_t* pools = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(recs) + ((sizeof(PfWinRec) * (size_t)n * PF_W2_WCAP + 255) / 256) * 256);
     static int gx = 0;
     if (gx == 0) { const char* e = getenv("EPID_WA_GRID"); gx = e ? atoi(e) : WA_GRID_X; if (gx < 1 || gx > 64) gx = WA_GRID_X; }
     static int loader = -1;
     if (loader < 0) { const char* e = getenv("EPID_WA_LOADER"); loader = e ? atoi(e) : 0; }
     if (loader == 1) {
         EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<true>, smem);
-        k_pf_win_medians<true><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs);
+        k_pf_win_medians<true><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs, pools);
     } else {
-        k_pf_win_medians<false><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs);
+        EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<false>, smem);
+        k_pf_win_medians<false><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs, pools);
     }
     ctx->launches++;
     if (tm) { int rc = tm->mark(stream, PF_STAGE_WIN_MEDIANS); if (rc != EPID_OK) return rc; }
-    k_pf_win_fwxm<<<dim3(PF_W2_WCAP / WB_THREADS, n), WB_THREADS, 0, stream>>>(cst, fr, recs, wins);
+    k_pf_win_fwxm<<<dim3(PF_W2_WCAP / WB_THREADS, n), WB_THREADS, 0, stream>>>(cst, fr, recs, pools, wins);
     ctx->launches++;
     if (tm) { int rc = tm->mark(stream, PF_STAGE_WIN_FWXM); if (rc != EPID_OK) return rc; }
     EPID_CUDA(cudaGetLastError());

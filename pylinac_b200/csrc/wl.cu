@@ -545,6 +545,9 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     else if (bb_d <= 1.5) tol = 2.0;
     else if (bb_d >= 30.0) tol = 4.0;
     else { const double slope = (4.0 - 2.0) / (30.0 - 1.5); tol = slope * (bb_d - 1.5) + 2.0; }
+    // detection conditions (metrics/features.py): all five for Winston-Lutz, the caller's subset for the stand-alone locator
+    const int cm = loc ? c.loc.conditions : 31;
+    const bool c_size = cm & 1, c_round = cm & 2, c_circ = cm & 4, c_sym = cm & 8, c_solid = cm & 16;
     const int max_number = loc ? min(max(c.loc.max_number, 1), WL_MAXPTS) : 1;
     const double min_sep = loc ? c.loc.min_separation_px : 5.0 * dpmm;      // deduplicate_points_and_boundaries (metrics/utils.py:14-37)
     const double PI = 3.141592653589793;
@@ -616,10 +619,10 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             const int bh = by1 - by0, bw = bx1 - bx0;
             const double bbox_area = (double)bh * (double)bw;
             // cheap necessary conditions of is_right_size_bb: area <= area_filled <= bbox area
-            if (!(smaller_area < bbox_area / (dpmm * dpmm)) || !((double)comp->area[id] / (dpmm * dpmm) < larger_area)) continue;
+            if (c_size && (!(smaller_area < bbox_area / (dpmm * dpmm)) || !((double)comp->area[id] / (dpmm * dpmm) < larger_area))) continue;
             if (bh + 2 > WL_TILE || bw + 2 > WL_TILE) {
                 // a region this large cannot be round, symmetric and of the right size at once unless the tile is too small
-                if (bbox_area * (PI / 4 * 0.8) / (dpmm * dpmm) < larger_area) fatal = 1;
+                if (!c_size || !c_round || bbox_area * (PI / 4 * 0.8) / (dpmm * dpmm) < larger_area) fatal = 1;
                 continue;
             }
             const int th = bh + 2, tw = bw + 2;
@@ -644,10 +647,10 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             __syncthreads();
             // is_right_size_bb
             const double bb_area = (double)filled / (dpmm * dpmm);
-            if (!(smaller_area < bb_area && bb_area < larger_area)) continue;
+            if (c_size && !(smaller_area < bb_area && bb_area < larger_area)) continue;
             // is_round
             const double ratio = (double)filled / bbox_area;
-            if (!(PI / 4 * 1.2 > ratio && ratio > PI / 4 * 0.8)) continue;
+            if (c_round && !(PI / 4 * 1.2 > ratio && ratio > PI / 4 * 0.8)) continue;
             // is_right_circumference: skimage.measure.perimeter(image, neighborhood=4) on the region mask (tile2 = mask)
             if (tid < 50) s_hist50[tid] = 0;
             __syncthreads();
@@ -688,11 +691,11 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             }
             __syncthreads();
             const double per_mm = perim / dpmm;
-            if (!(2 * PI * (radius_mm + tol) > per_mm && per_mm > 2 * PI * (radius_mm - tol))) continue;
+            if (c_circ && !(2 * PI * (radius_mm + tol) > per_mm && per_mm > 2 * PI * (radius_mm - tol))) continue;
             // is_symmetric
             {
                 const double y = (double)bh, x = (double)bw;
-                if (x > fmax(y * 1.05, y + 3) || x < fmin(y * 0.95, y - 3)) continue;
+                if (c_sym && (x > fmax(y * 1.05, y + 3) || x < fmin(y * 0.95, y - 3))) continue;
             }
             // is_solid: area / area_convex > 0.9; convex hull of the pixels' diamond offsets (r +- 0.5, c), (r, c +- 0.5).
             // Per half-row level L = 2 r + {-1, 0, 1} keep the extreme doubled column coordinates; the hull's column extent at an
@@ -735,7 +738,7 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             convex = 0;
             for (int k = 0; k < WL_WARPS; k++) convex += s_i[1 + k];
             __syncthreads();
-            if (!((double)comp->area[id] / (double)convex > 0.9)) continue;
+            if (c_solid && !((double)comp->area[id] / (double)convex > 0.9)) continue;
             // -- accepted: centroid_weighted (local moments of the stretched sample over the region, + bbox origin)
             if (tid < 4) s_lvl[tid] = 0;      // (the hull levels are no longer needed) 64-bit accumulators of the unweighted moments
             __syncthreads();
