@@ -237,6 +237,11 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
  * device except the last), return the CUDA-event time of the whole region and of the frame-statistics kernel. */
 int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters,
                       float* total_ms, float* stats_kernel_ms, int64_t* launches);
+/* the same timed region with CUDA-event marks between the kernels: total_ms of `iters` back-to-back passes, stage_ms[k] summed over
+ * the passes (stage ids as for epid_pf_bench_stages), kernel launches and the number of frames the per-frame exact fallback re-ran
+ * (when the batch contains deferred frames the passes are timed with the host round trip of the fallback included) */
+int32_t epid_pf_bench_timed(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* total_ms,
+                            float* stage_ms, int32_t nstages, int64_t* launches, int64_t* redone_frames);
 /* per-stage device times of `iters` passes (CUDA events between the kernels; bench.py's per-kernel roofline table):
  * stage_ms[0..9] = init + pilot, stream, tail, windows (per-window kernel), windows (generic), finalize, exact front end (fallback
  * only), windows (leaf-band kernel), windows (two-kernel path: medians), windows (two-kernel path: per-window analysis) */

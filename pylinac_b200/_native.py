@@ -266,6 +266,8 @@ _SIGNATURES = {
     "epid_pf_bench": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float),
                       C.POINTER(C.c_int64)],
     "epid_pf_bench_stages": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.c_int32],
+    "epid_pf_bench_timed": [_P, _P, C.POINTER(PFParams), C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32,
+                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
     "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
     "epid_circle_profile": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_double,
                             C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)],
@@ -571,6 +573,16 @@ def pf_bench(ctx: Context, batch: Batch, params: PFParams, iters: int):
 
 PF_STAGE_NAMES = ("k_pf_init + k_pf_pilot", "k_pf_stream", "k_pf_tail", "k_pf_windows_fast", "k_pf_windows (generic)", "k_pf_finalize",
                   "exact front end (fallback)", "k_pf_leafband", "k_pf_win_medians", "k_pf_win_fwxm")
+
+
+def pf_bench_timed(ctx: Context, batch: Batch, params: PFParams, iters: int):
+    """(total_ms of `iters` passes, {stage name: ms per pass}, launches, frames re-run by the per-frame fallback)"""
+    out = (C.c_float * 16)()
+    total = C.c_float()
+    launches, redone = C.c_int64(), C.c_int64()
+    check(lib().epid_pf_bench_timed(ctx.handle, batch.handle, C.byref(params), iters, C.byref(total), out, 16, C.byref(launches),
+                                    C.byref(redone)))
+    return total.value, {name: out[k] / iters for k, name in enumerate(PF_STAGE_NAMES)}, launches.value, redone.value
 
 
 def pf_bench_stages(ctx: Context, batch: Batch, params: PFParams, iters: int) -> dict:

@@ -58,8 +58,12 @@ struct epid_ctx {
     size_t scratch_bytes = 0;
     void* scratch2 = nullptr;            // work area of the per-frame exact re-run (pf.cu)
     size_t scratch2_bytes = 0;
+    void* hist_scratch = nullptr;        // histograms + column partials of the multi-CTA frame statistics (stats.cu)
+    size_t hist_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    void* pinned_ring = nullptr;         // page-locked staging ring for pageable source frames (pf.cu)
+    size_t pinned_ring_bytes = 0;
     // options / diagnostics (epid_set_option / epid_get_counter)
     int pf_exact_only = 0;               // 1: never use the fused sample-guided front kernel
     int pf_leafband = 0;                 // 1: experimental leaf-band window kernel for the frames it covers (default: per-window kernel)

@@ -104,6 +104,9 @@ int32_t epid_ctx_destroy(epid_ctx* ctx) {
     if (ctx->nccl_comm) epid_comm_destroy(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
+    if (ctx->hist_scratch) cudaFree(ctx->hist_scratch);
+    if (ctx->pinned_ring) cudaFreeHost(ctx->pinned_ring);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->copy_stream[0]);

@@ -21,6 +21,10 @@
 //   k_pf_windows    ~0.5 read per (leaf, picket) window: validity, median profile, FWHM edges
 //   k_pf_finalize   -        leaf-row pruning, per-picket line fit, errors, aggregates
 #include <cmath>
+#include <condition_variable>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
 
 #include "pf_common.cuh"
 
@@ -715,6 +719,15 @@ static int pf_redo_deferred(epid_ctx* ctx, cudaStream_t stream, const uint16_t* 
     return EPID_OK;
 }
 
+static int ensure_pinned_ring(epid_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_ring_bytes >= bytes) return EPID_OK;
+    if (ctx->pinned_ring) { EPID_CUDA(cudaStreamSynchronize(ctx->copy_stream[0])); EPID_CUDA(cudaFreeHost(ctx->pinned_ring)); ctx->pinned_ring = nullptr; ctx->pinned_ring_bytes = 0; }
+    cudaError_t e = cudaMallocHost(&ctx->pinned_ring, bytes);
+    if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); return EPID_ERR_NOMEM; }
+    ctx->pinned_ring_bytes = bytes;
+    return EPID_OK;
+}
+
 static int pf_validate(const epid_pf_params* p, int H0, int W0, int meas_cap) {
     EPID_REQUIRE(p, EPID_ERR_INVALID, "params is NULL");
     EPID_REQUIRE(p->dpmm > 0, EPID_ERR_INVALID, "dpmm must be positive");
@@ -734,6 +747,71 @@ static int pf_validate(const epid_pf_params* p, int H0, int W0, int meas_cap) {
 using namespace epid;
 
 namespace {
+
+// Persistent host threads that copy a pageable chunk into the page-locked staging ring in parallel slices: one thread moves
+// ~10 GB/s, the PCIe link takes ~54 GB/s, so a pageable source needs several copy streams to keep the link busy.
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool p;
+        return p;
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        const int T = (int)workers_.size();
+        if (T == 0 || bytes < (8u << 20)) { memcpy(dst, src, bytes); return; }
+        std::unique_lock<std::mutex> lk(m_);
+        dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
+        pending_ = T;
+        gen_++;
+        cv_.notify_all();
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    int threads() const { return (int)workers_.size(); }
+
+private:
+    CopyPool() {
+        int T = 8;
+        if (const char* e = getenv("EPID_COPY_THREADS")) T = atoi(e);
+        const int hw = (int)std::thread::hardware_concurrency();
+        if (hw > 0 && T > hw) T = hw;
+        if (T < 0) T = 0;
+        for (int i = 0; i < T; i++) workers_.emplace_back([this, i, T] { run(i, T); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run(int i, int T) {
+        unsigned long long seen = 0;
+        for (;;) {
+            char* d; const char* s; size_t b;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                d = dst_; s = src_; b = bytes_;
+            }
+            const size_t per = ((b + T - 1) / T + 4095) & ~(size_t)4095;
+            const size_t o = per * (size_t)i;
+            if (o < b) memcpy(d + o, s + o, b - o < per ? b - o : per);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0;
+    int pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
 
 struct PfResultCopy {   // async D2H of one chunk's results + the counters ([2] = number of deferred frames)
     static int enqueue(cudaStream_t st, const PfWork& w, int cnt, int meas_cap, epid_pf_summary* summ, epid_pf_meas* meas, int* counters2) {
@@ -788,9 +866,10 @@ int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_p
     return rc;
 }
 
-int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* total_ms,
-                      float* stats_kernel_ms, int64_t* launches) {
+static int32_t pf_bench_impl(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* total_ms,
+                             float* stats_kernel_ms, int64_t* launches, float* stage_ms, int32_t nstages, int64_t* redone) {
     EPID_REQUIRE(ctx && frames && p && iters > 0, EPID_ERR_INVALID, "bad argument");
+    EPID_REQUIRE(!stage_ms || nstages >= PF_NSTAGES, EPID_ERR_INVALID, "stage_ms needs %d entries", PF_NSTAGES);
     EPID_REQUIRE(frames->dtype == EPID_U16, EPID_ERR_UNSUPPORTED, "picket fence frames must be uint16");
     const int meas_cap = 1024;
     int rc = pf_validate(p, frames->h, frames->w, meas_cap);
@@ -812,7 +891,8 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
     for (int mode = 0; mode < 2; mode++) {
         PfTimers tm;
         tm.on = true;
-        const int64_t l0 = ctx->launches;
+        tm.stages = stage_ms != nullptr;
+        const int64_t l0 = ctx->launches, rd0 = ctx->pf_redone_frames;
         int cnt3[3] = {0, 0, 0};
         EPID_CUDA(cudaStreamSynchronize(ctx->stream));
         EPID_CUDA(cudaEventRecord(t0, ctx->stream));
@@ -832,6 +912,8 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
         if (total_ms) *total_ms = ms;
         if (stats_kernel_ms) *stats_kernel_ms = tm.total_ms();
         if (launches) *launches = ctx->launches - l0;
+        if (redone) *redone = ctx->pf_redone_frames - rd0;
+        if (stage_ms) tm.stage_ms(stage_ms, PF_NSTAGES);
         tm.destroy();
         if (rc != EPID_OK || !fast || mode == 1 || cnt3[2] == 0) break;
         ctx->pf_fallbacks++;
@@ -839,6 +921,16 @@ int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_par
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
     return rc;
+}
+
+int32_t epid_pf_bench(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* total_ms,
+                      float* stats_kernel_ms, int64_t* launches) {
+    return pf_bench_impl(ctx, frames, p, iters, total_ms, stats_kernel_ms, launches, nullptr, 0, nullptr);
+}
+
+int32_t epid_pf_bench_timed(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* total_ms, float* stage_ms,
+                            int32_t nstages, int64_t* launches, int64_t* redone_frames) {
+    return pf_bench_impl(ctx, frames, p, iters, total_ms, nullptr, launches, stage_ms, nstages, redone_frames);
 }
 
 int32_t epid_pf_bench_stages(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, int32_t iters, float* stage_ms, int32_t nstages) {
@@ -915,6 +1007,15 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
         return a.type == cudaMemoryTypeHost;
     };
     const bool direct = pinned_host(summary) && pinned_host(meas);
+    // pageable source frames: staged through a page-locked ring, filled by parallel host copies that overlap the previous chunk's DMA
+    const bool src_pinned = pinned_host(frames);
+    char* ring[2] = {nullptr, nullptr};
+    if (!src_pinned) {
+        rc = ensure_pinned_ring(ctx, 2 * buf_bytes);
+        if (rc != EPID_OK) return rc;
+        ring[0] = (char*)ctx->pinned_ring;
+        ring[1] = ring[0] + buf_bytes;
+    }
     cudaEvent_t copied[2], computed[2];
     for (int s = 0; s < 2; s++) { EPID_CUDA(cudaEventCreateWithFlags(&copied[s], cudaEventDisableTiming)); EPID_CUDA(cudaEventCreateWithFlags(&computed[s], cudaEventDisableTiming)); }
     uint16_t* pools[3] = {nullptr, nullptr, nullptr};
@@ -923,7 +1024,15 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
     auto enqueue_copy = [&](int ci) -> int {
         const int s = ci & 1;
         // the buffer is free once the compute that last used it has finished (finish(ci - 2) already waited for it)
-        EPID_CUDA(cudaMemcpyAsync(bufs[s], frames + (size_t)ci * chunk * h * w_, fbytes * count_of(ci), cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+        const uint16_t* src = frames + (size_t)ci * chunk * h * w_;
+        if (!src_pinned) {
+            // ring slot s was last read by the DMA of chunk ci - 2: its `copied` event has been waited for by the compute stream
+            // two iterations ago, but the HOST must see it finished before overwriting the slot
+            if (ci >= 2) EPID_CUDA(cudaEventSynchronize(copied[s]));
+            CopyPool::get().copy(ring[s], src, fbytes * count_of(ci));
+            src = (const uint16_t*)ring[s];
+        }
+        EPID_CUDA(cudaMemcpyAsync(bufs[s], src, fbytes * count_of(ci), cudaMemcpyHostToDevice, ctx->copy_stream[0]));
         EPID_CUDA(cudaEventRecord(copied[s], ctx->copy_stream[0]));
         return EPID_OK;
     };

@@ -14,6 +14,8 @@
 // a frame share one value; that is detected exactly (the decoded bin total then differs from the pixel count)
 // and the frame is re-run by the MODE 1 variant (32-bit counters over value>>1 plus a second pass resolving
 // the low bit), so results are always exact.
+#include <cstdlib>
+
 #include "stats.cuh"
 
 namespace epid {
@@ -297,12 +299,234 @@ k_frame_stats(const StatsGeom g, const FrameRef* __restrict__ frames, const int*
     }
 }
 
+// ------------------------------------------------------------------------------------------------ multi-CTA variant
+// The single-CTA kernel above keeps a frame's histogram in shared memory, which ties a frame to one SM (~1 GB/s per frame).  This
+// variant spreads a frame over HV_PARTS CTAs: each streams a block of rows with 16-byte loads, merges equal values of a warp
+// (__match_any_sync) into a direct-mapped shared-memory cache of histogram bins (first claimant owns a slot, losers go to the global
+// histogram; one global atomic per occupied slot at the end), keeps column sums in registers and writes row sums directly; a
+// second kernel (one CTA per frame) turns the 65536-bin histogram into min / max / sum / order statistics and adds the column
+// partials.  Exact like the single-CTA kernel (32-bit counters, no overflow path).  Views up to 2040 columns.
+constexpr int HV_PARTS = 16;
+constexpr int HV_THREADS = 256;
+constexpr int HV_WARPS = HV_THREADS / 32;
+constexpr int HV_SLOTS = 4096;
+
+template <int VPL>
+__global__ void __launch_bounds__(HV_THREADS)
+k_hist_view(const StatsGeom g, const FrameRef* __restrict__ frames, uint32_t* __restrict__ hist, uint32_t* __restrict__ rowsum_out,
+            uint32_t* __restrict__ colpart, int wa) {
+    __shared__ uint32_t s_tag[HV_SLOTS];     // value + 1, 0 = free
+    __shared__ uint32_t s_cnt[HV_SLOTS];
+    extern __shared__ uint32_t s_col[];      // wa column accumulators of the CTA
+    const int fi = blockIdx.y, part = blockIdx.x;
+    const FrameRef fr = frames[fi];
+    const uint16_t* __restrict__ f = fr.origin;
+    const int pitch = fr.pitch;
+    uint32_t* h = hist + (size_t)fi * 65536;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool aligned = (pitch % 8) == 0;
+    const int mis = aligned ? (int)((reinterpret_cast<uintptr_t>(f) >> 1) & 7) : 0;
+    for (int i = tid; i < HV_SLOTS; i += HV_THREADS) { s_tag[i] = 0; s_cnt[i] = 0; }
+    for (int i = tid; i < wa; i += HV_THREADS) s_col[i] = 0;
+    __syncthreads();
+    auto add = [&](uint32_t v, bool in) {
+        const unsigned m = __match_any_sync(0xffffffffu, in ? v : 0x10000u);
+        if (in && lane == __ffs(m) - 1) {
+            const uint32_t cn = (uint32_t)__popc(m), slot = v & (HV_SLOTS - 1);
+            const uint32_t old = atomicCAS(&s_tag[slot], 0u, v + 1u);
+            if (old == 0u || old == v + 1u) atomicAdd(&s_cnt[slot], cn);
+            else atomicAdd(&h[v], cn);
+        }
+    };
+    const int rp = (g.H + HV_PARTS - 1) / HV_PARTS;
+    const int r0 = part * rp, r1 = min(g.H, r0 + rp);
+    uint32_t csum[VPL][8];
+#pragma unroll
+    for (int k = 0; k < VPL; k++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) csum[k][e] = 0;
+    for (int r = r0 + wid; r < r1; r += HV_WARPS) {
+        const uint16_t* rowp = f + (size_t)r * pitch;
+        uint32_t rs = 0;
+        uint4 q[VPL];
+        uint32_t valid[VPL];
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            const int col_first = (lane + 32 * k) * 8 - mis;
+            uint32_t vm = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) { const int cidx = col_first + e; if (cidx >= 0 && cidx < g.W) vm |= 1u << e; }
+            valid[k] = vm;
+            q[k] = make_uint4(0, 0, 0, 0);
+            if (vm) {
+                if (aligned) q[k] = ldg_stream16(rowp + col_first);
+                else {
+                    uint32_t w4[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int e = 0; e < 8; e++) if (vm >> e & 1) w4[e >> 1] |= (uint32_t)__ldg(rowp + col_first + e) << ((e & 1) * 16);
+                    q[k] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VPL; k++) {
+            const uint32_t w4[4] = {q[k].x, q[k].y, q[k].z, q[k].w};
+            const bool any = __any_sync(0xffffffffu, valid[k] != 0);
+            if (!any) continue;     // warp-uniform
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t v = (w4[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+                const bool in = valid[k] >> e & 1;
+                add(v, in);
+                if (in) { csum[k][e] += v; rs += v; }
+            }
+        }
+        rs = warp_sum(rs);
+        if (lane == 0 && rowsum_out) rowsum_out[(size_t)fi * g.H + r] = rs;
+    }
+    // column partials: registers -> CTA accumulators -> one partial row per (frame, part)
+#pragma unroll
+    for (int k = 0; k < VPL; k++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int ac = (lane + 32 * k) * 8 + e;
+            if (ac < wa && csum[k][e]) atomicAdd(&s_col[ac], csum[k][e]);
+        }
+    __syncthreads();
+    if (colpart) for (int i = tid; i < wa; i += HV_THREADS) colpart[((size_t)fi * HV_PARTS + part) * wa + i] = s_col[i];
+    for (int i = tid; i < HV_SLOTS; i += HV_THREADS) {
+        const uint32_t tg = s_tag[i];
+        if (tg) atomicAdd(&h[tg - 1u], s_cnt[i]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_stats_from_hist(const StatsGeom g, const FrameRef* __restrict__ frames, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ colpart,
+                  int wa, FrameStats* __restrict__ stats, uint32_t* __restrict__ colsum_out) {
+    __shared__ uint32_t s_part[256];
+    __shared__ unsigned long long s_wsum[256];
+    __shared__ uint32_t s_first, s_last;
+    __shared__ unsigned long long s_corner;
+    __shared__ uint32_t s_val[STATS_MAX_RANKS];
+    const int fi = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const uint32_t* h = hist + (size_t)fi * 65536;
+    const FrameRef fr = frames[fi];
+    uint32_t cnt = 0, lo_bin = 0xffffffffu, hi_bin = 0;
+    unsigned long long ws = 0;
+    for (int b = tid * 256; b < (tid + 1) * 256; b++) {
+        const uint32_t hb = h[b];
+        cnt += hb;
+        ws += (unsigned long long)hb * (unsigned)b;
+        if (hb) { if (lo_bin == 0xffffffffu) lo_bin = b; hi_bin = b; }
+    }
+    s_part[tid] = cnt;
+    s_wsum[tid] = ws;
+    if (tid == 0) { s_first = 0xffffffffu; s_last = 0; s_corner = 0; }
+    __syncthreads();
+    if (lo_bin != 0xffffffffu) { atomicMin(&s_first, lo_bin); atomicMax(&s_last, hi_bin); }
+    uint32_t excl = 0;
+    for (int k = 0; k < tid; k++) excl += s_part[k];
+    for (int qi = 0; qi < g.nranks; qi++) {
+        const uint32_t k = g.ranks[qi];
+        if (k >= excl && k < excl + cnt) {
+            uint32_t acc = excl;
+            for (int b = tid * 256; b < (tid + 1) * 256; b++) {
+                const uint32_t hb = h[b];
+                if (k < acc + hb) { s_val[qi] = (uint32_t)b; break; }
+                acc += hb;
+            }
+        }
+    }
+    // corner boxes (core/image.py:881-894)
+    if (g.box > 0) {
+        const int per = g.box * g.box;
+        unsigned long long cs = 0;
+        for (int i = tid; i < 4 * per; i += 256) {
+            const int b = i / per, o = i - b * per;
+            const int y = o / g.box, x = o - y * g.box;
+            const int rr = ((b & 2) ? g.H - g.rp - g.box : g.rp) + y;
+            const int cc = ((b & 1) ? g.W - g.cp - g.box : g.cp) + x;
+            if (rr >= 0 && rr < g.H && cc >= 0 && cc < g.W) cs += __ldg(fr.origin + (size_t)rr * fr.pitch + cc);
+        }
+        cs = warp_sum(cs);
+        if (lane == 0 && cs) atomicAdd(&s_corner, cs);
+    }
+    // column sums: the parts' partial rows (vector-grid columns) -> view columns
+    if (colsum_out && colpart) {
+        const bool aligned = (fr.pitch % 8) == 0;
+        const int mis = aligned ? (int)((reinterpret_cast<uintptr_t>(fr.origin) >> 1) & 7) : 0;
+        for (int x = tid; x < g.W; x += 256) {
+            uint32_t sum = 0;
+            for (int p = 0; p < HV_PARTS; p++) sum += colpart[((size_t)fi * HV_PARTS + p) * wa + x + mis];
+            colsum_out[(size_t)fi * g.W + x] = sum;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long tot = 0;
+        for (int k = 0; k < 256; k++) tot += s_wsum[k];
+        FrameStats& o = stats[fi];
+        o.mn = s_first;
+        o.mx = s_last;
+        o.npix = (uint32_t)g.H * (uint32_t)g.W;
+        o.sum = tot;
+        o.corner_sum = s_corner;
+        o.overflow = 0;
+        for (int qi = 0; qi < g.nranks; qi++) o.ostat[qi] = s_val[qi];
+    }
+}
+
+static int ensure_hist_scratch(epid_ctx* ctx, size_t bytes) {
+    if (ctx->hist_bytes >= bytes) return EPID_OK;
+    if (ctx->hist_scratch) { EPID_CUDA(cudaStreamSynchronize(ctx->stream)); EPID_CUDA(cudaFree(ctx->hist_scratch)); ctx->hist_scratch = nullptr; ctx->hist_bytes = 0; }
+    cudaError_t e = cudaMalloc(&ctx->hist_scratch, bytes);
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return EPID_ERR_NOMEM; }
+    ctx->hist_bytes = bytes;
+    return EPID_OK;
+}
+
+template <int VPL>
+static int launch_hist_view(cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames, int cn, uint32_t* hist, uint32_t* rowsum,
+                            uint32_t* colpart, int wa) {
+    k_hist_view<VPL><<<dim3(HV_PARTS, cn), HV_THREADS, sizeof(uint32_t) * wa, stream>>>(g, d_frames, hist, rowsum, colpart, wa);
+    return EPID_OK;
+}
+
+static int launch_frame_stats_v2(epid_ctx* ctx, cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames, int n, FrameStats* d_stats,
+                                 uint32_t* d_rowsum, uint32_t* d_colsum) {
+    const int nvec = (g.W + 7 + 7) / 8;
+    const int vpl = (nvec + 31) / 32;
+    const int wa = vpl * 32 * 8;                 // columns of the vector grid
+    const int chunk = n < 256 ? n : 256;
+    const size_t hist_b = sizeof(uint32_t) * (size_t)chunk * 65536, col_b = sizeof(uint32_t) * (size_t)chunk * HV_PARTS * wa;
+    int rc = ensure_hist_scratch(ctx, hist_b + col_b + 512);
+    if (rc != EPID_OK) return rc;
+    uint32_t* hist = (uint32_t*)ctx->hist_scratch;
+    uint32_t* colpart = d_colsum ? (uint32_t*)((char*)ctx->hist_scratch + (hist_b + 255) / 256 * 256) : nullptr;
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int cn = n - c0 < chunk ? n - c0 : chunk;
+        EPID_CUDA(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (size_t)cn * 65536, stream));
+        uint32_t* rs = d_rowsum ? d_rowsum + (size_t)c0 * g.H : nullptr;
+        if (vpl <= 4) rc = launch_hist_view<4>(stream, g, d_frames + c0, cn, hist, rs, colpart, wa);
+        else rc = launch_hist_view<8>(stream, g, d_frames + c0, cn, hist, rs, colpart, wa);
+        k_stats_from_hist<<<cn, 256, 0, stream>>>(g, d_frames + c0, hist, colpart, wa, d_stats + c0, d_colsum ? d_colsum + (size_t)c0 * g.W : nullptr);
+        ctx->launches += 2;
+        EPID_CUDA(cudaGetLastError());
+    }
+    return EPID_OK;
+}
+
 static size_t stats_smem_bytes(const StatsGeom& g) {
     return sizeof(uint32_t) * (size_t)(HIST_WORDS + STATS_THREADS * 8 + g.H + 40 + 8 + 3 * STATS_MAX_RANKS);
 }
 
 int launch_frame_stats(epid_ctx* ctx, cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames,
                        const int* d_out_index, int n, FrameStats* d_stats, uint32_t* d_rowsum, uint32_t* d_colsum) {
+    // multi-CTA histogram path for every view it covers (d_out_index is not used by any caller of that path)
+    static int v1 = -1;
+    if (v1 < 0) { const char* e = getenv("EPID_STATS_V1"); v1 = e ? atoi(e) : 0; }
+    if (!v1 && !d_out_index && g.W <= 2040 && g.nranks <= STATS_MAX_RANKS)
+        return launch_frame_stats_v2(ctx, stream, g, d_frames, n, d_stats, d_rowsum, d_colsum);
     const size_t smem = stats_smem_bytes(g);
     EPID_SMEM_OPT_IN(ctx, k_frame_stats<0>, 220 * 1024);
     EPID_SMEM_OPT_IN(ctx, k_frame_stats<1>, 220 * 1024);
