@@ -62,15 +62,14 @@ constexpr int PF_W2_NCW = 64;      // travel samples per window
 constexpr int PF_W2_NRW = 32;      // rows per window
 constexpr int PF_W2_WCAP = 1024;   // windows per frame (in-view leaves x pickets)
 constexpr int PF_W2_POOL = PF_W2_WCAP * PF_W2_NCW;     // median samples per frame (bands of neighbouring windows share columns)
-struct alignas(16) PfWinRec {              // one per window, 48 bytes (read with 16-byte loads)
+struct alignas(16) PfWinRec {              // one per window, 400 bytes
     uint32_t hdr;                          // nc | nr << 16 (signed 16-bit each)
     uint32_t moff;                         // first sample of the window in the frame's median pool
-    uint32_t gmax;                         // largest g inside the window
-    uint32_t pad;
-    unsigned long long kmax, ka, kb;       // variance numerators nc * S2 - S1^2 of the rows: largest, and the two middle order statistics
-    unsigned long long pad2;
+    uint32_t pad[2];
+    unsigned long long num[PF_W2_NRW];     // nc * S2 - S1^2 per row (variance numerator along travel)
+    uint32_t ext[PF_W2_NRW];               // raw row maximum << 16 | raw row minimum, inside the window
 };
-static_assert(sizeof(PfWinRec) == 48, "PfWinRec layout");
+static_assert(sizeof(PfWinRec) == 400, "PfWinRec layout");
 
 // numpy _lerp (numpy/lib/_function_base_impl.py): a + (b-a)*t, and b - (b-a)*(1-t) where t >= 0.5
 __device__ __forceinline__ double np_lerp(double a, double b, double t) {

@@ -213,11 +213,11 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
         const uint32_t bar = sl ? bar1 : bar0;
         const uint32_t bytes = (uint32_t)nvec * 16u;
         if (lane == 0) mbar_expect_tx(bar, (uint32_t)nr * bytes);
-        const uint32_t dst0 = smem_u32(slot0 + (size_t)sl * WA_SLOT);
-        for (int r = 0; r < nr; r++) {               // warp-uniform loop: one lane issues, every operand is uniform
-            int row = b0 + r - sag;                  // np.roll(sag) folded into the source row
+        __syncwarp();
+        if (lane < nr) {                             // one bulk copy per row, each issued by the lane of that row
+            int row = b0 + lane - sag;               // np.roll(sag) folded into the source row
             if (sag) { row %= H; if (row < 0) row += H; }
-            if (lane == 0) tma_load_1d(dst0 + (uint32_t)(r * RS), frf.origin + ((ptrdiff_t)row * frf.pitch + cs), bytes, bar);
+            tma_load_1d(smem_u32(slot0 + (size_t)sl * WA_SLOT + (size_t)lane * RS), frf.origin + ((ptrdiff_t)row * frf.pitch + cs), bytes, bar);
         }
     };
 
@@ -265,107 +265,76 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
             if (wlo == whi) { mfirst &= mlast; }
             const unsigned long long ncl = (unsigned long long)(a1 - a0);
             const int nk = (nr + RPI - 1) / RPI;                       // <= WA_KMAX
-            unsigned long long num[WA_KMAX];
 #pragma unroll
             for (int k = 0; k < WA_KMAX; k++) {
-                num[k] = 0;
                 if (k < nk) {
                     const int r = k * RPI + rr;
-                    if (win_on && r < nr) {
-                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(band + (size_t)r * RS);
-                        uint32_t s1 = 0, sA = 0, sB = 0;
-                        auto acc = [&](uint32_t x) {
-                            // lo^2 + hi^2 = 256 * (lo * (lo >> 8) + hi * (hi >> 8)) + (lo * (lo & 255) + hi * (hi & 255)): two IDP.2A
-                            s1 = __dp2a_lo(x, 0x0101u, s1);
-                            sA = __dp2a_lo(x, __byte_perm(x, 0u, 0x4431), sA);
-                            sB = __dp2a_lo(x, __byte_perm(x, 0u, 0x4420), sB);
-                        };
-                        acc(wp[wlo] & mfirst);
+                    if (lane_on && r < nr) {
+                        unsigned long long numv = 0;
+                        uint32_t e = 0x0000ffffu;
+                        if (win_on) {
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(band + (size_t)r * RS);
+                            uint32_t s1 = 0, sA = 0, sB = 0, mx2 = 0, mn2 = 0xffffffffu;
+                            auto acc = [&](uint32_t x) {
+                                // lo^2 + hi^2 = 256 * (lo * (lo >> 8) + hi * (hi >> 8)) + (lo * (lo & 255) + hi * (hi & 255)): two IDP.2A
+                                s1 = __dp2a_lo(x, 0x0101u, s1);
+                                sA = __dp2a_lo(x, __byte_perm(x, 0u, 0x4431), sA);
+                                sB = __dp2a_lo(x, __byte_perm(x, 0u, 0x4420), sB);
+                                mx2 = __vmaxu2(mx2, x);
+                            };
+                            // the masked edge words: zero for the sums and the maximum, all-ones for the minimum
+                            const uint32_t xf = wp[wlo];
+                            acc(xf & mfirst);
+                            mn2 = __vminu2(mn2, xf | ~mfirst);
 #pragma unroll 8
-                        for (int w = wlo + 1; w < whi; w++) acc(wp[w]);
-                        if (whi > wlo) acc(wp[whi] & mlast);
-                        const unsigned long long s2 = ((unsigned long long)sA << 8) + (unsigned long long)sB;
-                        num[k] = ncl * s2 - (unsigned long long)s1 * s1;
-                    }
-                }
-            }
-            // ---- rank the numerators of every window across its lanes: largest, and the two middle order statistics
-            int rank[WA_KMAX];
-#pragma unroll
-            for (int k = 0; k < WA_KMAX; k++) rank[k] = 0;
-            unsigned long long kmx = 0;
-            for (int s = 0; s < RPI; s++) {
-                const int src = q * RPI + s;
-#pragma unroll
-                for (int k2 = 0; k2 < WA_KMAX; k2++) {
-                    if (k2 < nk) {
-                        const unsigned long long o = __shfl_sync(0xffffffffu, num[k2], src & 31);
-                        const int orow = k2 * RPI + s;
-                        if (orow < nr) {
-                            kmx = o > kmx ? o : kmx;
-#pragma unroll
-                            for (int k = 0; k < WA_KMAX; k++) {
-                                const int myrow = k * RPI + rr;
-                                if (o < num[k] || (o == num[k] && orow < myrow)) rank[k]++;
-                            }
+                            for (int w = wlo + 1; w < whi; w++) { const uint32_t x = wp[w]; acc(x); mn2 = __vminu2(mn2, x); }
+                            if (whi > wlo) { const uint32_t xl = wp[whi]; acc(xl & mlast); mn2 = __vminu2(mn2, xl | ~mlast); }
+                            const unsigned long long s2 = ((unsigned long long)sA << 8) + (unsigned long long)sB;
+                            numv = ncl * s2 - (unsigned long long)s1 * s1;
+                            e = (max(mx2 & 0xffffu, mx2 >> 16) << 16) | min(mn2 & 0xffffu, mn2 >> 16);
                         }
+                        lrec[q].num[r] = numv;
+                        lrec[q].ext[r] = e;
                     }
                 }
-            }
-            if (win_on) {
-                const int k1 = (nr - 1) / 2, k2m = nr / 2;
-#pragma unroll
-                for (int k = 0; k < WA_KMAX; k++) {
-                    const int myrow = k * RPI + rr;
-                    if (k < nk && myrow < nr) {
-                        if (rank[k] == k1) lrec[q].ka = num[k];
-                        if (rank[k] == k2m) lrec[q].kb = num[k];
-                    }
-                }
-                if (rr == 0) lrec[q].kmax = kmx;
             }
         }
-        // ---- P2: 2 * median over the rows for every pair of band columns between the group's first and last window; column
-        //      extremes -> the largest g of every window (lane q keeps window q's)
+        // ---- P2: 2 * median over the rows for every pair of band columns between the group's first and last window
         {
             const uint16_t* px = reinterpret_cast<const uint16_t*>(band);
             const int S = RS >> 1;
-            uint32_t wext = inv ? 0xffffu : 0u;        // raw extreme of window `lane` (minimum when inverted)
-            const int qa0 = lane < Gn ? s_a0[g * G + lane] : 0, qa1 = lane < Gn ? s_a1[g * G + lane] : 0;
-            for (int tb = t_lo; tb < t_hi; tb += 32) {
-                const int t = tb + lane;
-                uint32_t elo = inv ? 0xffffu : 0u, ehi = elo;
-                if (t < t_hi) {
-                    const uint3 mm = pair_median_ext_any(px, S, nr, t, inv != 0);
-                    const uint32_t g0 = inv ? 2u * mx - mm.x : mm.x - 2u * mn;
-                    const uint32_t g1 = inv ? 2u * mx - mm.y : mm.y - 2u * mn;
-                    *reinterpret_cast<uint2*>(pool + boff + 2 * (t - t_lo)) = make_uint2(g0, g1);
-                    elo = mm.z & 0xffffu;
-                    ehi = mm.z >> 16;
-                }
-                const int c0 = 2 * t + cs;                 // view column of the low half
-                for (int q = 0; q < Gn; q++) {
-                    const int x0 = __shfl_sync(0xffffffffu, qa0, q), x1 = __shfl_sync(0xffffffffu, qa1, q);
-                    const bool in0 = c0 >= x0 && c0 < x1, in1 = c0 + 1 >= x0 && c0 + 1 < x1;
-                    uint32_t v;
-                    if (inv) {
-                        v = min(in0 ? elo : 0xffffu, in1 ? ehi : 0xffffu);
-                        v = __reduce_min_sync(0xffffffffu, v);
-                        if (lane == q) wext = min(wext, v);
-                    } else {
-                        v = max(in0 ? elo : 0u, in1 ? ehi : 0u);
-                        v = __reduce_max_sync(0xffffffffu, v);
-                        if (lane == q) wext = max(wext, v);
-                    }
-                }
+            for (int t = t_lo + lane; t < t_hi; t += 32) {
+                const uint2 mm = pair_median_any(px, S, nr, t);
+                const uint32_t g0 = inv ? 2u * mx - mm.x : mm.x - 2u * mn;
+                const uint32_t g1 = inv ? 2u * mx - mm.y : mm.y - 2u * mn;
+                *reinterpret_cast<uint2*>(pool + boff + 2 * (t - t_lo)) = make_uint2(g0, g1);
             }
-            if (lane < Gn && qa1 > qa0) lrec[lane].gmax = inv ? mx - wext : wext - mn;
         }
         __syncwarp();       // every lane is done with the slot: the next iteration may overwrite the other one... and this one after it
     }
 }
 
-__global__ void __launch_bounds__(WB_THREADS, 6)
+// max, and the two middle order statistics of the nr keys a thread reads through key(i) (i < N slots, slots >= nr padded)
+template <int N, class F>
+__device__ __forceinline__ void rank_keys(F key, int nr, unsigned long long& kmax, unsigned long long& ka, unsigned long long& kb) {
+    unsigned long long r[N];
+    kmax = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        r[i] = i < nr ? key(i) : ~0ull;
+        if (i < nr && r[i] > kmax) kmax = r[i];
+    }
+    sort_net_u64<N>(r);
+    const int k1 = (nr - 1) / 2, k2 = nr / 2;
+    ka = 0; kb = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        if (i == k1) ka = r[i];
+        if (i == k2) kb = r[i];
+    }
+}
+
+__global__ void __launch_bounds__(WB_THREADS, 4)
 k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __restrict__ recs, const uint32_t* __restrict__ pools,
               PfWin* __restrict__ wins) {
     __shared__ uint32_t s_buf[WB_THREADS / 32][PF_W2_NCW * WB_ST];
@@ -383,14 +352,12 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     uint32_t* buf = s_buf[wid];
     const int w = wbase + lane;
     const bool active = w < total;
-    // ---- this thread's window record (40 bytes: two 16-byte loads and one 8-byte load, independent)
-    const PfWinRec* rp = frecs + (active ? w : total - 1);
-    const uint4 h4 = *reinterpret_cast<const uint4*>(rp);
-    const ulonglong2 k2 = *reinterpret_cast<const ulonglong2*>(&rp->kmax);
-    const unsigned long long kb = rp->kb;
-    const int my_nc = (int)(short)(h4.x & 0xffffu), my_nr = (int)(short)(h4.x >> 16);
-    const uint32_t my_moff = h4.y, my_gmax = h4.z;
-    const unsigned long long kmax = k2.x, ka = k2.y;
+    // ---- this thread's window: header, row extremes and variance numerators straight into registers (independent loads, all
+    //      in flight at once; lanes read records 400 bytes apart)
+    const PfWinRec& rec = frecs[active ? w : total - 1];
+    const uint2 h2 = *reinterpret_cast<const uint2*>(&rec);
+    const int my_nc = (int)(short)(h2.x & 0xffffu), my_nr = (int)(short)(h2.x >> 16);
+    const uint32_t my_moff = h2.y;
     int li = 0, pk = 0;
     if (active) { li = w / np; pk = w - li * np; }
     PfWin& out = wins[((size_t)fi * PF_L + li) * PF_P + pk];
@@ -402,14 +369,32 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
             run = true;
         }
     }
+    const int nrr = run ? my_nr : 0;
+    const int nr_all = __reduce_max_sync(0xffffffffu, nrr);
     // ---- _is_mlc_peak_in_window (picketfence.py:847-857): std along travel per row = sqrt(num) / (nc * D)
+    unsigned long long kmax = 0, ka = 0, kb = 0;
+    uint32_t my_vmx = 0, my_vmn = 0xffffu;
+    {
+        auto key = [&](int i) { return rec.num[i]; };
+        if (nr_all <= 16) rank_keys<16>(key, nrr, kmax, ka, kb);       // warp-uniform choice
+        else rank_keys<32>(key, nrr, kmax, ka, kb);
+#pragma unroll
+        for (int i = 0; i < PF_W2_NRW; i++) {
+            if (i < nrr) {
+                const uint32_t e = rec.ext[i];
+                my_vmx = max(my_vmx, e >> 16);
+                my_vmn = min(my_vmn, e & 0xffffu);
+            }
+        }
+    }
     if (run) {
         const double Dd = (double)f.D;
         const double dn = (double)my_nc * Dd;
         const double sd_max = sqrt((double)kmax) / dn;
         const double sa = sqrt((double)ka) / dn, sb = sqrt((double)kb) / dn;
         const double sd_med = (my_nr & 1) ? sa : (sa + sb) / 2.0;
-        const bool above = ((double)my_gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
+        const uint32_t gmax = f.inv ? f.mx - my_vmn : my_vmx - f.mn;
+        const bool above = ((double)gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
         const bool not_edge = sd_max < c.p.edge_threshold * sd_med;
         if (!(above && not_edge)) {
             out.valid = 0; out.l = 0; out.r = 0;

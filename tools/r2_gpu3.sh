@@ -13,3 +13,5 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pf
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_pf_win_fwxm -s 1 -c 1 -o gpurun_out/prof_wfwxm_r2c -f python tools/prof_pf.py 1 512 > gpurun_out/r2c_ncu2.log 2>&1
 tail -n 3 gpurun_out/r2c_ncu1.log gpurun_out/r2c_ncu2.log
 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/r2c_pytest_all.log
+python bench.py --steps 10 --warmup 3 > gpurun_out/r2c_bench.json 2> gpurun_out/r2c_bench.err; tail -c 3000 gpurun_out/r2c_bench.json; tail -5 gpurun_out/r2c_bench.err
+python tools/r2_stages.py --win2 1 --mixed 5 | tee -a gpurun_out/r2c_stages.log
