@@ -186,19 +186,76 @@ __device__ __forceinline__ uint32_t warp_select_u32(const uint32_t* __restrict__
     return lo;
 }
 
-// (p99 - p85) of two arrays at once (np.percentile 'linear'): the 8 order statistics are independent selection problems,
-// one per warp.  `sel` : 8 words of shared scratch.
+// order statistics r_prev <= r_next (adjacent or equal ranks, 0-based) of src[0..n), n <= 1024, by ONE warp: the array lives in
+// registers (32 values per lane), the value bisection runs between the array's own minimum and maximum (a sum vector spans ~2^26,
+// not 2^32), and the next order statistic is derived from the first: the same value if it occurs often enough, else the smallest
+// larger one.
+__device__ __forceinline__ void warp_select_pair_u32(const uint32_t* __restrict__ src, int n, int r_prev, int r_next, uint32_t& v_prev,
+                                                     uint32_t& v_next) {
+    const int lane = threadIdx.x & 31;
+    uint32_t x[32];
+    uint32_t mnv = 0xffffffffu, mxv = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const int i = lane + 32 * k;
+        x[k] = i < n ? src[i] : 0xffffffffu;      // padding sorts last and is never counted (see below)
+        if (i < n) { mnv = min(mnv, x[k]); mxv = max(mxv, x[k]); }
+    }
+    uint32_t lo = __reduce_min_sync(0xffffffffu, mnv), hi = __reduce_max_sync(0xffffffffu, mxv);
+    const uint32_t npad = 32u * 32u - (uint32_t)n;      // padding values equal 0xffffffff: counted only when mid == 0xffffffff
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+            c0 += x[k] <= mid ? 1u : 0u;
+            c1 += x[k + 1] <= mid ? 1u : 0u;
+            c2 += x[k + 2] <= mid ? 1u : 0u;
+            c3 += x[k + 3] <= mid ? 1u : 0u;
+        }
+        uint32_t cnt = __reduce_add_sync(0xffffffffu, (c0 + c1) + (c2 + c3));
+        if (mid == 0xffffffffu) cnt -= npad;
+        if (cnt >= (uint32_t)r_prev + 1u) hi = mid; else lo = mid + 1u;
+    }
+    v_prev = lo;
+    // how many values are <= v_prev, and the smallest value above it
+    uint32_t c = 0, above = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const int i = lane + 32 * k;
+        if (i < n) {
+            c += x[k] <= lo ? 1u : 0u;
+            if (x[k] > lo) above = min(above, x[k]);
+        }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    above = __reduce_min_sync(0xffffffffu, above);
+    v_next = (c >= (uint32_t)r_next + 1u) ? lo : above;
+}
+
+// (p99 - p85) of two arrays at once (np.percentile 'linear'): four independent (array, percentile) selection problems, one per warp
+// (each yields the pair of neighbouring order statistics numpy interpolates between).  `sel` : 8 words of shared scratch.
 __device__ inline void block_pct_ranges2(const uint32_t* __restrict__ a0, int n0, const PctPlan& p85_0, const PctPlan& p99_0,
                                          const uint32_t* __restrict__ a1, int n1, const PctPlan& p85_1, const PctPlan& p99_1,
                                          uint32_t* sel, double& range0, double& range1) {
     const int wid = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31;
     __syncthreads();
-    for (int s = wid; s < 8; s += nw) {
-        const bool second = s >= 4;
-        const PctPlan& pp = (s & 2) ? (second ? p99_1 : p99_0) : (second ? p85_1 : p85_0);
-        const int r = (s & 1) ? pp.next : pp.prev;
-        const uint32_t v = warp_select_u32(second ? a1 : a0, second ? n1 : n0, r);
-        if (lane == 0) sel[s] = v;
+    if (n0 <= 1024 && n1 <= 1024) {
+        for (int s = wid; s < 4; s += nw) {
+            const bool second = s >= 2;
+            const PctPlan& pp = (s & 1) ? (second ? p99_1 : p99_0) : (second ? p85_1 : p85_0);
+            uint32_t va, vb;
+            warp_select_pair_u32(second ? a1 : a0, second ? n1 : n0, pp.prev, pp.next, va, vb);
+            if (lane == 0) { sel[2 * s] = va; sel[2 * s + 1] = vb; }
+        }
+    } else {
+        for (int s = wid; s < 8; s += nw) {
+            const bool second = s >= 4;
+            const PctPlan& pp = (s & 2) ? (second ? p99_1 : p99_0) : (second ? p85_1 : p85_0);
+            const int r = (s & 1) ? pp.next : pp.prev;
+            const uint32_t v = warp_select_u32(second ? a1 : a0, second ? n1 : n0, r);
+            if (lane == 0) sel[s] = v;
+        }
     }
     __syncthreads();
     range0 = np_lerp((double)sel[2], (double)sel[3], p99_0.gamma) - np_lerp((double)sel[0], (double)sel[1], p85_0.gamma);

@@ -16,19 +16,73 @@ namespace epid {
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int FIN_LPL = (PF_L + 31) / 32;       // leaf slots per lane
 
-__device__ inline void block_sort_f64(double* a, int m) {
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < m; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const double x = a[i], y = a[l];
-                    if (up ? (y < x) : (x < y)) { a[i] = y; a[l] = x; }
+// np.median of n non-negative doubles a[0..n) (shared memory) by the whole block: radix selection of the lower middle order
+// statistic on the bit patterns (for non-negative doubles the unsigned order of the bits is the order of the values), eight 8-bit
+// digits, warp-aggregated shared-memory histograms; the upper middle value is the same value if it occurs often enough, else the
+// smallest larger one.  Thread 0 returns the median; every thread must call.
+__device__ inline double block_median_nonneg_f64(const double* __restrict__ a, int n) {
+    __shared__ uint32_t s_hist[256];
+    __shared__ unsigned long long s_prefix, s_above;
+    __shared__ uint32_t s_k, s_cle;
+    const int tid = threadIdx.x, lane = tid & 31;
+    auto keyat = [&](int i) { return (unsigned long long)__double_as_longlong(a[i]); };
+    const int nround = (n + FIN_THREADS - 1) / FIN_THREADS * FIN_THREADS;      // every thread takes the same number of trips
+    const int k1 = (n - 1) / 2, k2 = n / 2;
+    unsigned long long prefix = 0, mask = 0;
+    uint32_t k = (uint32_t)k1;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        s_hist[tid & 255] = 0;
+        __syncthreads();
+        for (int i = tid; i < nround; i += FIN_THREADS) {
+            const unsigned long long kv = i < n ? keyat(i) : 0ull;
+            const bool on = i < n && (kv & mask) == prefix;
+            const uint32_t d = (uint32_t)(kv >> shift) & 255u;
+            const unsigned m = __match_any_sync(0xffffffffu, on ? d : 256u);
+            if (on && lane == __ffs(m) - 1) atomicAdd(&s_hist[d], (uint32_t)__popc(m));
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) { loc[e] = s_hist[tid * 8 + e]; sum += loc[e]; }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            uint32_t cum = inc - sum;
+            if (k >= cum && k < inc) {      // exactly one lane
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (k >= cum && k < cum + loc[e]) { s_k = k - cum; s_prefix = prefix | ((unsigned long long)(tid * 8 + e) << shift); }
+                    cum += loc[e];
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
+        prefix = s_prefix;
+        k = s_k;
+        mask |= 0xffull << shift;
+    }
+    // upper middle value
+    if (tid == 0) { s_cle = 0; s_above = ~0ull; }
+    __syncthreads();
+    uint32_t c = 0;
+    unsigned long long above = ~0ull;
+    for (int i = tid; i < n; i += FIN_THREADS) {
+        const unsigned long long kv = keyat(i);
+        c += kv <= prefix ? 1u : 0u;
+        if (kv > prefix && kv < above) above = kv;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, above, o); above = t < above ? t : above; }
+    if (lane == 0) { atomicAdd(&s_cle, c); atomicMin(&s_above, above); }
+    __syncthreads();
+    const double v1 = __longlong_as_double((long long)prefix);
+    const double v2 = (s_cle >= (uint32_t)k2 + 1u) ? v1 : __longlong_as_double((long long)s_above);
+    return (n & 1) ? v1 : (v1 + v2) / 2.0;
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -338,10 +392,10 @@ k_pf_finalize(const PfConst* __restrict__ cc, PfFrame* fr, const PfWin* __restri
     }
     // ---- median of |errors| (np.median)
     __syncthreads();
-    block_sort_f64(s_err, m2n);
-    if (tid == 0) {
+    {
         const int ne = M * npos;
-        S.abs_median_error_mm = (ne & 1) ? s_err[ne / 2] : (s_err[ne / 2 - 1] + s_err[ne / 2]) / 2.0;
+        const double med = block_median_nonneg_f64(s_err, ne);
+        if (tid == 0) S.abs_median_error_mm = med;
     }
 }
 

@@ -65,6 +65,21 @@ template <int N, int... I>
 __device__ __forceinline__ void apply_net_u64(unsigned long long (&r)[N], std::integer_sequence<int, I...>) {
     (cmpswap_u64<BatcherNet<N>::L.a[I], BatcherNet<N>::L.b[I], N>(r), ...);
 }
+template <int A, int B, int N>
+__device__ __forceinline__ void cmpswap_f64(double (&r)[N]) {
+    const double a = r[A], b = r[B];
+    r[A] = fmin(a, b);
+    r[B] = fmax(a, b);
+}
+template <int N, int... I>
+__device__ __forceinline__ void apply_net_f64(double (&r)[N], std::integer_sequence<int, I...>) {
+    (cmpswap_f64<BatcherNet<N>::L.a[I], BatcherNet<N>::L.b[I], N>(r), ...);
+}
+template <int N>
+__device__ __forceinline__ void sort_net_f64(double (&r)[N]) {
+    apply_net_f64<N>(r, std::make_integer_sequence<int, BatcherNet<N>::L.n>{});
+}
+
 template <int N>
 __device__ __forceinline__ void sort_net_u64(unsigned long long (&r)[N]) {
     apply_net_u64<N>(r, std::make_integer_sequence<int, BatcherNet<N>::L.n>{});

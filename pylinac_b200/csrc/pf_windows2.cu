@@ -35,7 +35,8 @@
 namespace epid {
 
 constexpr int WA_WARPS = 8;
-constexpr int WA_SLOT = 6656;          // bytes per staging slot (26 rows x 256 B: two 51-sample windows of a 10 mm leaf at 2.56 px/mm)
+constexpr int WA_SLOT_BIG = 6656;      // bytes per staging slot: 26 rows x 256 B (two 51-sample windows of a 10 mm leaf at 2.56 px/mm), 2 CTAs / SM
+constexpr int WA_SLOT_SMALL = 4416;    // 13 rows x 336 B (three such windows of a 5 mm leaf), 3 CTAs / SM
 constexpr int WA_GRID_X = 4;           // CTAs per frame
 constexpr int WA_GMAX = 4;             // pickets per task
 constexpr int WA_KMAX = 4;             // rows per lane in P1: ceil(32 rows / (32 lanes / 4 pickets))
@@ -50,8 +51,8 @@ struct W2Geo {
     int gtot[WA_GMAX + 1];      // median-pool samples of one leaf when pickets are taken g at a time
 };
 
-template <bool LDGSTS>
-__global__ void __launch_bounds__(WA_WARPS * 32, 2)
+template <int WA_SLOT, int MINB>
+__global__ void __launch_bounds__(WA_WARPS * 32, MINB)
 k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ frames, PfFrame* fr, PfWinRec* __restrict__ recs,
                  uint32_t* __restrict__ pools) {
     extern __shared__ __align__(128) unsigned char smraw[];          // WA_WARPS x 2 slots
@@ -70,7 +71,8 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
     const PfConst& c = *cc;
     PfFrame& f = fr[fi];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);           // warp-uniform for the compiler: task geometry lives in uniform registers
+    constexpr bool LDGSTS = false;          // (an LDGSTS loader was measured at the same speed as the TMA row copies: profiles/r2_summary.md)
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);           // warp-uniform for the compiler
     const int H = c.H, W = c.W;
     const FrameRef frf = frames[fi];
     const int mis = (int)((reinterpret_cast<uintptr_t>(frf.origin) >> 1) & 7);
@@ -315,18 +317,19 @@ k_pf_win_medians(const PfConst* __restrict__ cc, const FrameRef* __restrict__ fr
 }
 
 // max, and the two middle order statistics of the nr keys a thread reads through key(i) (i < N slots, slots >= nr padded)
+// The numerators are integers below 2^53 (nc <= 64, pixels < 2^16): exact as doubles, so the network runs on DMNMX pairs.
 template <int N, class F>
-__device__ __forceinline__ void rank_keys(F key, int nr, unsigned long long& kmax, unsigned long long& ka, unsigned long long& kb) {
-    unsigned long long r[N];
-    kmax = 0;
+__device__ __forceinline__ void rank_keys(F key, int nr, double& kmax, double& ka, double& kb) {
+    double r[N];
+    kmax = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        r[i] = i < nr ? key(i) : ~0ull;
-        if (i < nr && r[i] > kmax) kmax = r[i];
+        r[i] = i < nr ? (double)key(i) : __longlong_as_double(0x7ff0000000000000LL);
+        if (i < nr) kmax = fmax(kmax, r[i]);
     }
-    sort_net_u64<N>(r);
+    sort_net_f64<N>(r);
     const int k1 = (nr - 1) / 2, k2 = nr / 2;
-    ka = 0; kb = 0;
+    ka = 0.0; kb = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
         if (i == k1) ka = r[i];
@@ -372,7 +375,7 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     const int nrr = run ? my_nr : 0;
     const int nr_all = __reduce_max_sync(0xffffffffu, nrr);
     // ---- _is_mlc_peak_in_window (picketfence.py:847-857): std along travel per row = sqrt(num) / (nc * D)
-    unsigned long long kmax = 0, ka = 0, kb = 0;
+    double kmax = 0, ka = 0, kb = 0;
     uint32_t my_vmx = 0, my_vmn = 0xffffu;
     {
         auto key = [&](int i) { return rec.num[i]; };
@@ -390,8 +393,8 @@ k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __res
     if (run) {
         const double Dd = (double)f.D;
         const double dn = (double)my_nc * Dd;
-        const double sd_max = sqrt((double)kmax) / dn;
-        const double sa = sqrt((double)ka) / dn, sb = sqrt((double)kb) / dn;
+        const double sd_max = sqrt(kmax) / dn;
+        const double sa = sqrt(ka) / dn, sb = sqrt(kb) / dn;
         const double sd_med = (my_nr & 1) ? sa : (sa + sb) / 2.0;
         const uint32_t gmax = f.inv ? f.mx - my_vmn : my_vmx - f.mn;
         const bool above = ((double)gmax / Dd) > c.p.height_threshold * f.picket_val[pk];
@@ -432,18 +435,19 @@ size_t pf_win2_scratch_bytes(int n) {
 
 int launch_pf_windows2(epid_ctx* ctx, cudaStream_t stream, const PfConst* cst, const FrameRef* refs, PfFrame* fr, PfWinRec* recs, PfWin* wins,
                        int n, PfTimers* tm) {
-    const size_t smem = (size_t)WA_WARPS * 2 * WA_SLOT;
     uint32_t* pools = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(recs) + ((sizeof(PfWinRec) * (size_t)n * PF_W2_WCAP + 255) / 256) * 256);
     static int gx = 0;
     if (gx == 0) { const char* e = getenv("EPID_WA_GRID"); gx = e ? atoi(e) : WA_GRID_X; if (gx < 1 || gx > 64) gx = WA_GRID_X; }
-    static int loader = -1;
-    if (loader < 0) { const char* e = getenv("EPID_WA_LOADER"); loader = e ? atoi(e) : 0; }
-    if (loader == 1) {
-        EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<true>, smem);
-        k_pf_win_medians<true><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs, pools);
+    static int small_slots = -1;
+    if (small_slots < 0) { const char* e = getenv("EPID_WA_SMALL"); small_slots = e ? atoi(e) : 0; }
+    if (small_slots == 1) {
+        const size_t smem = (size_t)WA_WARPS * 2 * WA_SLOT_SMALL;
+        EPID_SMEM_OPT_IN(ctx, (k_pf_win_medians<WA_SLOT_SMALL, 3>), smem);
+        k_pf_win_medians<WA_SLOT_SMALL, 3><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs, pools);
     } else {
-        EPID_SMEM_OPT_IN(ctx, k_pf_win_medians<false>, smem);
-        k_pf_win_medians<false><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs, pools);
+        const size_t smem = (size_t)WA_WARPS * 2 * WA_SLOT_BIG;
+        EPID_SMEM_OPT_IN(ctx, (k_pf_win_medians<WA_SLOT_BIG, 2>), smem);
+        k_pf_win_medians<WA_SLOT_BIG, 2><<<dim3(gx, n), WA_WARPS * 32, smem, stream>>>(cst, refs, fr, recs, pools);
     }
     ctx->launches++;
     if (tm) { int rc = tm->mark(stream, PF_STAGE_WIN_MEDIANS); if (rc != EPID_OK) return rc; }
