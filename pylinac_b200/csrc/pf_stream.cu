@@ -487,7 +487,8 @@ k_pf_stream(const StreamGeom sg, const FrameRef* __restrict__ frames, const Pilo
 }
 
 // ------------------------------------------------------------------------------------------------ tail
-__global__ void __launch_bounds__(TAIL_THREADS)
+// 4 CTAs / SM: 512 frames fit in one wave of the 148 SMs (the kernel is a chain of short block-wide phases: latency, not issue)
+__global__ void __launch_bounds__(TAIL_THREADS, 4)
 k_pf_tail(const PfConst* __restrict__ cc, const StatsGeom g, const StreamGeom sg, const FrameRef* __restrict__ frames,
           const PilotOut* __restrict__ pilot, const ItemOut* __restrict__ items, const uint32_t* __restrict__ col_raw,
           const uint32_t* __restrict__ col_cl, const uint32_t* __restrict__ row_raw, const uint32_t* __restrict__ row_cl,
