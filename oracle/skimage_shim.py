@@ -149,6 +149,58 @@ def find_boundaries(label_img, **kwargs):
     return np.zeros(np.asarray(label_img).shape, bool)
 
 
+def polygon(r, c, shape=None):
+    """skimage.draw.polygon(r, c, shape): integer pixel coordinates inside the polygon or on its boundary (skimage's
+    point_in_polygon returns non-zero for vertex / edge hits), rows int(max(0, min r)) .. ceil(max r), clipped to ``shape``.
+    Restated without the skimage source at hand (UNPINNED, like the other functions of this module); evaluated here with exact
+    rational arithmetic on the float vertices (winding by the crossing rule, boundary by collinearity + range test)."""
+    from fractions import Fraction
+
+    r = [Fraction(float(v)) for v in r]
+    c = [Fraction(float(v)) for v in c]
+    minr, maxr = int(max(0, min(r))), int(np.ceil(float(max(r))))
+    minc, maxc = int(max(0, min(c))), int(np.ceil(float(max(c))))
+    if shape is not None:
+        maxr, maxc = min(shape[0] - 1, maxr), min(shape[1] - 1, maxc)
+    n = len(r)
+    rr, cc = [], []
+    for y in range(minr, maxr + 1):
+        for x in range(minc, maxc + 1):
+            inside, on = False, False
+            for i in range(n):
+                y0, x0, y1, x1 = r[i - 1], c[i - 1], r[i], c[i]
+                cross = (x1 - x0) * (y - y0) - (y1 - y0) * (x - x0)
+                if cross == 0 and min(x0, x1) <= x <= max(x0, x1) and min(y0, y1) <= y <= max(y0, y1):
+                    on = True
+                    break
+                if (y0 > y) != (y1 > y):
+                    xi = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+                    if x < xi:
+                        inside = not inside
+            if on or inside:
+                rr.append(y)
+                cc.append(x)
+    return np.array(rr, dtype=np.intp), np.array(cc, dtype=np.intp)
+
+
+class EuclideanTransform:
+    """skimage.transform.EuclideanTransform(rotation=, translation=): params = [[cos, -sin, tx], [sin, cos, ty], [0, 0, 1]]"""
+
+    def __init__(self, rotation=0.0, translation=(0, 0), **kwargs):
+        cs, sn = np.cos(rotation), np.sin(rotation)
+        self.params = np.array([[cs, -sn, translation[0]], [sn, cs, translation[1]], [0, 0, 1]], dtype=float)
+
+
+def matrix_transform(coords, matrix):
+    """skimage.transform.matrix_transform: homogeneous coordinates times the transposed matrix, de-homogenised"""
+    m = matrix.params if hasattr(matrix, "params") else np.asarray(matrix)
+    coords = np.atleast_2d(np.asarray(coords, dtype=float))
+    src = np.hstack([coords, np.ones((coords.shape[0], 1))])
+    dst = src @ m.T
+    dst[dst[:, 2] == 0, 2] = np.finfo(float).eps
+    return dst[:, :2] / dst[:, 2:3]
+
+
 def install():
     """Bind the restated functions where the reference looks them up (after oracle.refstub.import_reference()): the modules that
     did ``from skimage import measure, segmentation`` hold stub objects, so the names are replaced in those modules."""
@@ -165,3 +217,9 @@ def install():
     rutils.RegionProperties = RegionProperties
     rutils.find_boundaries = find_boundaries       # plotting only: an empty outline of the right shape
     rfeatures.RegionProperties = RegionProperties
+    import pylinac.core.roi as rroi
+
+    rroi.polygon = polygon
+    import pylinac.core.geometry as rgeo
+
+    rgeo.transform = types.SimpleNamespace(EuclideanTransform=EuclideanTransform, matrix_transform=matrix_transform)

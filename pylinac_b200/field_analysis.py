@@ -6,8 +6,8 @@ profiles, SingleProfile interpolation / normalisation / edge detection, penumbra
 symmetry) runs in CUDA (pylinac_b200/csrc/field.cu).  ``analyze_batch(frames, dpmm, ...)`` is the batched entry point.
 
 Supported: interpolation NONE / LINEAR, edge detection FWHM / INFLECTION_DERIVATIVE, every normalisation, protocols NONE /
-VARIAN / SIEMENS / ELEKTA.  Not on the GPU path: SPLINE interpolation, INFLECTION_HILL, the central ROI statistics
-(skimage polygon rasterisation), plotting / PDF export.  The ``top_*`` results are the exact vertex of the fitted parabola (the
+VARIAN / SIEMENS / ELEKTA; the central ROI statistics are device reductions (csrc/roi.cu).  Not on the GPU path: SPLINE
+interpolation, INFLECTION_HILL, plotting / PDF export.  The ``top_*`` results are the exact vertex of the fitted parabola (the
 reference's L-BFGS-B run is noise-limited).
 """
 from __future__ import annotations
@@ -124,6 +124,33 @@ class FieldResult(ResultBase):
     right_slope_percent_mm: float
     top_slope_percent_mm: float
     bottom_slope_percent_mm: float
+    central_roi_mean: float = 0
+    central_roi_max: float = 0
+    central_roi_std: float = 0
+    central_roi_min: float = 0
+
+
+class _CentralROI:
+    """RectangleROI statistics of the reference's ``central_roi`` (field_analysis.py:755-766): the rectangle between the vertical
+    and the horizontal extraction strips, evaluated on the image as ``analyze()`` leaves it (i.e. after the histogram / manual
+    inversions: for a uint16 image inverted an odd number of times the statistics of max + min - v follow from those of v)."""
+
+    def __init__(self, frame_u16: np.ndarray, row, inverted: bool):
+        from .core.geometry import Point
+        from .core.roi import RectangleROI
+
+        left, right = int(row["strip_cols"][0]), int(row["strip_cols"][1])
+        upper, lower = int(row["strip_rows"][0]), int(row["strip_rows"][1])
+        self.width = max(abs(left - right), 2)
+        self.height = max(abs(upper - lower), 2)
+        self.center = Point(self.width / 2 + left, self.height / 2 + upper)
+        roi = RectangleROI(frame_u16, width=self.width, height=self.height, center=self.center)
+        mean, std, mn, mx = roi.mean, roi.std, roi.min, roi.max
+        if inverted:
+            s = float(int(frame_u16.max()) + int(frame_u16.min()))      # array_utils.invert: -a + max + min
+            mean, mn, mx = s - mean, s - mx, s - mn
+        self.mean, self.std, self.min, self.max = mean, std, mn, mx
+        self.pixel_value = mean
 
 
 def make_params(dpmm: float, *, protocol=Protocol.VARIAN, centering=Centering.BEAM_CENTER, vert_position: float = 0.5,
@@ -279,6 +306,11 @@ class FieldAnalysis(ResultsDataMixin[FieldResult]):
         self._result = res
         self._results = res.results_dict()
         self._extra_results = res.protocol_results()
+        # the reference mutates its image: check_inversion_by_histogram() in the constructor, invert() in analyze()
+        inverted = bool(int(res.r["hist_inverted"])) != bool(invert)
+        self.central_roi = _CentralROI(self._frame_u16(), res.r, inverted)
+        self._results.update(central_roi_mean=self.central_roi.mean, central_roi_max=self.central_roi.max,
+                             central_roi_std=self.central_roi.std, central_roi_min=self.central_roi.min)
         self._is_analyzed = True
 
     def results(self, as_str: bool = True):
@@ -295,6 +327,8 @@ class FieldAnalysis(ResultsDataMixin[FieldResult]):
                "Field Size:", f"Horizontal: {r['field_size_horizontal_mm']:3.1f}mm", f"Vertical: {r['field_size_vertical_mm']:3.1f}mm", "",
                "CAX to edge distances:", f"CAX -> Top edge: {r['cax_to_top_mm']:3.1f}mm", f"CAX -> Bottom edge: {r['cax_to_bottom_mm']:3.1f}mm",
                f"CAX -> Left edge: {r['cax_to_left_mm']:3.1f}mm", f"CAX -> Right edge: {r['cax_to_right_mm']:3.1f}mm", ""]
+        out += ["Central ROI stats:", f"Mean: {self.central_roi.mean}", f"Max: {self.central_roi.max}", f"Min: {self.central_roi.min}",
+                f"Standard deviation: {self.central_roi.std}", ""]
         for name in ("symmetry", "flatness"):
             if f"{name}_horizontal" in self._extra_results:
                 out += [f"Vertical {name}: {self._extra_results[name + '_vertical']:3.3f}",

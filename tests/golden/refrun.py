@@ -97,9 +97,11 @@ def reference_starshot(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
 
 
 def reference_field(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
-    """Run the UNMODIFIED reference FieldAnalysis on an ndarray -> flat dict of its _results / _extra_results.
-    (central_roi_* need skimage.draw.polygon, absent here, and are not part of the golden.)"""
-    import_reference()
+    """Run the UNMODIFIED reference FieldAnalysis on an ndarray -> flat dict of its _results / _extra_results, plus the central ROI
+    statistics (skimage.draw.polygon is served by oracle/skimage_shim.py: restated, unpinned at that boundary)."""
+    from oracle import skimage_shim
+
+    skimage_shim.install()
     from pylinac import field_analysis as fa
 
     kw = dict(analyze_kwargs or {})
@@ -112,6 +114,8 @@ def reference_field(frame, pixel_spacing_mm, sid, analyze_kwargs=None):
         out[k] = np.asarray(v, dtype=float)
     for k, v in f._extra_results.items():
         out[k] = float(v)
+    for k in ("mean", "max", "min", "std"):
+        out[f"central_roi_{k}"] = float(getattr(f.central_roi, k))
     out["strip_rows"] = np.array([f._upper_h_index, f._lower_h_index])
     out["strip_cols"] = np.array([f._left_v_index, f._right_v_index])
     out["profile_len"] = np.array([len(f.horiz_profile.values), len(f.vert_profile.values)])

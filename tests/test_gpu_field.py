@@ -16,7 +16,7 @@ GOLD = np.load("tests/golden/field_golden.npz")
 TOL = 1e-6
 TOP_KEYS = {"top_position_index_x_y", "top_horizontal_distance_from_cax_mm", "top_vertical_distance_from_cax_mm",
             "top_horizontal_distance_from_beam_center_mm", "top_vertical_distance_from_beam_center_mm"}
-META = {"input_sha1", "strip_rows", "strip_cols", "profile_len"}
+META = {"input_sha1", "strip_rows", "strip_cols", "profile_len", "central_roi_mean", "central_roi_max", "central_roi_min", "central_roi_std"}
 
 
 def gpu_kwargs(ak):
@@ -88,3 +88,23 @@ def test_field_batch_is_frame_independent_and_class_api():
     assert "Field Analysis Results" in f.results()
     with pytest.raises(NotImplementedError):
         f.analyze(edge_detection_method=fa.Edge.INFLECTION_HILL)
+
+
+@pytest.mark.parametrize("name", ["as1200_150", "as1200_offset", "inverted", "manual_strips", "fff"])
+def test_field_central_roi_matches_reference(name):
+    """central_roi_* of FieldResult (field_analysis.py:755-766, core/roi.py:533-706): the golden comes from the unmodified reference
+    with skimage.draw.polygon served by the restated shim; on these integer-cornered rectangles the pixel set is a plain slice."""
+    from pylinac_b200 import field_analysis as fa
+
+    if name not in CASES:
+        pytest.skip("case not defined")
+    a, ps, sid, ak = case_frame(name)
+    f = fa.FieldAnalysis(a, image_kwargs={"dpi": 25.4 / ps, "sid": sid})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f.analyze(**gpu_kwargs(ak))
+    rd = f.results_data()
+    for k in ("mean", "max", "min"):
+        assert getattr(rd, f"central_roi_{k}") == float(GOLD[f"{name}/central_roi_{k}"]), k
+    assert rd.central_roi_std == pytest.approx(float(GOLD[f"{name}/central_roi_std"]), rel=1e-12)
+    assert "Central ROI stats" in f.results()
