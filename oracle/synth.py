@@ -238,20 +238,16 @@ def bench_pf_batch(n: int, start: int = 0, shape=(1024, 1024), unique: int | Non
 
 # ------------------------------------------------------------------------------ Winston-Lutz
 def bb_projection_with_rotation(offset_left, offset_up, offset_in, gantry, couch=0.0, sad=1000.0):
-    """winston_lutz.py:3401-3460 restated: project a BB offset (mm) to the EPID plane at ``sad``."""
-    bb = np.array([-offset_left, offset_up, offset_in], float)  # x: right negative-left, y: up, z: in
-    # couch rotation about the vertical (y) axis, gantry rotation about the long (z) axis
-    c, s = np.cos(np.radians(couch)), np.sin(np.radians(couch))
-    x, y, z = bb
-    xr = x * c + z * s
-    zr = -x * s + z * c
-    yr = y
-    g = np.radians(gantry)
-    # coordinates in the gantry frame: lateral (in the gantry plane, perpendicular to the beam) and depth along the beam
-    lat = xr * np.cos(g) + yr * np.sin(g)
-    depth = -xr * np.sin(g) + yr * np.cos(g)  # toward the source is +
-    magf = sad / (sad - depth)
-    return lat * magf, zr * magf
+    """winston_lutz.py:3401-3460 restated: isoplane projection of a BB offset (mm) for a gantry / couch position (IEC 61217).
+    The reference rotates (up, left, in) with scipy's Rotation.from_euler("xyz", [-couch, 0, gantry]) -- extrinsic rotations about
+    x (by -couch) then z (by gantry), i.e. Rz(gantry) @ Rx(-couch) -- and magnifies by sad / (sad - rotated_up).
+    tests/test_oracle_synth.py checks this restatement against the reference function itself."""
+    a, g = np.radians(-couch), np.radians(gantry)
+    rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    rz = np.array([[np.cos(g), -np.sin(g), 0], [np.sin(g), np.cos(g), 0], [0, 0, 1]])
+    v = rz @ rx @ np.array([offset_up, offset_left, offset_in], float)
+    mag = sad / (sad - v[0])
+    return -v[1] * mag, v[2] * mag
 
 
 def winstonlutz_frame(frame: Frame, *, field_size_mm=(20, 20), bb_size_mm=5.0, offset_mm_left=0.0, offset_mm_up=0.0,

@@ -482,3 +482,47 @@ def test_pf_mixed_batch_matches_the_oracle_frame_by_frame():
         np.testing.assert_allclose(r.m["error"][:, :1], o["meas_error"], rtol=0, atol=ERR_TOL_MM, err_msg=f"{i} {kind}")
         np.testing.assert_allclose(float(r.s["max_error_mm"]), float(o["max_error"]), rtol=0, atol=ERR_TOL_MM)
     assert n_noise >= 2, "the mixed batch should contain frames that trigger the reference's noise filter"
+
+
+@pytest.mark.parametrize("name", ["noisy_wide_gap_up_down", "offset_picket", "perfect_left_right"])
+def test_picketfence_reads_the_reference_dicom_files(name, tmp_path):
+    """File -> pylinac_b200.dicom -> LinacDicomImage -> PicketFence(path).analyze(): the reference's docs fixtures end to end (the
+    array is float64 after the identity rescale, like pydicom's; dpmm comes from ImagePlanePixelSpacing x RTImageSID / SAD)."""
+    from pylinac_b200.picketfence import PicketFence
+    from tests.golden import pf_docs_cases as dc
+
+    p = tmp_path / (name + ".dcm")
+    p.write_bytes(dc.docs_dcm_bytes(name))
+    _, ps, sid, ak = dc.docs_frame(name)
+    pfo = PicketFence(str(p))
+    assert pfo._raw.array.dtype == np.float64 and pfo._raw.dpmm == pytest.approx((1 / ps) * sid / 1000.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pfo.analyze(**ak)
+    _compare_with_golden(pfo._result, name, np.load("tests/golden/pf_docs_golden.npz"))
+    assert "Gantry Angle" in pfo.results()
+
+
+def test_picketfence_on_a_rescaled_dicom_equals_the_stored_pixels(tmp_path):
+    """A clinical file with RescaleSlope / RescaleIntercept (float pixel data in the reference): the device pipeline analyses the
+    stored integers (image.frame_u16); positions agree with the analysis of the raw array to fp64 rounding, counts exactly."""
+    from oracle import synth
+    from pylinac_b200.picketfence import PicketFence
+    from tests.dicom_writer import write_dicom
+
+    a = synth.bench_pf_frame(17)
+    p = write_dicom(tmp_path / "rs.dcm", a, pixel_spacing_mm=0.390625, sid=1000.0, slope=0.37, intercept=-12.5, gantry=0.0, coll=0.0, couch=0.0)
+    f1 = PicketFence(p)
+    f1.analyze()
+    f2 = PicketFence(a, image_kwargs={"dpi": 25.4 / 0.390625, "sid": 1000})
+    f2.analyze()
+    assert f1._raw.array.dtype == np.float64 and not np.array_equal(f1._raw.array, np.floor(f1._raw.array))
+    assert f1.num_pickets == f2.num_pickets == 10 and len(f1.mlc_meas) == len(f2.mlc_meas) == 500
+    np.testing.assert_allclose(f1._result.m["position"], f2._result.m["position"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(f1.max_error, f2.max_error, rtol=0, atol=1e-9)
+    # PixelIntensityRelationshipSign = -1 flips the stored values; the corner inversion check flips them back
+    p3 = write_dicom(tmp_path / "neg.dcm", a, pixel_spacing_mm=0.390625, sid=1000.0, slope=1.0, intercept=0.0, sign=-1)
+    f3 = PicketFence(p3)
+    f3.analyze()
+    assert f3.num_pickets == 10 and len(f3.mlc_meas) == 500
+    np.testing.assert_allclose(np.sort(f3._result.m["position"][:, 0]), np.sort(f2._result.m["position"][:, 0]), rtol=0, atol=1e-9)
