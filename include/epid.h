@@ -468,6 +468,14 @@ typedef struct {
 
 int32_t epid_disk_locate(epid_ctx* ctx, const epid_batch* frames, const epid_disk_params* p, epid_disk_result* results);
 
+/* ----------------------------------------------------------------------------------------- gamma map
+ * BaseImage.gamma (core/image.py:928-1017), Bakai eq. 6: ref / comp are the float64 images AFTER the reference's inversion check,
+ * ground() and normalize(); threshold_abs = threshold * max(ref); dose_frac = doseTA / 100; dist_px = distTA * dpmm.  The Sobel
+ * gradient (scipy.ndimage.sobel on the float32 reference with nan below the threshold, mode reflect), hypot and the division are
+ * one fused kernel; out: a new float64 batch (nan where the reference is below the threshold). */
+int32_t epid_gamma(epid_ctx* ctx, const epid_batch* ref, const epid_batch* comp, double threshold_abs, double dose_frac, double dist_px,
+                   epid_batch** out);
+
 /* ----------------------------------------------------------------------------------------- ROI statistics / weighted centroid
  * RectangleROI.mean / std / min / max (core/roi.py:533-706): pixels of a rectangle given by its corners verts_xy[nroi][4][(x, y)]
  * (any rotation), selected like skimage.draw.polygon (pixel centres inside or on the boundary, clipped to the image).  Every ROI is

@@ -165,6 +165,43 @@ class BaseImage:
     def as_type(self, dtype):
         return self.array.astype(dtype)
 
+    def gamma(self, comparison_image, doseTA: float = 1, distTA: float = 1, threshold: float = 0.1, ground: bool = True,
+              normalize: bool = True) -> np.ndarray:
+        """core/image.py:928-1017: Bakai gamma between this (reference) image and ``comparison_image`` -> float64 map (nan below the
+        dose threshold).  The per-image preparation is the reference's (inversion check by histogram, ground, normalize: native
+        operators); the Sobel gradient / hypot / division run in one fused kernel (csrc/gamma.cu)."""
+        if not 0.0 <= threshold <= 1.0:
+            raise ValueError("threshold must be between 0 and 1")
+        if abs(self.dpi - comparison_image.dpi) > 0.1:
+            raise AttributeError(f"The image DPIs to not match: {self.dpi:.2f} vs. {comparison_image.dpi:.2f}")
+        same_x = abs(self.shape[1] - comparison_image.shape[1]) <= 1.1
+        same_y = abs(self.shape[0] - comparison_image.shape[0]) <= 1.1
+        if not (same_x and same_y) or self.shape != comparison_image.shape:
+            raise AttributeError(f"The images are not the same size: {self.shape} vs. {comparison_image.shape}")
+
+        def prepared(img) -> np.ndarray:
+            tmp = ArrayImage(np.array(img.array, copy=True))
+            tmp.check_inversion_by_histogram()
+            if ground:
+                tmp.ground()
+            if normalize:
+                tmp.normalize()
+            return np.ascontiguousarray(tmp.array, dtype=np.float64)
+
+        ref, comp = prepared(self), prepared(comparison_image)
+        ctx = nat.Context.default()
+        rb = nat.Batch.upload(ctx, ref[None])
+        cb = nat.Batch.upload(ctx, comp[None])
+        try:
+            out = rb._unary2(nat.lib().epid_gamma, cb, float(threshold * np.max(ref)), doseTA / 100.0, float(self.dpmm * distTA))
+            try:
+                return out.download()[0]
+            finally:
+                out.free()
+        finally:
+            rb.free()
+            cb.free()
+
     def compute(self, metrics):
         """core/image.py:1022-1054: inject this image into the metric(s), calculate, store under a unique name."""
         from ..metrics.image import MetricBase
