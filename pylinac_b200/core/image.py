@@ -186,6 +186,8 @@ class BaseImage:
                 tmp.ground()
             if normalize:
                 tmp.normalize()
+            if tmp.array.dtype.kind in "iub":     # ``array[below threshold] = nan`` on an integer array (core/image.py:1000)
+                raise ValueError("cannot convert float NaN to integer")
             return np.ascontiguousarray(tmp.array, dtype=np.float64)
 
         ref, comp = prepared(self), prepared(comparison_image)

@@ -217,3 +217,25 @@ def test_circle_profiles_match_map_coordinates(frame):
         np.testing.assert_allclose(p.y_locations, np.sin(rads) * r + cy, rtol=0, atol=1e-9)
     with pytest.raises(ValueError):
         CircleProfile((900, 900), 400, img)
+
+
+@pytest.mark.parametrize("name", ["gauss_shifted", "defaults", "no_ground", "inverted_pair"])
+def test_gamma_matches_the_reference(name):
+    """BaseImage.gamma (core/image.py:928-1017) against maps produced by the unmodified reference (tests/golden/make_gamma_golden.py):
+    same nan pattern; values to 1e-6 relative (the float32 hypot / sqrt of the denominator may differ from glibc's in the last ulp)."""
+    from pylinac_b200.core import image
+    from tests.golden.gamma_cases import case_images
+
+    a, b, dpi, kw = case_images(name)
+    g = image.ArrayImage(a, dpi=dpi).gamma(image.ArrayImage(b, dpi=dpi), **kw)
+    ref = np.load("tests/golden/gamma_golden.npz")[name]
+    assert g.dtype == np.float64 and g.shape == ref.shape
+    assert np.array_equal(np.isnan(g), np.isnan(ref))
+    m = ~np.isnan(ref)
+    np.testing.assert_allclose(g[m], ref[m], rtol=1e-6, atol=1e-12)
+    with pytest.raises(AttributeError):
+        image.ArrayImage(a, dpi=dpi).gamma(image.ArrayImage(b, dpi=dpi + 5))
+    with pytest.raises(AttributeError):
+        image.ArrayImage(a, dpi=dpi).gamma(image.ArrayImage(b[:-4], dpi=dpi))
+    with pytest.raises(ValueError):      # integer images cannot take the nan threshold mask: the reference raises the same way
+        image.ArrayImage(a, dpi=dpi).gamma(image.ArrayImage(b, dpi=dpi), normalize=False)
