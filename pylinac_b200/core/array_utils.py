@@ -52,7 +52,11 @@ def _run(a, fn, *args):
     try:
         out = b._unary(fn, *args)
         try:
-            return out.download().reshape(shape)
+            res = out.download()
+            if res.size == int(np.prod(shape)):
+                return res.reshape(shape)
+            # shape-changing operators (zoom): drop the batch / row axes the input did not have
+            return res.reshape(res.shape[-1]) if len(shape) == 1 else (res[0] if len(shape) == 2 else res)
         finally:
             out.free()
     finally:
@@ -144,6 +148,16 @@ def gaussian_filter(array: np.ndarray, sigma: float, truncate: float = 4.0) -> n
     return _run(a, nat.lib().epid_correlate1d_passes, w.ctypes.data_as(C.c_void_p), lw, axes)
 
 
+def zoom(array: np.ndarray, zoom: float, order: int = 3, mode: str = "constant", grid_mode: bool = False) -> np.ndarray:
+    """scipy.ndimage.zoom(array, zoom, order=order, mode=mode, grid_mode=grid_mode) -> float64 (2-D frames: both axes; 1-D profiles:
+    the sample axis).  Cubic (order 3) or linear (order 1) B-spline interpolation on the device (csrc/zoom.cu)."""
+    if mode not in ("constant", "nearest"):
+        raise ValueError("zoom mode must be 'constant' or 'nearest'")
+    if grid_mode and mode != "nearest":
+        raise ValueError("grid_mode zoom is implemented for mode 'nearest'")
+    return _run(array, nat.lib().epid_zoom, float(zoom), int(order), (0 if mode == "constant" else 1) | (2 if grid_mode else 0))
+
+
 def sobel(array: np.ndarray, axis: int = -1) -> np.ndarray:
     return _run(array, nat.lib().epid_sobel, int(axis))
 
@@ -168,6 +182,20 @@ def stretch(array: np.ndarray, min: int = 0, max: int = 1) -> np.ndarray:  # :14
         raise ValueError(f"Min of {min} was smaller than the allowed datatype minimum of {info.min}")
     scaled = normalize(ground(array)) * (max - min)  # scalar multiply on the host-resident result
     return ground(scaled, value=min)
+
+
+def stretcharray(array: np.ndarray, min: int = 0, max: int = 1, fill_dtype=None) -> np.ndarray:
+    """core/profile.py:44-83 (the deprecated ``profile.stretch`` that ``load_multiples`` still uses): (a - a.min()) / (a.max() - a.min())
+    as float64 -- native ground then normalize, the same integer subtraction and one fp64 division per pixel -- times ``max`` (or the
+    largest value of ``fill_dtype``, then cast)."""
+    new_max = max
+    if fill_dtype is not None:
+        new_max = get_dtype_info(fill_dtype).max
+    stretched = normalize(ground(array))
+    stretched = stretched * new_max
+    if fill_dtype:
+        stretched = stretched.astype(fill_dtype)
+    return stretched
 
 
 def convert_to_dtype(array: np.ndarray, dtype) -> np.ndarray:  # :172-198

@@ -65,6 +65,88 @@ def load(path, **kwargs):
     raise TypeError(f"The argument `{path}` was not found to be a valid DICOM file, Image file, or array")
 
 
+def equate_images(image1, image2):
+    """core/image.py:169-220: crop the physically larger image and zoom the second one (cubic spline, scipy.ndimage.zoom semantics,
+    on the device) so that both have the same pixel dimensions and DPI.  Returns (image1, image2) copies."""
+    import copy
+
+    image1, image2 = copy.deepcopy(image1), copy.deepcopy(image2)
+    physical_height_diff = image1.physical_shape[0] - image2.physical_shape[0]
+    img = image2 if physical_height_diff < 0 else image1
+    pixel_height_diff = abs(int(round(-physical_height_diff * img.dpmm / 2)))
+    if pixel_height_diff > 0:
+        img.crop(pixel_height_diff, edges=("top", "bottom"))
+    physical_width_diff = image1.physical_shape[1] - image2.physical_shape[1]
+    img = image1 if physical_width_diff > 0 else image2
+    pixel_width_diff = abs(int(round(physical_width_diff * img.dpmm / 2)))
+    if pixel_width_diff > 0:
+        img.crop(pixel_width_diff, edges=("left", "right"))
+    zoom_factor = image1.shape[1] / image2.shape[1]
+    image2_array = au.zoom(image2.as_type(float), zoom_factor)
+    image2 = load(image2_array, dpi=image2.dpi * zoom_factor)
+    return image1, image2
+
+
+def load_multiples(image_file_list, method: str = "mean", stretch_each: bool = True, loader=None, **kwargs):
+    """core/image.py:306-360: superimpose several images (files, arrays or image objects) into the first one.  With
+    ``stretch_each`` every image is first stretched over the range of ``kwargs['dtype']`` ([0, 1] when absent; native ground /
+    normalize), then the stack is reduced by 'mean' / 'max' / 'sum'.  The first image object carries the result and is flagged
+    ``_raw_pixels`` (a later DICOM save converts instead of un-rescaling)."""
+    reducers = {"mean": np.mean, "max": np.max, "sum": np.sum}
+    if method not in reducers:
+        raise ValueError("method must be one of 'mean', 'max', 'sum'")
+    loader = loader or load
+    images = [loader(item, **kwargs) for item in image_file_list]
+    carrier = images[0]
+    if any(im.shape != carrier.shape for im in images):
+        raise ValueError("Images were not the same shape")
+    planes = [au.stretcharray(im.array, fill_dtype=kwargs.get("dtype")) if stretch_each else im.array for im in images]
+    carrier.array = reducers[method](np.stack(planes, axis=-1), axis=-1)
+    carrier._raw_pixels = True
+    return carrier
+
+
+def _resaved(img):
+    """What the reference obtains by writing a combined image to an in-memory DICOM and reading it back
+    (DicomImage.save, core/image.py:1453-1489, then the constructor's rescale :363-389), without a DICOM writer:
+
+    * values outside the stored dtype, and every ``_raw_pixels`` image, go through ``convert_to_dtype`` to the ORIGINAL stored
+      dtype (full-range re-quantisation; otherwise the rescale is undone), then the plain ``astype``;
+    * the reload applies RescaleSlope / RescaleIntercept and the PixelIntensityRelationshipSign flip of the file's own tags.
+
+    Returns ``img`` with ``array`` / ``_stored`` / ``_stored_map`` replaced.  Array / file images are re-quantised to uint16."""
+    a = np.asarray(img.array)
+    if not isinstance(img, DicomImage):
+        q = au.convert_to_dtype(a, np.uint16) if a.dtype.kind == "f" else a
+        return ArrayImage(q, dpi=getattr(img, "_dpi", None) or img.dpi, sid=img.sid)
+    if img._raw_pixels:
+        un = a
+    else:
+        slope, intercept, flipped = img._stored_map
+        un = a.max() + a.min() - a if flipped else a
+        if img.metadata.get("RescaleSlope") is not None and img.metadata.get("RescaleIntercept") is not None:
+            un = (un - intercept) / slope
+    info = au.get_dtype_info(img._original_dtype)
+    if un.max() > info.max or un.min() < info.min:
+        import warnings
+
+        warnings.warn("The pixel values of image were detected to be outside the range of the stored datatype and will be "
+                      "normalized to fit it")
+        un = au.convert_to_dtype(un, img._original_dtype)
+    if img._raw_pixels:
+        un = au.convert_to_dtype(un, img._original_dtype)
+    stored = un.astype(img._original_dtype)
+    img._raw_pixels = False
+    img.array = _rescale_dicom_values(stored.copy(), img.metadata, False, None)
+    slope, intercept = img.metadata.get("RescaleSlope"), img.metadata.get("RescaleIntercept")
+    has = slope is not None and intercept is not None
+    img._stored = stored
+    img._stored_map = (float(slope) if has else 1.0, float(intercept) if has else 0.0,
+                       img.metadata.get("PixelIntensityRelationshipSign") == -1)
+    img._invert_pixels = None
+    return img
+
+
 def frame_u16(img, what: str = "GPU") -> np.ndarray:
     """The integer frame the device pipelines analyse, from an image object or an array.
 

@@ -479,6 +479,42 @@ class ProfileBase(ProfileMixin):
     def field_values(self, in_field_ratio: float = 0.8) -> np.ndarray:
         return self.y_at_x(self.field_x_values(in_field_ratio))
 
+    # -- resampling (core/profile.py:355-437)
+    def _resample_kwargs(self) -> dict:
+        """The constructor arguments a resampled copy keeps (the per-class ``as_resampled`` overrides of the reference)."""
+        return {}
+
+    def _warn_small_int_range(self) -> None:
+        arr_range = self.values.max() - self.values.min()
+        if self.values.dtype != float and arr_range < 100:
+            import warnings
+
+            warnings.warn(f"Array range is small ({arr_range}) and is not a float. Interpolation may look step-like. "
+                          "Consider converting the array to a float before passing it to this method.", UserWarning)
+
+    def as_resampled(self, interpolation_factor: float = 10, order: int = 3):
+        """A new profile of the same class ``interpolation_factor`` times denser: spline zoom of the values on the device
+        (scipy.ndimage.zoom(order, mode='nearest', grid_mode=False) semantics, csrc/zoom.cu), x values spread linearly over the
+        same extent."""
+        self._warn_small_int_range()
+        new_y = utils.zoom(self.values, interpolation_factor, order=order, mode="nearest")
+        new_x = np.linspace(self.x_values.min(), self.x_values.max(), len(new_y))
+        return type(self)(values=new_y, x_values=new_x, ground=False, normalization=Normalization.NONE, **self._resample_kwargs())
+
+    def resample_to(self, target_profile):
+        """The values of THIS profile linearly interpolated at the x positions of ``target_profile`` (physical positions for
+        physical profiles); no extrapolation.  Returns a non-physical profile of this profile's class."""
+        target_x = target_profile.physical_x_values if isinstance(target_profile, PhysicalProfileMixin) else target_profile.x_values
+        self_x = self.physical_x_values if isinstance(self, PhysicalProfileMixin) else self.x_values
+        target_x = np.asarray(target_x, dtype=np.float64)
+        self_x = np.asarray(self_x, dtype=np.float64)
+        if target_x.min() < self_x.min() or target_x.max() > self_x.max():
+            raise ValueError("The target profile x-values are outside this profiles range. Extrapolation is not allowed. "
+                             f"self x-values: {self_x.min()} to {self_x.max()}. target x-values: {target_x.min()} to {target_x.max()}. ")
+        target_y = _linear_spline(self_x, self.values, target_x)
+        output_type = type(self).__bases__[-1] if isinstance(self, PhysicalProfileMixin) else type(self)
+        return output_type(values=target_y, x_values=target_x)
+
     # -- metric plug-ins (core/profile.py:541-575)
     def compute(self, metrics):
         from ..metrics.profile import ProfileMetric
@@ -508,6 +544,9 @@ class FWXMProfile(ProfileBase):
     def __init__(self, values, x_values=None, ground: bool = False, normalization=Normalization.NONE, fwxm_height: float = 50):
         self.fwxm_height = fwxm_height
         super().__init__(values, x_values=x_values, ground=ground, normalization=normalization)
+
+    def _resample_kwargs(self) -> dict:
+        return {"fwxm_height": self.fwxm_height}
 
     def field_edge_idx(self, side: str) -> float:
         _, props = find_peaks(self.values, fwxm_height=self.fwxm_height / 100, max_number=1)
@@ -583,6 +622,9 @@ class InflectionDerivativeProfile(ProfileBase):
         self.edge_smoothing_ratio = edge_smoothing_ratio
         super().__init__(values, x_values=x_values, ground=ground, normalization=normalization)
 
+    def _resample_kwargs(self) -> dict:
+        return {"edge_smoothing_ratio": self.edge_smoothing_ratio}
+
     def _derivative(self):
         if "diff" not in self._cache:
             filtered = utils.gaussian_filter(self.values, self.edge_smoothing_ratio * len(self.values))
@@ -597,6 +639,31 @@ class InflectionDerivativeProfile(ProfileBase):
         if side == "left":
             return _cubic_stationary_near(xs, diff, M, int(np.argmax(diff)), want_max=True)
         return _cubic_stationary_near(xs, diff, M, int(np.argmin(diff)), want_max=False)
+
+
+class HillProfile(InflectionDerivativeProfile):
+    """core/profile.py:682-740: field edges = inflection points of Hill functions fitted to the penumbrae, each over a window
+    of +/- ``hill_window_ratio`` x (distance between the two derivative edges) around its derivative edge."""
+
+    def __init__(self, values, x_values=None, ground: bool = False, normalization=Normalization.NONE,
+                 edge_smoothing_ratio: float = 0.003, hill_window_ratio: float = 0.1):
+        self.hill_window_ratio = hill_window_ratio
+        super().__init__(values, x_values=x_values, ground=ground, normalization=normalization,
+                         edge_smoothing_ratio=edge_smoothing_ratio)
+
+    def _resample_kwargs(self) -> dict:
+        return {"edge_smoothing_ratio": self.edge_smoothing_ratio, "hill_window_ratio": self.hill_window_ratio}
+
+    def field_edge_idx(self, side: str) -> float:
+        from .hill import Hill
+
+        left_infl = InflectionDerivativeProfile.field_edge_idx(self, "left")
+        right_infl = InflectionDerivativeProfile.field_edge_idx(self, "right")
+        window = (right_infl - left_infl) * self.hill_window_ratio
+        centre = left_infl if side == "left" else right_infl
+        lo, hi = self.x_idx_at_x(centre - window), self.x_idx_at_x(centre + window)
+        fit = Hill.fit(self.x_values[lo:hi + 1], self.values[lo:hi + 1])
+        return fit.inflection_idx()["index (exact)"]
 
 
 class PhysicalProfileMixin:
@@ -616,6 +683,21 @@ class PhysicalProfileMixin:
     def field_width_mm(self) -> float:
         return self.field_width_px / self.implicit_dpmm
 
+    def as_simple_profile(self):
+        """core/profile.py:932-949: the non-physical parent class over the physical x positions"""
+        return type(self).__bases__[-1](values=self.values, x_values=self.physical_x_values)
+
+    def as_resampled(self, interpolation_resolution_mm: float = 0.1, order: int = 3, grid: bool = True):
+        """core/profile.py:951-1013: resample to ``interpolation_resolution_mm`` per sample.  ``grid`` treats samples as pixels of
+        physical size (scipy zoom grid_mode): the new x values then start / end half an (old minus new) pixel outside the old
+        ones."""
+        self._warn_small_int_range()
+        factor = 1 / (self.dpmm * interpolation_resolution_mm)
+        new_y = utils.zoom(self.values, factor, order=order, mode="nearest", grid_mode=grid)
+        offset = 0.5 - 1 / (2 * factor) if grid else 0.0
+        new_x = np.linspace(self.x_values.min() - offset, self.x_values.max() + offset, len(new_y))
+        return type(self)(values=new_y, x_values=new_x, ground=False, normalization=Normalization.NONE, dpmm=factor * self.dpmm)
+
 
 class FWXMProfilePhysical(PhysicalProfileMixin, FWXMProfile):
     """core/profile.py:1016-1047"""
@@ -633,4 +715,14 @@ class InflectionDerivativeProfilePhysical(PhysicalProfileMixin, InflectionDeriva
                  edge_smoothing_ratio: float = 0.003):
         InflectionDerivativeProfile.__init__(self, values, x_values=x_values, ground=ground, normalization=normalization,
                                              edge_smoothing_ratio=edge_smoothing_ratio)
+        self._init_physical(dpmm)
+
+
+class HillProfilePhysical(PhysicalProfileMixin, HillProfile):
+    """core/profile.py:1084-1116"""
+
+    def __init__(self, values, dpmm: float | None = None, x_values=None, ground: bool = False, normalization=Normalization.NONE,
+                 edge_smoothing_ratio: float = 0.003, hill_window_ratio: float = 0.1):
+        HillProfile.__init__(self, values, x_values=x_values, ground=ground, normalization=normalization,
+                             edge_smoothing_ratio=edge_smoothing_ratio, hill_window_ratio=hill_window_ratio)
         self._init_physical(dpmm)

@@ -478,8 +478,31 @@ __device__ inline SpField sp_field_data(const Sp& s, double ifr, double ser) {
                 if (vv > best_v) { best_v = vv; best_u = vx; }
             }
         }
-        f.top = best_u * sc + xm;
-        f.top_val = best_v;
+        // The reference does not take the vertex: it runs scipy.optimize.minimize(-parabola, x0 = middle of the window, bounds =
+        // window), i.e. L-BFGS-B with a finite-difference gradient (core/profile.py:1533-1542).  Field tops are nearly flat in index
+        // units (curvature ~1e-6 / px^2), so the run ends in one of L-BFGS-B's first two tests, restated here for a 1-D parabola:
+        //   projected gradient at x0 <= pgtol (1e-5)                                   -> x0
+        //   x1 = x0 - g0 (Cauchy step of the unit-Hessian model; boxed problem: step 1), then
+        //   projected gradient at x1 <= pgtol, or f0 - f1 <= ftol max(|f0|, |f1|, 1)   -> x1      (ftol = 2.22e-9)
+        //   otherwise the iteration converges to the constrained minimum               -> vertex / better bound (above)
+        {
+            const double lo_x = sp_x(s, a0), hi_x = sp_x(s, a1 - 1);
+            auto par = [&](double x) { const double u = (x - xm) / sc; return c2 * u * u + c1 * u + c0; };
+            auto grad = [&](double x) { return -(2 * c2 * ((x - xm) / sc) + c1) / sc; };
+            auto proj = [&](double x, double g) { return g < 0 ? fmax(x - hi_x, g) : fmin(x - lo_x, g); };
+            const double x0 = lo_x + fabs(hi_x - lo_x) / 2;
+            const double g0 = grad(x0);
+            double top = best_u * sc + xm;
+            if (fabs(proj(x0, g0)) <= 1e-5) {
+                top = x0;
+            } else {
+                const double x1 = fmin(fmax(x0 - g0, lo_x), hi_x);
+                const double f0 = -par(x0), f1 = -par(x1);
+                if (fabs(proj(x1, grad(x1))) <= 1e-5 || f0 - f1 <= 2.220446049250313e-09 * fmax(fmax(fabs(f0), fabs(f1)), 1.0)) top = x1;
+            }
+            f.top = top;
+            f.top_val = par(top);
+        }
         // coefficients of np.polyfit in the abscissa itself: u = (x - xm) / sc
         f.top_params[0] = c2 / (sc * sc);
         f.top_params[1] = c1 / sc - 2 * c2 * xm / (sc * sc);

@@ -366,6 +366,14 @@ class _MLCValueView:
         return f"Leaf: {self.leaf_num}, Picket: {self.picket_num}"
 
 
+def _pf_loader(path, **kwargs):
+    """What ``PFDicomImage(path, crop_mm=0, **kwargs)`` loads in from_multiple_images (picketfence.py:384-391): the un-cropped linac
+    DICOM image (arrays / image objects go through the generic loader)."""
+    if isinstance(path, (np.ndarray, image.BaseImage)):
+        return image.load(path, **kwargs)
+    return image.LinacDicomImage(path, **kwargs)
+
+
 @capture_warnings
 class PicketFence(ResultsDataMixin[PFResult]):
     """picketfence.py:263-329, 439-562, 636-845, 1292-1363 -- same constructor / analyze() signature."""
@@ -393,8 +401,16 @@ class PicketFence(ResultsDataMixin[PFResult]):
         self._warnings: list = []
 
     @classmethod
-    def from_multiple_images(cls, *a, **k):
-        raise NotImplementedError("load_multiples is an ingest feature outside the accelerated hot path (SURVEY.md 8f)")
+    def from_multiple_images(cls, path_list, stretch_each: bool = True, method: str = "mean", mlc=MLC.MILLENNIUM, **kwargs):
+        """picketfence.py:357-400: superimpose several images (e.g. one picket each) and analyse the composite.  The reference
+        combines un-cropped images, writes the composite to an in-memory DICOM (a full-range re-quantisation to the stored dtype,
+        core/image.py:1480-1485) and constructs the PicketFence from that file; ``image._resaved`` reproduces the write / read
+        pair, so the device pipeline receives the same stored integers the reference analyses.  ``crop_mm`` goes to the
+        constructor only; the loader's ``use_filenames`` becomes the constructor's ``use_filename``."""
+        crop_mm = kwargs.pop("crop_mm", 3)
+        combined = image.load_multiples(path_list, stretch_each=stretch_each, method=method, loader=_pf_loader, **kwargs)
+        use_filename = kwargs.pop("use_filenames", False)
+        return cls(image._resaved(combined), mlc=mlc, use_filename=use_filename, crop_mm=crop_mm, **kwargs)
 
     # the frame the GPU analyses: uint16, un-cropped (the crop is a device-side view)
     def _frame_u16(self) -> np.ndarray:

@@ -5,7 +5,7 @@ per-frame pipeline (histogram inversion check, ground, FW80M start point, collap
 peaks, line matching, Nelder-Mead wobble circle, recursive parameter search) runs in CUDA (pylinac_b200/csrc/starshot.cu).
 ``analyze_batch(frames, dpmm, ...)`` is the batched entry point (one result per frame).
 
-Out of scope: plotting, PDF / QuAAC export, from_multiple_images (ingest).
+Out of scope: plotting, PDF / QuAAC export.
 """
 from __future__ import annotations
 
@@ -172,8 +172,12 @@ class Starshot(ResultsDataMixin[StarshotResults]):
         self._result: StarFrameResult | None = None
 
     @classmethod
-    def from_multiple_images(cls, *a, **k):
-        raise NotImplementedError("load_multiples is an ingest feature outside the accelerated hot path (SURVEY.md 8f)")
+    def from_multiple_images(cls, filepath_list, stretch_each: bool = True, method: str = "sum", **kwargs):
+        """starshot.py:148-174: superimpose the images of the individual spokes (``load_multiples``), then construct from the
+        composite as the reference does after its in-memory DICOM write / read (``image._resaved``: full-range re-quantisation
+        to the stored dtype, then the file's own rescale tags)."""
+        combined = image.load_multiples(filepath_list, stretch_each=stretch_each, method=method, **kwargs)
+        return cls(image._resaved(combined), **kwargs)
 
     def _frame_u16(self) -> np.ndarray:
         return image.frame_u16(self.image, "GPU starshot")

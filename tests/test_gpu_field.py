@@ -1,8 +1,8 @@
 """GPU parity: FieldAnalysis pipeline in CUDA (through the C-ABI) vs the committed reference goldens.
 
 Bars (BASELINE.json north_star): bit-exact for the integer quantities (strip bounds, profile lengths); <= 0.01 px for edge
-indices / beam centre (we assert 1e-6 px / mm / %).  The top_* fields are outside the bar: the reference's L-BFGS-B run on the
-fitted parabola is noise-limited (tests/test_oracle_field.py); ours is the exact vertex and is compared with the oracle."""
+indices / beam centre (we assert 1e-6 px / mm / %).  The top_* fields reproduce the stopping rule of the reference's L-BFGS-B run on
+the fitted parabola (tests/test_oracle_field.py::test_lbfgsb_top_against_scipy_minimize) and are held to the same goldens."""
 import warnings
 
 import numpy as np
@@ -46,14 +46,17 @@ def test_field_matches_reference_golden(name):
     assert np.array_equal(row["strip_rows"], GOLD[f"{name}/strip_rows"])
     assert np.array_equal(row["strip_cols"], GOLD[f"{name}/strip_cols"])
     assert np.array_equal(row["profile_len"], GOLD[f"{name}/profile_len"])
-    keys = [k.split("/", 1)[1] for k in GOLD.files if k.startswith(name + "/") and k.split("/", 1)[1] not in META | TOP_KEYS]
-    assert len(keys) >= 20
+    keys = [k.split("/", 1)[1] for k in GOLD.files if k.startswith(name + "/") and k.split("/", 1)[1] not in META]
+    assert len(keys) >= 25
     for k in keys:
-        np.testing.assert_allclose(np.asarray(row[k], dtype=float), GOLD[f"{name}/{k}"], rtol=0, atol=TOL, err_msg=k)
+        # the five "top" fields follow the reference's L-BFGS-B stopping rule on the fitted parabola (csrc/field.cu, sp_field_data);
+        # its first iterate carries ~1e-8 px of finite-difference gradient noise in the reference
+        np.testing.assert_allclose(np.asarray(row[k], dtype=float), GOLD[f"{name}/{k}"], rtol=0, atol=1e-6 if k in TOP_KEYS else TOL,
+                                   err_msg=k)
 
 
 @pytest.mark.parametrize("name", ["as1200_150", "as1200_offset", "fwhm_edges", "no_interp"])
-def test_field_top_matches_oracle_vertex(name):
+def test_field_top_matches_oracle(name):
     from oracle import field_oracle
 
     r, dpmm, ak = gpu_run(name)
