@@ -366,10 +366,14 @@ int32_t epid_field_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_f
  * original samples (x_values = range(len(values))); the interpolated abscissae are linspace(x_start, x_stop, n). */
 typedef struct {
     double dpmm;                       /* <= 0: None (interpolation_factor is used) */
-    int32_t interpolation;             /* 0 NONE, 1 LINEAR */
+    int32_t interpolation;             /* 0 NONE, 1 LINEAR, 2 = values are already sampled on linspace(x_start, x_stop, n0): cubic
+                                          (Interpolation.SPLINE) interpolation or custom uniform x_values, prepared by the caller */
     double interpolation_resolution_mm, interpolation_factor;
-    int32_t ground, normalization, edge, centering;   /* codes as in epid_field_params; centering 2 = GEOMETRIC_CENTER */
+    int32_t ground, normalization, edge, centering;   /* codes as in epid_field_params; centering 2 = GEOMETRIC_CENTER; edge 2 = the
+                                          field edges are supplied (edge_left / edge_right: Hill-function inflection points) */
     double edge_smoothing_ratio;
+    double x_start, x_stop;            /* interpolation == 2 */
+    double edge_left, edge_right;      /* edge == 2 */
 } epid_sp_params;
 
 typedef struct {
@@ -389,9 +393,10 @@ typedef struct {
     double fd_beam_center_value, fd_cax_value, fd_left_value, fd_right_value;
 } epid_sp_result;
 
-/* gauss: gaussian_filter1d weights for sigma = edge_smoothing_ratio * n_expect (NULL when edge == 0).  values_out (cap):
+/* x_values: NULL, or with interpolation == 2 the n0 increasing (possibly unevenly spaced) abscissae of `values` (x_start / x_stop are
+ * then x_values[0] / x_values[n0 - 1]).  gauss: gaussian_filter1d weights for sigma = edge_smoothing_ratio * n_expect (NULL when edge == 0).  values_out (cap):
  * the interpolated / grounded / normalised values; field_values_out (cap): field_data()["field values"]. */
-int32_t epid_single_profile(epid_ctx* ctx, const double* values, int32_t n0, const epid_sp_params* p, const double* gauss, int32_t lw,
+int32_t epid_single_profile(epid_ctx* ctx, const double* values, const double* x_values, int32_t n0, const epid_sp_params* p, const double* gauss, int32_t lw,
                             int32_t n_expect, double fwxm_x, double pen_lower, double pen_upper, double in_field_ratio,
                             double slope_exclusion_ratio, epid_sp_result* result, double* values_out, double* field_values_out,
                             int32_t cap);

@@ -161,7 +161,8 @@ assert FIELD_RESULT_DTYPE.itemsize == C.sizeof(FieldResult), (FIELD_RESULT_DTYPE
 class SpParams(C.Structure):
     _fields_ = [("dpmm", C.c_double), ("interpolation", C.c_int32), ("interpolation_resolution_mm", C.c_double),
                 ("interpolation_factor", C.c_double), ("ground", C.c_int32), ("normalization", C.c_int32), ("edge", C.c_int32),
-                ("centering", C.c_int32), ("edge_smoothing_ratio", C.c_double)]
+                ("centering", C.c_int32), ("edge_smoothing_ratio", C.c_double), ("x_start", C.c_double), ("x_stop", C.c_double),
+                ("edge_left", C.c_double), ("edge_right", C.c_double)]
 
 
 _SP_LAYOUT = [
@@ -271,7 +272,7 @@ _SIGNATURES = {
     "epid_starshot_analyze": [_P, _P, C.POINTER(StarParams), _P, _P, C.c_int32, _P],
     "epid_circle_profile": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, C.c_double,
                             C.c_int32, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)],
-    "epid_single_profile": [_P, _P, C.c_int32, C.POINTER(SpParams), _P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+    "epid_single_profile": [_P, _P, _P, C.c_int32, C.POINTER(SpParams), _P, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                             C.c_double, C.c_double, _P, _P, _P, C.c_int32],
     "epid_field_profile_len": [C.c_int32, C.c_double, C.c_int32, C.c_double],
     "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
@@ -766,19 +767,22 @@ def circle_profile(ctx: Context, image: np.ndarray, center, radius: float, start
 
 
 def single_profile(ctx: Context, values, params: SpParams, *, fwxm_x=50.0, penumbra=(20.0, 80.0), in_field_ratio=0.8,
-                   slope_exclusion_ratio=0.2):
+                   slope_exclusion_ratio=0.2, x_values=None):
     """SingleProfile(values, ...) + every query method in one launch -> (result row, values, field values)."""
     v = np.ascontiguousarray(values, dtype=np.float64)
     n0 = v.size
-    if params.interpolation:
+    if params.interpolation == 1:
         n = int(round(n0 / (params.dpmm * params.interpolation_resolution_mm))) if params.dpmm > 0 else int(round(n0 * params.interpolation_factor))
     else:
         n = n0
-    gw, lw = (gaussian_kernel1d(params.edge_smoothing_ratio * n) if params.edge != 0 else (None, 0))
+    gw, lw = (gaussian_kernel1d(params.edge_smoothing_ratio * n) if params.edge == 1 else (None, 0))
     res = np.zeros(1, SP_RESULT_DTYPE)
     cap = n + 8
     vals, fv = np.empty(cap), np.empty(cap)
-    check(lib().epid_single_profile(ctx.handle, _ptr(v), n0, C.byref(params), _ptr(gw), lw, n, float(fwxm_x), float(penumbra[0]),
+    xv = None if x_values is None else np.ascontiguousarray(x_values, dtype=np.float64)
+    if xv is not None and xv.size != n0:
+        raise ValueError("x_values and values must have the same length")
+    check(lib().epid_single_profile(ctx.handle, _ptr(v), _ptr(xv), n0, C.byref(params), _ptr(gw), lw, n, float(fwxm_x), float(penumbra[0]),
                                     float(penumbra[1]), float(in_field_ratio), float(slope_exclusion_ratio), _ptr(res), _ptr(vals),
                                     _ptr(fv), cap))
     r = res[0]

@@ -190,7 +190,14 @@ _NORM_CODE = {Normalization.NONE: 0, Normalization.GEOMETRIC_CENTER: 1, Normaliz
 class SingleProfile(ProfileMixin):
     """core/profile.py:1119-1937 -- same constructor and query methods; the numerics (interpolation, grounding, normalisation,
     FWXM / inflection edges, penumbra, field data) are the device engine of csrc/field.cu behind ``epid_single_profile``.
-    Supported: interpolation NONE / LINEAR, edge detection FWHM / INFLECTION_DERIVATIVE, x_values = range(len(values))."""
+
+    * Interpolation NONE / LINEAR over ``range(len(values))`` happens on the device.  Interpolation SPLINE (cubic ``interp1d``:
+      not-a-knot spline) and custom ``x_values`` are resampled on the host onto the reference's ``linspace`` grid (one tridiagonal
+      solve over the few hundred raw samples) and handed to the engine as a pre-sampled profile; custom ``x_values`` with
+      interpolation NONE (possibly unevenly spaced, e.g. ion-chamber arrays) travel to the engine as explicit abscissae.
+    * Edge.INFLECTION_HILL: the derivative edges come from the engine, the two 4-parameter Hill fits (a few dozen samples each,
+      core/hill.py) run on the host, and the fitted inflection points go back to the engine as the field edges for everything
+      downstream (beam centre, normalisation, field data)."""
 
     def __init__(self, values, dpmm: float | None = None, interpolation=Interpolation.LINEAR, ground: bool = True,
                  interpolation_resolution_mm: float = 0.1, interpolation_factor: float = 10,
@@ -200,16 +207,9 @@ class SingleProfile(ProfileMixin):
         self._norm_method = normalization_method if isinstance(normalization_method, Normalization) else Normalization(normalization_method)
         self._edge_method = edge_detection_method if isinstance(edge_detection_method, Edge) else Edge(edge_detection_method)
         self._centering = centering if isinstance(centering, Centering) else Centering(centering)
-        if self._interp_method == Interpolation.SPLINE:
-            raise NotImplementedError("Interpolation.SPLINE (cubic interp1d) is outside the accelerated hot path")
-        if self._edge_method == Edge.INFLECTION_HILL:
-            raise NotImplementedError("Edge.INFLECTION_HILL (Hill-function fits) is outside the accelerated hot path")
         raw = np.asarray(values, dtype=np.float64)
         if raw.ndim != 1:
             raise ValueError("Profile values must be 1-D")
-        if x_values is not None and not np.array_equal(np.asarray(x_values), np.arange(len(raw))):
-            raise NotImplementedError("custom x_values are outside the accelerated hot path")
-        self._raw = raw
         self.dpmm = dpmm
         self._interpolation_res = interpolation_resolution_mm
         self._interpolation_factor = interpolation_factor
@@ -221,24 +221,98 @@ class SingleProfile(ProfileMixin):
         sp.interpolation = 0 if self._interp_method == Interpolation.NONE else 1
         sp.interpolation_resolution_mm = float(interpolation_resolution_mm)
         sp.interpolation_factor = float(interpolation_factor)
+        custom_x = x_values is not None and not np.array_equal(np.asarray(x_values), np.arange(len(raw)))
+        if custom_x or self._interp_method == Interpolation.SPLINE:
+            raw, self._x_explicit = self._presample(raw, x_values)
+            sp.interpolation, sp.x_start, sp.x_stop = 2, float(self._x_explicit[0]), float(self._x_explicit[-1])
+        else:
+            self._x_explicit = None
+        self._raw = raw
         sp.ground = 1 if ground else 0
         sp.normalization = _NORM_CODE[self._norm_method]
-        sp.edge = 0 if self._edge_method == Edge.FWHM else 1
+        sp.edge = {Edge.FWHM: 0, Edge.INFLECTION_DERIVATIVE: 1, Edge.INFLECTION_HILL: 2}[self._edge_method]
         sp.centering = 2 if self._centering == Centering.GEOMETRIC_CENTER else 1
         sp.edge_smoothing_ratio = float(edge_smoothing_ratio)
         self._params = sp
         self._cache = {}
+        if self._edge_method == Edge.INFLECTION_HILL:
+            self._hill_first_pass()
         r, vals, _ = self._query()
         if int(r["status"]) != 0:
             raise IndexError("no peak was found in the profile")       # what find_peaks(...)[0] raises in the reference
         self.values = vals
-        self.x_indices = np.linspace(float(r["x_start"]), float(r["x_stop"]), num=int(r["n"]))
+        self.x_indices = self._x_explicit if self._x_explicit is not None else \
+            np.linspace(float(r["x_start"]), float(r["x_stop"]), num=int(r["n"]))
+
+    # -- _interpolate (core/profile.py:1306-1360) for the cases the device interpolation does not cover
+    def _presample(self, raw: np.ndarray, x_values):
+        x = np.arange(len(raw), dtype=np.float64) if x_values is None else np.asarray(x_values, dtype=np.float64)
+        if len(x) != len(raw):
+            raise ValueError("x_values and values must have the same length")
+        if np.diff(x).min() < 0:
+            raise ValueError("Profile values must be monotonically increasing")
+        if self._interp_method == Interpolation.NONE:
+            return raw, x
+        samples = int(round(len(x) / (self.dpmm * self._interpolation_res))) if self.dpmm is not None \
+            else int(round(len(x) * self._interpolation_factor))
+        resampling_factor = samples / len(raw)
+        offset = 0.5 - 1 / (2 * resampling_factor)
+        new_x = np.linspace(x[0] - offset, x[-1] + offset, num=samples)
+        if self._interp_method == Interpolation.LINEAR:
+            new_y = _linear_spline(x, raw, new_x)            # interp1d(kind="linear", fill_value="extrapolate")
+        else:
+            new_y = _cubic_spline_eval(x, raw, _not_a_knot_cubic(x, raw), new_x)     # interp1d(kind="cubic", fill_value="extrapolate")
+        return new_y, new_x
+
+    # -- Edge.INFLECTION_HILL (core/profile.py:1678-1721)
+    def _y_at(self, values: np.ndarray, x_grid: np.ndarray, q):
+        return _linear_spline(x_grid, values, q)
+
+    def _fit_hills(self, values: np.ndarray, x_grid: np.ndarray, left_idx: float, right_idx: float):
+        from .hill import Hill
+
+        half = int(round(self._hill_window_ratio * abs(right_idx - left_idx) / 2))
+        xl = np.arange(left_idx - half, left_idx + half)
+        xl = xl[xl >= 0]
+        xr = np.arange(right_idx - half, right_idx + half)
+        xr = xr[xr < len(values)]
+        return Hill.fit(xl, self._y_at(values, x_grid, xl)), Hill.fit(xr, self._y_at(values, x_grid, xr))
+
+    def _hill_first_pass(self) -> None:
+        """Derivative edges and un-normalised values from the engine, Hill fits on the host, fitted inflection points -> engine."""
+        import copy
+
+        first = copy.copy(self._params)
+        first.edge, first.normalization = 1, 0
+        r, vals, _ = nat.single_profile(nat.Context.default(), self._raw, first, x_values=self._x_explicit)
+        if int(r["status"]) != 0 or not r["infl_ok"]:
+            raise IndexError("no inflection points were found")
+        self._deriv_edges = (float(r["infl_left"]), float(r["infl_right"]))
+        grid = self._x_explicit if self._x_explicit is not None else np.linspace(float(r["x_start"]), float(r["x_stop"]), num=int(r["n"]))
+        lh, rh = self._fit_hills(vals, grid, *self._deriv_edges)
+        self._params.edge_left = lh.inflection_idx()["index (exact)"]
+        self._params.edge_right = rh.inflection_idx()["index (exact)"]
+
+    def _hills(self):
+        """The fits ``inflection_data()`` of the reference makes on the final (normalised) values."""
+        if "hills" not in self._cache:
+            self._cache["hills"] = self._fit_hills(self.values, self.x_indices, *self._deriv_edges)
+        return self._cache["hills"]
+
+    def resample(self, interpolation_factor: int = 10, interpolation_resolution_mm: float = 0.1) -> "SingleProfile":
+        """core/profile.py:1283-1304"""
+        return SingleProfile(values=self.values, x_values=self.x_indices, dpmm=1 / self._interpolation_res if self.dpmm else None,
+                             interpolation=self._interp_method, ground=self._ground,
+                             interpolation_resolution_mm=interpolation_resolution_mm, interpolation_factor=interpolation_factor,
+                             normalization_method=self._norm_method, edge_detection_method=self._edge_method,
+                             edge_smoothing_ratio=self._edge_smoothing_ratio, hill_window_ratio=self._hill_window_ratio)
 
     def _query(self, fwxm_x=50.0, penumbra=(20.0, 80.0), in_field_ratio=0.8, slope_exclusion_ratio=0.2):
         key = (float(fwxm_x), float(penumbra[0]), float(penumbra[1]), float(in_field_ratio), float(slope_exclusion_ratio))
         if key not in self._cache:
             self._cache[key] = nat.single_profile(nat.Context.default(), self._raw, self._params, fwxm_x=fwxm_x, penumbra=penumbra,
-                                                  in_field_ratio=in_field_ratio, slope_exclusion_ratio=slope_exclusion_ratio)
+                                                  in_field_ratio=in_field_ratio, slope_exclusion_ratio=slope_exclusion_ratio,
+                                                  x_values=self._x_explicit)
         return self._cache[key]
 
     # -- core/profile.py:1373-1409
@@ -278,6 +352,13 @@ class SingleProfile(ProfileMixin):
     def inflection_data(self) -> dict:
         if self._edge_method == Edge.FWHM:
             raise ValueError("FWHM edge method does not have inflection points. Use a different edge detection method")
+        if self._edge_method == Edge.INFLECTION_HILL:
+            lh, rh = self._hills()
+            li, ri = lh.inflection_idx(), rh.inflection_idx()
+            return {"left index (rounded)": li["index (rounded)"], "left index (exact)": li["index (exact)"],
+                    "right index (rounded)": ri["index (rounded)"], "right index (exact)": ri["index (exact)"],
+                    "left value (@exact)": lh.y(li["index (exact)"]), "right value (@exact)": rh.y(ri["index (exact)"]),
+                    "left Hill params": lh.params, "right Hill params": rh.params}
         r, _, _ = self._query()
         if not r["infl_ok"]:
             raise IndexError("no inflection points were found")
@@ -291,6 +372,8 @@ class SingleProfile(ProfileMixin):
     def penumbra(self, lower: int = 20, upper: int = 80) -> dict:
         if lower > upper:
             raise ValueError("Upper penumbra value must be larger than the lower penumbra value")
+        if self._edge_method == Edge.INFLECTION_HILL:
+            return self._hill_penumbra(lower, upper)
         r, _, _ = self._query(penumbra=(lower, upper))
         if not r["pen_ok"]:
             raise IndexError("no field edges were found")
@@ -301,6 +384,28 @@ class SingleProfile(ProfileMixin):
         if self.dpmm:
             data["left penumbra width (exact) mm"] = data["left penumbra width (exact)"] / self.dpmm
             data["right penumbra width (exact) mm"] = data["right penumbra width (exact)"] / self.dpmm
+        return data
+
+    def _hill_penumbra(self, lower, upper) -> dict:
+        """core/profile.py:1853-1907: positions where the fitted Hill curves reach lower / 50 and upper / 50 of their inflection
+        values"""
+        infl = self.inflection_data()
+        lh, rh = self._hills()
+        ll_v, ul_v = infl["left value (@exact)"] * lower / 50, infl["left value (@exact)"] * upper / 50
+        lr_v, ur_v = infl["right value (@exact)"] * lower / 50, infl["right value (@exact)"] * upper / 50
+        ll, ul, lr, ur = lh.x(ll_v), lh.x(ul_v), rh.x(lr_v), rh.x(ur_v)
+        data = {f"left {lower}% index (exact)": ll, f"left {lower}% value (exact)": ll_v, f"left {upper}% index (exact)": ul,
+                f"left {upper}% value (exact)": ul_v, f"right {lower}% index (exact)": lr, f"right {lower}% value (exact)": lr_v,
+                f"right {upper}% index (exact)": ur, f"right {upper}% value (exact)": ur_v,
+                "left values": self.values[int(round(ll)):int(round(ul))], "right values": self.values[int(round(ur)):int(round(lr))],
+                "left penumbra width (exact)": abs(ul - ll), "right penumbra width (exact)": abs(ur - lr),
+                "left gradient (exact)": lh.gradient_at(infl["left index (exact)"]),
+                "right gradient (exact)": rh.gradient_at(infl["right index (exact)"])}
+        if self.dpmm:
+            data["left penumbra width (exact) mm"] = data["left penumbra width (exact)"] / self.dpmm
+            data["left gradient (exact) %/mm"] = data["left gradient (exact)"] * self.dpmm * 100
+            data["right penumbra width (exact) mm"] = data["right penumbra width (exact)"] / self.dpmm
+            data["right gradient (exact) %/mm"] = data["right gradient (exact)"] * self.dpmm * 100
         return data
 
     # -- core/profile.py:1463-1633
@@ -588,6 +693,17 @@ def _not_a_knot_cubic(x: np.ndarray, y: np.ndarray):
     M[0] = ((h0 + h1) * M[1] - h0 * M[2]) / h1
     M[n - 1] = ((hl + hk) * M[n - 2] - hl * M[n - 3]) / hk
     return M
+
+
+def _cubic_spline_eval(x: np.ndarray, y: np.ndarray, M: np.ndarray, xq) -> np.ndarray:
+    """The cubic spline with knot second derivatives M at xq; outside [x[0], x[-1]] the first / last polynomial piece continues
+    (interp1d(fill_value="extrapolate") on a BSpline)."""
+    xq = np.asarray(xq, dtype=np.float64)
+    i = np.clip(np.searchsorted(x, xq, side="right") - 1, 0, len(x) - 2)
+    h = x[i + 1] - x[i]
+    t = xq - x[i]
+    b = (y[i + 1] - y[i]) / h - h * (2 * M[i] + M[i + 1]) / 6
+    return y[i] + t * (b + t * (M[i] / 2 + t * (M[i + 1] - M[i]) / (6 * h)))
 
 
 def _cubic_stationary_near(x: np.ndarray, y: np.ndarray, M: np.ndarray, i0: int, want_max: bool) -> float:

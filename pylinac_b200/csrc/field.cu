@@ -138,7 +138,9 @@ struct Sp {
     int n, n0;
     double start, stop, step;
     double dpmm;              // the detector's dpmm (indices are reported in detector pixels)
-    int edge;                 // 0 FWHM, 1 inflection derivative
+    int edge;                 // 0 FWHM, 1 inflection derivative, 2 edges supplied by the caller (Hill fits made on the host)
+    double ov_l, ov_r;        // edge == 2: the supplied left / right edge positions
+    const double* xg = nullptr;   // explicit (possibly uneven) abscissae of a pre-sampled profile, else the analytic linspace
     int centering;            // 2 geometric centre, else beam centre
     double smoothing;
     const double* gw;         // gaussian weights (2 * lw + 1) for this profile length, may be null
@@ -152,7 +154,10 @@ struct Sp {
     int* status;
 };
 
-__device__ __forceinline__ double sp_x(const Sp& s, int i) { return i == s.n - 1 && s.n > 1 ? s.stop : (double)i * s.step + s.start; }
+__device__ __forceinline__ double sp_x(const Sp& s, int i) {
+    if (s.xg) return s.xg[i];
+    return i == s.n - 1 && s.n > 1 ? s.stop : (double)i * s.step + s.start;
+}
 
 // np.interp(loc, arange(n), x_indices)  (interp1d(range(n), x_indices): interior only)
 __device__ __forceinline__ double sp_x_orig(const Sp& s, double loc) {
@@ -272,7 +277,12 @@ struct SpBeam { double idx, val_at_rounded; bool ok; double infl_l, infl_r; };
 __device__ inline SpBeam sp_beam_center(const Sp& s) {
     SpBeam b;
     b.infl_l = b.infl_r = 0.0;
-    if (s.edge == 0) {
+    if (s.edge == 2) {
+        b.ok = true;
+        b.infl_l = s.ov_l;
+        b.infl_r = s.ov_r;
+        b.idx = s.ov_l + (s.ov_r - s.ov_l) / 2;
+    } else if (s.edge == 0) {
         double l, r;
         b.ok = sp_fwxm(s, 50.0, &l, &r);
         if (!b.ok) { b.idx = 0; b.val_at_rounded = 1.0; return b; }
@@ -292,11 +302,18 @@ __device__ inline SpBeam sp_beam_center(const Sp& s) {
 __device__ __forceinline__ double sp_geom_index(const Sp& s) { return sp_x_orig(s, (double)(s.n - 1) / 2.0); }
 
 // SingleProfile.__init__: interpolation (NONE / LINEAR), ground, normalisation.  raw: n0 values.  Returns false on failure.
-__device__ inline bool sp_build(Sp& s, const double* __restrict__ raw, int n0, bool interpolate, bool use_dpmm, double res_or_factor,
-                                bool ground, int norm) {
+// interpolate: 0 none, 1 linear, 2 = `raw` is already sampled on np.linspace(xs, xe, n0) (host-side cubic interpolation / custom x_values)
+__device__ inline bool sp_build(Sp& s, const double* __restrict__ raw, int n0, int interpolate, bool use_dpmm, double res_or_factor,
+                                bool ground, int norm, double xs = 0.0, double xe = 0.0) {
     const int tid = threadIdx.x;
     s.n0 = n0;
-    if (!interpolate) {
+    if (interpolate == 2) {
+        s.n = n0;
+        s.start = xs;
+        s.stop = xe;
+        s.step = (xe - xs) / (double)(n0 - 1);
+        for (int i = tid; i < n0; i += FA_THREADS) s.v[i] = raw[i];
+    } else if (!interpolate) {
         s.n = n0;
         s.start = 0.0;
         s.stop = (double)(n0 - 1);
@@ -820,7 +837,7 @@ k_field_profile(const FieldConst* __restrict__ cc, const double* __restrict__ gw
 // SingleProfile(values, dpmm, ...) and its query methods for ONE host profile (core/profile.py:1125-1937): the same engine as
 // k_field_profile, every query evaluated in one launch.
 __global__ void __launch_bounds__(FA_THREADS)
-k_single_profile(const epid_sp_params p, const double* __restrict__ raw, int n0, int nmax, int pcap, const double* __restrict__ gw, int lw,
+k_single_profile(const epid_sp_params p, const double* __restrict__ raw, const double* __restrict__ xg, int n0, int nmax, int pcap, const double* __restrict__ gw, int lw,
                  int n_expect, double fwxm_x, double pen_lower, double pen_upper, double ifr, double ser, double* __restrict__ work,
                  epid_sp_result* __restrict__ out, double* __restrict__ values_out, double* __restrict__ fv_out) {
     __shared__ int s_small[FA_THREADS + 8];
@@ -833,6 +850,9 @@ k_single_profile(const epid_sp_params p, const double* __restrict__ raw, int n0,
     Sp s;
     s.dpmm = p.dpmm;
     s.edge = p.edge;
+    s.ov_l = p.edge_left;
+    s.ov_r = p.edge_right;
+    s.xg = p.interpolation == 2 ? xg : nullptr;
     s.centering = p.centering;
     s.smoothing = p.edge_smoothing_ratio;
     s.gw = gw;
@@ -847,8 +867,8 @@ k_single_profile(const epid_sp_params p, const double* __restrict__ raw, int n0,
     epid_sp_result R;
     memset(&R, 0, sizeof(R));
     const bool use_dpmm = p.dpmm > 0;
-    bool ok = sp_build(s, raw, n0, p.interpolation != 0, use_dpmm, use_dpmm ? p.interpolation_resolution_mm : p.interpolation_factor,
-                       p.ground != 0, p.normalization);
+    bool ok = sp_build(s, raw, n0, p.interpolation, use_dpmm, use_dpmm ? p.interpolation_resolution_mm : p.interpolation_factor,
+                       p.ground != 0, p.normalization, p.x_start, p.x_stop);
     if (ok && s.edge == 1 && s.n != n_expect) ok = false;
     R.status = ok ? 0 : 1;
     R.n = s.n;
@@ -884,6 +904,14 @@ k_single_profile(const epid_sp_params p, const double* __restrict__ raw, int n0,
                 R.infl_left_value_rounded = sp_y_at(s, s.v, rint(il));
                 R.infl_right_value_rounded = sp_y_at(s, s.v, rint(ir));
             }
+        } else if (s.edge == 2) {
+            R.infl_ok = 1;
+            R.infl_left = s.ov_l;
+            R.infl_right = s.ov_r;
+            R.infl_left_value_exact = sp_y_at(s, s.v, s.ov_l);
+            R.infl_right_value_exact = sp_y_at(s, s.v, s.ov_r);
+            R.infl_left_value_rounded = sp_y_at(s, s.v, rint(s.ov_l));
+            R.infl_right_value_rounded = sp_y_at(s, s.v, rint(s.ov_r));
         }
         // beam_center()
         const SpBeam b = sp_beam_center(s);
@@ -894,6 +922,8 @@ k_single_profile(const epid_sp_params p, const double* __restrict__ raw, int n0,
             bool pk;
             if (s.edge == 0) {
                 pk = sp_fwxm(s, pen_upper, &ul, &ur) && sp_fwxm(s, pen_lower, &ll, &lr);
+            } else if (s.edge == 2) {
+                pk = false;                 // Hill penumbra: closed form of the fitted parameters, evaluated by the caller
             } else {
                 pk = R.infl_ok != 0;
                 if (pk) {
@@ -1053,24 +1083,28 @@ extern "C" int32_t epid_field_analyze(epid_ctx* ctx, const epid_batch* frames, c
     return EPID_OK;
 }
 
-extern "C" int32_t epid_single_profile(epid_ctx* ctx, const double* values, int32_t n0, const epid_sp_params* p, const double* gauss,
+extern "C" int32_t epid_single_profile(epid_ctx* ctx, const double* values, const double* x_values, int32_t n0, const epid_sp_params* p, const double* gauss,
                                        int32_t lw, int32_t n_expect, double fwxm_x, double pen_lower, double pen_upper,
                                        double in_field_ratio, double slope_exclusion_ratio, epid_sp_result* result, double* values_out,
                                        double* field_values_out, int32_t cap) {
     EPID_REQUIRE(ctx && values && p && result && values_out && field_values_out, EPID_ERR_INVALID, "NULL argument");
     EPID_REQUIRE(n0 >= 3, EPID_ERR_INVALID, "profile too short");
-    EPID_REQUIRE(p->edge == 0 || gauss, EPID_ERR_INVALID, "gaussian weights missing");
+    EPID_REQUIRE(p->edge != 1 || gauss, EPID_ERR_INVALID, "gaussian weights missing");
+    EPID_REQUIRE(p->interpolation >= 0 && p->interpolation <= 2, EPID_ERR_INVALID, "interpolation code %d", p->interpolation);
+    EPID_REQUIRE(p->interpolation != 2 || p->x_stop > p->x_start, EPID_ERR_INVALID, "pre-sampled profile needs x_stop > x_start");
+    EPID_REQUIRE(!x_values || p->interpolation == 2, EPID_ERR_INVALID, "explicit abscissae need interpolation == 2");
     EPID_REQUIRE(fwxm_x >= 0 && fwxm_x <= 100, EPID_ERR_INVALID, "x must be between 0 and 100");
     EPID_REQUIRE(pen_lower <= pen_upper, EPID_ERR_INVALID, "Upper penumbra value must be larger than the lower penumbra value");
     EPID_CUDA(cudaSetDevice(ctx->device));
     int n = n0;
-    if (p->interpolation) n = (int)rint(p->dpmm > 0 ? (double)n0 / (p->dpmm * p->interpolation_resolution_mm) : (double)n0 * p->interpolation_factor);
+    if (p->interpolation == 1) n = (int)rint(p->dpmm > 0 ? (double)n0 / (p->dpmm * p->interpolation_resolution_mm) : (double)n0 * p->interpolation_factor);
     EPID_REQUIRE(n >= 3 && n <= cap, EPID_ERR_INVALID, "output capacity %d too small for %d samples", cap, n);
     const int nmax = n + 16;
     int pcap = 1;
     while (pcap < nmax / 2 + 8) pcap <<= 1;
     size_t o = 0;
     auto sz = [&](size_t b) { const size_t r = o; o += (b + 255) / 256 * 256; return r; };
+    const size_t o_x = sz(sizeof(double) * n0);
     const size_t o_raw = sz(sizeof(double) * n0), o_gw = sz(sizeof(double) * (size_t)(2 * lw + 1)), o_res = sz(sizeof(epid_sp_result));
     const size_t o_val = sz(sizeof(double) * n), o_fv = sz(sizeof(double) * n), o_wk = sz(sizeof(double) * (3 * (size_t)nmax + 8 * (size_t)pcap));
     int rc = ensure_scratch(ctx, o);
@@ -1078,8 +1112,9 @@ extern "C" int32_t epid_single_profile(epid_ctx* ctx, const double* values, int3
     char* base = (char*)ctx->scratch;
     cudaStream_t st = ctx->stream;
     EPID_CUDA(cudaMemcpyAsync(base + o_raw, values, sizeof(double) * n0, cudaMemcpyHostToDevice, st));
-    if (p->edge != 0) EPID_CUDA(cudaMemcpyAsync(base + o_gw, gauss, sizeof(double) * (size_t)(2 * lw + 1), cudaMemcpyHostToDevice, st));
-    k_single_profile<<<1, FA_THREADS, 0, st>>>(*p, (const double*)(base + o_raw), n0, nmax, pcap, (const double*)(base + o_gw), lw, n_expect, fwxm_x,
+    if (x_values) EPID_CUDA(cudaMemcpyAsync(base + o_x, x_values, sizeof(double) * n0, cudaMemcpyHostToDevice, st));
+    if (p->edge == 1) EPID_CUDA(cudaMemcpyAsync(base + o_gw, gauss, sizeof(double) * (size_t)(2 * lw + 1), cudaMemcpyHostToDevice, st));
+    k_single_profile<<<1, FA_THREADS, 0, st>>>(*p, (const double*)(base + o_raw), x_values ? (const double*)(base + o_x) : nullptr, n0, nmax, pcap, (const double*)(base + o_gw), lw, n_expect, fwxm_x,
                                                pen_lower, pen_upper, in_field_ratio, slope_exclusion_ratio, (double*)(base + o_wk),
                                                (epid_sp_result*)(base + o_res), (double*)(base + o_val), (double*)(base + o_fv));
     ctx->launches++;

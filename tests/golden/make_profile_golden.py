@@ -44,7 +44,13 @@ def main():
         lo, up = q["penumbra"]
         store[f"{name}/penumbra"] = np.array([pen[f"left {lo}% index (exact)"], pen[f"left {up}% index (exact)"],
                                               pen[f"right {lo}% index (exact)"], pen[f"right {up}% index (exact)"]])
-        if rkw.get("edge_detection_method", rp.Edge.FWHM) != rp.Edge.FWHM:
+        if rkw.get("edge_detection_method", rp.Edge.FWHM) == rp.Edge.INFLECTION_HILL:
+            inf = sp.inflection_data()
+            store[f"{name}/hill"] = np.array([inf["left index (exact)"], inf["right index (exact)"], inf["left value (@exact)"],
+                                              inf["right value (@exact)"]])
+            store[f"{name}/hill_params"] = np.array([inf["left Hill params"], inf["right Hill params"]])
+            store[f"{name}/hill_gradients"] = np.array([pen["left gradient (exact)"], pen["right gradient (exact)"]])
+        elif rkw.get("edge_detection_method", rp.Edge.FWHM) != rp.Edge.FWHM:
             inf = sp.inflection_data()
             store[f"{name}/inflection"] = np.array([inf["left index (exact)"], inf["right index (exact)"], inf["left value (@exact)"],
                                                     inf["right value (@exact)"], inf["left value (@rounded)"], inf["right value (@rounded)"]])

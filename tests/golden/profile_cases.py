@@ -5,7 +5,8 @@ import numpy as np
 from scipy import special
 
 CASES = ["default", "dpmm_linear", "inflection", "inflection_dpmm", "no_interp", "norm_max", "norm_geo", "no_ground", "geo_centering",
-         "narrow"]
+         "narrow", "spline", "spline_dpmm_inflection", "hill", "hill_dpmm_fff", "hill_spline_none_norm", "xvals_linear",
+         "xvals_none_uneven", "xvals_spline_hill"]
 
 
 def _field(n, left, right, pen, seed, horns=0.0, tilt=0.0, floor=0.02, noise=0.004):
@@ -41,4 +42,25 @@ def case_profile(name):
         return _field(600, 150.0, 420.0, 7.0, 9, tilt=0.05), {"centering": "Geometric center", "dpmm": 2.0, "interpolation_resolution_mm": 0.2}, q
     if name == "narrow":
         return _field(300, 130.0, 170.0, 4.0, 10), {"interpolation_factor": 20}, dict(q, in_field_ratio=0.9)
+    if name == "spline":
+        return _field(400, 100.3, 310.6, 6.0, 21), {"interpolation": "Spline"}, q
+    if name == "spline_dpmm_inflection":
+        return _field(512, 140.2, 380.9, 7.0, 22, horns=0.15), {"interpolation": "Spline", "dpmm": 2.56,
+                                                                "edge_detection_method": "Inflection Derivative"}, q
+    if name == "hill":
+        return _field(500, 120.7, 390.1, 7.0, 23, horns=0.2), {"edge_detection_method": "Inflection Hill"}, q
+    if name == "hill_dpmm_fff":
+        return _field(640, 170.4, 470.2, 9.0, 24, horns=-1.3), {"edge_detection_method": "Inflection Hill", "dpmm": 2.56,
+                                                                 "hill_window_ratio": 0.15}, dict(q, penumbra=(10, 90))
+    if name == "hill_spline_none_norm":
+        return _field(450, 110.0, 340.0, 6.0, 25), {"edge_detection_method": "Inflection Hill", "interpolation": "Spline",
+                                                     "normalization_method": None, "ground": False}, q
+    if name == "xvals_linear":
+        return _field(300, 80.0, 220.0, 5.0, 26), {"x_values": np.linspace(-75.0, 74.5, 300)}, q
+    if name == "xvals_none_uneven":
+        x = np.cumsum(np.where(np.arange(260) % 7 == 3, 1.5, 1.0)) - 140.0
+        return _field(260, 70.0, 190.0, 5.0, 27), {"x_values": x, "interpolation": None}, q
+    if name == "xvals_spline_hill":
+        return _field(200, 50.0, 150.0, 4.0, 28, horns=0.1), {"x_values": np.arange(200) * 0.5 + 3.0, "interpolation": "Spline",
+                                                                "edge_detection_method": "Inflection Hill", "interpolation_factor": 4}, q
     raise KeyError(name)

@@ -1,0 +1,71 @@
+"""ProfileBase family beyond the edges: ``as_resampled`` (device spline zoom), ``resample_to``, ``as_simple_profile`` and the
+Hill-function edges (core/profile.py:355-437, 682-740, 932-1013, 1084-1116; core/hill.py) against the UNMODIFIED reference
+(tests/golden/make_profile_ext_golden.py)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.golden.make_profile_ext_golden import CASES, PHYS, values_of
+
+G = np.load("tests/golden/profile_ext_golden.npz")
+# zoomed values: scipy's recursive prefilter vs one tridiagonal solve (rounding level); edges: FWXM / cubic-extremum / Hill fit
+# (Levenberg-Marquardt to the same minimum, solver tolerance ~1e-8 relative)
+VTOL, ETOL = 1e-10, 2e-6
+
+
+def _check(tag, prof, etol=ETOL):
+    np.testing.assert_allclose(prof.values, G[f"{tag}/values"], rtol=0, atol=VTOL, err_msg=tag)
+    np.testing.assert_allclose(prof.x_values, G[f"{tag}/x_values"], rtol=0, atol=1e-10, err_msg=tag)
+    got = [prof.field_edge_idx("left"), prof.field_edge_idx("right"), prof.center_idx, prof.field_width_px]
+    np.testing.assert_allclose(got, G[f"{tag}/edges"], rtol=0, atol=etol, err_msg=tag)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_resampled_profiles(name):
+    from pylinac_b200.core import profile as pp
+
+    args, cls, kw = CASES[name]
+    prof = getattr(pp, cls)(values_of(args), **kw)
+    _check(name, prof)
+    r = prof.as_resampled()
+    assert type(r) is type(prof)
+    for k, v in kw.items():
+        assert getattr(r, k) == v                      # the per-class keyword survives the resampling
+    _check(f"{name}/res10", r)
+    _check(f"{name}/res2.5_o1", prof.as_resampled(interpolation_factor=2.5, order=1))
+    _check(f"{name}/res0.5", prof.as_resampled(interpolation_factor=0.5), etol=1e-5)
+
+
+@pytest.mark.parametrize("name", list(PHYS))
+def test_physical_resampling(name):
+    from pylinac_b200.core import profile as pp
+
+    args, cls, kw = PHYS[name]
+    prof = getattr(pp, cls)(values_of(args), **kw)
+    _check(name, prof)
+    np.testing.assert_allclose(prof.physical_x_values, G[f"{name}/physical_x"], rtol=0, atol=1e-12)
+    assert abs(prof.field_width_mm - float(G[f"{name}/width_mm"])) < ETOL
+    r = prof.as_resampled()
+    assert type(r) is type(prof)
+    _check(f"{name}/res", r)
+    assert abs(r.dpmm - float(G[f"{name}/res/dpmm"])) < 1e-12
+    assert abs(r.field_width_mm - float(G[f"{name}/res/width_mm"])) < ETOL
+    _check(f"{name}/res_nogrid", prof.as_resampled(interpolation_resolution_mm=0.25, order=1, grid=False))
+    sp = prof.as_simple_profile()
+    assert type(sp).__name__ == cls.replace("Physical", "")
+    _check(f"{name}/simple", sp)
+
+
+def test_resample_to():
+    from pylinac_b200.core import profile as pp
+
+    epid = pp.FWXMProfilePhysical(values_of(PHYS["fwxm_phys"][0]), dpmm=2.56)
+    ic_x = np.linspace(10.0, 110.0, 41)
+    ic = pp.FWXMProfile(np.interp(ic_x, epid.physical_x_values, epid.values) * 1.01, x_values=ic_x)
+    out = epid.resample_to(ic)
+    assert type(out).__name__ == str(G["resample_to/type"])
+    np.testing.assert_allclose(out.values, G["resample_to/values"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out.x_values, G["resample_to/x_values"], rtol=0, atol=1e-12)
+    with pytest.raises(ValueError, match="Extrapolation is not allowed"):
+        ic.resample_to(epid)
