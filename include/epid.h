@@ -476,8 +476,14 @@ int32_t epid_disk_locate(epid_ctx* ctx, const epid_batch* frames, const epid_dis
 /* ----------------------------------------------------------------------------------------- spline zoom
  * scipy.ndimage.zoom(a, zoom, order, mode) for 2-D frames (both axes) or 1-D profiles (h == 1: the sample axis) ->
  * float64 batch of shape round(shape * zoom).  order 1 or 3; mode 0 = 'constant' (equate_images, core/image.py:217), 1 = 'nearest'
- * (ProfileBase.as_resampled, core/profile.py:384-390). */
+ * (ProfileBase.as_resampled, core/profile.py:384-390), 3 = 'nearest' with grid_mode=True (PhysicalProfileMixin.as_resampled,
+ * core/profile.py:951-1013). */
 int32_t epid_zoom(epid_ctx* ctx, const epid_batch* in, double zoom, int32_t order, int32_t mode, epid_batch** out);
+
+/* BaseImage.rotate(angle, mode) (core/image.py:780-783): skimage.transform.rotate(order 1) semantics -- img_as_float conversion
+ * (uint8 / 255, uint16 / 65535), counter-clockwise rotation by angle_deg about (cols / 2 - 0.5, rows / 2 - 0.5), bilinear sampling;
+ * mode 0 = 'constant' (0 outside), 1 = 'edge'.  float64 output of the input shape. */
+int32_t epid_rotate(epid_ctx* ctx, const epid_batch* in, double angle_deg, int32_t mode, epid_batch** out);
 
 /* ----------------------------------------------------------------------------------------- gamma map
  * BaseImage.gamma (core/image.py:928-1017), Bakai eq. 6: ref / comp are the float64 images AFTER the reference's inversion check,

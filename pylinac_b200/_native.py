@@ -278,6 +278,7 @@ _SIGNATURES = {
     "epid_field_analyze": [_P, _P, C.POINTER(FieldParams), _P, C.c_int32, _P, C.c_int32, _P],
     "epid_wl2d_analyze": [_P, _P, C.POINTER(WlParams), _P],
     "epid_zoom": [_P, _P, C.c_double, C.c_int32, C.c_int32, C.POINTER(_P)],
+    "epid_rotate": [_P, _P, C.c_double, C.c_int32, C.POINTER(_P)],
     "epid_gamma": [_P, _P, _P, C.c_double, C.c_double, C.c_double, C.POINTER(_P)],
     "epid_disk_locate": [_P, _P, _P, _P],
     "epid_roi_stats": [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P],

@@ -158,6 +158,14 @@ def zoom(array: np.ndarray, zoom: float, order: int = 3, mode: str = "constant",
     return _run(array, nat.lib().epid_zoom, float(zoom), int(order), (0 if mode == "constant" else 1) | (2 if grid_mode else 0))
 
 
+def rotate(array: np.ndarray, angle: float, mode: str = "edge") -> np.ndarray:
+    """skimage.transform.rotate(array, angle, mode=mode) with its defaults (bilinear, no resize, img_as_float conversion of integer
+    images: uint8 / 255, uint16 / 65535) -> float64, on the device (csrc/zoom.cu)."""
+    if mode not in ("edge", "constant"):
+        raise ValueError("rotate mode must be 'edge' or 'constant'")
+    return _run(array, nat.lib().epid_rotate, float(angle), 1 if mode == "edge" else 0)
+
+
 def sobel(array: np.ndarray, axis: int = -1) -> np.ndarray:
     return _run(array, nat.lib().epid_sobel, int(axis))
 

@@ -343,6 +343,13 @@ class BaseImage:
         axis = 1 if direction == "x" else 0
         self.array = np.roll(self.array, amount, axis=axis)
 
+    def rotate(self, angle: float, mode: str = "edge", *args, **kwargs) -> None:  # core/image.py:780-783
+        """Counter-clockwise rotation, scikit-image ``transform.rotate`` semantics with its defaults (bilinear, same shape; integer
+        images are first scaled to [0, 1] like ``img_as_float``).  Other skimage keywords are not supported."""
+        if args or kwargs:
+            raise NotImplementedError("only rotate(angle, mode='edge' | 'constant') is implemented on the device")
+        self.array = au.rotate(self.array, angle, mode=mode)
+
     def rot90(self, n: int = 1) -> None:
         self.array = np.rot90(self.array, n)
 

@@ -194,3 +194,71 @@ extern "C" int32_t epid_zoom(epid_ctx* ctx, const epid_batch* in, double zoom, i
     if (rc != EPID_OK) { epid_batch_free(*out); *out = nullptr; }
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------------ rotation
+// skimage.transform.rotate(image, angle, resize=False, order=1, mode='edge' | 'constant', clip=True, preserve_range=False) as
+// BaseImage.rotate calls it (core/image.py:780-783): the image is converted to float first (img_as_float: uint8 / 255, uint16 /
+// 65535, floats unchanged), every output pixel (x, y) samples the input bilinearly at R(angle) (x - c, y - c) + c with
+// c = (cols / 2 - 0.5, rows / 2 - 0.5), taps outside the frame clamped to the edge ('edge') or read as 0 ('constant').  A bilinear
+// sample is a convex combination of four input pixels, so the reference's final clip to the input range is the identity.
+// scikit-image is not installed here: restated from its documented algorithm (transform/_warps.py rotate / warp, _warps_cy.pyx
+// bilinear_interpolation), validated against scipy.ndimage.affine_transform(order=1) on the same matrix.
+namespace epid {
+
+template <typename T>
+__global__ void k_rotate(const T* __restrict__ in, int n, int H, int W, double ca, double sa, double cx, double cy, double scale, int mode,
+                         double* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const T* __restrict__ src = in + (size_t)f * H * W;
+    const double dx = (double)x - cx, dy = (double)y - cy;
+    const double c = ca * dx - sa * dy + cx, r = sa * dx + ca * dy + cy;
+    const double fr = floor(r), fc = floor(c);
+    const long r0 = (long)fr, c0 = (long)fc, r1 = (long)ceil(r), c1 = (long)ceil(c);
+    const double dr = r - fr, dc = c - fc;
+    auto px = [&](long rr, long cc) -> double {
+        if (mode == 0) {
+            if (rr < 0 || rr >= H || cc < 0 || cc >= W) return 0.0;
+        } else {
+            rr = rr < 0 ? 0 : (rr >= H ? H - 1 : rr);
+            cc = cc < 0 ? 0 : (cc >= W ? W - 1 : cc);
+        }
+        return (double)src[rr * W + cc] * scale;
+    };
+    const double top = (1 - dc) * px(r0, c0) + dc * px(r0, c1);
+    const double bot = (1 - dc) * px(r1, c0) + dc * px(r1, c1);
+    out[((size_t)f * H + y) * W + x] = (1 - dr) * top + dr * bot;
+}
+
+template <typename T>
+static void launch_rotate(epid_ctx* ctx, const epid_batch* in, double ca, double sa, double scale, int mode, double* out) {
+    const dim3 block(32, 8), grid((in->w + 31) / 32, (in->h + 7) / 8, in->n);
+    k_rotate<T><<<grid, block, 0, ctx->stream>>>((const T*)in->dptr, in->n, in->h, in->w, ca, sa, in->w / 2.0 - 0.5, in->h / 2.0 - 0.5, scale,
+                                                  mode, out);
+    ctx->launches++;
+}
+
+}  // namespace epid
+
+extern "C" int32_t epid_rotate(epid_ctx* ctx, const epid_batch* in, double angle_deg, int32_t mode, epid_batch** out) {
+    EPID_REQUIRE(ctx && in && out, EPID_ERR_INVALID, "NULL argument");
+    EPID_REQUIRE(mode == 0 || mode == 1, EPID_ERR_UNSUPPORTED, "rotate mode must be 0 (constant) or 1 (edge)");
+    EPID_CUDA(cudaSetDevice(ctx->device));
+    int rc = epid_batch_alloc(ctx, EPID_F64, in->n, in->h, in->w, out);
+    if (rc != EPID_OK) return rc;
+    const double a = angle_deg * 3.14159265358979323846 / 180.0;
+    const double ca = cos(a), sa = sin(a);
+    double* dst = (double*)(*out)->dptr;
+    switch (in->dtype) {
+        case EPID_U8: launch_rotate<uint8_t>(ctx, in, ca, sa, 1.0 / 255.0, mode, dst); break;
+        case EPID_U16: launch_rotate<uint16_t>(ctx, in, ca, sa, 1.0 / 65535.0, mode, dst); break;
+        case EPID_F32: launch_rotate<float>(ctx, in, ca, sa, 1.0, mode, dst); break;
+        case EPID_F64: launch_rotate<double>(ctx, in, ca, sa, 1.0, mode, dst); break;
+        default: set_error("rotate: dtype %d is not supported (uint8, uint16, float32, float64)", in->dtype); rc = EPID_ERR_UNSUPPORTED;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (rc == EPID_OK && e != cudaSuccess) { set_error("rotate failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
+    if (rc != EPID_OK) { epid_batch_free(*out); *out = nullptr; }
+    return rc;
+}

@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _native as nat
 from .core import image
-from .core.profile import Centering, Edge, Interpolation, Normalization
+from .core.profile import Centering, Edge, Interpolation, Normalization, SingleProfile
 from .core.utilities import ResultBase, ResultsDataMixin, convert_to_enum
 
 
@@ -88,6 +88,15 @@ def symmetry_area(profile, in_field_ratio: float, **kwargs) -> float:
     n = len(fv)
     left, right = np.sum(fv[: math.floor(n / 2)]), np.sum(fv[math.ceil(n / 2):])
     return float(100 * (left - right) / (left + right))
+
+
+# field_analysis.py:233-289: the calculation table of each protocol
+_PROTOCOL_CALCS = {
+    Protocol.NONE: {},
+    Protocol.VARIAN: {"symmetry": symmetry_point_difference, "flatness": flatness_dose_difference},
+    Protocol.SIEMENS: {"symmetry": symmetry_area, "flatness": flatness_dose_difference},
+    Protocol.ELEKTA: {"symmetry": symmetry_pdq_iec, "flatness": flatness_dose_ratio},
+}
 
 
 class FieldResult(ResultBase):
@@ -167,10 +176,8 @@ def make_params(dpmm: float, *, protocol=Protocol.VARIAN, centering=Centering.BE
     cent = convert_to_enum(centering, Centering)
     if is_FFF and edge == Edge.FWHM:
         warnings.warn("Using FWHM for an FFF beam is not advised. Consider using INFLECTION_DERIVATIVE or INFLECTION_HILL")
-    if edge == Edge.INFLECTION_HILL:
-        raise NotImplementedError("Edge.INFLECTION_HILL (Hill-function fits) is outside the accelerated hot path")
-    if interp == Interpolation.SPLINE:
-        raise NotImplementedError("Interpolation.SPLINE (cubic interp1d) is outside the accelerated hot path")
+    if edge == Edge.INFLECTION_HILL or interp == Interpolation.SPLINE:
+        raise NotImplementedError("Edge.INFLECTION_HILL / Interpolation.SPLINE go through analyze_batch's per-profile path")
     if slope_exclusion_ratio >= in_field_ratio or slope_exclusion_ratio >= 1.0:
         raise ValueError("The exclusion region must be smaller than the field ratio")
     if penumbra[0] > penumbra[1]:
@@ -196,9 +203,10 @@ def make_params(dpmm: float, *, protocol=Protocol.VARIAN, centering=Centering.BE
 class FieldFrameResult:
     """One frame's results (a row of the struct-of-arrays the GPU returns)."""
 
-    def __init__(self, row, protocol: Protocol):
+    def __init__(self, row, protocol: Protocol, extra: dict | None = None):
         self.r = row
         self.protocol = protocol
+        self.extra = extra or {}          # Edge.INFLECTION_HILL adds the four *_penumbra_percent_mm entries (field_analysis.py:775-787)
 
     @property
     def status(self) -> int:
@@ -215,6 +223,7 @@ class FieldFrameResult:
         for k in _RESULT_KEYS:
             v = self.r[k]
             out[k] = tuple(float(x) for x in v) if np.ndim(v) else float(v)
+        out.update(self.extra)
         return out
 
     def protocol_results(self) -> dict:
@@ -224,21 +233,105 @@ class FieldFrameResult:
 
 
 class FieldBatchResult(Sequence):
-    def __init__(self, rows: np.ndarray, protocol: Protocol):
+    def __init__(self, rows: np.ndarray, protocol: Protocol, extras: list | None = None):
         self.rows = rows
         self.protocol = protocol
+        self.extras = extras
 
     def __len__(self):
         return len(self.rows)
 
     def __getitem__(self, i) -> FieldFrameResult:
-        return FieldFrameResult(self.rows[i], self.protocol)
+        return FieldFrameResult(self.rows[i], self.protocol, self.extras[i] if self.extras else None)
+
+
+def _analyze_per_profile(ctx, frames: "nat.Batch", dpmm: float, kw: dict) -> FieldBatchResult:
+    """Edge.INFLECTION_HILL and / or Interpolation.SPLINE (field_analysis.py:503-562, 703-864).
+
+    The frame work stays on the device: histogram inversion check, centre determination and strip bounds come from the batched
+    pipeline (they do not depend on the edge method or the interpolation), the strip profiles are the exact integer column / row
+    sums of the strips (``epid_frame_stats`` views) divided by the strip width.  Each profile then goes through the
+    ``SingleProfile`` engine (cubic pre-sampling and Hill fits prepared on the host, core/profile.py) and the results are
+    assembled as ``_analyze`` does.  Four engine launches and four small fits per frame: a per-image path, not a throughput path."""
+    protocol = kw.get("protocol", Protocol.VARIAN)
+    protocol = Protocol[protocol] if isinstance(protocol, str) else protocol
+    edge = convert_to_enum(kw.get("edge_detection_method", Edge.INFLECTION_DERIVATIVE), Edge)
+    interp = convert_to_enum(kw.get("interpolation", Interpolation.LINEAR), Interpolation)
+    base_kw = dict(kw, edge_detection_method=Edge.FWHM, interpolation=Interpolation.NONE, protocol=Protocol.NONE, is_FFF=False)
+    base = nat.field_analyze(ctx, frames, make_params(dpmm, **base_kw))
+    (n, h, w), _ = frames.shape_dtype
+    in_field_ratio = kw.get("in_field_ratio", 0.8)
+    ser = kw.get("slope_exclusion_ratio", 0.2)
+    penumbra = kw.get("penumbra", (20, 80))
+    sp_kw = dict(dpmm=dpmm, interpolation=interp, interpolation_resolution_mm=kw.get("interpolation_resolution_mm", 0.1),
+                 ground=kw.get("ground", True), edge_detection_method=edge, edge_smoothing_ratio=kw.get("edge_smoothing_ratio", 0.003),
+                 normalization_method=kw.get("normalization_method", Normalization.BEAM_CENTER),
+                 hill_window_ratio=kw.get("hill_window_ratio", 0.15))
+    full = nat.frame_stats(ctx, frames)
+    rows = np.zeros(n, nat.FIELD_RESULT_DTYPE)
+    extras = []
+    strip_stats: dict = {}
+    for i in range(n):
+        row = rows[i]
+        for k in ("hist_inverted", "strip_rows", "strip_cols"):
+            row[k] = base[i][k]
+        extras.append({})
+        if int(base[i]["status"]) == 2:
+            row["status"] = 2
+            continue
+        bottom, top = (int(v) for v in base[i]["strip_rows"])
+        left, right = (int(v) for v in base[i]["strip_cols"])
+        hv, vv = (bottom, 0, top - bottom, w), (0, left, h, right - left)
+        for view in (hv, vv):                      # frames of one batch nearly always share their strips: one launch per distinct view
+            if view not in strip_stats:
+                strip_stats[view] = nat.frame_stats(ctx, frames, view=view)
+        horiz = strip_stats[hv]["colsum"][i] / (top - bottom)
+        vert = strip_stats[vv]["rowsum"][i] / (right - left)
+        if bool(int(base[i]["hist_inverted"])) != bool(kw.get("invert", False)):
+            s_ = float(full["max"][i]) + float(full["min"][i])       # array_utils.invert: -a + max + min, exact on integers
+            horiz, vert = s_ - horiz, s_ - vert
+        try:
+            hp, vp = SingleProfile(horiz, **sp_kw), SingleProfile(vert, **sp_kw)
+            row["profile_len"] = (len(hp.values), len(vp.values))
+            v_pen, h_pen = vp.penumbra(*penumbra), hp.penumbra(*penumbra)
+            row["top_penumbra_mm"], row["bottom_penumbra_mm"] = v_pen["left penumbra width (exact) mm"], v_pen["right penumbra width (exact) mm"]
+            row["left_penumbra_mm"], row["right_penumbra_mm"] = h_pen["left penumbra width (exact) mm"], h_pen["right penumbra width (exact) mm"]
+            if edge == Edge.INFLECTION_HILL:
+                extras[i] = {"top_penumbra_percent_mm": abs(v_pen["left gradient (exact) %/mm"]),
+                             "bottom_penumbra_percent_mm": abs(v_pen["right gradient (exact) %/mm"]),
+                             "left_penumbra_percent_mm": abs(h_pen["left gradient (exact) %/mm"]),
+                             "right_penumbra_percent_mm": abs(h_pen["right gradient (exact) %/mm"])}
+            row["geometric_center_index_x_y"] = (hp.geometric_center()["index (exact)"], vp.geometric_center()["index (exact)"])
+            row["beam_center_index_x_y"] = (hp.beam_center()["index (exact)"], vp.beam_center()["index (exact)"])
+            v1, h1 = vp.field_data(1.0, ser), hp.field_data(1.0, ser)
+            row["field_size_vertical_mm"], row["field_size_horizontal_mm"] = v1["width (exact) mm"], h1["width (exact) mm"]
+            row["beam_center_to_top_mm"] = v1["left distance->beam center (exact) mm"]
+            row["beam_center_to_bottom_mm"] = v1["right distance->beam center (exact) mm"]
+            row["beam_center_to_left_mm"] = h1["left distance->beam center (exact) mm"]
+            row["beam_center_to_right_mm"] = h1["right distance->beam center (exact) mm"]
+            row["cax_to_top_mm"], row["cax_to_bottom_mm"] = v1["left distance->CAX (exact) mm"], v1["right distance->CAX (exact) mm"]
+            row["cax_to_left_mm"], row["cax_to_right_mm"] = h1["left distance->CAX (exact) mm"], h1["right distance->CAX (exact) mm"]
+            hf, vf = hp.field_data(in_field_ratio, ser), vp.field_data(in_field_ratio, ser)
+            row["top_position_index_x_y"] = (hf['"top" index (exact)'], vf['"top" index (exact)'])
+            row["top_horizontal_distance_from_cax_mm"], row["top_vertical_distance_from_cax_mm"] = hf['"top"->CAX (exact) mm'], vf['"top"->CAX (exact) mm']
+            row["top_horizontal_distance_from_beam_center_mm"] = hf['"top"->beam center (exact) mm']
+            row["top_vertical_distance_from_beam_center_mm"] = vf['"top"->beam center (exact) mm']
+            row["left_slope_percent_mm"], row["right_slope_percent_mm"] = hf["left slope (%/mm)"], hf["right slope (%/mm)"]
+            row["top_slope_percent_mm"], row["bottom_slope_percent_mm"] = vf["left slope (%/mm)"], vf["right slope (%/mm)"]
+            for name, calc in _PROTOCOL_CALCS[protocol].items():
+                row[f"{name}_horizontal"] = calc(hp, in_field_ratio, slope_exclusion_ratio=ser)
+                row[f"{name}_vertical"] = calc(vp, in_field_ratio, slope_exclusion_ratio=ser)
+        except IndexError:
+            row["status"] = 1
+    return FieldBatchResult(rows, protocol, extras)
 
 
 def analyze_batch(frames, dpmm: float, *, device: int | None = None, filter: int | None = None, **kwargs) -> FieldBatchResult:
     """FieldAnalysis(frame, filter=filter).analyze(**kwargs) for every frame of ``frames`` (uint16 [n,h,w] ndarray or Batch)."""
     ctx = nat.Context.default(device)
-    params = make_params(dpmm, **kwargs)
+    per_profile = (convert_to_enum(kwargs.get("edge_detection_method", Edge.INFLECTION_DERIVATIVE), Edge) == Edge.INFLECTION_HILL
+                   or convert_to_enum(kwargs.get("interpolation", Interpolation.LINEAR), Interpolation) == Interpolation.SPLINE)
+    params = None if per_profile else make_params(dpmm, **kwargs)
     protocol = kwargs.get("protocol", Protocol.VARIAN)
     protocol = Protocol[protocol] if isinstance(protocol, str) else protocol
     own = None
@@ -251,9 +344,13 @@ def analyze_batch(frames, dpmm: float, *, device: int | None = None, filter: int
         if filter:
             filtered = frames._unary(nat.lib().epid_median_filter, int(filter))   # image.filter(size=filter) (field_analysis.py:466)
             try:
+                if per_profile:
+                    return _analyze_per_profile(ctx, filtered, dpmm, kwargs)
                 rows = nat.field_analyze(ctx, filtered, params)
             finally:
                 filtered.free()
+        elif per_profile:
+            return _analyze_per_profile(ctx, frames, dpmm, kwargs)
         else:
             rows = nat.field_analyze(ctx, frames, params)
     finally:

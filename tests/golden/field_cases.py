@@ -8,6 +8,10 @@ CASES = ["as1200_150", "as1200_offset", "epid1024_100", "fwhm_edges", "geometric
          "inverted", "no_interp", "fff", "norm_max", "slope", "no_ground"]
 
 
+# Edge.INFLECTION_HILL / Interpolation.SPLINE: reference goldens only (the numpy oracle restates the LINEAR / derivative engine)
+EXT_CASES = ["hill", "hill_fff_siemens", "spline", "hill_spline_inverted"]
+
+
 def case_frame(name):
     """-> (frame uint16, pixel_spacing_mm, sid, analyze_kwargs)"""
     if name == "as1200_150":
@@ -54,4 +58,19 @@ def case_frame(name):
     if name == "no_ground":
         fr = synth.as1200(1000.0)
         return synth.openfield_frame(fr, seed=44), fr.pixel_size, 1000.0, {"ground": False, "interpolation_resolution_mm": 0.25}
+    if name == "hill":
+        fr = synth.as1200(1000.0)
+        return synth.openfield_frame(fr, seed=51), fr.pixel_size, 1000.0, {"edge_detection_method": "Inflection Hill"}
+    if name == "hill_fff_siemens":
+        fr = synth.as1200(1000.0)
+        return synth.openfield_frame(fr, field="fff", field_size_mm=(140, 160), cax_offset_mm=(3.0, -2.0), seed=52), fr.pixel_size, 1000.0, \
+            {"edge_detection_method": "Inflection Hill", "is_FFF": True, "protocol": "SIEMENS", "hill_window_ratio": 0.2, "penumbra": (10, 90)}
+    if name == "spline":
+        fr = synth.epid1024()
+        return synth.openfield_frame(fr, field_size_mm=(110, 90), seed=53), fr.pixel_size, 1000.0, {"interpolation": "Spline"}
+    if name == "hill_spline_inverted":
+        fr = synth.as1200(1000.0)
+        synth.openfield_frame(fr, seed=54, field_size_mm=(100, 130))
+        return fr.inverted(), fr.pixel_size, 1000.0, {"edge_detection_method": "Inflection Hill", "interpolation": "Spline",
+                                                       "protocol": "ELEKTA", "interpolation_resolution_mm": 0.2}
     raise KeyError(name)

@@ -15,6 +15,8 @@ CASES = {
     "norm_beam": ("slope", {"normalization": "Beam center"}),
     "inverted_frame": ("inverted", {}),
     "fff": ("fff", {"edge_type": "FWHM"}),
+    "hill": ("as1200_150", {"edge_type": "Inflection Hill"}),
+    "hill_fff_offset": ("hill_fff_siemens", {"edge_type": "Inflection Hill", "x_width": 0.02, "y_width": 0.02, "hill_window_ratio": 0.15}),
     # enum MEMBERS (resolved by name in case()): only these normalise in the reference, plain strings do not
     "enum_norm_max": ("epid1024_100", {"normalization": "Normalization.MAX", "edge_type": "FWHM"}),
     "enum_norm_beam": ("as1200_offset", {"normalization": "Normalization.BEAM_CENTER", "edge_type": "FWHM", "ground": False}),

@@ -11,14 +11,14 @@ import warnings
 
 import numpy as np
 
-from tests.golden.field_cases import CASES, case_frame
+from tests.golden.field_cases import CASES, EXT_CASES, case_frame
 from tests.golden.refrun import reference_field
 
 
 def main():
     store = {}
     warnings.simplefilter("ignore")
-    for name in CASES:
+    for name in CASES + EXT_CASES:
         a, ps, sid, ak = case_frame(name)
         store[f"{name}/input_sha1"] = np.frombuffer(hashlib.sha1(a.tobytes()).digest(), dtype=np.uint8)
         ref = reference_field(a, ps, sid, ak)

@@ -23,7 +23,10 @@ def reference_fpa(frame, ps, sid, kw):
 
     f = fpa.FieldProfileAnalysis(np.array(frame), dpi=25.4 / ps, sid=sid)
     f.analyze(**resolve_enums(kw, Normalization))
-    out = {}
+    from oracle import skimage_shim
+
+    skimage_shim.install()           # RectangleROI statistics rasterise with skimage.draw.polygon (restated, unpinned at that boundary)
+    out = {"center": np.array([f.center_rect.mean, f.center_rect.std, f.center_rect.min, f.center_rect.max], dtype=float)}
     for ax, p in (("x", f.x_profile), ("y", f.y_profile)):
         out[f"{ax}/metric_names"] = np.array(list(p.metric_values.keys()))
         out[f"{ax}/metric_values"] = np.array([float(v) for v in p.metric_values.values()])

@@ -8,7 +8,7 @@ import warnings
 import numpy as np
 import pytest
 
-from tests.golden.field_cases import CASES, case_frame
+from tests.golden.field_cases import CASES, EXT_CASES, case_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +38,7 @@ def gpu_run(name):
         return fa.analyze_batch(a[None], dpmm, **gpu_kwargs(ak))[0], dpmm, ak
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + EXT_CASES)
 def test_field_matches_reference_golden(name):
     r, dpmm, ak = gpu_run(name)
     assert r.status == 0, r.status
@@ -48,11 +48,18 @@ def test_field_matches_reference_golden(name):
     assert np.array_equal(row["profile_len"], GOLD[f"{name}/profile_len"])
     keys = [k.split("/", 1)[1] for k in GOLD.files if k.startswith(name + "/") and k.split("/", 1)[1] not in META]
     assert len(keys) >= 25
+    got = {k: row[k] for k in row.dtype.names}
+    got.update(r.extra)                    # Edge.INFLECTION_HILL: the four *_penumbra_percent_mm entries
+    # Hill edges come from two least-squares solvers that stop within 1.5e-8 of the same minimum (tests/test_hill_host.py); the
+    # penumbra gradients are ~1 %/mm-scale derivatives of those fits
+    hill = "Hill" in str(ak.get("edge_detection_method", ""))
     for k in keys:
         # the five "top" fields follow the reference's L-BFGS-B stopping rule on the fitted parabola (csrc/field.cu, sp_field_data);
         # its first iterate carries ~1e-8 px of finite-difference gradient noise in the reference
-        np.testing.assert_allclose(np.asarray(row[k], dtype=float), GOLD[f"{name}/{k}"], rtol=0, atol=1e-6 if k in TOP_KEYS else TOL,
-                                   err_msg=k)
+        tol = 1e-6 if k in TOP_KEYS else TOL
+        if hill:
+            tol = 1e-4 if k.endswith("percent_mm") else 5e-6
+        np.testing.assert_allclose(np.asarray(got[k], dtype=float), GOLD[f"{name}/{k}"], rtol=0, atol=tol, err_msg=k)
 
 
 @pytest.mark.parametrize("name", ["as1200_150", "as1200_offset", "fwhm_edges", "no_interp"])
@@ -89,8 +96,8 @@ def test_field_batch_is_frame_independent_and_class_api():
     assert abs(rd.field_size_horizontal_mm - float(GOLD["as1200_150/field_size_horizontal_mm"])) < TOL
     assert abs(rd.protocol_results["flatness_vertical"] - float(GOLD["as1200_150/flatness_vertical"])) < TOL
     assert "Field Analysis Results" in f.results()
-    with pytest.raises(NotImplementedError):
-        f.analyze(edge_detection_method=fa.Edge.INFLECTION_HILL)
+    f.analyze(edge_detection_method=fa.Edge.INFLECTION_HILL)          # per-profile path (Hill fits on the host, engine per profile)
+    assert "top_penumbra_percent_mm" in f._results and abs(f.results_data().field_size_horizontal_mm - 150) < 1.0
 
 
 @pytest.mark.parametrize("name", ["as1200_150", "as1200_offset", "inverted", "manual_strips", "fff"])

@@ -239,3 +239,32 @@ def test_gamma_matches_the_reference(name):
         image.ArrayImage(a, dpi=dpi).gamma(image.ArrayImage(b[:-4], dpi=dpi))
     with pytest.raises(ValueError):      # integer images cannot take the nan threshold mask: the reference raises the same way
         image.ArrayImage(a, dpi=dpi).gamma(image.ArrayImage(b, dpi=dpi), normalize=False)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint8, np.float64])
+@pytest.mark.parametrize("angle,mode", [(17.3, "edge"), (-90.0, "edge"), (45.0, "constant"), (180.0, "edge")])
+def test_rotate_matches_bilinear_warp(dtype, angle, mode):
+    """BaseImage.rotate (core/image.py:780-783 -> skimage.transform.rotate defaults; scikit-image is absent, so the check is an
+    independent restatement with scipy.ndimage.affine_transform(order=1) on the same inverse map and img_as_float scaling)."""
+    from scipy import ndimage
+
+    from pylinac_b200.core import image
+
+    rng = np.random.default_rng(3)
+    a = (rng.random((61, 83)) * (255 if dtype == np.uint8 else 60000)).astype(dtype)
+    img = image.ArrayImage(a.copy(), dpi=100, sid=1000)
+    img.rotate(angle, mode=mode)
+    assert img.array.dtype == np.float64 and img.shape == a.shape
+    scale = {np.uint8: 1 / 255.0, np.uint16: 1 / 65535.0, np.float64: 1.0}[dtype]
+    t = np.deg2rad(angle)
+    ca, sa = np.cos(t), np.sin(t)
+    cy, cx = a.shape[0] / 2 - 0.5, a.shape[1] / 2 - 0.5
+    m = np.array([[ca, sa], [-sa, ca]])                       # (row, col) of the input as a function of (row, col) of the output
+    off = np.array([cy, cx]) - m @ np.array([cy, cx])
+    want = ndimage.affine_transform(a.astype(np.float64) * scale, m, offset=off, order=1,
+                                    mode="nearest" if mode == "edge" else "grid-constant", cval=0.0)
+    np.testing.assert_allclose(img.array, want, rtol=0, atol=1e-9 * max(1.0, float(want.max())))
+    if angle == 180.0:                                         # exact half turn: the flipped image, scaled
+        np.testing.assert_allclose(img.array, a[::-1, ::-1].astype(np.float64) * scale, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        img.rotate(10, mode="wrap")

@@ -9,12 +9,18 @@ pytestmark = pytest.mark.gpu
 from tests.golden.make_profile_ext_golden import CASES, PHYS, values_of
 
 G = np.load("tests/golden/profile_ext_golden.npz")
-# zoomed values: scipy's recursive prefilter vs one tridiagonal solve (rounding level); edges: FWXM / cubic-extremum / Hill fit
-# (Levenberg-Marquardt to the same minimum, solver tolerance ~1e-8 relative)
-VTOL, ETOL = 1e-10, 2e-6
+# zoomed values: scipy's recursive prefilter vs one tridiagonal solve (rounding level).  Edges (bar: 0.01 px):
+#   FWXM                    the same arithmetic                                                                      -> 2e-6
+#   inflection derivative   the reference stops a BFGS run on the cubic interpolant of the gradient where |slope| <= 1e-5, i.e. within
+#                           1e-5 / |curvature| (~1e-3 px) of the stationary point we compute in closed form          -> 5e-3
+#   Hill                    fit windows are cut at samples nearest to (derivative edge -+ window): a derivative edge that moves by
+#                           ~1e-3 px can move a window by one sample, which moves the fitted inflection by ~5e-4 px  -> 2e-3
+VTOL = 1e-10
+ETOL = {"FWXMProfile": 2e-6, "InflectionDerivativeProfile": 5e-3, "HillProfile": 2e-3}
 
 
-def _check(tag, prof, etol=ETOL):
+def _check(tag, prof, etol=None):
+    etol = etol or ETOL[type(prof).__name__.replace("Physical", "")]
     np.testing.assert_allclose(prof.values, G[f"{tag}/values"], rtol=0, atol=VTOL, err_msg=tag)
     np.testing.assert_allclose(prof.x_values, G[f"{tag}/x_values"], rtol=0, atol=1e-10, err_msg=tag)
     got = [prof.field_edge_idx("left"), prof.field_edge_idx("right"), prof.center_idx, prof.field_width_px]
@@ -34,7 +40,7 @@ def test_resampled_profiles(name):
         assert getattr(r, k) == v                      # the per-class keyword survives the resampling
     _check(f"{name}/res10", r)
     _check(f"{name}/res2.5_o1", prof.as_resampled(interpolation_factor=2.5, order=1))
-    _check(f"{name}/res0.5", prof.as_resampled(interpolation_factor=0.5), etol=1e-5)
+    _check(f"{name}/res0.5", prof.as_resampled(interpolation_factor=0.5), etol=max(1e-5, ETOL[cls]))
 
 
 @pytest.mark.parametrize("name", list(PHYS))
@@ -45,12 +51,13 @@ def test_physical_resampling(name):
     prof = getattr(pp, cls)(values_of(args), **kw)
     _check(name, prof)
     np.testing.assert_allclose(prof.physical_x_values, G[f"{name}/physical_x"], rtol=0, atol=1e-12)
-    assert abs(prof.field_width_mm - float(G[f"{name}/width_mm"])) < ETOL
+    etol = ETOL[cls.replace("Physical", "")]
+    assert abs(prof.field_width_mm - float(G[f"{name}/width_mm"])) < etol
     r = prof.as_resampled()
     assert type(r) is type(prof)
     _check(f"{name}/res", r)
     assert abs(r.dpmm - float(G[f"{name}/res/dpmm"])) < 1e-12
-    assert abs(r.field_width_mm - float(G[f"{name}/res/width_mm"])) < ETOL
+    assert abs(r.field_width_mm - float(G[f"{name}/res/width_mm"])) < etol
     _check(f"{name}/res_nogrid", prof.as_resampled(interpolation_resolution_mm=0.25, order=1, grid=False))
     sp = prof.as_simple_profile()
     assert type(sp).__name__ == cls.replace("Physical", "")
