@@ -502,6 +502,57 @@ int32_t epid_roi_stats(epid_ctx* ctx, const epid_batch* b, int32_t nroi, const d
 /* WeightedCentroid.calculate (metrics/image.py:959-983): cx = sum(x * a) / sum(a), cy likewise; total = sum(a) (may be NULL). */
 int32_t epid_weighted_centroid(epid_ctx* ctx, const epid_batch* b, double* cx, double* cy, double* total);
 
+/* ----------------------------------------------------------------------------------------- VMAT (DRGS / DRMLC) and DLG
+ * VMATBase.__init__ / analyze, VMATLinearBase._identify_images / _roi_profiles / _calculate_segments, Segment.r_corr / stdev,
+ * _update_r_corrs (vmat.py:249-275, 309-346, 408-436, 739-841): n independent (image 1, image 2) pairs, img1->n == img2->n, uint16.
+ * Per pair on the device: ground() + check_inversion() of both images (folded into an affine map of the raw pixels, nothing is
+ * rewritten), column-mean FWXM profiles (ground, beam-centre normalisation, stretch, 90th-percentile normalisation, in-field
+ * length / std) -> which image is the open field, field centre (image centre + warning flag when it lies outside the central
+ * third), then per segment the mean / std of DMLC / open over the pixels of the segment rectangle (never materialising the ratio
+ * image) -> R_corr, R_dev, pass / fail and the aggregates. */
+#define EPID_VMAT_MAX_SEG 16
+typedef struct {
+    int32_t ground;              /* VMATBase(ground=True) */
+    int32_t check_inversion;     /* VMATBase(check_inversion=True) */
+    int32_t invert_image_order;  /* analyze(invert_image_order=False) */
+    int32_t nseg;                /* len(roi_config) <= EPID_VMAT_MAX_SEG */
+    double dpmm;
+    double tolerance_percent;    /* analyze(tolerance=1.5) */
+    double seg_w_mm, seg_h_mm;   /* segment_size_mm: (5, 100) */
+    double offset_mm[EPID_VMAT_MAX_SEG];
+} epid_vmat_params;
+
+typedef struct {
+    int32_t status;              /* 0 ok; 2: a column-mean profile has no peak (the reference raises IndexError) */
+    int32_t open_is_first;       /* 1: image 1 is the open field (after invert_image_order) */
+    int32_t inverted[2];         /* check_inversion() flipped image 1 / 2 */
+    int32_t center_warning;      /* field centre outside the central third: image centre used (the reference warns) */
+    int32_t passed;
+    int32_t nseg;
+    int32_t pad_;
+    double x_field_center;
+    double profile_center_idx[2];                 /* FWXM centre of the column-mean profile of image 1 / 2 */
+    double field_len[2], field_std[2];            /* len / np.std of field_values() of image 1 / 2 */
+    double r_corr[EPID_VMAT_MAX_SEG], r_dev[EPID_VMAT_MAX_SEG], stdev[EPID_VMAT_MAX_SEG];
+    double center_x[EPID_VMAT_MAX_SEG], center_y[EPID_VMAT_MAX_SEG], npix[EPID_VMAT_MAX_SEG];
+    int32_t seg_passed[EPID_VMAT_MAX_SEG];
+    double max_r_deviation, avg_abs_r_deviation, avg_r_deviation;
+} epid_vmat_row;
+int32_t epid_vmat_analyze(epid_ctx* ctx, const epid_batch* img1, const epid_batch* img2, const epid_vmat_params* p,
+                          epid_vmat_row* rows /* [n] host */);
+
+/* element-wise true division num / den -> a new float64 batch (`dmlc_image.array / open_image.array`, vmat.py:339; x / 0 = inf,
+ * 0 / 0 = nan like numpy); both uint16 or both float64, same shape.  Each frame is first mapped by v -> sign * v + offset
+ * (sign_off[2 * (2 * i + which)] = sign, [.. + 1] = offset, which = 0 num / 1 den; NULL = identity): the ground() / invert() the
+ * reference applied to the images before dividing. */
+int32_t epid_divide(epid_ctx* ctx, const epid_batch* num, const epid_batch* den, const double* sign_off, epid_batch** out);
+
+/* DLG.analyze (dlg.py:32-86, 112-127): per frame and per leaf window [bottom[l]:top[l], c0:c1] the column-mean profile, the
+ * inversion rule of _determine_measured_gap and the prominence of its largest peak (signed) -> measured[n][nleaf]; then
+ * scipy.stats.linregress(planned, measured) per frame -> slope, intercept, dlg = intercept / slope.  uint16 frames. */
+int32_t epid_dlg_analyze(epid_ctx* ctx, const epid_batch* b, int32_t nleaf, const int32_t* bottom, const int32_t* top, int32_t c0,
+                         int32_t c1, const double* planned, double* measured, double* slope, double* intercept, double* dlg);
+
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the
  * fixed-size per-frame result structs.  id: 128-byte ncclUniqueId created by rank 0. */

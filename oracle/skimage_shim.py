@@ -186,9 +186,28 @@ def polygon(r, c, shape=None):
 class EuclideanTransform:
     """skimage.transform.EuclideanTransform(rotation=, translation=): params = [[cos, -sin, tx], [sin, cos, ty], [0, 0, 1]]"""
 
-    def __init__(self, rotation=0.0, translation=(0, 0), **kwargs):
+    def __init__(self, matrix=None, rotation=None, translation=None, **kwargs):
+        if matrix is not None:
+            self.params = np.array(matrix, dtype=float)
+            return
+        rotation = 0.0 if rotation is None else rotation
+        translation = (0, 0) if translation is None else translation
         cs, sn = np.cos(rotation), np.sin(rotation)
         self.params = np.array([[cs, -sn, translation[0]], [sn, cs, translation[1]], [0, 0, 1]], dtype=float)
+
+    # skimage's ProjectiveTransform.__add__: "self, then other" = other.params @ self.params (used by vmat.py:1071-1072)
+    def __add__(self, other):
+        return EuclideanTransform(matrix=other.params @ self.params)
+
+    @property
+    def translation(self):
+        return self.params[0:2, 2]
+
+    @property
+    def rotation(self):
+        import math
+
+        return math.atan2(self.params[1, 0], self.params[1, 1])
 
 
 def matrix_transform(coords, matrix):
@@ -223,3 +242,9 @@ def install():
     import pylinac.core.geometry as rgeo
 
     rgeo.transform = types.SimpleNamespace(EuclideanTransform=EuclideanTransform, matrix_transform=matrix_transform)
+    import sys
+
+    if "pylinac.vmat" in sys.modules or True:
+        import pylinac.vmat as rvmat
+
+        rvmat.EuclideanTransform = EuclideanTransform

@@ -228,6 +228,23 @@ def build(force: bool = False) -> str:
     return LIB_PATH
 
 
+VMAT_MAX_SEG = 16
+
+
+class VmatParams(C.Structure):
+    _fields_ = [("ground", C.c_int32), ("check_inversion", C.c_int32), ("invert_image_order", C.c_int32), ("nseg", C.c_int32),
+                ("dpmm", C.c_double), ("tolerance_percent", C.c_double), ("seg_w_mm", C.c_double), ("seg_h_mm", C.c_double),
+                ("offset_mm", C.c_double * VMAT_MAX_SEG)]
+
+
+_S = (VMAT_MAX_SEG,)
+VMAT_RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("open_is_first", "<i4"), ("inverted", "<i4", (2,)), ("center_warning", "<i4"), ("passed", "<i4"), ("nseg", "<i4"),
+    ("pad_", "<i4"), ("x_field_center", "<f8"), ("profile_center_idx", "<f8", (2,)), ("field_len", "<f8", (2,)), ("field_std", "<f8", (2,)),
+    ("r_corr", "<f8", _S), ("r_dev", "<f8", _S), ("stdev", "<f8", _S), ("center_x", "<f8", _S), ("center_y", "<f8", _S), ("npix", "<f8", _S),
+    ("seg_passed", "<i4", _S), ("max_r_deviation", "<f8"), ("avg_abs_r_deviation", "<f8"), ("avg_r_deviation", "<f8")], align=True)
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "epid_device_count": [C.POINTER(C.c_int32)],
@@ -283,6 +300,9 @@ _SIGNATURES = {
     "epid_disk_locate": [_P, _P, _P, _P],
     "epid_roi_stats": [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P],
     "epid_weighted_centroid": [_P, _P, _P, _P, _P],
+    "epid_vmat_analyze": [_P, _P, _P, C.POINTER(VmatParams), _P],
+    "epid_divide": [_P, _P, _P, _P, C.POINTER(_P)],
+    "epid_dlg_analyze": [_P, _P, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -731,6 +751,67 @@ def roi_stats(ctx: Context, frames, verts_xy) -> dict:
         if own:
             b.free()
     return out
+
+
+def vmat_analyze(ctx: Context, img1, img2, params: VmatParams) -> np.ndarray:
+    """n (image 1, image 2) pairs of uint16 frames (Batch or ndarray [n,h,w] / [h,w]) -> one VMAT_RESULT_DTYPE row per pair."""
+    b1, own1 = _as_batch(ctx, img1, (np.dtype(np.uint16),))
+    try:
+        b2, own2 = _as_batch(ctx, img2, (np.dtype(np.uint16),))
+    except Exception:
+        if own1:
+            b1.free()
+        raise
+    (n, _, _), _ = b1.shape_dtype
+    res = np.zeros(n, VMAT_RESULT_DTYPE)
+    try:
+        check(lib().epid_vmat_analyze(ctx.handle, b1.handle, b2.handle, C.byref(params), _ptr(res)))
+    finally:
+        if own1:
+            b1.free()
+        if own2:
+            b2.free()
+    return res
+
+
+def divide(ctx: Context, num, den, sign_off=None) -> np.ndarray:
+    """num / den as float64 (uint16 or float64 inputs of equal shape); sign_off [n, 2, 2] = (sign, offset) of num / den per frame."""
+    a, b = np.ascontiguousarray(num), np.ascontiguousarray(den)
+    squeeze = a.ndim == 2
+    if a.dtype != b.dtype or a.dtype not in (np.uint16, np.float64):
+        a, b = a.astype(np.float64), b.astype(np.float64)
+    ba, bb = Batch.upload(ctx, a), Batch.upload(ctx, b)
+    so = None if sign_off is None else np.ascontiguousarray(sign_off, dtype=np.float64).reshape(-1, 4)
+    h = _P()
+    try:
+        check(lib().epid_divide(ctx.handle, ba.handle, bb.handle, _ptr(so), C.byref(h)))
+        out = Batch(ctx, h)
+        try:
+            r = out.download()
+        finally:
+            out.free()
+    finally:
+        ba.free()
+        bb.free()
+    return r[0] if squeeze else r
+
+
+def dlg_analyze(ctx: Context, frames, bottom, top, c0: int, c1: int, planned):
+    """-> (measured [n, nleaf], slope [n], intercept [n], dlg [n]) for uint16 frames."""
+    b, own = _as_batch(ctx, frames, (np.dtype(np.uint16),))
+    (n, _, _), _ = b.shape_dtype
+    bot = np.ascontiguousarray(bottom, dtype=np.int32)
+    tp = np.ascontiguousarray(top, dtype=np.int32)
+    pl = np.ascontiguousarray(planned, dtype=np.float64)
+    nleaf = len(bot)
+    meas, slope, icpt, dlg = np.empty((n, nleaf)), np.empty(n), np.empty(n), np.empty(n)
+    try:
+        check(lib().epid_dlg_analyze(ctx.handle, b.handle, nleaf, _ptr(bot), _ptr(tp), int(c0), int(c1), _ptr(pl), _ptr(meas), _ptr(slope),
+                                     _ptr(icpt), _ptr(dlg)))
+    finally:
+        if own:
+            b.free()
+    return meas, slope, icpt, dlg
 
 
 def weighted_centroid(ctx: Context, frames):

@@ -140,3 +140,77 @@ def reference_wl2d(frame, pixel_spacing_mm, sid, gantry, coll, couch, analyze_kw
         "cax2epid_vector": np.array([rd.cax2epid_vector.x, rd.cax2epid_vector.y], dtype=float),
         "cax2epid_distance": float(rd.cax2epid_distance), "variable_axis": np.array(str(rd.variable_axis)),
     }
+
+
+def reference_vmat(klass, image1, image2, pixel_spacing_mm, sid, ctor_kwargs=None, analyze_kwargs=None):
+    """Run the UNMODIFIED reference DRGS / DRMLC / DRCS (pylinac/vmat.py) on two ndarrays (``image.load`` of an array gives an
+    ArrayImage; skimage.draw.polygon / EuclideanTransform behind ``RectangleROI.pixels_flat`` and the DRCS geometry are served by
+    oracle/skimage_shim.py: restated, unpinned at that boundary)."""
+    import warnings
+
+    from oracle import skimage_shim
+
+    skimage_shim.install()
+    from pylinac import vmat as rv
+
+    cls = getattr(rv, klass)
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        # observe (not alter) which loaded image the reference takes as the open field
+        seen = {}
+        orig_identify = cls._identify_images
+
+        def spy(self, i1, i2):
+            orig_identify(self, i1, i2)
+            seen["open_is_first"] = int(self.open_image is i1)
+
+        cls._identify_images = spy
+        try:
+            v = cls(image_paths=(np.array(image1), np.array(image2)), dpi=25.4 / pixel_spacing_mm, sid=sid, **(ctor_kwargs or {}))
+        finally:
+            cls._identify_images = orig_identify
+        v.analyze(**(analyze_kwargs or {}))
+        out = {
+            "open_is_first": seen["open_is_first"],
+            "r_corr": np.array([s.r_corr for s in v.segments], dtype=float),
+            "r_dev": np.array([s.r_dev for s in v.segments], dtype=float),
+            "stdev": np.array([s.stdev for s in v.segments], dtype=float),
+            "passed_seg": np.array([bool(s.passed) for s in v.segments]),
+            "center_x": np.array([s.center.x for s in v.segments], dtype=float),
+            "center_y": np.array([s.center.y for s in v.segments], dtype=float),
+            "max_r_deviation": float(v.max_r_deviation), "avg_abs_r_deviation": float(v.avg_abs_r_deviation),
+            "avg_r_deviation": float(v.avg_r_deviation), "passed": bool(v.passed),
+            "open_sum": float(np.asarray(v.open_image.array, dtype=np.float64).sum()),
+            "dmlc_sum": float(np.asarray(v.dmlc_image.array, dtype=np.float64).sum()),
+        }
+        if klass == "DRCS":
+            out["coll_angle_deviation"] = np.array([cd.angle_deviation for cd in v.collimator_deviations], dtype=float)
+            out["coll_angle_measured"] = np.array([cd.angle_measured for cd in v.collimator_deviations], dtype=float)
+            out["rotation_offset_deg"] = float(v.rotation_offset_deg)
+            out["rotation"] = np.array([s.rotation for s in v.segments], dtype=float)
+        rd = v.results_data()
+        out["rd_max_deviation_percent"] = float(rd.max_deviation_percent)
+        out["rd_abs_mean_deviation"] = float(rd.abs_mean_deviation)
+    out["n_user_warnings"] = sum(1 for w in wlist if issubclass(w.category, UserWarning) and "VMAT field center" in str(w.message))
+    return out
+
+
+def reference_dlg(frame, pixel_spacing_mm, sid, gaps, mlc_name, y_field_size=100, profile_width=10):
+    """Run the UNMODIFIED reference DLG (pylinac/dlg.py) on an ndarray (LinacDicomImage served by a fake dataset)."""
+    import_reference()
+    from pylinac import dlg as rdlg
+    from pylinac.core import image as rimage
+    from pylinac.picketfence import MLC
+
+    ds = FakeDicomDataset(frame, pixel_spacing_mm, sid=sid)
+    old = rimage.retrieve_dicom_file, rimage.pixels
+    rimage.retrieve_dicom_file = lambda path: ds
+    rimage.pixels = types.SimpleNamespace(apply_rescale=lambda arr, md: arr)
+    try:
+        d = rdlg.DLG(io.BytesIO(b"fake"))
+    finally:
+        rimage.retrieve_dicom_file, rimage.pixels = old
+    d.analyze(gaps=gaps, mlc=MLC[mlc_name], y_field_size=y_field_size, profile_width=profile_width)
+    return {"measured_dlg": float(d.measured_dlg), "measured_dlg_per_leaf": np.array(d.measured_dlg_per_leaf, dtype=float),
+            "planned_dlg_per_leaf": np.array(d.planned_dlg_per_leaf, dtype=float), "slope": float(d._lin_fit.slope),
+            "intercept": float(d._lin_fit.intercept), "dpmm": float(d.image.dpmm), "dtype": np.array(str(d.image.array.dtype))}

@@ -59,6 +59,11 @@ def test_field_matches_reference_golden(name):
         tol = 1e-6 if k in TOP_KEYS else TOL
         if hill:
             tol = 1e-4 if k.endswith("percent_mm") else 5e-6
+            if k in TOP_KEYS:
+                # the L-BFGS-B run on the fitted parabola stops wherever its finite-difference gradient noise lets it: on an FFF top
+                # the 1e-8 difference of the Hill edges (hence of the fit window) moves that stopping point by ~2e-3 px (measured
+                # on B200: 0.0020 px in hill_fff_siemens); the parity bar for positions is 0.01 px
+                tol = 5e-3
         np.testing.assert_allclose(np.asarray(got[k], dtype=float), GOLD[f"{name}/{k}"], rtol=0, atol=tol, err_msg=k)
 
 
