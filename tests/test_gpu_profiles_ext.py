@@ -19,12 +19,43 @@ VTOL = 1e-10
 ETOL = {"FWXMProfile": 2e-6, "InflectionDerivativeProfile": 5e-3, "HillProfile": 2e-3}
 
 
+def _bfgs_stop_radius(prof, x_star):
+    """How far from the stationary point x_star of the gradient's cubic interpolant the reference's BFGS run may stop: it ends at the
+    first iterate with |S'(x)| <= gtol = 1e-5 (scipy.optimize.minimize default), i.e. anywhere within gtol / |S''(x_star)|."""
+    diff, M = prof._derivative()
+    xs = prof.x_values.astype(np.float64)
+    i = int(np.clip(np.searchsorted(xs, x_star, side="right") - 1, 0, len(xs) - 2))
+    t = (x_star - xs[i]) / (xs[i + 1] - xs[i])
+    curv = M[i] + (M[i + 1] - M[i]) * t                     # the second derivative of a cubic spline is piecewise linear
+    return 1e-5 / abs(curv)
+
+
 def _check(tag, prof, etol=None):
-    etol = etol or ETOL[type(prof).__name__.replace("Physical", "")]
+    cls = type(prof).__name__.replace("Physical", "")
+    etol = etol or ETOL[cls]
     np.testing.assert_allclose(prof.values, G[f"{tag}/values"], rtol=0, atol=VTOL, err_msg=tag)
     np.testing.assert_allclose(prof.x_values, G[f"{tag}/x_values"], rtol=0, atol=1e-10, err_msg=tag)
     got = [prof.field_edge_idx("left"), prof.field_edge_idx("right"), prof.center_idx, prof.field_width_px]
-    np.testing.assert_allclose(got, G[f"{tag}/edges"], rtol=0, atol=etol, err_msg=tag)
+    want = G[f"{tag}/edges"]
+    if cls == "InflectionDerivativeProfile":
+        # the reference's edge is wherever its BFGS run stopped; ours is the stationary point itself.  Two checks instead of one fixed
+        # tolerance: (1) the reference's edge lies inside its own stop radius around ours (on a 10 x resampled profile the gradient is
+        # 100 x flatter in index units and the radius grows to ~0.03 px: infl/res10 measured 0.027), (2) at the reference's edge OUR
+        # interpolant's slope is below the reference's gtol -- i.e. the two interpolants agree and the reference would have stopped there
+        from pylinac_b200.core.profile import _cubic_spline_eval
+
+        diff, M = prof._derivative()
+        xs = prof.x_values.astype(np.float64)
+        rad = [_bfgs_stop_radius(prof, got[0]), _bfgs_stop_radius(prof, got[1])]
+        for k in (0, 1):
+            assert abs(got[k] - want[k]) <= max(etol, 1.2 * rad[k]), (tag, k, got[k], want[k], rad[k])
+            h = 1e-4 * (xs[1] - xs[0])
+            slope = (_cubic_spline_eval(xs, diff, M, want[k] + h) - _cubic_spline_eval(xs, diff, M, want[k] - h)) / (2 * h)
+            assert abs(slope) <= 1.5e-5, (tag, k, slope)
+        assert abs(got[2] - want[2]) <= max(etol, 0.6 * (rad[0] + rad[1]))
+        assert abs(got[3] - want[3]) <= max(etol, 1.2 * (rad[0] + rad[1]))
+        return
+    np.testing.assert_allclose(got, want, rtol=0, atol=etol, err_msg=tag)
 
 
 @pytest.mark.parametrize("name", list(CASES))
