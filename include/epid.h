@@ -454,7 +454,7 @@ typedef struct {
     int32_t invert;
     int32_t max_number;
     int32_t conditions;                /* bit mask of the detection conditions: 1 is_right_size_bb, 2 is_round, 4 is_right_circumference,
-                                          8 is_symmetric, 16 is_solid (metrics/features.py:7-68) */
+                                          8 is_symmetric, 16 is_solid (metrics/features.py:7-68), 32 is_modest_size (winston_lutz.py:598-606) */
     int32_t pad;
 } epid_disk_params;
 
@@ -552,6 +552,41 @@ int32_t epid_divide(epid_ctx* ctx, const epid_batch* num, const epid_batch* den,
  * scipy.stats.linregress(planned, measured) per frame -> slope, intercept, dlg = intercept / slope.  uint16 frames. */
 int32_t epid_dlg_analyze(epid_ctx* ctx, const epid_batch* b, int32_t nleaf, const int32_t* bottom, const int32_t* top, int32_t c0,
                          int32_t c1, const double* planned, double* measured, double* slope, double* intercept, double* dlg);
+
+/* ----------------------------------------------------------------------------------------- whole-frame feature finders
+ * GlobalSizedDiskLocator.calculate (metrics/image.py:329-354 -> find_features, metrics/utils.py:66-190) and GlobalSizedFieldLocator /
+ * GlobalFieldLocator.calculate (metrics/image.py:817-897): the whole frame is binarised at the reference's rising thresholds,
+ * labelled (4-connectivity for disks, 8 for fields), cleared at the border and every region is put through the detection conditions.
+ * The device returns every region that passed, for every threshold, ordered like the reference visits them (threshold, then label);
+ * the reference's point de-duplication / stop rule (which depends on what was found so far) is scalar work on these records in the
+ * binding.  uint16 frames. */
+typedef struct {
+    int32_t mode;            /* 0: find_features (stretch(invert?(array)), cutoffs imin + k * step, k = 1..), 1: field locator (array as is,
+                                cutoffs imin + (5 + k) * step) */
+    int32_t invert;          /* mode 0: GlobalSizedDiskLocator(invert=True) */
+    int32_t sample_kind;     /* 0: image.array is the integer frame; 1: image.array is the ground()-ed + normalize()-d float image of the
+                                frame (Winston-Lutz images after analyze()) */
+    int32_t conditions;      /* bit mask: 1 is_right_size_bb, 2 is_round, 4 is_right_circumference, 8 is_symmetric, 32 is_modest_size,
+                                64 is_square, 128 is_right_square_size, 256 is_right_square_perimeter, 512 is_right_area_square
+                                (metrics/features.py, winston_lutz.py:598-621) */
+    double dpmm;
+    double radius_mm, tolerance_mm;                              /* bb_size / tolerance of the disk conditions */
+    double field_width_mm, field_height_mm, field_tolerance_mm;  /* field conditions */
+    double bb_size_mm, rad_size_mm;                              /* is_modest_size / is_right_square_size */
+} epid_locate_params;
+
+typedef struct {
+    int32_t threshold_index;     /* 0-based position of the threshold in the reference's sweep */
+    int32_t label_root;          /* raster index of the region's first pixel (= order of skimage's labels) */
+    int32_t bbox[4];             /* min_row, min_col, max_row, max_col (half-open) */
+    double area, area_filled, perimeter, equivalent_diameter;
+    double centroid_y, centroid_x, wcentroid_y, wcentroid_x;
+} epid_region;
+
+/* regions: [n][region_cap]; counts[n]: accepted regions per frame; flags[n]: 1 = more candidates than the device list holds at some
+ * threshold, 2 = more accepted regions than region_cap */
+int32_t epid_global_locate(epid_ctx* ctx, const epid_batch* frames, const epid_locate_params* p, epid_region* regions, int32_t region_cap,
+                           int32_t* counts, int32_t* flags);
 
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the

@@ -23,19 +23,25 @@ from scipy import ndimage
 _STREL4 = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], dtype=bool)
 
 
-def label(image, connectivity=1, **kwargs):
+def label(image, connectivity=None, **kwargs):
+    """skimage.measure.label: connectivity None = full (8 neighbours in 2-D), 1 = 4 neighbours; raster-order numbering"""
     structure = _STREL4 if connectivity == 1 else np.ones((3, 3), bool)
     lab, _ = ndimage.label(np.asarray(image) != 0, structure=structure)
     return lab
 
 
-def clear_border(labels, **kwargs):
+def clear_border(labels, buffer_size=0, **kwargs):
+    """skimage.segmentation.clear_border: every object with a pixel in the outer ``buffer_size + 1`` rows / columns is removed.
+    A boolean input is labelled with full connectivity first (what skimage's internal re-labelling does); a label image keeps its
+    labels (equal-valued pixels that touch are one object either way)."""
     labels = np.array(labels)
     border = np.zeros(labels.shape, bool)
-    border[0, :] = border[-1, :] = border[:, 0] = border[:, -1] = True
-    for v in np.unique(labels[border]):
-        if v != 0:
-            labels[labels == v] = 0
+    ext = buffer_size + 1
+    border[:ext, :] = border[-ext:, :] = border[:, :ext] = border[:, -ext:] = True
+    objs = label(labels, connectivity=None) if labels.dtype == bool else labels
+    touching = np.unique(objs[border])
+    touching = touching[touching != 0]
+    labels[np.isin(objs, touching)] = 0
     return labels
 
 
@@ -94,13 +100,25 @@ def _monotone_chain(pts):
 
 
 class RegionProperties:
-    def __init__(self, lab, label_img, intensity):
+    def __init__(self, lab, label_img, intensity, sl=None):
         self.label = lab
-        sl = ndimage.find_objects((label_img == lab).astype(np.int32))[0]
+        if sl is None:
+            sl = ndimage.find_objects((label_img == lab).astype(np.int32))[0]
         self.slice = sl
         self.bbox = (sl[0].start, sl[1].start, sl[0].stop, sl[1].stop)
         self.image = label_img[sl] == lab
         self._intensity = None if intensity is None else intensity[sl]
+
+    @property
+    def centroid(self):
+        rr, cc = np.nonzero(self.image)
+        return (float(rr.mean()) + self.bbox[0], float(cc.mean()) + self.bbox[1])
+
+    @property
+    def equivalent_diameter_area(self):
+        return float(np.sqrt(4 * self.area / np.pi))
+
+    equivalent_diameter = equivalent_diameter_area
 
     @property
     def area(self):
@@ -141,8 +159,11 @@ class RegionProperties:
 
 
 def regionprops(label_image, intensity_image=None, **kwargs):
-    labs = [v for v in np.unique(label_image) if v != 0]
-    return [RegionProperties(v, label_image, intensity_image) for v in labs]
+    label_image = np.asarray(label_image)
+    if label_image.dtype == bool:
+        label_image = label_image.astype(np.int32)
+    slices = ndimage.find_objects(label_image)          # one pass for every label (None for labels that do not occur)
+    return [RegionProperties(i + 1, label_image, intensity_image, sl) for i, sl in enumerate(slices) if sl is not None]
 
 
 def find_boundaries(label_img, **kwargs):
@@ -236,6 +257,10 @@ def install():
     rutils.RegionProperties = RegionProperties
     rutils.find_boundaries = find_boundaries       # plotting only: an empty outline of the right shape
     rfeatures.RegionProperties = RegionProperties
+    import pylinac.metrics.image as rmimage
+
+    rmimage.measure = types.SimpleNamespace(label=label, regionprops=regionprops)
+    rmimage.segmentation = types.SimpleNamespace(clear_border=clear_border, find_boundaries=find_boundaries)
     import pylinac.core.roi as rroi
 
     rroi.polygon = polygon

@@ -245,6 +245,17 @@ VMAT_RESULT_DTYPE = np.dtype([
     ("seg_passed", "<i4", _S), ("max_r_deviation", "<f8"), ("avg_abs_r_deviation", "<f8"), ("avg_r_deviation", "<f8")], align=True)
 
 
+
+class LocateParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("invert", C.c_int32), ("sample_kind", C.c_int32), ("conditions", C.c_int32), ("dpmm", C.c_double),
+                ("radius_mm", C.c_double), ("tolerance_mm", C.c_double), ("field_width_mm", C.c_double), ("field_height_mm", C.c_double),
+                ("field_tolerance_mm", C.c_double), ("bb_size_mm", C.c_double), ("rad_size_mm", C.c_double)]
+
+
+REGION_DTYPE = np.dtype([("threshold_index", "<i4"), ("label_root", "<i4"), ("bbox", "<i4", (4,)), ("area", "<f8"), ("area_filled", "<f8"),
+                         ("perimeter", "<f8"), ("equivalent_diameter", "<f8"), ("centroid_y", "<f8"), ("centroid_x", "<f8"),
+                         ("wcentroid_y", "<f8"), ("wcentroid_x", "<f8")], align=True)
+
 _P = C.c_void_p
 _SIGNATURES = {
     "epid_device_count": [C.POINTER(C.c_int32)],
@@ -303,6 +314,7 @@ _SIGNATURES = {
     "epid_vmat_analyze": [_P, _P, _P, C.POINTER(VmatParams), _P],
     "epid_divide": [_P, _P, _P, _P, C.POINTER(_P)],
     "epid_dlg_analyze": [_P, _P, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P],
+    "epid_global_locate": [_P, _P, C.POINTER(LocateParams), _P, C.c_int32, _P, _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -812,6 +824,22 @@ def dlg_analyze(ctx: Context, frames, bottom, top, c0: int, c1: int, planned):
         if own:
             b.free()
     return meas, slope, icpt, dlg
+
+
+def global_locate(ctx: Context, frames, params: LocateParams, region_cap: int = 1024):
+    """Whole-frame threshold sweep: -> list (per frame) of REGION_DTYPE arrays in the reference's visiting order."""
+    b, own = _as_batch(ctx, frames, (np.dtype(np.uint16),))
+    (n, _, _), _ = b.shape_dtype
+    regs = np.zeros((n, region_cap), REGION_DTYPE)
+    counts, flags = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    try:
+        check(lib().epid_global_locate(ctx.handle, b.handle, C.byref(params), _ptr(regs), int(region_cap), _ptr(counts), _ptr(flags)))
+    finally:
+        if own:
+            b.free()
+    if (flags != 0).any():
+        raise MemoryError(f"global locator: device lists overflowed (flags {flags.tolist()}); raise region_cap or pre-filter the frame")
+    return [regs[i, : counts[i]].copy() for i in range(n)]
 
 
 def weighted_centroid(ctx: Context, frames):

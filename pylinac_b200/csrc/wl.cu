@@ -547,7 +547,7 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
     else { const double slope = (4.0 - 2.0) / (30.0 - 1.5); tol = slope * (bb_d - 1.5) + 2.0; }
     // detection conditions (metrics/features.py): all five for Winston-Lutz, the caller's subset for the stand-alone locator
     const int cm = loc ? c.loc.conditions : 31;
-    const bool c_size = cm & 1, c_round = cm & 2, c_circ = cm & 4, c_sym = cm & 8, c_solid = cm & 16;
+    const bool c_size = cm & 1, c_round = cm & 2, c_circ = cm & 4, c_sym = cm & 8, c_solid = cm & 16, c_modest = cm & 32;
     const int max_number = loc ? min(max(c.loc.max_number, 1), WL_MAXPTS) : 1;
     const double min_sep = loc ? c.loc.min_separation_px : 5.0 * dpmm;      // deduplicate_points_and_boundaries (metrics/utils.py:14-37)
     const double PI = 3.141592653589793;
@@ -648,6 +648,9 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
             // is_right_size_bb
             const double bb_area = (double)filled / (dpmm * dpmm);
             if (c_size && !(smaller_area < bb_area && bb_area < larger_area)) continue;
+            // is_modest_size (winston_lutz.py:598-606); find_features hands it the RADIUS as bb_size (metrics/utils.py:144-150)
+            if (c_modest && !(fmax(PI * (((radius_mm - 2) / 2) * ((radius_mm - 2) / 2)), 2.0) < bb_area &&
+                              bb_area < PI * (((radius_mm + 2) / 2) * ((radius_mm + 2) / 2)))) continue;
             // is_round
             const double ratio = (double)filled / bbox_area;
             if (c_round && !(PI / 4 * 1.2 > ratio && ratio > PI / 4 * 0.8)) continue;

@@ -59,6 +59,44 @@ is_right_circumference = _Condition("is_right_circumference", 4, _is_right_circu
 is_symmetric = _Condition("is_symmetric", 8, _is_symmetric)
 is_solid = _Condition("is_solid", 16, _is_solid)
 
+
+
+def _is_square(region, **kwargs) -> bool:  # :85-88
+    return region.filled_area / region.bbox_area > 0.8
+
+
+def _is_right_square_perimeter(region, **kwargs) -> bool:  # :71-82
+    actual = region.perimeter / kwargs["dpmm"]
+    upper = 1.20 * 2 * (kwargs["field_width_mm"] + kwargs["field_tolerance_mm"]) + 2 * (kwargs["field_height_mm"] + kwargs["field_tolerance_mm"])
+    lower = 2 * (kwargs["field_width_mm"] - kwargs["field_tolerance_mm"]) + 2 * (kwargs["field_height_mm"] - kwargs["field_tolerance_mm"])
+    return upper > actual > lower
+
+
+def _is_right_area_square(region, **kwargs) -> bool:  # :91-101
+    field_area = region.area_filled / (kwargs["dpmm"] ** 2)
+    low = (kwargs["field_width_mm"] - kwargs["field_tolerance_mm"]) * (kwargs["field_height_mm"] - kwargs["field_tolerance_mm"])
+    high = (kwargs["field_width_mm"] + kwargs["field_tolerance_mm"]) * (kwargs["field_height_mm"] + kwargs["field_tolerance_mm"])
+    return low < field_area < high
+
+
+def _is_modest_size(region, **kwargs) -> bool:  # winston_lutz.py:598-606
+    bb_area = region.area_filled / (kwargs["dpmm"] ** 2)
+    bb_size = kwargs["bb_size"]
+    return max((math.pi * ((bb_size - 2) / 2) ** 2, 2)) < bb_area < math.pi * ((bb_size + 2) / 2) ** 2
+
+
+def _is_right_square_size(region, **kwargs) -> bool:  # winston_lutz.py:615-621
+    field_area = region.area_filled / (kwargs["dpmm"] ** 2)
+    rad_size = max((kwargs["rad_size"], 5))
+    return (rad_size - 5) ** 2 < field_area < (rad_size + 5) ** 2
+
+
+is_modest_size = _Condition("is_modest_size", 32, _is_modest_size)
+is_square = _Condition("is_square", 64, _is_square)
+is_right_square_size = _Condition("is_right_square_size", 128, _is_right_square_size)
+is_right_square_perimeter = _Condition("is_right_square_perimeter", 256, _is_right_square_perimeter)
+is_right_area_square = _Condition("is_right_area_square", 512, _is_right_area_square)
+
 DEFAULT_CONDITIONS = (is_right_size_bb, is_round, is_right_circumference, is_symmetric, is_solid)
 
 

@@ -185,3 +185,155 @@ class WeightedCentroid(MetricBase):
         if total[0] == 0:
             raise ValueError("Image is blank; cannot calculate weighted centroid")
         return Point(float(cx[0]), float(cy[0]))
+
+
+# ---------------------------------------------------------------------------------------------- whole-frame locators
+def _dedupe(total: list[Point], new_points: list[Point], min_separation_px: float) -> list[Point]:
+    """metrics/utils.py:14-37: a new point is dropped when it is closer than the separation to any point kept so far (including the
+    ones added in this very call: the reference iterates the list it appends to)"""
+    for p in new_points:
+        if all(p.distance_to(q) >= min_separation_px for q in total):
+            total.append(p)
+    return total
+
+
+def _by_threshold(regions: np.ndarray):
+    """the accepted regions grouped by threshold, thresholds and labels ascending (the order the reference visits them)"""
+    if len(regions) == 0:
+        return
+    cuts = np.flatnonzero(np.diff(regions["threshold_index"])) + 1
+    yield from np.split(regions, cuts)
+
+
+class GlobalSizedDiskLocator(MetricBase):
+    """metrics/image.py:275-354: BBs anywhere in the image.  The threshold sweep, labelling and region analysis of the WHOLE frame
+    run on the device (``epid_global_locate``, csrc/locate.cu); the reference's point bookkeeping runs on the returned records."""
+
+    def __init__(self, radius_mm: float, radius_tolerance_mm: float, detection_conditions=None, invert: bool = True, min_number: int = 1,
+                 max_number: int | None = None, min_separation_mm: float = 5, name="Global Disk Locator"):
+        from .features import is_right_circumference, is_right_size_bb, is_round
+
+        self.radius = radius_mm
+        self.radius_tolerance = radius_tolerance_mm
+        self.detection_conditions = detection_conditions if detection_conditions is not None else (is_round, is_right_size_bb, is_right_circumference)
+        self.name = name
+        self.invert = invert
+        self.min_number = min_number
+        self.max_number = max_number or 1e3
+        self.min_separation_mm = min_separation_mm
+
+    def _params(self, dpmm: float, sample_kind: int = 0) -> "nat.LocateParams":
+        p = nat.LocateParams()
+        p.mode, p.invert, p.sample_kind = 0, int(bool(self.invert)), sample_kind
+        p.conditions = conditions_mask(self.detection_conditions)
+        p.dpmm = float(dpmm)
+        p.radius_mm, p.tolerance_mm = float(self.radius), float(self.radius_tolerance)
+        p.bb_size_mm = float(self.radius)           # find_features passes the radius as bb_size (metrics/utils.py:144-150)
+        return p
+
+    def _merge(self, regions: np.ndarray, dpmm: float) -> list[Point]:
+        total: list[Point] = []
+        self.regions = []
+        for grp in _by_threshold(regions):
+            if len(total) >= self.max_number:
+                break
+            _dedupe(total, [Point(float(r["wcentroid_x"]), float(r["wcentroid_y"])) for r in grp], self.min_separation_mm * dpmm)
+            self.regions = grp
+        if len(total) < self.min_number:
+            raise ValueError(f"Couldn't find the minimum number of disks in the image. Found {len(total)}; required: {self.min_number}")
+        return total
+
+    def calculate(self) -> list[Point]:
+        from ..core import image as _image
+
+        dpmm = self.image.dpmm
+        frame = _image.frame_u16(self.image, "global disk locator")
+        regs = nat.global_locate(nat.Context.default(), frame, self._params(dpmm))[0]
+        self.points = self._merge(regs, dpmm)
+        self.y_boundaries, self.x_boundaries = [], []       # plot-only outlines: not produced
+        return self.points
+
+
+def locate_disks_batch(frames, dpmm: float, radius_mm: float, radius_tolerance_mm: float, **kwargs) -> list[list[Point]]:
+    """GlobalSizedDiskLocator on n uint16 frames [n, H, W] in one device sweep -> one point list per frame ([] where the reference
+    would raise for too few disks)."""
+    m = GlobalSizedDiskLocator(radius_mm, radius_tolerance_mm, **kwargs)
+    out = []
+    for regs in nat.global_locate(nat.Context.default(), frames, m._params(dpmm)):
+        try:
+            out.append(m._merge(regs, dpmm))
+        except ValueError:
+            out.append([])
+    return out
+
+
+class GlobalSizedFieldLocator(MetricBase):
+    """metrics/image.py:727-920: radiation fields anywhere in the image (8-connectivity, clear_border(buffer_size=3), unweighted
+    centroids, separation = the largest equivalent diameter of the threshold's fields / dpmm, like the reference)."""
+
+    is_from_physical: bool = False
+
+    def __init__(self, field_width_px: float, field_height_px: float, field_tolerance_px: float, min_number: int = 1,
+                 max_number: int | None = None, name: str = "Field Finder", detection_conditions=None):
+        from .features import is_right_area_square, is_right_square_perimeter
+
+        self.field_width_mm = field_width_px
+        self.field_height_mm = field_height_px
+        self.field_tolerance_mm = field_tolerance_px
+        self.min_number = min_number
+        self.max_number = max_number or 1e6
+        self.name = name
+        self.detection_conditions = detection_conditions if detection_conditions is not None else (is_right_square_perimeter, is_right_area_square)
+
+    @classmethod
+    def from_physical(cls, field_width_mm: float, field_height_mm: float, field_tolerance_mm: float, min_number: int = 1,
+                      max_number: int | None = None, name: str = "Field Finder", detection_conditions=None):
+        inst = cls(field_width_mm, field_height_mm, field_tolerance_mm, min_number, max_number, name, detection_conditions)
+        inst.is_from_physical = True
+        return inst
+
+    def _params(self, dpmm: float, sample_kind: int = 0) -> "nat.LocateParams":
+        p = nat.LocateParams()
+        p.mode, p.invert, p.sample_kind = 1, 0, sample_kind
+        p.conditions = conditions_mask(self.detection_conditions)
+        p.dpmm = float(dpmm)
+        p.field_width_mm, p.field_height_mm, p.field_tolerance_mm = float(self.field_width_mm), float(self.field_height_mm), float(self.field_tolerance_mm)
+        return p
+
+    def _merge(self, regions: np.ndarray, dpmm: float) -> list[Point]:
+        fields: list[Point] = []
+        for grp in _by_threshold(regions):
+            if len(fields) >= self.max_number:
+                break
+            sep = float(grp["equivalent_diameter"].max()) / dpmm          # metrics/image.py:880-884
+            _dedupe(fields, [Point(float(r["centroid_x"]), float(r["centroid_y"])) for r in grp], sep)
+        if len(fields) < self.min_number:
+            raise ValueError(f"Couldn't find the minimum number of fields in the image. Found {len(fields)}; required: {self.min_number}")
+        return fields
+
+    def calculate(self, sample_kind: int | None = None) -> list[Point]:
+        from ..core import image as _image
+
+        dpmm = self.image.dpmm
+        if not self.is_from_physical:          # converted in place on every call, like the reference (:820-823)
+            self.field_width_mm /= dpmm
+            self.field_height_mm /= dpmm
+            self.field_tolerance_mm /= dpmm
+        frame = _image.frame_u16(self.image, "global field locator")
+        kind = getattr(self.image, "_locator_sample_kind", 0) if sample_kind is None else sample_kind
+        regs = nat.global_locate(nat.Context.default(), frame, self._params(dpmm, kind))[0]
+        self.fields = self._merge(regs, dpmm)
+        self.boundaries = []
+        return self.fields
+
+
+class GlobalFieldLocator(GlobalSizedFieldLocator):
+    """metrics/image.py:923-956: fields of any size (the size window is opened to 1e4)."""
+
+    def __init__(self, min_number: int = 1, max_number: int | None = None, name: str = "Field Finder", detection_conditions=None):
+        super().__init__(field_width_px=1e4, field_height_px=1e4, field_tolerance_px=1e4, min_number=min_number, max_number=max_number,
+                         name=name, detection_conditions=detection_conditions)
+
+    @classmethod
+    def from_physical(cls, *args, **kwargs):
+        raise NotImplementedError("This method is not implemented for global field-finding. Use the standard initializer instead.")

@@ -118,8 +118,11 @@ def make_params(dpmm: float, *, bb_size_mm: float = 5, low_density_bb: bool = Fa
 class WLFrameResult:
     """One frame's results (a row of the struct-of-arrays the GPU returns)."""
 
-    def __init__(self, row):
+    def __init__(self, row, bb_shift_px=None, dpmm: float | None = None):
         self.r = row
+        # virtual BB shift (WLBaseImage.analyze(shift_vector=...), winston_lutz.py:719-736): added to the detected BB, pixels
+        self._shift = bb_shift_px
+        self._dpmm = dpmm
 
     @property
     def status(self) -> int:
@@ -135,6 +138,8 @@ class WLFrameResult:
 
     @property
     def bb(self) -> Point:
+        if self._shift is not None:
+            return Point(float(self.r["bb_x"]) + self._shift[0], float(self.r["bb_y"]) + self._shift[1])
         return Point(float(self.r["bb_x"]), float(self.r["bb_y"]))
 
     @property
@@ -147,10 +152,15 @@ class WLFrameResult:
 
     @property
     def cax2bb_vector(self) -> Vector:
+        if self._shift is not None:      # winston_lutz.py:1189-1192 on the shifted BB
+            d = (self.bb - self.field_cax) / self._dpmm
+            return Vector(d.x, d.y, d.z)
         return Vector(float(self.r["cax2bb_x"]), float(self.r["cax2bb_y"]), 0.0)
 
     @property
     def cax2bb_distance(self) -> float:
+        if self._shift is not None:      # winston_lutz.py:1195-1198
+            return self.field_cax.distance_to(self.bb) / self._dpmm
         return float(self.r["cax2bb_distance"])
 
     @property
@@ -180,6 +190,30 @@ def analyze_batch(frames, dpmm: float, *, device: int | None = None, bb_size_mm:
     params = make_params(dpmm, bb_size_mm=bb_size_mm, low_density_bb=low_density_bb, open_field=open_field,
                          bb_proximity_mm=bb_proximity_mm)
     return WLBatchResult(nat.wl2d_analyze(ctx, frames, params))
+
+
+def bb_projection_with_rotation(offset_left: float, offset_up: float, offset_in: float, gantry: float, couch: float = 0.0,
+                                sad: float = 1000, machine_scale=None) -> tuple[float, float]:
+    """winston_lutz.py:3401-3463: isoplane projection (left/right, sup/inf) of a point given by its phantom offsets.  The reference
+    builds scipy's Rotation.from_euler("xyz", [-couch, 0, gantry]) (extrinsic: about x, then z) and applies it to (up, left, in);
+    written out here."""
+    if machine_scale is not None and machine_scale != MachineScale.IEC61217:
+        gantry, _, couch = convert_scale(machine_scale, MachineScale.IEC61217, gantry, 0, couch)
+    a, c = math.radians(-couch), math.radians(gantry)
+    x, y, z = offset_up, offset_left, offset_in
+    # Rx(a)
+    y1, z1 = y * math.cos(a) - z * math.sin(a), y * math.sin(a) + z * math.cos(a)
+    # Rz(c)
+    x2, y2 = x * math.cos(c) - y1 * math.sin(c), x * math.sin(c) + y1 * math.cos(c)
+    mag = sad / (sad - x2)
+    return -(y2 * mag), z1 * mag
+
+
+def _virtual_shift_px(shift_vector, dpmm: float, gantry: float, couch: float, sad: float, machine_scale) -> tuple[float, float]:
+    """winston_lutz.py:719-736: the image-space displacement (pixels) a phantom shift produces for the BB of one image"""
+    lat, sup_inf = bb_projection_with_rotation(offset_left=-shift_vector.x, offset_up=shift_vector.z, offset_in=shift_vector.y, sad=sad,
+                                               gantry=gantry, couch=couch, machine_scale=machine_scale)
+    return lat * dpmm, -(sup_inf * dpmm)
 
 
 @capture_warnings
@@ -220,15 +254,23 @@ class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
                 snap_tolerance: float = 3, gantry_reference: float = 0, collimator_reference: float = 0,
                 couch_reference: float = 0, bb_proximity_mm: float = 20, machine_scale=None) -> None:
         """winston_lutz.py:1152-1183"""
-        if shift_vector is not None:
-            raise NotImplementedError("virtual BB shifts (shift_vector) are outside the accelerated per-image path")
+        if snap_tolerance < 0:
+            raise ValueError("Snap tolerance must be >= 0")
         self._snap_tolerance = snap_tolerance
         self._gantry_reference = gantry_reference
         self._collimator_reference = collimator_reference
         self._couch_reference = couch_reference
-        res = analyze_batch(self._frame_u16(), self.dpmm, bb_size_mm=bb_size_mm, low_density_bb=low_density_bb,
-                            open_field=open_field, bb_proximity_mm=bb_proximity_mm)[0]
+        # with a virtual shift the proximity test applies to the SHIFTED BB (find_bb_matches runs after the shift): the device finds
+        # the BB without the test, the test is repeated here on the shifted point
+        res = analyze_batch(self._frame_u16(), self.dpmm, bb_size_mm=bb_size_mm, low_density_bb=low_density_bb, open_field=open_field,
+                            bb_proximity_mm=1e9 if shift_vector else bb_proximity_mm)[0]
         res.raise_for_status()
+        if shift_vector:
+            sad = float(getattr(self.image, "sad", 1000.0) or 1000.0)
+            res = WLFrameResult(res.r, _virtual_shift_px(shift_vector, self.dpmm, self.gantry_angle, self.couch_angle, sad, machine_scale),
+                                self.dpmm)
+            if not res.epid.distance_to(res.bb) < bb_proximity_mm * self.dpmm:      # nominal position of the single BB = EPID centre
+                raise ValueError(BB_ERROR_MESSAGE)
         self._result = res
         self._is_analyzed = True
         self.bb = res.bb
@@ -489,8 +531,6 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
                 open_field: bool = False, apply_virtual_shift: bool = False, snap_tolerance: float = 3, gantry_reference: float = 0,
                 collimator_reference: float = 0, couch_reference: float = 0, bb_proximity_mm: float = 20) -> None:
         """winston_lutz.py:1519-1611"""
-        if apply_virtual_shift:
-            raise NotImplementedError("virtual BB shifts are outside the accelerated per-image path")
         self.machine_scale = machine_scale
         rows = analyze_batch(self._frames, self.dpmm, bb_size_mm=bb_size_mm, low_density_bb=low_density_bb, open_field=open_field,
                              bb_proximity_mm=bb_proximity_mm)
@@ -501,8 +541,26 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
             rows[k].raise_for_status()
             self.images.append(_SetImage(rows[k], self.dpmm, g, c, p, refs))
         self._minimized = {}
+        if apply_virtual_shift:
+            self._apply_virtual_shift(refs)
         self._bb_diameter = bb_size_mm
         self._is_analyzed = True
+
+    def _apply_virtual_shift(self, refs: dict) -> None:
+        """winston_lutz.py:1587-1601: the shift that would bring the BB to the radiation isocentre is applied to the detected BB of
+        every image (the second pass of the reference re-detects the same BBs; its proximity default of 20 mm applies) and all
+        set-level results are taken from the shifted BBs."""
+        shift = self.bb_shift_vector
+        self._virtual_shift = self.bb_shift_instructions()
+        sad = float(getattr(self, "_sad", 1000.0))
+        shifted = []
+        for im in self.images:
+            r = WLFrameResult(im.r.r, _virtual_shift_px(shift, self.dpmm, im.gantry_angle, im.couch_angle, sad, self.machine_scale), self.dpmm)
+            if not r.epid.distance_to(r.bb) < 20 * self.dpmm:
+                raise ValueError(BB_ERROR_MESSAGE)
+            shifted.append(_SetImage(r, self.dpmm, im.gantry_angle, im.collimator_angle, im.couch_angle, refs))
+        self.images = shifted
+        self._minimized = {}
 
     # ---- BB3D (winston_lutz.py:313-362)
     def _solve(self, which: str) -> Point:

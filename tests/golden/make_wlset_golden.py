@@ -11,7 +11,7 @@ import warnings
 
 import numpy as np
 
-from tests.golden.wlset_cases import SETS, set_frames
+from tests.golden.wlset_cases import SETS, VSHIFT_SETS, set_frames
 
 SCALARS = ["max_2d_cax_to_bb_mm", "median_2d_cax_to_bb_mm", "mean_2d_cax_to_bb_mm", "max_2d_cax_to_epid_mm",
            "median_2d_cax_to_epid_mm", "mean_2d_cax_to_epid_mm", "gantry_3d_iso_diameter_mm", "coll_2d_iso_diameter_mm",
@@ -20,7 +20,7 @@ SCALARS = ["max_2d_cax_to_bb_mm", "median_2d_cax_to_bb_mm", "mean_2d_cax_to_bb_m
            "max_epid_rms_deviation_mm", "max_coll_rms_deviation_mm", "max_couch_rms_deviation_mm"]
 
 
-def reference_wlset(frames, ps, sid, axes):
+def reference_wlset(frames, ps, sid, axes, **analyze_kwargs):
     from oracle import skimage_shim
     from oracle.refstub import reference_image_from_array
 
@@ -35,7 +35,7 @@ def reference_wlset(frames, ps, sid, axes):
     st._captured_warnings, st._warnings_lock = [], threading.Lock()      # WarningCollectorMixin.__init__ (core/warnings.py:14-17)
     st._is_analyzed = False
     st.is_from_cbct = False
-    st.analyze()
+    st.analyze(**analyze_kwargs)
     rd = st.results_data()
     out = {k: np.asarray(getattr(rd, k)) for k in SCALARS}
     sv = st.bb_shift_vector
@@ -64,6 +64,13 @@ def main():
             store[f"{name}/{k}"] = v
         print(name, {k: (float(v) if v.ndim == 0 and v.dtype.kind == "f" else v.tolist()) for k, v in ref.items() if k in
                      ("gantry_3d_iso_diameter_mm", "coll_2d_iso_diameter_mm", "couch_2d_iso_diameter_mm", "bb_shift_vector", "variable_axes")})
+    # analyze(apply_virtual_shift=True) (winston_lutz.py:1587-1601): the BBs are moved by the computed shift and everything is redone
+    for name in VSHIFT_SETS:
+        frames, ps, sid, axes = set_frames(name)
+        ref = reference_wlset(frames, ps, sid, axes, apply_virtual_shift=True)
+        for k, v in ref.items():
+            store[f"{name}_vshift/{k}"] = v
+        print(name, "virtual shift", ref["bb_shift_vector"].tolist(), float(ref["max_2d_cax_to_bb_mm"]))
     np.savez_compressed("tests/golden/wlset_golden.npz", **store)
 
 

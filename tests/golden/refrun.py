@@ -214,3 +214,19 @@ def reference_dlg(frame, pixel_spacing_mm, sid, gaps, mlc_name, y_field_size=100
     return {"measured_dlg": float(d.measured_dlg), "measured_dlg_per_leaf": np.array(d.measured_dlg_per_leaf, dtype=float),
             "planned_dlg_per_leaf": np.array(d.planned_dlg_per_leaf, dtype=float), "slope": float(d._lin_fit.slope),
             "intercept": float(d._lin_fit.intercept), "dpmm": float(d.image.dpmm), "dtype": np.array(str(d.image.array.dtype))}
+
+
+def reference_locator(frame, pixel_spacing_mm, sid, spec):
+    """Run the UNMODIFIED reference's whole-frame locator metric (metrics/image.py) on an ArrayImage; skimage label / clear_border /
+    regionprops are served by oracle/skimage_shim.py (restated, unpinned at that boundary).  -> points [k, 2] (x, y) or raises."""
+    from oracle import skimage_shim
+
+    skimage_shim.install()
+    from pylinac.core import image as rimage
+    from pylinac.metrics import image as rmi
+
+    img = rimage.ArrayImage(np.array(frame), dpi=25.4 / pixel_spacing_mm, sid=sid)
+    cls = getattr(rmi, spec["cls"])
+    metric = cls.from_physical(**spec["kw"]) if spec.get("physical") else cls(**spec["kw"])
+    pts = img.compute(metrics=metric)
+    return np.array([[p.x, p.y] for p in pts], dtype=float).reshape(-1, 2)

@@ -13,6 +13,8 @@ SETS = {
     "combo": ((0.3, 0.2, -0.7), [(0, 0, 0), (120, 30, 0), (240, 330, 0), (60, 0, 30), (1.5, 0, 358)]),
 }
 
+VSHIFT_SETS = ["standard", "combo"]
+
 
 def set_frames(name):
     """-> (frames uint16 [n,h,w], pixel_spacing_mm, sid, axes)"""

@@ -65,3 +65,19 @@ def test_scale_conversion_and_axis_snap():
     assert wl.variable_axis(10, 10, 10) == wl.Axis.GBP_COMBO
     with pytest.raises(ValueError):
         wl.is_close_degrees(1, 2, delta=-1)
+
+
+@pytest.mark.parametrize("name", ["standard", "combo"])
+def test_virtual_shift_matches_reference(name):
+    """analyze(apply_virtual_shift=True) (winston_lutz.py:1587-1601): BBs moved by the projected shift, everything recomputed."""
+    rows, dpmm = rows_from_golden(name)
+    st = build_set(name, rows, dpmm)
+    st._apply_virtual_shift(dict(snap_tolerance=3, gantry_reference=0, collimator_reference=0, couch_reference=0))
+    v = f"{name}_vshift"
+    np.testing.assert_allclose([[im.bb.x, im.bb.y] for im in st.images], GOLD[f"{v}/bbs"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose([im.cax2bb_distance for im in st.images], GOLD[f"{v}/cax2bb_distances"], rtol=0, atol=1e-9)
+    rd = st.results_data()
+    for k in SCALARS:
+        np.testing.assert_allclose(getattr(rd, k), GOLD[f"{v}/{k}"], rtol=0, atol=1e-7, err_msg=k)
+    sv = st.bb_shift_vector
+    np.testing.assert_allclose([sv.x, sv.y, sv.z], GOLD[f"{v}/bb_shift_vector"], rtol=0, atol=1e-9)
