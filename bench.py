@@ -270,7 +270,50 @@ def bench_modules(ctx, nat, peak, cores):
                      "one_read_frac": frames.nbytes / dev_s / 1e9 / peak, "h2d_bytes": int(frames.nbytes),
                      "note": "device-resident time includes the D2H of the result rows"}
         del frames
+    # VMAT (DRGS): image pairs, 1280 x 1280; algorithmic bytes = one read of BOTH frames of a pair
+    try:
+        from pylinac_b200 import vmat as vm
+
+        pairs = [_gen_vmat_pair(i) for i in range(4)]
+        count = 1024
+        f1 = nat.pinned_empty((count,) + pairs[0][0].shape, np.uint16)
+        f2 = nat.pinned_empty((count,) + pairs[0][0].shape, np.uint16)
+        for k in range(count):
+            f1[k], f2[k] = pairs[k % 4][k % 2], pairs[k % 4][1 - k % 2]      # either order: the open image is identified per pair
+        params = vm._make_params(1 / 0.336, 1.5, (5, 100), [-60, -40, -20, 0, 20, 40, 60], True, True, False)
+        b1, b2 = nat.Batch.upload(ctx, f1), nat.Batch.upload(ctx, f2)
+        nat.vmat_analyze(ctx, b1, b2, params)
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            rows = nat.vmat_analyze(ctx, b1, b2, params)
+        ctx.sync()
+        dev_s = (time.perf_counter() - t0) / 3
+        b1.free()
+        b2.free()
+        out["vmat_drgs"] = {"workload": "1024 synthetic DRGS (open, DMLC) pairs, 1280x1280, 7 segments", "pairs": count,
+                            "device_resident_pairs_per_s": count / dev_s, "ms_per_batch": dev_s * 1e3, "status_ok": int((rows["status"] == 0).sum()),
+                            "one_read_frac": (f1.nbytes + f2.nbytes) / dev_s / 1e9 / peak,
+                            "note": "one read of both frames of a pair is the algorithmic traffic; time includes the D2H of the result rows"}
+        del f1, f2
+    except Exception as e:
+        out["vmat_drgs"] = {"error": repr(e)}
     return out
+
+
+def _gen_vmat_pair(i):
+    from oracle import synth
+
+    o = synth.as1200(1000.0)
+    o.add_filtered_field((150, 150), alpha=0.6)
+    o.gaussian(2.0)
+    o.noise(0.002, seed=400 + i)
+    d = synth.as1200(1000.0)
+    for off, a in zip((-60, -40, -20, 0, 20, 40, 60), (0.30, 0.302, 0.299, 0.30, 0.301, 0.298, 0.30)):
+        d.add_filtered_field((150, 18), cax_offset_mm=(0, off), alpha=a)
+    d.gaussian(1.5)
+    d.noise(0.002, seed=500 + i)
+    return o.image, d.image
 
 
 def main():

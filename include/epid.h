@@ -55,7 +55,9 @@ int32_t epid_version(void);
  * EPID_OPT_PF_EXACT_ONLY: 1 = always use the exact-histogram PicketFence pipeline (default 0: fused sample-guided front
  * kernel with automatic per-batch fallback to the exact pipeline).  EPID_CTR_PF_FALLBACKS: batches / chunks re-run exactly. */
 enum { EPID_OPT_PF_EXACT_ONLY = 1, EPID_OPT_PF_LEAFBAND = 2 /* 1 = experimental leaf-band window kernel (bit-identical results; default 0) */,
-       EPID_OPT_PF_WIN2 = 3 /* 1 (default) = two-kernel window path (medians + per-window analysis); 0 = single per-window kernel (bit-identical) */ };
+       EPID_OPT_PF_WIN2 = 3 /* 1 (default) = two-kernel window path (medians + per-window analysis); 0 = single per-window kernel (bit-identical) */,
+       EPID_OPT_PF_SPLIT = 4 /* S >= 2: a device-resident batch runs as S sub-batches on S streams, so that the latency-bound per-frame
+                                kernels of one sub-batch overlap the streaming kernels of another (bit-identical results); 0 / 1 = one stream */ };
 enum { EPID_CTR_PF_FALLBACKS = 1, EPID_CTR_PF_REDONE_FRAMES = 2 /* frames re-run individually by the exact pipeline */ };
 int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value);
 int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value);

@@ -67,6 +67,8 @@ struct epid_ctx {
     // options / diagnostics (epid_set_option / epid_get_counter)
     int pf_exact_only = 0;               // 1: never use the fused sample-guided front kernel
     int pf_leafband = 0;                 // 1: experimental leaf-band window kernel for the frames it covers (default: per-window kernel)
+    int pf_split = 0;                    // >= 2: sub-batches on that many streams (EPID_OPT_PF_SPLIT)
+    cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // created on first use
     int pf_win2 = 1;                     // 1 (default): two-kernel window path for the frames it covers (pf_windows2.cu)
     int64_t pf_fallbacks = 0;            // batches (or chunks) re-run by the exact pipeline
     int64_t pf_redone_frames = 0;        // frames re-run by the exact pipeline (per-frame fallback)

@@ -20,6 +20,7 @@
 // The host merges the per-threshold records in the reference's order (threshold, then label) with its de-duplication and stop rule.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -350,7 +351,7 @@ __device__ void gl_analyze_one(const GlCfg& c, int k, int f, const uint16_t* __r
     if (tid < 50) s_hist50[tid] = 0;
     __syncthreads();
     for (int i = tid; i < th * tw; i += GL_THREADS) {
-        if (!(tile[i] & 1)) return;
+        if (!(tile[i] & 1)) continue;
         const bool er = (tile[i - 1] & 1) && (tile[i + 1] & 1) && (tile[i - tw] & 1) && (tile[i + tw] & 1);      // the margin guarantees neighbours
         if (!er) tile[i] |= 4;
     }
@@ -361,7 +362,7 @@ __device__ void gl_analyze_one(const GlCfg& c, int k, int f, const uint16_t* __r
         for (int dy = -1; dy <= 1; dy++)
             for (int dx = -1; dx <= 1; dx++) {
                 const int yy = ty + dy, xx = tx + dx;
-                if (yy < 0 || yy >= th || xx < 0 || xx >= tw) return;
+                if (yy < 0 || yy >= th || xx < 0 || xx >= tw) continue;
                 if (tile[yy * tw + xx] & 4) v += (dy == 0 && dx == 0) ? 1 : ((dy == 0 || dx == 0) ? 2 : 10);
             }
         if (v > 0 && v < 50) atomicAdd(&s_hist50[v], 1);
@@ -392,7 +393,7 @@ __device__ void gl_analyze_one(const GlCfg& c, int k, int f, const uint16_t* __r
     const unsigned int D = F.mx - F.mn;
     for (int i = tid; i < bh * bw; i += GL_THREADS) {
         const int r = i / bw, cidx = i - r * bw;
-        if (!(tile[(r + 1) * tw + (cidx + 1)] & 1)) return;
+        if (!(tile[(r + 1) * tw + (cidx + 1)] & 1)) continue;
         const double wv = gl_sample(c.mode, c.kind, c.invert, img[(q.y0 + r) * c.W + (q.x0 + cidx)], F.mn, D);
         sw += wv; swr += (double)r * wv; swc += (double)cidx * wv;
         sr += (double)r; sc += (double)cidx;
@@ -515,6 +516,20 @@ extern "C" int32_t epid_global_locate(epid_ctx* ctx, const epid_batch* frames, c
         k_gl_analyze<<<dim3(8, n), GL_THREADS, GL_TILE_BYTES, ctx->stream>>>(c, 1, fr, d_gf, k, d_par, d_cand, d_ncand, d_big, d_acc, d_nacc,
                                                                           region_cap, d_over);
         ctx->launches += 7;  // init, union, flatten, props, select, analyze x 2
+        if (getenv("EPID_DEBUG_LOCATE")) {      // diagnostics: per threshold the plan, candidates and accepted regions of frame 0
+            GlFrame hf;
+            int hc = 0, ha = 0;
+            cudaMemcpyAsync(&hf, d_gf, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(&hc, d_ncand, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(&ha, d_nacc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            std::vector<int> hp((size_t)HW);
+            cudaMemcpy(hp.data(), d_par, sizeof(int) * (size_t)HW, cudaMemcpyDeviceToHost);
+            long fg = 0, roots = 0;
+            for (int i = 0; i < HW; i++) { fg += hp[i] >= 0; roots += hp[i] == i; }
+            fprintf(stderr, "[locate] k %d (%s) mn %u mx %u nthr %d dir %d T %u cutoff %g fg %ld roots %ld ncand %d nacc %d\n", k, cudaGetErrorString(e), hf.mn,
+                    hf.mx, hf.nthr, k < GL_MAXTHR ? hf.dir[k] : 0, k < GL_MAXTHR ? hf.T[k] : 0u, k < GL_MAXTHR ? hf.cutoff[k] : 0.0, fg, roots, hc, ha);
+        }
     }
     EPID_CUDA(cudaGetLastError());
     std::vector<int> h_n(n), h_o(n);

@@ -829,6 +829,55 @@ bool pf_fast_ok(const epid_ctx* ctx, const epid_pf_params* p, int H0, int W0) {
 
 }  // namespace
 
+// S sub-batches on S streams (EPID_OPT_PF_SPLIT): every sub-batch is a complete, independent pipeline with its own work area, so the
+// results are those of the single-stream run; the streams fork from and join into ctx->stream.
+struct PfSplit {
+    int S = 0;
+    PfWork w[4];
+    int n0[4], nn[4];
+    cudaStream_t st[4];
+    cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+    int prepare(epid_ctx* ctx, int n, int H, int W, int meas_cap) {
+        S = ctx->pf_split < n ? ctx->pf_split : n;
+        if (S < 2) { S = 0; return EPID_OK; }
+        size_t tot = 0, off[4];
+        for (int k = 0; k < S; k++) {
+            n0[k] = (int)((long long)n * k / S);
+            nn[k] = (int)((long long)n * (k + 1) / S) - n0[k];
+            carve(w[k], nullptr, nn[k], H, W, meas_cap);
+            off[k] = tot;
+            tot += align_up(w[k].total, 512);
+        }
+        int rc = ensure_scratch(ctx, tot);
+        if (rc != EPID_OK) return rc;
+        for (int k = 0; k < S; k++) carve(w[k], (char*)ctx->scratch + off[k], nn[k], H, W, meas_cap);
+        st[0] = ctx->stream;
+        for (int k = 1; k < S; k++) {
+            if (!ctx->aux_stream[k]) EPID_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream[k], cudaStreamNonBlocking));
+            st[k] = ctx->aux_stream[k];
+        }
+        EPID_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        for (int k = 1; k < S; k++) EPID_CUDA(cudaEventCreateWithFlags(&join[k], cudaEventDisableTiming));
+        return EPID_OK;
+    }
+    int do_fork(epid_ctx* ctx) {
+        EPID_CUDA(cudaEventRecord(fork, ctx->stream));
+        for (int k = 1; k < S; k++) EPID_CUDA(cudaStreamWaitEvent(st[k], fork, 0));
+        return EPID_OK;
+    }
+    int do_join(epid_ctx* ctx) {
+        for (int k = 1; k < S; k++) {
+            EPID_CUDA(cudaEventRecord(join[k], st[k]));
+            EPID_CUDA(cudaStreamWaitEvent(ctx->stream, join[k], 0));
+        }
+        return EPID_OK;
+    }
+    void destroy() {
+        if (fork) cudaEventDestroy(fork);
+        for (int k = 1; k < 4; k++) if (join[k]) cudaEventDestroy(join[k]);
+    }
+};
+
 extern "C" {
 
 int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_params* p, epid_pf_summary* summary,
@@ -853,6 +902,36 @@ int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_p
         return r;
     };
     int cnt3[3] = {0, 0, 0};
+    if (fast && ctx->pf_split >= 2 && n >= 2 * ctx->pf_split) {
+        // sub-batches on several streams, each with its own work area; result rows are copied per sub-batch.  A sub-batch with
+        // deferred frames makes the call fall back to the single-stream path below (rare: noisy / undecidable frames).
+        PfSplit sp;
+        rc = sp.prepare(ctx, n, H, W, meas_cap);
+        bool deferred = false;
+        if (rc == EPID_OK && sp.S >= 2) {
+            const size_t per = (size_t)frames->h * frames->w;
+            rc = sp.do_fork(ctx);
+            int cnt[4][3] = {};
+            for (int k = 0; k < sp.S && rc == EPID_OK; k++) {
+                rc = pf_run(ctx, sp.st[k], (const uint16_t*)frames->dptr + per * sp.n0[k], sp.nn[k], frames->h, frames->w, p, meas_cap, sp.w[k],
+                            pools, nullptr, true);
+                if (rc == EPID_OK) rc = PfResultCopy::enqueue(sp.st[k], sp.w[k], sp.nn[k], meas_cap, summary + sp.n0[k], meas + (size_t)sp.n0[k] * meas_cap, cnt[k]);
+            }
+            if (rc == EPID_OK) rc = sp.do_join(ctx);
+            cudaError_t e = cudaStreamSynchronize(ctx->stream);
+            for (int k = 1; k < sp.S; k++) cudaStreamSynchronize(sp.st[k]);
+            if (rc == EPID_OK && e != cudaSuccess) { set_error("PF pipeline failed: %s", cudaGetErrorString(e)); rc = EPID_ERR_CUDA; }
+            for (int k = 0; k < sp.S; k++) deferred = deferred || cnt[k][2] > 0;
+        }
+        sp.destroy();
+        if (rc != EPID_OK || (sp.S >= 2 && !deferred)) {
+            for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+            return rc;
+        }
+        rc = ensure_scratch(ctx, w.total);
+        if (rc != EPID_OK) return rc;
+        carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
+    }
     rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr, fast);
     if (rc == EPID_OK) rc = copy_and_wait(cnt3); else cudaStreamSynchronize(ctx->stream);
     if (rc == EPID_OK && fast && cnt3[2] > 0) {
@@ -886,6 +965,46 @@ static int32_t pf_bench_impl(epid_ctx* ctx, const epid_batch* frames, const epid
     cudaEvent_t t0, t1;
     EPID_CUDA(cudaEventCreate(&t0));
     EPID_CUDA(cudaEventCreate(&t1));
+    if (fast && ctx->pf_split >= 2 && n >= 2 * ctx->pf_split && !stage_ms) {
+        // sub-batches on several streams; falls through to the single-stream path when a frame was deferred
+        PfSplit sp;
+        rc = sp.prepare(ctx, n, H, W, meas_cap);
+        bool deferred = false;
+        if (rc == EPID_OK && sp.S >= 2) {
+            const int64_t l0 = ctx->launches;
+            const size_t per = (size_t)frames->h * frames->w;
+            EPID_CUDA(cudaStreamSynchronize(ctx->stream));
+            EPID_CUDA(cudaEventRecord(t0, ctx->stream));
+            rc = sp.do_fork(ctx);
+            for (int it = 0; it < iters && rc == EPID_OK; it++)
+                for (int k = 0; k < sp.S && rc == EPID_OK; k++)
+                    rc = pf_run(ctx, sp.st[k], (const uint16_t*)frames->dptr + per * sp.n0[k], sp.nn[k], frames->h, frames->w, p, meas_cap, sp.w[k],
+                                pools, nullptr, true);
+            if (rc == EPID_OK) rc = sp.do_join(ctx);
+            cudaEventRecord(t1, ctx->stream);
+            int cnt[4][3] = {};
+            for (int k = 0; k < sp.S; k++) cudaMemcpyAsync(cnt[k], sp.w[k].counters, sizeof(cnt[k]), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            for (int k = 1; k < sp.S; k++) cudaStreamSynchronize(sp.st[k]);
+            for (int k = 0; k < sp.S; k++) deferred = deferred || cnt[k][2] > 0;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, t0, t1);
+            if (total_ms) *total_ms = ms;
+            if (stats_kernel_ms) *stats_kernel_ms = 0.f;
+            if (launches) *launches = ctx->launches - l0;
+            if (redone) *redone = 0;
+        }
+        sp.destroy();
+        if (rc != EPID_OK || (sp.S >= 2 && !deferred)) {
+            cudaEventDestroy(t0); cudaEventDestroy(t1);
+            for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+            return rc;
+        }
+        // carve() above re-used the scratch: restore the single-batch work area
+        rc = ensure_scratch(ctx, w.total);
+        if (rc != EPID_OK) return rc;
+        carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
+    }
     // pass 0: back-to-back passes, no host round trip (what an ordinary batch costs).  If that left deferred frames, pass 1 times
     // the real control flow: after every fast pass the host reads the deferred count and enqueues the per-frame exact re-run.
     for (int mode = 0; mode < 2; mode++) {

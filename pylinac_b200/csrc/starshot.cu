@@ -42,6 +42,7 @@ struct StarConst {
     PctPlan p4, p50, p96;             // of the frame
     PctPlan p90;                      // of the central third
     int nmax;                         // capacity of the per-frame profile arrays
+    int npad;                         // capacity of the padded (rolled + reflected) copy the gaussian reads: nmax + 2 * filter radius
     int max_sigma;                    // gaussian table covers sigma = 1 .. max_sigma
 };
 
@@ -271,7 +272,7 @@ __device__ inline void nelder_mead3(const StarLine* lines, int nl, double x0, do
 __global__ void __launch_bounds__(SS_THREADS)
 k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ frames, const StarFrame* __restrict__ sf,
               const double* __restrict__ gauss_w, const int* __restrict__ gauss_off, double* __restrict__ prof_a,
-              double* __restrict__ prof_b, epid_star_result* __restrict__ res) {
+              double* __restrict__ prof_b, double* __restrict__ prof_c, epid_star_result* __restrict__ res) {
     __shared__ double s_prom[SS_PEAK_CAP], s_wh[SS_PEAK_CAP], s_lip[SS_PEAK_CAP], s_rip[SS_PEAK_CAP], s_skey[SS_PEAK_CAP];
     __shared__ int s_idx[SS_PEAK_CAP], s_lb[SS_PEAK_CAP], s_rb[SS_PEAK_CAP], s_flag[SS_PEAK_CAP], s_sidx[SS_PEAK_CAP];
     __shared__ int s_small[SS_THREADS + 8];
@@ -288,6 +289,7 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
     const int H = c.H, W = c.W;
     double* pa = prof_a + (size_t)fi * c.nmax;
     double* pb = prof_b + (size_t)fi * c.nmax;
+    double* pc = prof_c + (size_t)fi * c.npad;
     const double dpmm = c.p.dpmm;
     const double fx = c.p.has_start_point ? c.p.start_x : (double)f.sx;
     const double fy = c.p.has_start_point ? c.p.start_y : (double)f.sy;
@@ -371,10 +373,15 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
                 if (j >= n) j -= n;
                 return pa[j];
             };
+            // the rolled profile with its reflected margins, laid out contiguously once: the 2 * rad_w + 1 taps of every output sample
+            // are then plain coalesced loads (same operands, same order of additions as before)
+            for (int l = tid; l < n + 2 * rad_w; l += SS_THREADS) pc[l] = at(l - rad_w);
+            __syncthreads();
             double tmin = INFINITY;
             for (int l = tid; l < n; l += SS_THREADS) {
-                double tmp = at(l) * gw[rad_w];
-                for (int ll = -rad_w; ll < 0; ll++) tmp += (at(l + ll) + at(l - ll)) * gw[ll + rad_w];
+                const double* __restrict__ q = pc + l + rad_w;
+                double tmp = q[0] * gw[rad_w];
+                for (int ll = -rad_w; ll < 0; ll++) tmp += (q[ll] + q[-ll]) * gw[ll + rad_w];
                 pb[l] = tmp;
                 tmin = fmin(tmin, tmp);
             }
@@ -595,6 +602,7 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
     hc.p90 = star_pct_plan(hc.ch * hc.cw, 90.0);
     hc.nmax = 10 * (H > W ? H : W) + 64;
     hc.max_sigma = max_sigma;
+    hc.npad = hc.nmax + 2 * (int)(4.0 * max_sigma + 0.5) + 8;
     const size_t gw_count = (size_t)gauss_offsets[max_sigma] + (size_t)(2 * (int)(4.0 * max_sigma + 0.5) + 1);
     // scratch
     size_t o = 0;
@@ -603,6 +611,7 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
     const size_t o_sf = sz(sizeof(FrameStats) * n), o_sc = sz(sizeof(FrameStats) * n), o_fr = sz(sizeof(StarFrame) * n);
     const size_t o_res = sz(sizeof(epid_star_result) * n), o_gw = sz(sizeof(double) * gw_count), o_go = sz(sizeof(int) * (max_sigma + 1));
     const size_t o_pa = sz(sizeof(double) * (size_t)n * hc.nmax), o_pb = sz(sizeof(double) * (size_t)n * hc.nmax);
+    const size_t o_pc = sz(sizeof(double) * (size_t)n * hc.npad);
     int rc = ensure_scratch(ctx, o);
     if (rc != EPID_OK) return rc;
     char* base = (char*)ctx->scratch;
@@ -651,7 +660,7 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
         k_star_front<<<n, SS_THREADS, smem, st>>>(d_cst, d_rf, d_sf, d_sc, d_fr, d_res);
         ctx->launches++;
     }
-    k_star_wobble<<<n, SS_THREADS, 0, st>>>(d_cst, d_rf, d_fr, d_gw, d_go, (double*)(base + o_pa), (double*)(base + o_pb), d_res);
+    k_star_wobble<<<n, SS_THREADS, 0, st>>>(d_cst, d_rf, d_fr, d_gw, d_go, (double*)(base + o_pa), (double*)(base + o_pb), (double*)(base + o_pc), d_res);
     ctx->launches++;
     EPID_CUDA(cudaGetLastError());
     EPID_CUDA(cudaMemcpyAsync(results, d_res, sizeof(epid_star_result) * n, cudaMemcpyDeviceToHost, st));

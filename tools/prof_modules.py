@@ -24,3 +24,5 @@ t0 = time.perf_counter()
 rows = spec[1](ctx, b, spec[0]())
 ctx.sync()
 print(kind, count, "frames", (time.perf_counter() - t0) * 1e3, "ms", "ok", int((rows["status"] == 0).sum()))
+if kind == "star":
+    print("iterations per frame (StarProfile constructions):", rows["iterations"][:8].tolist(), "mean", float(rows["iterations"].mean()))
