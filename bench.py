@@ -416,16 +416,29 @@ def main():
     ctx.sync()
     e2e_page_s = (time.perf_counter() - t0) / psteps
     barrier()
+    # ---- the host -> device copy of one step alone (all ranks at the same time): what the end-to-end leg cannot go below, and what
+    # shows whether ranks slow each other down on the host side (shared memory controllers / PCIe root complexes)
+    batch.write(pinned)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.write(pinned)
+    h2d_only_s = (time.perf_counter() - t0) / args.steps
+    barrier()
 
     # ---- max over ranks
     if dist is not None:
         import torch
 
-        t = torch.tensor([total_ms, e2e_s * 1e3, e2e_page_s * 1e3], dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_s * 1e3, e2e_page_s * 1e3, h2d_only_s * 1e3], dtype=torch.float64)
+        tmin = t.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms, e2e_page_ms = (float(x) for x in t)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        total_ms, e2e_ms, e2e_page_ms, h2d_only_ms = (float(x) for x in t)
+        h2d_only_min_ms = float(tmin[3])
     else:
-        e2e_ms, e2e_page_ms = e2e_s * 1e3, e2e_page_s * 1e3
+        e2e_ms, e2e_page_ms, h2d_only_ms = e2e_s * 1e3, e2e_page_s * 1e3, h2d_only_s * 1e3
+        h2d_only_min_ms = h2d_only_ms
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
@@ -481,7 +494,11 @@ def main():
         "e2e": {"value": frames_total / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(n * H0 * W0 * 2),
                 "d2h_bytes_per_step": int(summ_bytes + meas_bytes), "ms_per_step": e2e_ms / args.steps,
                 "api": "pylinac_b200.picketfence.analyze_batch(host uint16 frames in page-locked memory) -> per-frame results"
-                       + (" + ncclAllGather of the summaries" if world > 1 else "")},
+                       + (" + ncclAllGather of the summaries" if world > 1 else ""),
+                "h2d_only_ms_per_step": {"max_over_ranks": h2d_only_ms, "min_over_ranks": h2d_only_min_ms,
+                                         "GBps_per_rank_at_max": n * H0 * W0 * 2 / (h2d_only_ms * 1e-3) / 1e9,
+                                         "note": "the step's host->device copy alone, all ranks copying at the same time: the floor of "
+                                                 "the end-to-end step; growth with the rank count = host-side contention, not NVLink"}},
         "e2e_pageable": {"value": world * n / (e2e_page_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_page_ms, "steps": psteps,
                          "frac_of_pinned": (world * n / (e2e_page_ms * 1e-3)) / (frames_total / (e2e_ms * 1e-3)),
                          "api": "the same call on an ordinary (pageable) numpy array: chunks are staged through a page-locked ring"},

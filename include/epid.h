@@ -71,6 +71,7 @@ int32_t epid_host_free(void* p);
 int32_t epid_batch_upload(epid_ctx* ctx, const void* host, int32_t dtype, int32_t n, int32_t h, int32_t w, epid_batch** out);
 int32_t epid_batch_alloc(epid_ctx* ctx, int32_t dtype, int32_t n, int32_t h, int32_t w, epid_batch** out);
 int32_t epid_batch_download(epid_batch* b, void* host);        /* whole batch, native dtype */
+int32_t epid_batch_write(epid_batch* b, const void* host);     /* overwrite an existing batch from host memory (same shape / dtype) */
 int32_t epid_batch_free(epid_batch* b);
 int32_t epid_batch_shape(const epid_batch* b, int32_t* dtype, int32_t* n, int32_t* h, int32_t* w);
 int32_t epid_batch_device_ptr(const epid_batch* b, void** dptr);
@@ -589,6 +590,23 @@ typedef struct {
  * threshold, 2 = more accepted regions than region_cap */
 int32_t epid_global_locate(epid_ctx* ctx, const epid_batch* frames, const epid_locate_params* p, epid_region* regions, int32_t region_cap,
                            int32_t* counts, int32_t* flags);
+
+/* ----------------------------------------------------------------------------------------- Canny / Hough (JawOrthogonality)
+ * contrib/orthogonality.py:29-50: skimage.feature.canny(stretch(image)) -> skimage.transform.hough_line -> hough_line_peaks.
+ * scikit-image is absent from the build container: restated from the published algorithms, parity unpinned (oracle/edges_oracle.py).
+ * epid_canny: float64 frames; weights = scipy's gaussian kernel (2 * radius + 1 doubles) for the smoothing sigma; thresholds are
+ * absolute (skimage defaults for float images: 0.1 / 0.2) -> uint8 edge maps (a new batch).
+ * epid_hough_line: one uint8 edge map, ntheta angles (radians) -> int32 accumulator batch [1][2 * offset + 1][ntheta], offset =
+ * ceil(hypot(rows, cols)); the distance bins are linspace(-offset, offset, 2 * offset + 1).
+ * epid_hough_candidates: the device half of hough_line_peaks / _prominent_peaks: maximum filter (2 d + 1 per axis, mode 'constant'),
+ * pixels equal to their local maximum and > threshold (threshold < 0: 0.5 * max) as (row, col, value) triples; `filtered` keeps the
+ * max-filtered accumulator on the device for epid_gather_i32 (values at arbitrary (row, col) pairs). */
+int32_t epid_canny(epid_ctx* ctx, const epid_batch* in, const double* weights, int32_t radius, double low_threshold, double high_threshold,
+                   epid_batch** out);
+int32_t epid_hough_line(epid_ctx* ctx, const epid_batch* edges, int32_t ntheta, const double* theta, epid_batch** accum, int32_t* offset_out);
+int32_t epid_hough_candidates(epid_ctx* ctx, const epid_batch* accum, int32_t min_xdistance, int32_t min_ydistance, double threshold,
+                              int32_t cap, int32_t* cand_yxv, int32_t* count, int32_t* global_max, epid_batch** filtered);
+int32_t epid_gather_i32(epid_ctx* ctx, const epid_batch* img, int32_t npts, const int32_t* yx, int32_t* values);
 
 /* ----------------------------------------------------------------------------------------- multi-GPU (NCCL)
  * The batch shards by frame index with no data-path collective; the only exchange is the final gather of the

@@ -273,6 +273,7 @@ _SIGNATURES = {
     "epid_batch_upload": [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)],
     "epid_batch_alloc": [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)],
     "epid_batch_download": [_P, _P],
+    "epid_batch_write": [_P, _P],
     "epid_batch_free": [_P],
     "epid_batch_shape": [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "epid_batch_device_ptr": [_P, C.POINTER(_P)],
@@ -315,6 +316,11 @@ _SIGNATURES = {
     "epid_divide": [_P, _P, _P, _P, C.POINTER(_P)],
     "epid_dlg_analyze": [_P, _P, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P],
     "epid_global_locate": [_P, _P, C.POINTER(LocateParams), _P, C.c_int32, _P, _P],
+    "epid_canny": [_P, _P, _P, C.c_int32, C.c_double, C.c_double, C.POINTER(_P)],
+    "epid_hough_line": [_P, _P, C.c_int32, _P, C.POINTER(_P), C.POINTER(C.c_int32)],
+    "epid_hough_candidates": [_P, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                              C.POINTER(_P)],
+    "epid_gather_i32": [_P, _P, C.c_int32, _P, _P],
     "epid_comm_unique_id": [_P],
     "epid_comm_init": [_P, C.c_int32, C.c_int32, _P],
     "epid_comm_destroy": [_P],
@@ -448,6 +454,14 @@ class Batch:
         dt, n, h, w = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         check(lib().epid_batch_shape(self.handle, C.byref(dt), C.byref(n), C.byref(h), C.byref(w)))
         return (n.value, h.value, w.value), _DT2NP[dt.value]
+
+    def write(self, arr: np.ndarray) -> None:
+        """overwrite the batch from a host array of the same shape / dtype (one H2D copy, synchronous)"""
+        shape, dt = self.shape_dtype
+        a = np.ascontiguousarray(arr)
+        if a.shape != shape or a.dtype != dt:
+            raise ValueError(f"expected {shape} {dt}, got {a.shape} {a.dtype}")
+        check(lib().epid_batch_write(self.handle, _ptr(a)))
 
     def download(self) -> np.ndarray:
         shape, dt = self.shape_dtype
@@ -840,6 +854,56 @@ def global_locate(ctx: Context, frames, params: LocateParams, region_cap: int = 
     if (flags != 0).any():
         raise MemoryError(f"global locator: device lists overflowed (flags {flags.tolist()}); raise region_cap or pre-filter the frame")
     return [regs[i, : counts[i]].copy() for i in range(n)]
+
+
+def canny(ctx: Context, image: np.ndarray, sigma: float = 1.0, low_threshold: float = 0.1, high_threshold: float = 0.2) -> np.ndarray:
+    """skimage.feature.canny semantics for a float64 image [h, w] (or [n, h, w]) -> boolean edge map(s)."""
+    a = np.ascontiguousarray(image, dtype=np.float64)
+    squeeze = a.ndim == 2
+    w, lw = gaussian_kernel1d(float(sigma))
+    b = Batch.upload(ctx, a)
+    h = _P()
+    try:
+        check(lib().epid_canny(ctx.handle, b.handle, _ptr(w), int(lw), float(low_threshold), float(high_threshold), C.byref(h)))
+        out = Batch(ctx, h)
+        try:
+            r = out.download()
+        finally:
+            out.free()
+    finally:
+        b.free()
+    r = r.astype(bool)
+    return r[0] if squeeze else r
+
+
+def hough_line(ctx: Context, edges: np.ndarray, theta: np.ndarray):
+    """skimage.transform.hough_line: -> (accumulator Batch [1, 2 * offset + 1, ntheta] int32 on the device, offset)"""
+    e = np.ascontiguousarray(edges).astype(np.uint8)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    b = Batch.upload(ctx, e)
+    h, off = _P(), C.c_int32()
+    try:
+        check(lib().epid_hough_line(ctx.handle, b.handle, len(th), _ptr(th), C.byref(h), C.byref(off)))
+    finally:
+        b.free()
+    return Batch(ctx, h), off.value
+
+
+def hough_candidates(ctx: Context, accum: Batch, min_xdistance: int, min_ydistance: int, threshold: float | None = None, cap: int = 1 << 16):
+    """-> (candidates [k, 3] (row, col, value), global maximum, max-filtered accumulator Batch)"""
+    cand = np.zeros((cap, 3), np.int32)
+    cnt, gmax = C.c_int32(), C.c_int32()
+    h = _P()
+    check(lib().epid_hough_candidates(ctx.handle, accum.handle, int(min_xdistance), int(min_ydistance), -1.0 if threshold is None else float(threshold),
+                                      cap, _ptr(cand), C.byref(cnt), C.byref(gmax), C.byref(h)))
+    return cand[: cnt.value].copy(), gmax.value, Batch(ctx, h)
+
+
+def gather_i32(ctx: Context, img: Batch, yx: np.ndarray) -> np.ndarray:
+    pts = np.ascontiguousarray(yx, dtype=np.int32).reshape(-1, 2)
+    out = np.zeros(len(pts), np.int32)
+    check(lib().epid_gather_i32(ctx.handle, img.handle, len(pts), _ptr(pts), _ptr(out)))
+    return out
 
 
 def weighted_centroid(ctx: Context, frames):

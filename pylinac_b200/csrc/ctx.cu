@@ -221,6 +221,14 @@ int32_t epid_batch_upload(epid_ctx* ctx, const void* host, int32_t dtype, int32_
     return EPID_OK;
 }
 
+int32_t epid_batch_write(epid_batch* b, const void* host) {
+    EPID_REQUIRE(b && host, EPID_ERR_INVALID, "NULL argument");
+    EPID_CUDA(cudaSetDevice(b->ctx->device));
+    EPID_CUDA(cudaMemcpyAsync(b->dptr, host, b->bytes(), cudaMemcpyHostToDevice, b->ctx->stream));
+    EPID_CUDA(cudaStreamSynchronize(b->ctx->stream));
+    return EPID_OK;
+}
+
 int32_t epid_batch_download(epid_batch* b, void* host) {
     EPID_REQUIRE(b && host, EPID_ERR_INVALID, "NULL argument");
     EPID_CUDA(cudaSetDevice(b->ctx->device));

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ccl.cuh"
 
 namespace epid {
 
@@ -133,28 +134,6 @@ __global__ void k_gl_init(const uint16_t* __restrict__ frames, int HW, const GlF
     int* par = parent + (size_t)f * HW;
     const bool live = k < F.nthr;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) par[i] = live && gl_fg(F, k, img[i]) ? i : -1;
-}
-
-__device__ __forceinline__ int gl_find(int* parent, int i) {
-    while (true) {
-        const int p = parent[i];
-        if (p == i) return i;
-        const int gp = parent[p];
-        if (gp != p) atomicMin(&parent[i], gp);      // path halving; parents only ever decrease, so a concurrent hook is never lost
-        i = p;
-    }
-}
-
-__device__ __forceinline__ void gl_union(int* parent, int a, int b) {
-    while (true) {
-        a = gl_find(parent, a);
-        b = gl_find(parent, b);
-        if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }      // hook the larger root under the smaller one
-        const int old = atomicMin(&parent[a], b);
-        if (old == a) return;
-        a = old;
-    }
 }
 
 __global__ void k_gl_union(int H, int W, int conn8, int* __restrict__ parent) {

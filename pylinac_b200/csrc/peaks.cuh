@@ -13,6 +13,8 @@
 
 namespace epid {
 
+constexpr int PK_WALK = 48;      // samples a lane walks on its own before the warp takes over (block_find_peaks, prominences)
+
 struct PeakArgs {          // already parsed (= after _parse_peak_args, core/profile.py:2626-2649)
     double hmin;           // height threshold (may be -inf)
     int distance;          // ceil(distance); <= 1 disables the stage
@@ -161,20 +163,64 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
         count = compact_by_flag(w, count, false);
     }
 
-    // ---- 3. prominences (wlen = None)
-    for (int i = tid; i < count; i += nt) {
-        const int p = w.idx[i];
-        const double xp = x[p];
-        int k = p, lb = p;
-        double lmin = xp;
-        while (k >= 0 && x[k] <= xp) { if (x[k] < lmin) { lmin = x[k]; lb = k; } k--; }
-        k = p;
-        int rb = p;
-        double rmin = xp;
-        while (k <= n - 1 && x[k] <= xp) { if (x[k] < rmin) { rmin = x[k]; rb = k; } k++; }
-        w.prom[i] = xp - fmax(lmin, rmin);
-        w.lbase[i] = lb;
-        w.rbase[i] = rb;
+    // ---- 3. prominences (wlen = None).  Every lane walks its own peak for up to PK_WALK samples per side; walks that are still
+    // running after that (the few dominant peaks, whose walks cross most of the profile) are finished by the whole warp, 32 samples
+    // per step.  Same minima and bases as the sequential walk: the first (closest) sample wins among equal minima.
+    for (int base = 0; base < count; base += nt) {
+        const int i = base + tid;
+        const bool act = i < count;
+        const int p = act ? w.idx[i] : 0;
+        const double xp = act ? x[p] : 0.0;
+        int kl = p, lb = p, kr = p, rb = p;
+        double lmin = xp, rmin = xp;
+        bool runl = act, runr = act;
+        if (act) {
+            int steps = 0;
+            while (kl >= 0 && x[kl] <= xp && steps < PK_WALK) { if (x[kl] < lmin) { lmin = x[kl]; lb = kl; } kl--; steps++; }
+            runl = kl >= 0 && x[kl] <= xp;
+            steps = 0;
+            while (kr <= n - 1 && x[kr] <= xp && steps < PK_WALK) { if (x[kr] < rmin) { rmin = x[kr]; rb = kr; } kr++; steps++; }
+            runr = kr <= n - 1 && x[kr] <= xp;
+        }
+        const int lane = tid & 31;
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            unsigned pend = __ballot_sync(0xffffffffu, side == 0 ? runl : runr);
+            while (pend) {
+                const int src = __ffs(pend) - 1;
+                pend &= pend - 1;
+                int k0 = __shfl_sync(0xffffffffu, side == 0 ? kl : kr, src);
+                const double xps = __shfl_sync(0xffffffffu, xp, src);
+                double mn = __shfl_sync(0xffffffffu, side == 0 ? lmin : rmin, src);
+                int mb = __shfl_sync(0xffffffffu, side == 0 ? lb : rb, src);
+                while (true) {
+                    const int kk = side == 0 ? k0 - lane : k0 + lane;
+                    const bool inb = kk >= 0 && kk <= n - 1;
+                    const double v = inb ? x[kk] : 0.0;
+                    const bool stop = !(inb && v <= xps);
+                    const unsigned sm = __ballot_sync(0xffffffffu, stop);
+                    const int nvalid = sm ? __ffs(sm) - 1 : 32;
+                    // minimum over the lanes inside the walk, the lowest lane (= closest sample) among equals
+                    double bv = lane < nvalid ? v : __longlong_as_double(0x7ff0000000000000LL);
+                    int bl = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                        if (ov < bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+                    }
+                    if (nvalid > 0 && bv < mn) { mn = bv; mb = side == 0 ? k0 - bl : k0 + bl; }
+                    if (sm) break;
+                    k0 += side == 0 ? -32 : 32;
+                }
+                if (lane == src) { if (side == 0) { lmin = mn; lb = mb; } else { rmin = mn; rb = mb; } }
+            }
+        }
+        if (act) {
+            w.prom[i] = xp - fmax(lmin, rmin);
+            w.lbase[i] = lb;
+            w.rbase[i] = rb;
+        }
     }
     __syncthreads();
     // ---- 4/5. widths (computed before the prominence filter is applied; independent per peak)

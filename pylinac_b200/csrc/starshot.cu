@@ -31,6 +31,7 @@
 namespace epid {
 
 constexpr int SS_THREADS = 256;
+constexpr int SS_GW_CAP = 192;        // gaussian half-kernel (radius + 1 weights) kept in shared memory: sigma <= 47
 constexpr int SS_PEAK_CAP = 512;
 constexpr int SS_MAX_PEAKS = EPID_STAR_MAX_PEAKS;
 constexpr int SS_MAX_LINES = EPID_STAR_MAX_PEAKS / 2;
@@ -279,6 +280,7 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
     __shared__ double s_red[SS_THREADS / 32], s_bc[4];
     __shared__ int s_redi[SS_THREADS / 32], s_ctl[4];
     __shared__ StarLine s_lines[SS_MAX_LINES];
+    __shared__ double s_gw[SS_GW_CAP];
     const StarConst& c = *cc;
     const int fi = blockIdx.x;
     epid_star_result& R = res[fi];
@@ -377,13 +379,34 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
             // are then plain coalesced loads (same operands, same order of additions as before)
             for (int l = tid; l < n + 2 * rad_w; l += SS_THREADS) pc[l] = at(l - rad_w);
             __syncthreads();
+            // weights of the left half + centre in shared memory; four output samples per thread in flight (independent accumulators:
+            // the per-sample order of additions is unchanged, the loads of the four chains overlap)
+            const bool gw_sh = rad_w + 1 <= SS_GW_CAP;
+            if (gw_sh) for (int k = tid; k <= rad_w; k += SS_THREADS) s_gw[k] = gw[k];
+            __syncthreads();
+            const double* __restrict__ gwp = gw_sh ? s_gw : gw;
             double tmin = INFINITY;
-            for (int l = tid; l < n; l += SS_THREADS) {
-                const double* __restrict__ q = pc + l + rad_w;
-                double tmp = q[0] * gw[rad_w];
-                for (int ll = -rad_w; ll < 0; ll++) tmp += (q[ll] + q[-ll]) * gw[ll + rad_w];
-                pb[l] = tmp;
-                tmin = fmin(tmin, tmp);
+            for (int l0 = tid; l0 < n; l0 += 4 * SS_THREADS) {
+                const int l1 = l0 + SS_THREADS, l2 = l0 + 2 * SS_THREADS, l3 = l0 + 3 * SS_THREADS;
+                const bool v1 = l1 < n, v2 = l2 < n, v3 = l3 < n;
+                const double* __restrict__ q0 = pc + l0 + rad_w;
+                const double* __restrict__ q1 = v1 ? pc + l1 + rad_w : q0;
+                const double* __restrict__ q2 = v2 ? pc + l2 + rad_w : q0;
+                const double* __restrict__ q3 = v3 ? pc + l3 + rad_w : q0;
+                const double gc = gwp[rad_w];
+                double t0 = q0[0] * gc, t1 = q1[0] * gc, t2 = q2[0] * gc, t3 = q3[0] * gc;
+                for (int ll = -rad_w; ll < 0; ll++) {
+                    const double g = gwp[ll + rad_w];
+                    t0 += (q0[ll] + q0[-ll]) * g;
+                    t1 += (q1[ll] + q1[-ll]) * g;
+                    t2 += (q2[ll] + q2[-ll]) * g;
+                    t3 += (q3[ll] + q3[-ll]) * g;
+                }
+                pb[l0] = t0;
+                tmin = fmin(tmin, t0);
+                if (v1) { pb[l1] = t1; tmin = fmin(tmin, t1); }
+                if (v2) { pb[l2] = t2; tmin = fmin(tmin, t2); }
+                if (v3) { pb[l3] = t3; tmin = fmin(tmin, t3); }
             }
             tmin = warp_min(tmin);
             if (lane == 0) s_red[wid] = tmin;
