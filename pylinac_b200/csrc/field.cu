@@ -224,8 +224,15 @@ __device__ inline bool sp_inflection(const Sp& s, double* left, double* right) {
         return s.v[idx];
     };
     for (int l = tid; l < n; l += FA_THREADS) {
-        double tmp = at(l) * gw[lw];
-        for (int ll = -lw; ll < 0; ll++) tmp += (at(l + ll) + at(l - ll)) * gw[ll + lw];
+        double tmp;
+        if (l - lw >= 0 && l + lw < n) {      // interior: every tap is inside the profile (same operands and order, no reflection tests)
+            const double* __restrict__ q = s.v + l;
+            tmp = q[0] * gw[lw];
+            for (int ll = -lw; ll < 0; ll++) tmp += (q[ll] + q[-ll]) * gw[ll + lw];
+        } else {
+            tmp = at(l) * gw[lw];
+            for (int ll = -lw; ll < 0; ll++) tmp += (at(l + ll) + at(l - ll)) * gw[ll + lw];
+        }
         s.t1[l] = tmp;
     }
     __syncthreads();

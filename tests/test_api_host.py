@@ -86,3 +86,50 @@ def test_convert_to_dtype_formula():
     np.testing.assert_array_equal(au.convert_to_dtype(a, np.uint16), exp)
     with pytest.raises(ValueError):
         au.convert_to_dtype(np.array([], dtype=np.uint8), np.uint16)
+
+
+# ---------------------------------------------------------------------------------------------- VMAT / DLG / locators (host logic)
+def test_vmat_host_side_validation_and_geometry():
+    from pylinac_b200 import vmat
+
+    with pytest.raises(ValueError, match="Exactly 2 images"):
+        vmat.DRGS(image_paths=(np.zeros((64, 64), np.uint16),))
+    with pytest.raises(ValueError, match="at most"):
+        vmat._make_params(2.5, 1.5, (5, 100), list(range(20)), True, True, False)
+    p = vmat._make_params(2.5, 1.5, (5, 100), [-45, -15, 15, 45], True, False, True)
+    assert (p.nseg, p.ground, p.check_inversion, p.invert_image_order) == (4, 1, 0, 1) and p.offset_mm[3] == 45
+    assert vmat.wrap180(190) == -170 and vmat.wrap180(-180) == -180 and vmat.wrap180(180) == -180
+    # IEC angle of a line from image points (vmat.py:208-215)
+    from pylinac_b200.core.geometry import Point
+
+    assert vmat.CollimatorDeviation.calculate_angle_measured(Point(0, 0), Point(0, -10)) == pytest.approx(0.0)
+    assert vmat.CollimatorDeviation.calculate_angle_measured(Point(0, 0), Point(10, 0)) == pytest.approx(270.0)
+    assert list(vmat.DRGS._default_roi_config()) == [f"ROI {k}" for k in range(1, 8)]
+
+
+def test_dlg_windows_follow_the_reference_geometry():
+    from pylinac_b200 import dlg
+    from pylinac_b200.picketfence import MLC
+
+    bottoms, tops, c0, c1, planned = dlg._windows((1280, 1280), 1 / 0.336, (-0.9, -1.1, -1.3, -1.5, -1.7, -1.9), MLC.MILLENNIUM, 100, 10)
+    assert len(bottoms) == len(tops) == len(planned) == 20 and (c0, c1) == (610, 670)
+    assert all(t > b for b, t in zip(bottoms, tops))
+    assert sorted(set(planned)) == [-1.9, -1.7, -1.5, -1.3, -1.1, -0.9]
+    assert dlg._get_dlg_offset(100, 0.0, [-1.9, -1.7]) is None      # a centre exactly on a band edge, like the reference
+    with pytest.raises(TypeError):
+        dlg._windows((1280, 1280), 1 / 0.336, (-1.0, -1.2, -1.4, -1.6), MLC.MLCI, 100, 10)      # MLCi leaf centres (+-25 mm) sit on band edges
+
+
+def test_locator_point_bookkeeping_matches_the_reference_rules():
+    from pylinac_b200.core.geometry import Point
+    from pylinac_b200.metrics import image as mi
+
+    total = [Point(10, 10)]
+    mi._dedupe(total, [Point(12, 10), Point(30, 30), Point(31, 30)], 5)      # the second new point also blocks the third
+    assert [(p.x, p.y) for p in total] == [(10, 10), (30, 30)]
+    regs = np.zeros(5, mi.nat.REGION_DTYPE)
+    regs["threshold_index"] = [0, 0, 2, 2, 5]
+    assert [len(g) for g in mi._by_threshold(regs)] == [2, 2, 1]
+    assert list(mi._by_threshold(regs[:0])) == []
+    with pytest.raises(NotImplementedError):
+        mi.GlobalFieldLocator.from_physical(1, 2, 3)
