@@ -30,6 +30,7 @@ namespace epid {
 
 constexpr int GL_THREADS = 256;
 constexpr int GL_MAXTHR = 64;
+constexpr int GL_CHUNK = 32;            // frames labelled at a time (scratch: 24 B per pixel and frame)
 constexpr int GL_MAXCAND = 2048;          // candidates per frame and threshold
 constexpr int GL_TILE_BYTES = 200 * 1024; // large shared-memory tile of the per-candidate analysis (regions up to ~450 x 450)
 constexpr int GL_SMALL_TILE = 40 * 1024;  // small tile: the common case (regions up to ~200 x 200), several CTAs per SM
@@ -446,6 +447,18 @@ extern "C" int32_t epid_global_locate(epid_ctx* ctx, const epid_batch* frames, c
     EPID_REQUIRE(!(p->conditions & C_SOLID), EPID_ERR_UNSUPPORTED, "is_solid is not available in the whole-frame finder");
     EPID_REQUIRE(p->dpmm > 0, EPID_ERR_INVALID, "dpmm must be positive");
     EPID_CUDA(cudaSetDevice(ctx->device));
+    if (frames->n > GL_CHUNK) {
+        // 24 B of labelling scratch per pixel and frame: large batches run in chunks of GL_CHUNK frames
+        for (int c0 = 0; c0 < frames->n; c0 += GL_CHUNK) {
+            epid_batch sub = *frames;
+            sub.owns = false;
+            sub.n = std::min(GL_CHUNK, frames->n - c0);
+            sub.dptr = (char*)frames->dptr + (size_t)c0 * frames->h * frames->w * sizeof(uint16_t);
+            const int rc = epid_global_locate(ctx, &sub, p, regions + (size_t)c0 * region_cap, region_cap, counts + c0, flags + c0);
+            if (rc != EPID_OK) return rc;
+        }
+        return EPID_OK;
+    }
     const int n = frames->n, H = frames->h, W = frames->w, HW = H * W;
     EPID_REQUIRE((size_t)H * W < (1u << 30), EPID_ERR_UNSUPPORTED, "frame too large");
     GlCfg c;

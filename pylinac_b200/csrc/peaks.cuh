@@ -13,7 +13,8 @@
 
 namespace epid {
 
-constexpr int PK_WALK = 48;      // samples a lane walks on its own before the warp takes over (block_find_peaks, prominences)
+constexpr int PK_WALK = 64;      // samples per side a lane walks on its own per round (block_find_peaks, prominences)
+constexpr int PK_COOP = 32;      // unfinished walks in a warp after a round that the warp finishes cooperatively (32 = all: measured best on the field profiles)
 
 struct PeakArgs {          // already parsed (= after _parse_peak_args, core/profile.py:2626-2649)
     double hmin;           // height threshold (may be -inf)
@@ -163,9 +164,10 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
         count = compact_by_flag(w, count, false);
     }
 
-    // ---- 3. prominences (wlen = None).  Every lane walks its own peak for up to PK_WALK samples per side; walks that are still
-    // running after that (the few dominant peaks, whose walks cross most of the profile) are finished by the whole warp, 32 samples
-    // per step.  Same minima and bases as the sequential walk: the first (closest) sample wins among equal minima.
+    // ---- 3. prominences (wlen = None).  Lanes walk their own peaks in rounds of PK_WALK samples per side.  While many lanes of a
+    // warp are still walking that is the efficient shape; once only a few are left (the dominant peaks, whose walks cross most of
+    // the profile) the whole warp finishes each of them, 32 samples per step.  Same minima and bases as the sequential walk: the
+    // first (closest) sample wins among equal minima.
     for (int base = 0; base < count; base += nt) {
         const int i = base + tid;
         const bool act = i < count;
@@ -174,47 +176,55 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
         int kl = p, lb = p, kr = p, rb = p;
         double lmin = xp, rmin = xp;
         bool runl = act, runr = act;
-        if (act) {
-            int steps = 0;
-            while (kl >= 0 && x[kl] <= xp && steps < PK_WALK) { if (x[kl] < lmin) { lmin = x[kl]; lb = kl; } kl--; steps++; }
-            runl = kl >= 0 && x[kl] <= xp;
-            steps = 0;
-            while (kr <= n - 1 && x[kr] <= xp && steps < PK_WALK) { if (x[kr] < rmin) { rmin = x[kr]; rb = kr; } kr++; steps++; }
-            runr = kr <= n - 1 && x[kr] <= xp;
-        }
         const int lane = tid & 31;
-#pragma unroll 1
-        for (int side = 0; side < 2; side++) {
-            unsigned pend = __ballot_sync(0xffffffffu, side == 0 ? runl : runr);
-            while (pend) {
-                const int src = __ffs(pend) - 1;
-                pend &= pend - 1;
-                int k0 = __shfl_sync(0xffffffffu, side == 0 ? kl : kr, src);
-                const double xps = __shfl_sync(0xffffffffu, xp, src);
-                double mn = __shfl_sync(0xffffffffu, side == 0 ? lmin : rmin, src);
-                int mb = __shfl_sync(0xffffffffu, side == 0 ? lb : rb, src);
-                while (true) {
-                    const int kk = side == 0 ? k0 - lane : k0 + lane;
-                    const bool inb = kk >= 0 && kk <= n - 1;
-                    const double v = inb ? x[kk] : 0.0;
-                    const bool stop = !(inb && v <= xps);
-                    const unsigned sm = __ballot_sync(0xffffffffu, stop);
-                    const int nvalid = sm ? __ffs(sm) - 1 : 32;
-                    // minimum over the lanes inside the walk, the lowest lane (= closest sample) among equals
-                    double bv = lane < nvalid ? v : __longlong_as_double(0x7ff0000000000000LL);
-                    int bl = lane;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                        if (ov < bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
-                    }
-                    if (nvalid > 0 && bv < mn) { mn = bv; mb = side == 0 ? k0 - bl : k0 + bl; }
-                    if (sm) break;
-                    k0 += side == 0 ? -32 : 32;
-                }
-                if (lane == src) { if (side == 0) { lmin = mn; lb = mb; } else { rmin = mn; rb = mb; } }
+        while (true) {
+            if (runl) {
+                int steps = 0;
+                while (kl >= 0 && x[kl] <= xp && steps < PK_WALK) { if (x[kl] < lmin) { lmin = x[kl]; lb = kl; } kl--; steps++; }
+                runl = kl >= 0 && x[kl] <= xp;
             }
+            if (runr) {
+                int steps = 0;
+                while (kr <= n - 1 && x[kr] <= xp && steps < PK_WALK) { if (x[kr] < rmin) { rmin = x[kr]; rb = kr; } kr++; steps++; }
+                runr = kr <= n - 1 && x[kr] <= xp;
+            }
+            const unsigned pl = __ballot_sync(0xffffffffu, runl), pr = __ballot_sync(0xffffffffu, runr);
+            if ((pl | pr) == 0) break;
+            if (__popc(pl) + __popc(pr) > PK_COOP) continue;      // still many walkers: another round of per-lane walking
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                unsigned pend = side == 0 ? pl : pr;
+                while (pend) {
+                    const int src = __ffs(pend) - 1;
+                    pend &= pend - 1;
+                    int k0 = __shfl_sync(0xffffffffu, side == 0 ? kl : kr, src);
+                    const double xps = __shfl_sync(0xffffffffu, xp, src);
+                    double mn = __shfl_sync(0xffffffffu, side == 0 ? lmin : rmin, src);
+                    int mb = __shfl_sync(0xffffffffu, side == 0 ? lb : rb, src);
+                    while (true) {
+                        const int kk = side == 0 ? k0 - lane : k0 + lane;
+                        const bool inb = kk >= 0 && kk <= n - 1;
+                        const double v = inb ? x[kk] : 0.0;
+                        const bool stop = !(inb && v <= xps);
+                        const unsigned sm = __ballot_sync(0xffffffffu, stop);
+                        const int nvalid = sm ? __ffs(sm) - 1 : 32;
+                        // minimum over the lanes inside the walk, the lowest lane (= closest sample) among equals
+                        double bv = lane < nvalid ? v : __longlong_as_double(0x7ff0000000000000LL);
+                        int bl = lane;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                            const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                            if (ov < bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+                        }
+                        if (nvalid > 0 && bv < mn) { mn = bv; mb = side == 0 ? k0 - bl : k0 + bl; }
+                        if (sm) break;
+                        k0 += side == 0 ? -32 : 32;
+                    }
+                    if (lane == src) { if (side == 0) { lmin = mn; lb = mb; } else { rmin = mn; rb = mb; } }
+                }
+            }
+            break;
         }
         if (act) {
             w.prom[i] = xp - fmax(lmin, rmin);

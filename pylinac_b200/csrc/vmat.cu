@@ -91,6 +91,55 @@ __global__ void k_vmat_front(const uint16_t* __restrict__ a, const uint16_t* __r
     }
 }
 
+// W % 8 == 0: 16-byte loads, 8 columns per thread, RG row groups per CTA (blockDim = (W / 8) * RG); four independent loads per thread
+// in flight.  Column sums of the row groups are combined in shared memory before the global atomics.
+__global__ void k_vmat_front_v16(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, int n, int H, int W, int RG, VmAcc* acc,
+                                 unsigned long long* colsum) {
+    extern __shared__ unsigned int s_col[];      // [RG][W]
+    const int f = blockIdx.y;
+    const uint16_t* img = f < n ? a + (size_t)f * H * W : b + (size_t)(f - n) * H * W;
+    const int nvec = W >> 3;
+    const int j = threadIdx.x % nvec, g = threadIdx.x / nvec;
+    const int r0 = blockIdx.x * VM_ROWS, r1 = min(H, r0 + VM_ROWS);
+    const uint4* base = reinterpret_cast<const uint4*>(img) + j;
+    unsigned int cs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int mn2 = 0xffffffffu, mx2 = 0;
+    auto eat = [&](const uint4 q) {
+        const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            cs[2 * t] += w[t] & 0xffffu;
+            cs[2 * t + 1] += w[t] >> 16;
+            mn2 = __vminu2(mn2, w[t]);
+            mx2 = __vmaxu2(mx2, w[t]);
+        }
+    };
+    int r = r0 + g;
+    for (; r + 3 * RG < r1; r += 4 * RG) {
+        const uint4 q0 = ldg_stream16(base + (size_t)r * nvec), q1 = ldg_stream16(base + (size_t)(r + RG) * nvec);
+        const uint4 q2 = ldg_stream16(base + (size_t)(r + 2 * RG) * nvec), q3 = ldg_stream16(base + (size_t)(r + 3 * RG) * nvec);
+        eat(q0); eat(q1); eat(q2); eat(q3);
+    }
+    for (; r < r1; r += RG) eat(ldg_stream16(base + (size_t)r * nvec));
+#pragma unroll
+    for (int t = 0; t < 8; t++) s_col[(size_t)g * W + 8 * j + t] = cs[t];
+    __syncthreads();
+    unsigned long long tot = 0;
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        unsigned int sacc = 0;
+        for (int k = 0; k < RG; k++) sacc += s_col[(size_t)k * W + c];
+        atomicAdd(&colsum[(size_t)f * W + c], (unsigned long long)sacc);
+        tot += sacc;
+    }
+    unsigned int mn = min(mn2 & 0xffffu, mn2 >> 16), mx = max(mx2 & 0xffffu, mx2 >> 16);
+    mn = warp_min(mn); mx = warp_max(mx); tot = warp_sum(tot);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&acc[f].mn, mn);
+        atomicMax(&acc[f].mx, mx);
+        atomicAdd(&acc[f].sum, tot);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ block helpers (fp64)
 struct OpMin { __device__ static double f(double a, double b) { return fmin(a, b); } };
 struct OpMax { __device__ static double f(double a, double b) { return fmax(a, b); } };
@@ -556,9 +605,18 @@ extern "C" int32_t epid_vmat_analyze(epid_ctx* ctx, const epid_batch* img1, cons
     const uint16_t* a = (const uint16_t*)img1->dptr;
     const uint16_t* b = (const uint16_t*)img2->dptr;
     k_vmat_init<<<256, 256, 0, ctx->stream>>>(d_acc, d_col, (size_t)2 * n, (size_t)2 * n * W);
-    int ft = ((W & 1) ? W : W / 2);
-    ft = std::min(1024, (ft + 31) / 32 * 32);
-    k_vmat_front<<<dim3((H + VM_ROWS - 1) / VM_ROWS, 2 * n), ft, 0, ctx->stream>>>(a, b, n, H, W, d_acc, d_col);
+    const int nvec = W / 8;
+    if ((W & 7) == 0 && nvec <= 1024 && (nvec & 31) == 0) {
+        // warps must not straddle row groups for the final reductions to stay warp-uniform: nvec is a multiple of 32 here
+        int RG = std::max(1, std::min(VM_ROWS / 4, 640 / nvec));
+        while (nvec * RG > 1024) RG--;
+        k_vmat_front_v16<<<dim3((H + VM_ROWS - 1) / VM_ROWS, 2 * n), nvec * RG, sizeof(unsigned int) * (size_t)RG * W, ctx->stream>>>(
+            a, b, n, H, W, RG, d_acc, d_col);
+    } else {
+        int ft = ((W & 1) ? W : W / 2);
+        ft = std::min(1024, (ft + 31) / 32 * 32);
+        k_vmat_front<<<dim3((H + VM_ROWS - 1) / VM_ROWS, 2 * n), ft, 0, ctx->stream>>>(a, b, n, H, W, d_acc, d_col);
+    }
     k_vmat_profile<<<n, VM_THREADS, 0, ctx->stream>>>(a, b, n, H, W, *p, d_acc, d_col, d_work, work_stride, cap, cap2, d_pairs, d_rows);
     k_vmat_segments<<<dim3(p->nseg, n), VM_THREADS, 0, ctx->stream>>>(a, b, H, W, *p, d_pairs, d_rows);
     k_vmat_finalize<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, *p, d_rows);

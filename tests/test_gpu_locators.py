@@ -68,3 +68,15 @@ def test_large_field_goes_through_the_big_tile_path():
         assert len(pts) == 1
         # field centre: image centre + offset (x = second offset component)
         assert abs(pts[0].x - (640 - 0.5 - 2.0 * fr.dpmm)) < 1.0 and abs(pts[0].y - (640 - 0.5 + 3.0 * fr.dpmm)) < 1.0
+
+
+def test_disk_locator_chunks_large_batches():
+    """More frames than one labelling chunk (32): every frame still gets its own, identical answer."""
+    from pylinac_b200.metrics import image as mi
+
+    a, ps, sid, spec = case("disks4")
+    dpmm = (1 / ps) * sid / 1000.0
+    out = mi.locate_disks_batch(np.stack([a] * 35), dpmm, **spec["kw"])
+    want = GOLD["disks4/points"]
+    for k in (0, 31, 32, 34):
+        np.testing.assert_allclose(np.array([[p.x, p.y] for p in out[k]]), want, atol=1e-9)
