@@ -337,7 +337,7 @@ __device__ __forceinline__ void rank_keys(F key, int nr, unsigned long long& kma
     }
 }
 
-__global__ void __launch_bounds__(WB_THREADS, 6)
+__global__ void __launch_bounds__(WB_THREADS, 4)
 k_pf_win_fwxm(const PfConst* __restrict__ cc, PfFrame* fr, const PfWinRec* __restrict__ recs, const uint32_t* __restrict__ pools,
               PfWin* __restrict__ wins) {
     __shared__ uint32_t s_buf[WB_THREADS / 32][PF_W2_NCW * WB_ST];

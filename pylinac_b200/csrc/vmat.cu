@@ -171,22 +171,30 @@ __device__ inline void vm_invert(VmMap& m) {      // -a + max + min
     m.off = -m.off + m.mx + m.mn;
 }
 
-// BaseImage.check_inversion(box_size=20, position=(0, 0)) (core/image.py:868-897) on the mapped image; `total` = sum of raw pixels
-__device__ inline bool vm_check_inversion(const uint16_t* img, int H, int W, const VmMap& m, unsigned long long total) {
+// BaseImage.check_inversion(box_size=20, position=(0, 0)) (core/image.py:868-897) on the mapped image; `total` = sum of raw pixels.
+// Block-wide: the 4 x 400 box pixels are spread over the threads (a single thread walking them was most of the kernel's time).
+__device__ inline bool vm_check_inversion(const uint16_t* img, int H, int W, const VmMap& m, unsigned long long total, double* red) {
     // row_pos = col_pos = max(int(0 * N), 1) = 1; python slices [1:21] and [-21:-1], clipped like numpy
     const int bs = 20;
     auto clip = [](int v, int n) { return v < 0 ? max(v + n, 0) : min(v, n); };
-    const int ra0 = clip(1, H), ra1 = clip(1 + bs, H), rb0 = clip(-1 - bs, H), rb1 = clip(-1, H);
-    const int ca0 = clip(1, W), ca1 = clip(1 + bs, W), cb0 = clip(-1 - bs, W), cb1 = clip(-1, W);
-    const int rr[2][2] = {{ra0, ra1}, {rb0, rb1}}, cc[2][2] = {{ca0, ca1}, {cb0, cb1}};
+    const int rr0[2] = {clip(1, H), clip(-1 - bs, H)}, rr1[2] = {clip(1 + bs, H), clip(-1, H)};
+    const int cc0[2] = {clip(1, W), clip(-1 - bs, W)}, cc1[2] = {clip(1 + bs, W), clip(-1, W)};
     // np.mean((lt_upper, lt_lower, rt_upper, rt_lower)): the four boxes are stacked into one (4, 20, 20) array -> one mean over all
-    // 1600 pixels (exact integer sum / count)
-    long long s = 0, cnt = 0;
+    // 1600 pixels (exact integer sum / count; sums of < 2^27 are exact in the fp64 block reduction)
+    double s = 0, cnt = 0;
     for (int bi = 0; bi < 2; bi++)
-        for (int bj = 0; bj < 2; bj++)
-            for (int r = rr[bi][0]; r < rr[bi][1]; r++)
-                for (int c = cc[bj][0]; c < cc[bj][1]; c++) { s += m.sign * (long long)img[(size_t)r * W + c] + m.off; cnt++; }
-    const double avg = (double)s / (double)cnt;
+        for (int bj = 0; bj < 2; bj++) {
+            const int bh = rr1[bi] - rr0[bi], bw = cc1[bj] - cc0[bj];
+            if (bh <= 0 || bw <= 0) continue;
+            for (int i = threadIdx.x; i < bh * bw; i += blockDim.x) {
+                const int r = rr0[bi] + i / bw, c = cc0[bj] + i % bw;
+                s += (double)(m.sign * (long long)img[(size_t)r * W + c] + m.off);
+                cnt += 1.0;
+            }
+        }
+    s = blk_reduce<OpSum>(s, red);
+    cnt = blk_reduce<OpSum>(cnt, red);
+    const double avg = s / cnt;
     const long long tsum = m.sign * (long long)total + m.off * (long long)H * W;
     const double mean = (double)tsum / (double)((long long)H * W);
     return avg > mean;
@@ -340,23 +348,17 @@ k_vmat_profile(const uint16_t* __restrict__ a, const uint16_t* __restrict__ b, i
     for (int k = 0; k < 2; k++) {
         const int f = k == 0 ? pi : n + pi;
         const uint16_t* img = k == 0 ? a + (size_t)pi * H * W : b + (size_t)pi * H * W;
-        if (threadIdx.x == 0) {
-            VmMap m;
-            m.sign = 1; m.off = 0; m.mn = acc[f].mn; m.mx = acc[f].mx;
-            if (p.ground) vm_ground(m);                                           // _load_images (vmat.py:348-357)
-            int inv = 0;
-            if (p.check_inversion && vm_check_inversion(img, H, W, m, acc[f].sum)) { vm_invert(m); inv = 1; }   // vmat.py:721-725
-            smap[k] = m;
-            sinv[k] = inv;
-        }
+        VmMap m;      // every thread carries the same map (uniform decisions from block-wide reductions)
+        m.sign = 1; m.off = 0; m.mn = acc[f].mn; m.mx = acc[f].mx;
+        if (p.ground) vm_ground(m);                                               // _load_images (vmat.py:348-357)
+        int inv = 0;
+        if (p.check_inversion && vm_check_inversion(img, H, W, m, acc[f].sum, red)) { vm_invert(m); inv = 1; }   // vmat.py:721-725
+        if (threadIdx.x == 0) { smap[k] = m; sinv[k] = inv; }
         __syncthreads();
         // _roi_profiles works on a deep copy: ground() and check_inversion() once more (vmat.py:771-773)
-        VmMap c = smap[k];
+        VmMap c = m;
         vm_ground(c);
-        __shared__ int s_flip;
-        if (threadIdx.x == 0) s_flip = vm_check_inversion(img, H, W, c, acc[f].sum) ? 1 : 0;
-        __syncthreads();
-        if (s_flip) vm_invert(c);
+        if (vm_check_inversion(img, H, W, c, acc[f].sum, red)) vm_invert(c);
         vm_roi_profile(colsum + (size_t)f * W, H, W, c, wk, red, &pout[k]);
         __syncthreads();
     }

@@ -478,6 +478,7 @@ class DRCS(VMATBase):
         """vmat.py:1050-1082: EuclideanTransform(translation=(r, 0)) + rotation + translation(image centre), written out"""
         dpmm = self.open_image.dpmm
         cx, cy = self.open_image.center.x, self.open_image.center.y
+        geo = []
         for roi_data in self.roi_config.values():
             r_px = roi_data["radial_distance"] * dpmm
             angle_rad = np.deg2rad(-roi_data["angle"] - 90)
@@ -485,8 +486,13 @@ class DRCS(VMATBase):
             # composed matrix = T(centre) @ R(angle) @ T(r, 0): translation column and the rotation skimage reads back from it
             tx, ty = cs * r_px + cx, sn * r_px + cy
             rotation = math.atan2(sn, cs)
-            self.segments.append(Segment(Point(tx, ty), width=segment_size_mm[0] * dpmm, height=segment_size_mm[1] * dpmm,
-                                         tolerance=self._tolerance, rotation=float(np.rad2deg(rotation)), ratio_image=self.ratio_image))
+            geo.append((Point(tx, ty), segment_size_mm[0] * dpmm, segment_size_mm[1] * dpmm, float(np.rad2deg(rotation))))
+        # the statistics of all segments in one device call: the ratio image is uploaded once, one CTA per segment
+        rois = [RectangleROI(self.ratio_image, w, h, c, rot) for c, w, h, rot in geo]
+        st = nat.roi_stats(nat.Context.default(), self.ratio_image, np.stack([r._polygon_xy() for r in rois]))
+        for k, (c, w, h, rot) in enumerate(geo):
+            self.segments.append(Segment(c, width=w, height=h, tolerance=self._tolerance, rotation=rot, r_corr=float(st["mean"][0, k]) * 100,
+                                         stdev=float(st["std"][0, k])))
 
     def _calculate_collimator_deviations(self, collimator_config: dict[str, float], collimator_radial_distances):
         """vmat.py:1084-1149"""
