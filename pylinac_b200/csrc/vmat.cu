@@ -277,12 +277,30 @@ __device__ void vm_roi_profile(const unsigned long long* colsum, int H, int W, c
     const double g = vi - pf;
     if (tid == 0) { red[34] = NAN; red[35] = NAN; }      // a profile with nan has no such ranks: numpy's percentile is nan as well
     __syncthreads();
-    for (int i = tid; i < W; i += nt) {
-        const double xi = v[i];
-        int rank = 0;
-        for (int j = 0; j < W; j++) { const double xj = v[j]; rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
-        if (rank == ip) red[34] = xi;
-        if (rank == in) red[35] = xi;
+    if (W <= 8 * nt) {
+        // up to 8 samples per thread in registers, ONE pass over the profile (broadcast loads) ranks all of them
+        double xi[8];
+        int ii[8], rank[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) { ii[m] = tid + m * nt; xi[m] = ii[m] < W ? v[ii[m]] : 0.0; rank[m] = 0; }
+        for (int j = 0; j < W; j++) {
+            const double xj = v[j];
+#pragma unroll
+            for (int m = 0; m < 8; m++) rank[m] += (xj < xi[m] || (xj == xi[m] && j < ii[m])) ? 1 : 0;
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            if (ii[m] < W && rank[m] == ip) red[34] = xi[m];
+            if (ii[m] < W && rank[m] == in) red[35] = xi[m];
+        }
+    } else {
+        for (int i = tid; i < W; i += nt) {
+            const double xi = v[i];
+            int rank = 0;
+            for (int j = 0; j < W; j++) { const double xj = v[j]; rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
+            if (rank == ip) red[34] = xi;
+            if (rank == in) red[35] = xi;
+        }
     }
     __syncthreads();
     const double sa = red[34], sb = red[35];
