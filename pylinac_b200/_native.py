@@ -26,8 +26,12 @@ _DT2NP = {v: k for k, v in _NP2DT.items()}
 OPT_PF_EXACT_ONLY = 1
 OPT_PF_LEAFBAND = 2
 OPT_PF_WIN2 = 3
+OPT_PF_SPLIT = 4
+OPT_PF_FAST_REDO = 5
+OPT_PF_OVERLAP_REDO = 6
 CTR_PF_FALLBACKS = 1
 CTR_PF_REDONE_FRAMES = 2
+CTR_PF_EXACT_FRAMES = 3
 PF_MAX_PICKETS = 32
 PF_MAX_LEAVES = 160
 

@@ -71,7 +71,13 @@ struct epid_ctx {
     cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // created on first use
     int pf_win2 = 1;                     // 1 (default): two-kernel window path for the frames it covers (pf_windows2.cu)
     int64_t pf_fallbacks = 0;            // batches (or chunks) re-run by the exact pipeline
-    int64_t pf_redone_frames = 0;        // frames re-run by the exact pipeline (per-frame fallback)
+    int64_t pf_redone_frames = 0;        // frames re-run individually (per-frame fallback: certified-noise fast re-run or exact pipeline)
+    int64_t pf_exact_frames = 0;         // of those, frames that needed the exact-histogram pipeline
+    int pf_fast_redo = 1;                // 1 (default): deferred frames whose noise flag can be certified are median-filtered and re-run by the fast pipeline
+    int pf_overlap_redo = 1;             // 1 (default): device-resident batches re-run their deferred frames on redo_stream while the batch's window stages run
+    cudaStream_t redo_stream = nullptr;  // high-priority stream of the per-frame re-run
+    cudaEvent_t ev_front = nullptr, ev_main_done = nullptr, ev_redo_done = nullptr;
+    int* h_flags = nullptr;              // 64 page-locked, device-mapped ints: [0] deferred count written by k_pf_collect_deferred
     // dynamic shared memory opt-ins already made ON THIS DEVICE (cudaFuncSetAttribute is per device; one ctx per device)
     std::unordered_map<const void*, size_t> smem_optin;
 };

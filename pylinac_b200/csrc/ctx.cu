@@ -92,6 +92,16 @@ int32_t epid_ctx_create(int32_t device, epid_ctx** out) {
     EPID_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     EPID_CUDA(cudaStreamCreateWithFlags(&c->copy_stream[0], cudaStreamNonBlocking));
     EPID_CUDA(cudaStreamCreateWithFlags(&c->copy_stream[1], cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        EPID_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        EPID_CUDA(cudaStreamCreateWithPriority(&c->redo_stream, cudaStreamNonBlocking, hi));
+        EPID_CUDA(cudaEventCreateWithFlags(&c->ev_front, cudaEventDisableTiming));
+        EPID_CUDA(cudaEventCreateWithFlags(&c->ev_main_done, cudaEventDisableTiming));
+        EPID_CUDA(cudaEventCreateWithFlags(&c->ev_redo_done, cudaEventDisableTiming));
+        EPID_CUDA(cudaHostAlloc((void**)&c->h_flags, 64 * sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(c->h_flags, 0, 64 * sizeof(int));
+    }
     *out = c;
     return EPID_OK;
 }
@@ -112,6 +122,11 @@ int32_t epid_ctx_destroy(epid_ctx* ctx) {
     for (int k = 0; k < 4; k++) if (ctx->aux_stream[k]) cudaStreamDestroy(ctx->aux_stream[k]);
     cudaStreamDestroy(ctx->copy_stream[0]);
     cudaStreamDestroy(ctx->copy_stream[1]);
+    if (ctx->redo_stream) { cudaStreamSynchronize(ctx->redo_stream); cudaStreamDestroy(ctx->redo_stream); }
+    if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);
+    if (ctx->ev_main_done) cudaEventDestroy(ctx->ev_main_done);
+    if (ctx->ev_redo_done) cudaEventDestroy(ctx->ev_redo_done);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     delete ctx;
     return EPID_OK;
 }
@@ -151,6 +166,8 @@ int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value) {
         case EPID_OPT_PF_LEAFBAND: ctx->pf_leafband = value ? 1 : 0; return EPID_OK;
         case EPID_OPT_PF_WIN2: ctx->pf_win2 = value ? 1 : 0; return EPID_OK;
         case EPID_OPT_PF_SPLIT: ctx->pf_split = value < 2 ? 0 : (value > 4 ? 4 : (int)value); return EPID_OK;
+        case EPID_OPT_PF_FAST_REDO: ctx->pf_fast_redo = value ? 1 : 0; return EPID_OK;
+        case EPID_OPT_PF_OVERLAP_REDO: ctx->pf_overlap_redo = value ? 1 : 0; return EPID_OK;
     }
     set_error("unknown option %d", key);
     return EPID_ERR_INVALID;
@@ -161,6 +178,7 @@ int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value) {
     switch (key) {
         case EPID_CTR_PF_FALLBACKS: *value = ctx->pf_fallbacks; return EPID_OK;
         case EPID_CTR_PF_REDONE_FRAMES: *value = ctx->pf_redone_frames; return EPID_OK;
+        case EPID_CTR_PF_EXACT_FRAMES: *value = ctx->pf_exact_frames; return EPID_OK;
     }
     set_error("unknown counter %d", key);
     return EPID_ERR_INVALID;

@@ -498,8 +498,9 @@ int launch_pf_front(epid_ctx* ctx, cudaStream_t stream, const PfConst* d_cst, co
 
 // fast == true: fused front kernel (sample-guided exact selection), no host round trip; frames it cannot certify
 // (counters[1]) or that _check_for_noise flags (counters[0]) make the caller re-run the batch with fast == false.
-__global__ void k_pf_collect_deferred(const PfFrame* __restrict__ fr, int n, int* __restrict__ sel_idx, int* counters) {
-    // ascending list of the deferred frames (one block; n is a few hundred)
+__global__ void k_pf_collect_deferred(const PfFrame* __restrict__ fr, int n, int* __restrict__ sel_idx, int* counters, volatile int* host_flag) {
+    // ascending list of the deferred frames (one block; n is a few hundred); host_flag: device-mapped page-locked int that
+    // receives the count as well, so the host learns it from an event wait without a copy in the stream
     __shared__ int s_base;
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
@@ -518,7 +519,60 @@ __global__ void k_pf_collect_deferred(const PfFrame* __restrict__ fr, int n, int
         if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_w[k]; s_base += t; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) counters[2] = s_base;
+    if (threadIdx.x == 0) {
+        counters[2] = s_base;
+        if (host_flag) { *host_flag = s_base; __threadfence_system(); }
+    }
+}
+
+// ---- certified-noise fast re-run of deferred frames ------------------------------------------------------------------------
+// _has_noise() (picketfence.py:229-238) is True as soon as max > 1.25 * p99.5.  With U = the largest integer with 1.25 * U < max,
+// "#(pixels > U) <= npix - 1 - rank_next(99.5)" puts both order statistics behind the percentile at or below U, hence
+// p99.5 <= U and the criterion holds whatever the minimum does: one exact count certifies the flag.  Such a frame is 3 x 3 median
+// filtered like the reference does and handed to the certified fast pipeline as a new frame (which certifies "no noise" on the
+// filtered pixels or defers again -> exact pipeline from the raw frame).
+constexpr int CA_PARTS = 8;
+__global__ void __launch_bounds__(256)
+k_pf_count_above(const FrameRef* __restrict__ refs, const PfFrame* __restrict__ raw_fr, const int* __restrict__ sel, int H, int W, int* __restrict__ cnt) {
+    const int i = blockIdx.y;
+    const FrameRef fr = refs[i];
+    const uint32_t mx = raw_fr[sel[i]].mx;
+    const uint32_t U = (4u * mx + 4u) / 5u - 1u;            // ceil(0.8 mx) - 1: 1.25 U < mx (exact in binary64)
+    const int r0 = (int)((long long)H * blockIdx.x / gridDim.x), r1 = (int)((long long)H * (blockIdx.x + 1) / gridDim.x);
+    const int lane = threadIdx.x & 31;
+    uint32_t c = 0;
+    for (int r = r0 + (int)(threadIdx.x >> 5); r < r1; r += 8) {      // warp per row
+        const uint16_t* row = fr.origin + (size_t)r * fr.pitch;
+        int head = (int)((8 - ((uintptr_t)row & 7)) & 7) >> 1;        // pixels before the first 8-byte boundary
+        if (head > W) head = W;
+        if (lane < head) c += (uint32_t)row[lane] > U ? 1u : 0u;
+        const int nb = (W - head) >> 2;
+        const uint2* b = reinterpret_cast<const uint2*>(row + head);
+        for (int j = lane; j < nb; j += 32) {
+            const uint2 v = __ldg(b + j);
+            c += ((v.x & 0xffffu) > U ? 1u : 0u) + ((v.x >> 16) > U ? 1u : 0u) + ((v.y & 0xffffu) > U ? 1u : 0u) + ((v.y >> 16) > U ? 1u : 0u);
+        }
+        const int t0 = head + nb * 4;
+        if (t0 + lane < W) c += (uint32_t)row[t0 + lane] > U ? 1u : 0u;
+    }
+    c = warp_sum(c);
+    if (lane == 0 && c) atomicAdd(&cnt[i], (int)c);
+}
+
+__global__ void k_pf_mark_certified(const int* __restrict__ cnt, int n, int limit, int* __restrict__ select) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) select[i] = cnt[i] <= limit ? 1 : 0;
+}
+
+__global__ void k_pf_set_passes(PfFrame* fr, const int* __restrict__ select, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && select[i]) fr[i].noise_passes = 1;
+}
+
+// local indices of the frames a re-run deferred again (loc, count in counters[2]) -> batch indices, in place
+__global__ void k_pf_compose_sel(int* loc, const int* __restrict__ counters, const int* __restrict__ sel) {
+    const int m = counters[2];
+    for (int j = threadIdx.x; j < m; j += blockDim.x) loc[j] = sel[loc[j]];
 }
 
 __global__ void k_pf_scatter_results(const int* __restrict__ sel_idx, int m, const epid_pf_summary* __restrict__ s_src, const epid_pf_meas* __restrict__ m_src,
@@ -535,8 +589,16 @@ __global__ void k_pf_scatter_results(const int* __restrict__ sel_idx, int m, con
     for (int k = threadIdx.x; k < (int)(sizeof(epid_pf_meas) / 4) * meas_cap; k += blockDim.x) e[k] = c[k];
 }
 
+constexpr int PF_REDO_CHUNK = 64;   // frames per sub-batch of the per-frame re-run
+
+struct PfRedoIn {            // fast re-run of deferred frames (pf_redo_deferred)
+    const PfFrame* raw_fr;   // PfFrame records of the batch's fast pass (mx of the raw frame)
+    uint16_t* pool;          // room for n filtered frames (H x Wp uint16 each)
+};
+
 static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int n, int H0, int W0, const epid_pf_params* p,
-                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm, bool fast, const int* d_sel = nullptr) {
+                  int meas_cap, PfWork& w, uint16_t** pool3, PfTimers* tm, bool fast, const int* d_sel = nullptr,
+                  cudaEvent_t front_evt = nullptr, int* host_flag = nullptr, const PfRedoIn* redo = nullptr) {
     const int crop = p->crop_px;
     const int H = H0 - 2 * crop, W = W0 - 2 * crop;
     StatsGeom g;
@@ -570,7 +632,25 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     ctx->launches++;
     // bench timers: around the frame-streaming kernel only (k_pf_stream inside launch_pf_front, k_frame_stats otherwise)
     if (fast) {
+        if (redo) {      // certify _has_noise() == True by one exact count, filter those frames into the pool (see k_pf_count_above)
+            const int Wp = (W + 7) / 8 * 8;
+            EPID_CUDA(cudaMemsetAsync(w.sel_idx, 0, sizeof(int) * n, stream));
+            k_pf_count_above<<<dim3(CA_PARTS, n), 256, 0, stream>>>(w.refs, redo->raw_fr, d_sel, H, W, w.sel_idx);
+            k_pf_mark_certified<<<nb, tb, 0, stream>>>(w.sel_idx, n, npix - 1 - (int)hc.hi.next, w.select);
+            k_pf_set_dst_refs<<<nb, tb, 0, stream>>>(w.refs_b, redo->pool, n, H, Wp);
+            ctx->launches += 3;
+            rc = launch_median_u16(ctx, stream, w.refs, w.refs_b, nullptr, w.select, n, H, W, 3);
+            if (rc != EPID_OK) return rc;
+            k_pf_swap_refs<<<nb, tb, 0, stream>>>(w.refs, w.refs_b, w.select, n);
+            ctx->launches++;
+        }
         rc = launch_pf_front(ctx, stream, w.cst, g, w.refs, n, w.fr, w.stats, w.counters, w.front, tm);
+        if (rc != EPID_OK) return rc;
+        if (redo) { k_pf_set_passes<<<nb, tb, 0, stream>>>(w.fr, w.select, n); ctx->launches++; }
+        // which frames were deferred (none on ordinary batches): list + count for the per-frame re-run, known as soon as the front end is done
+        k_pf_collect_deferred<<<1, 256, 0, stream>>>(w.fr, n, w.sel_idx, w.counters, host_flag);
+        ctx->launches++;
+        if (front_evt) EPID_CUDA(cudaEventRecord(front_evt, stream));
     } else {
         if (tm && tm->on) { rc = tm->record(stream); if (rc != EPID_OK) return rc; }
         rc = launch_frame_stats(ctx, stream, g, w.refs, nullptr, n, w.stats, w.rowsum, w.colsum);
@@ -585,7 +665,8 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     EPID_CUDA(cudaMemcpyAsync(&n_noisy, w.counters, sizeof(int), cudaMemcpyDeviceToHost, stream));
     EPID_CUDA(cudaStreamSynchronize(stream));
     const int Wp = (W + 7) / 8 * 8;
-    const size_t pool_bytes = sizeof(uint16_t) * (size_t)n * H * Wp;
+    // the pools live until the end of the API call; re-run sub-batches of different sizes (<= PF_REDO_CHUNK) share them
+    const size_t pool_bytes = sizeof(uint16_t) * (size_t)(n < PF_REDO_CHUNK ? PF_REDO_CHUNK : n) * H * Wp + 512;
     int pass = 0;
     uint16_t** pools = pool3;   // [0],[1]: ping-pong for the noise passes, [2]: PicketFence(filter=k)
     auto ensure_pool = [&](int which) -> int {
@@ -676,10 +757,6 @@ static int pf_run(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, 
     }
     rc = launch_pf_finalize(ctx, stream, w.cst, w.fr, w.wins, w.summ, w.meas, n, meas_cap);
     if (rc != EPID_OK) return rc;
-    if (fast) {      // which frames were deferred (none on ordinary batches): list + count for the per-frame re-run
-        k_pf_collect_deferred<<<1, 256, 0, stream>>>(w.fr, n, w.sel_idx, w.counters);
-        ctx->launches++;
-    }
     if (tm) { rc = tm->mark(stream, PF_STAGE_FINALIZE); if (rc != EPID_OK) return rc; }
     EPID_CUDA(cudaGetLastError());
     return EPID_OK;
@@ -696,26 +773,81 @@ static int ensure_scratch2(epid_ctx* ctx, size_t bytes) {
     return EPID_OK;
 }
 
-constexpr int PF_REDO_CHUNK = 64;
-
-static int pf_redo_deferred(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int m, int H0, int W0, const epid_pf_params* p,
-                            int meas_cap, PfWork& w, uint16_t** pools) {
+static bool pf_fast_ok(const epid_ctx* ctx, const epid_pf_params* p, int H0, int W0) {
     const int H = H0 - 2 * p->crop_px, W = W0 - 2 * p->crop_px;
+    return !ctx->pf_exact_only && p->filter_size == 0 && pf_front_supported(H, W, W0);
+}
+
+
+// Re-run of the m frames the fast pass deferred (w.sel_idx, ascending) on `stream`, in sub-batches whose work area lives in
+// ctx->scratch2; result rows are scattered into the batch's device result arrays (after `after`, the event that marks the end of the
+// batch's own pass, when the re-run is overlapped with it on another stream).  ctx->pf_fast_redo: first the certified-noise fast
+// re-run (pf_run with PfRedoIn), then the exact-histogram pipeline for whatever that deferred again; otherwise exact for all.
+static int pf_redo_deferred(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int m, int H0, int W0, const epid_pf_params* p,
+                            int meas_cap, PfWork& w, uint16_t** pools, cudaEvent_t after = nullptr) {
+    const int H = H0 - 2 * p->crop_px, W = W0 - 2 * p->crop_px;
+    const int Wp = (W + 7) / 8 * 8;
     const int chunk = m < PF_REDO_CHUNK ? m : PF_REDO_CHUNK;
+    const bool fast_redo = ctx->pf_fast_redo && pf_fast_ok(ctx, p, H0, W0);
     PfWork rw;
     carve(rw, nullptr, chunk, H, W, meas_cap);
-    int rc = ensure_scratch2(ctx, rw.total);
+    const size_t work_bytes = align_up(rw.total, 256);
+    const size_t pool_bytes = fast_redo ? align_up(sizeof(uint16_t) * (size_t)chunk * H * Wp + 512, 256) : 0;
+    int rc = ensure_scratch2(ctx, work_bytes + pool_bytes);
     if (rc != EPID_OK) return rc;
     carve(rw, (char*)ctx->scratch2, chunk, H, W, meas_cap);
+    PfRedoIn rin;
+    rin.raw_fr = w.fr;
+    rin.pool = (uint16_t*)((char*)ctx->scratch2 + work_bytes);
+    bool waited = after == nullptr;
     for (int c0 = 0; c0 < m; c0 += chunk) {
         const int cn = m - c0 < chunk ? m - c0 : chunk;
-        rc = pf_run(ctx, stream, d_frames, cn, H0, W0, p, meas_cap, rw, pools, nullptr, false, w.sel_idx + c0);
-        if (rc != EPID_OK) return rc;
+        int left = fast_redo ? 0 : -1;      // -1: exact pipeline for the whole sub-batch
+        if (fast_redo) {
+            rc = pf_run(ctx, stream, d_frames, cn, H0, W0, p, meas_cap, rw, pools, nullptr, true, w.sel_idx + c0, nullptr, ctx->h_flags + 1, &rin);
+            if (rc != EPID_OK) return rc;
+            k_pf_compose_sel<<<1, 64, 0, stream>>>(rw.sel_idx, rw.counters, w.sel_idx + c0);
+            ctx->launches++;
+            EPID_CUDA(cudaStreamSynchronize(stream));      // the host needs the number of frames that were deferred again
+            left = ctx->h_flags[1];
+        } else {
+            rc = pf_run(ctx, stream, d_frames, cn, H0, W0, p, meas_cap, rw, pools, nullptr, false, w.sel_idx + c0);
+            if (rc != EPID_OK) return rc;
+            ctx->pf_exact_frames += cn;
+        }
+        if (!waited) { EPID_CUDA(cudaStreamWaitEvent(stream, after, 0)); waited = true; }
         k_pf_scatter_results<<<cn, 256, 0, stream>>>(w.sel_idx + c0, cn, rw.summ, rw.meas, w.summ, w.meas, meas_cap);
         ctx->launches++;
+        if (left > 0) {
+            rc = pf_run(ctx, stream, d_frames, left, H0, W0, p, meas_cap, rw, pools, nullptr, false, rw.sel_idx);
+            if (rc != EPID_OK) return rc;
+            k_pf_scatter_results<<<left, 256, 0, stream>>>(rw.sel_idx, left, rw.summ, rw.meas, w.summ, w.meas, meas_cap);
+            ctx->launches++;
+            ctx->pf_exact_frames += left;
+        }
     }
     ctx->pf_redone_frames += m;
     EPID_CUDA(cudaGetLastError());
+    return EPID_OK;
+}
+
+// One device-resident batch: the fast pass on `stream`; the host waits for the front end only (ctx->ev_front), reads the number of
+// deferred frames from the mapped flag and, if there are any, runs their re-run on ctx->redo_stream while the window / finalize
+// stages of the batch are still running; `stream` continues after the re-run's rows have been scattered.
+static int pf_run_overlapped(epid_ctx* ctx, cudaStream_t stream, const uint16_t* d_frames, int n, int H0, int W0, const epid_pf_params* p,
+                             int meas_cap, PfWork& w, uint16_t** pools, PfTimers* tm, int* n_deferred) {
+    int rc = pf_run(ctx, stream, d_frames, n, H0, W0, p, meas_cap, w, pools, tm, true, nullptr, ctx->ev_front, ctx->h_flags);
+    if (rc != EPID_OK) return rc;
+    EPID_CUDA(cudaEventSynchronize(ctx->ev_front));
+    const int m = ctx->h_flags[0];
+    if (n_deferred) *n_deferred = m;
+    if (m > 0) {
+        EPID_CUDA(cudaEventRecord(ctx->ev_main_done, stream));
+        rc = pf_redo_deferred(ctx, ctx->redo_stream, d_frames, m, H0, W0, p, meas_cap, w, pools, ctx->ev_main_done);
+        if (rc != EPID_OK) { cudaStreamSynchronize(ctx->redo_stream); return rc; }
+        EPID_CUDA(cudaEventRecord(ctx->ev_redo_done, ctx->redo_stream));
+        EPID_CUDA(cudaStreamWaitEvent(stream, ctx->ev_redo_done, 0));
+    }
     return EPID_OK;
 }
 
@@ -748,6 +880,10 @@ using namespace epid;
 
 namespace {
 
+}  // namespace
+namespace epid { void staging_copy(void* dst, const void* src, size_t bytes); }   // hostcopy.cpp: non-temporal stores
+namespace {
+
 // Persistent host threads that copy a pageable chunk into the page-locked staging ring in parallel slices: one thread moves
 // ~10 GB/s, the PCIe link takes ~54 GB/s, so a pageable source needs several copy streams to keep the link busy.
 class CopyPool {
@@ -758,7 +894,7 @@ public:
     }
     void copy(void* dst, const void* src, size_t bytes) {
         const int T = (int)workers_.size();
-        if (T == 0 || bytes < (8u << 20)) { memcpy(dst, src, bytes); return; }
+        if (T == 0 || bytes < (8u << 20)) { staging_copy(dst, src, bytes); return; }
         std::unique_lock<std::mutex> lk(m_);
         dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
         pending_ = T;
@@ -795,7 +931,7 @@ private:
             }
             const size_t per = ((b + T - 1) / T + 4095) & ~(size_t)4095;
             const size_t o = per * (size_t)i;
-            if (o < b) memcpy(d + o, s + o, b - o < per ? b - o : per);
+            if (o < b) staging_copy(d + o, s + o, b - o < per ? b - o : per);
             {
                 std::lock_guard<std::mutex> lk(m_);
                 if (--pending_ == 0) done_.notify_one();
@@ -821,11 +957,6 @@ struct PfResultCopy {   // async D2H of one chunk's results + the counters ([2] 
         return EPID_OK;
     }
 };
-
-bool pf_fast_ok(const epid_ctx* ctx, const epid_pf_params* p, int H0, int W0) {
-    const int H = H0 - 2 * p->crop_px, W = W0 - 2 * p->crop_px;
-    return !ctx->pf_exact_only && p->filter_size == 0 && pf_front_supported(H, W, W0);
-}
 
 }  // namespace
 
@@ -932,6 +1063,15 @@ int32_t epid_pf_analyze(epid_ctx* ctx, const epid_batch* frames, const epid_pf_p
         if (rc != EPID_OK) return rc;
         carve(w, (char*)ctx->scratch, n, H, W, meas_cap);
     }
+    if (fast && ctx->pf_overlap_redo) {
+        // the re-run of deferred frames (if any) overlaps the window stages of the batch on ctx->redo_stream
+        int m = 0;
+        rc = pf_run_overlapped(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr, &m);
+        if (m > 0) ctx->pf_fallbacks++;
+        if (rc == EPID_OK) rc = copy_and_wait(cnt3); else cudaStreamSynchronize(ctx->stream);
+        for (int k = 0; k < 3; k++) if (pools[k]) cudaFree(pools[k]);
+        return rc;
+    }
     rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, nullptr, fast);
     if (rc == EPID_OK) rc = copy_and_wait(cnt3); else cudaStreamSynchronize(ctx->stream);
     if (rc == EPID_OK && fast && cnt3[2] > 0) {
@@ -1016,6 +1156,10 @@ static int32_t pf_bench_impl(epid_ctx* ctx, const epid_batch* frames, const epid
         EPID_CUDA(cudaStreamSynchronize(ctx->stream));
         EPID_CUDA(cudaEventRecord(t0, ctx->stream));
         for (int it = 0; it < iters && rc == EPID_OK; it++) {
+            if (mode == 1 && ctx->pf_overlap_redo) {
+                rc = pf_run_overlapped(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm, nullptr);
+                continue;
+            }
             rc = pf_run(ctx, ctx->stream, (const uint16_t*)frames->dptr, n, frames->h, frames->w, p, meas_cap, w, pools, &tm, fast);
             if (mode == 1 && rc == EPID_OK) {
                 cudaMemcpyAsync(cnt3, w.counters, sizeof(cnt3), cudaMemcpyDeviceToHost, ctx->stream);
@@ -1170,12 +1314,14 @@ int32_t epid_pf_analyze_host(epid_ctx* ctx, const uint16_t* frames, int32_t n, i
         EPID_CUDA(cudaEventSynchronize(computed[s]));
         if (fast && h_cnt[s][2] > 0) {     // re-run exactly the frames the front end deferred, then fetch the chunk's rows again
             ctx->pf_fallbacks++;
-            int r = pf_redo_deferred(ctx, ctx->stream, bufs[s], h_cnt[s][2], h, w_, p, meas_cap, works[s], pools);
+            // on the re-run stream: the chunk's own pass has finished, the next chunk's pass keeps ctx->stream busy meanwhile
+            cudaStream_t rs = ctx->pf_overlap_redo ? ctx->redo_stream : ctx->stream;
+            int r = pf_redo_deferred(ctx, rs, bufs[s], h_cnt[s][2], h, w_, p, meas_cap, works[s], pools);
             if (r != EPID_OK) return r;
-            r = PfResultCopy::enqueue(ctx->stream, works[s], cnt, meas_cap, direct ? summary + (size_t)ci * chunk : h_summ[s],
+            r = PfResultCopy::enqueue(rs, works[s], cnt, meas_cap, direct ? summary + (size_t)ci * chunk : h_summ[s],
                                       direct ? meas + (size_t)ci * chunk * meas_cap : h_meas[s], h_cnt[s] + 4);
             if (r != EPID_OK) return r;
-            EPID_CUDA(cudaEventRecord(computed[s], ctx->stream));
+            EPID_CUDA(cudaEventRecord(computed[s], rs));
             EPID_CUDA(cudaEventSynchronize(computed[s]));
         }
         if (!direct) {

@@ -484,6 +484,91 @@ def test_pf_mixed_batch_matches_the_oracle_frame_by_frame():
     assert n_noise >= 2, "the mixed batch should contain frames that trigger the reference's noise filter"
 
 
+def _mixed_frames(seed=5, n=96):
+    """Benchmark frames with every 8th frame noisy: hot pixels (one median pass), every 24th with a hot 3 x 3 block (three passes)."""
+    from oracle import synth
+
+    rng = np.random.default_rng(seed)
+    uniq = [synth.bench_pf_frame(i) for i in range(400, 408)]
+    frames = np.stack([uniq[i % 8] for i in range(n)])
+    kinds = []
+    for i in range(n):
+        if i % 24 == 7:
+            a = frames[i] // 2
+            a[500:503, 100:103] = 65535
+            a[40, 40] = 65535
+            frames[i] = a
+            kinds.append("block")
+        elif i % 8 == 3:
+            a = frames[i] // 2
+            a.ravel()[rng.integers(0, a.size, 40)] = 65535
+            frames[i] = a
+            kinds.append("hot")
+        else:
+            kinds.append("clean")
+    return frames, kinds
+
+
+def _assert_same_results(a, b):
+    (sa, ma), (sb, mb) = a, b
+    for k in sa.dtype.names:
+        np.testing.assert_array_equal(sa[k], sb[k], err_msg=k)
+    for i in range(len(sa)):
+        m = int(sa["n_meas"][i])
+        for k in ma.dtype.names:
+            np.testing.assert_array_equal(ma[k][i, :m], mb[k][i, :m], err_msg=f"{k} frame {i}")
+
+
+def test_pf_certified_noise_rerun_equals_the_exact_rerun_and_overlaps():
+    """The per-frame fallback: frames whose _has_noise() the single exact count certifies are median filtered and re-run by the
+    certified fast pipeline (frames with a hot block are deferred again -> exact pipeline).  Every variant -- fast / exact re-run,
+    overlapped on the second stream or serial, device-resident or host entry point -- must return bit-identical rows, and the hot-pixel
+    frames must equal the oracle."""
+    from oracle import pf_oracle
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import picketfence as pf
+
+    frames, kinds = _mixed_frames()
+    ctx = nat.Context.default()
+    params = pf.make_params(2.56, frames.shape[1:])
+    b = nat.Batch.upload(ctx, frames)
+    results = {}
+    counts = {}
+    try:
+        for fast_redo in (1, 0):
+            for overlap in (1, 0):
+                ctx.set_option(nat.OPT_PF_FAST_REDO, fast_redo)
+                ctx.set_option(nat.OPT_PF_OVERLAP_REDO, overlap)
+                r0, e0 = ctx.counter(nat.CTR_PF_REDONE_FRAMES), ctx.counter(nat.CTR_PF_EXACT_FRAMES)
+                results[(fast_redo, overlap, "dev")] = nat.pf_analyze(ctx, b, params)
+                counts[(fast_redo, overlap)] = (ctx.counter(nat.CTR_PF_REDONE_FRAMES) - r0, ctx.counter(nat.CTR_PF_EXACT_FRAMES) - e0)
+                s, m = nat.pf_analyze(ctx, frames, params)
+                results[(fast_redo, overlap, "host")] = (s.copy(), m.copy())
+    finally:
+        ctx.set_option(nat.OPT_PF_FAST_REDO, 1)
+        ctx.set_option(nat.OPT_PF_OVERLAP_REDO, 1)
+        b.free()
+    n_hot, n_block = kinds.count("hot"), kinds.count("block")
+    assert n_hot >= 8 and n_block >= 4
+    for overlap in (1, 0):
+        assert counts[(1, overlap)] == (n_hot + n_block, n_block), counts      # only the hot-block frames need the exact pipeline
+        assert counts[(0, overlap)] == (n_hot + n_block, n_hot + n_block), counts
+    ref = results[(0, 0, "dev")]
+    for key, val in results.items():
+        _assert_same_results(ref, val)
+    s, m = ref
+    assert np.all(s["status"] == 0)
+    for i, kind in enumerate(kinds):
+        assert int(s["noise_median_passes"][i]) == {"clean": 0, "hot": 1, "block": 3}[kind], (i, kind)
+    for i in [kinds.index("hot"), kinds.index("block"), len(kinds) - 1 - kinds[::-1].index("hot")]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            o = pf_oracle.pf_analyze(frames[i], 2.56)
+        nm = int(s["n_meas"][i])
+        assert nm == o["n_meas"] and int(s["noise_median_passes"][i]) == o["noise_median_passes"]
+        np.testing.assert_allclose(m["position"][i, :nm, :1], o["meas_position"], rtol=0, atol=POS_TOL_PX)
+
+
 @pytest.mark.parametrize("name", ["noisy_wide_gap_up_down", "offset_picket", "perfect_left_right"])
 def test_picketfence_reads_the_reference_dicom_files(name, tmp_path):
     """File -> pylinac_b200.dicom -> LinacDicomImage -> PicketFence(path).analyze(): the reference's docs fixtures end to end (the
