@@ -572,12 +572,33 @@ class LinacDicomImage(DicomImage):
                 self._axis_overrides[axis] = kwargs.pop(axis)
         self._axes_precision = axes_precision
         self._missing_axis_value = missing_axis_value
-        super().__init__(path, **kwargs)
         self._use_filenames = use_filenames
+        super().__init__(path, **kwargs)
+
+    _AXIS_NAMES = {"gantry": "Gantry", "coll": "Coll", "couch": "Couch"}
 
     def _axis(self, key, tag):
+        """_get_axis_value (core/image.py:1655-1730): explicit value, else `<axis><number>` in the file name when use_filenames
+        (keyword absent -> missing_axis_value, the tags are not consulted), else the DICOM tag, else missing_axis_value."""
+        import os.path as osp
+        import re
+
+        name = self._AXIS_NAMES[key]
         if key in self._axis_overrides and self._axis_overrides[key] is not None:
             v = self._axis_overrides[key]
+        elif self._use_filenames:
+            filename = osp.basename(str(self.path)).lower()
+            if name.lower() not in filename:
+                if self._missing_axis_value == "raise":
+                    raise ValueError(f"{name} axis value was not found in the filename and `missing_axis_value` was `raise`. "
+                                     "Either provide an axis value or pass a numerical value for `missing_axis_value`.")
+                v = self._missing_axis_value
+            else:
+                m = re.search(rf"(?<={name.lower()})\d+", filename)
+                if m is None:
+                    raise ValueError(f"The filename contains '{name}' but could not read a number following it. "
+                                     f"Use the format '...{name}<#>...'")
+                v = float(m.group())
         else:
             v = self.metadata.get(tag)
             if v is None:

@@ -3,6 +3,7 @@
 // read-for-ownership of every destination line (3 -> 2 bytes of memory traffic per byte copied) and keep the ring out of the caches.
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -38,7 +39,7 @@ __attribute__((target("avx2"))) static void nt_copy_avx2(char* d, const char* s,
 
 void staging_copy(void* dst, const void* src, size_t bytes) {
 #if defined(__x86_64__)
-    static const bool avx2 = __builtin_cpu_supports("avx2");
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !(getenv("EPID_COPY_NT") && atoi(getenv("EPID_COPY_NT")) == 0);
     if (avx2 && bytes >= (1u << 16)) { nt_copy_avx2((char*)dst, (const char*)src, bytes); return; }
 #endif
     memcpy(dst, src, bytes);

@@ -21,8 +21,9 @@
 // Stages:
 //   k_frame_stats    exact order statistics of the frame (p4 / p50 / p96) and of its central third (p90)      (stats.cu)
 //   k_star_front     inversion decision, central-third column / row maxima, FW80M start point, local maximum
-//   k_star_wobble    CTA per frame: candidate loop { ring sampling (20 radii, nearest neighbour) -> roll -> gaussian ->
-//                    ground -> find_fwxm_peaks -> lines -> Nelder-Mead } until the wobble is reasonable
+//   k_star_rows      CTA per (frame, candidate row): ring sampling (20 radii, nearest neighbour) -> roll -> gaussian -> ground once per
+//                    radius, then per min_peak_height: find_fwxm_peaks -> lines -> Nelder-Mead until a candidate has a verdict
+//   k_star_pick      first row in the reference's candidate order that has a verdict = the wobble the serial loop stops at
 #include <cmath>
 
 #include "peaks.cuh"
@@ -270,10 +271,21 @@ __device__ inline void nelder_mead3(const StarLine* lines, int nl, double x0, do
     *fout = fmin_;
 }
 
+// One CTA per (frame, row of the candidate product).  _get_reasonable_wobble (starshot.py:344-376) tries, in this order, the caller's
+// (radius, min_peak_height) and then product(append(radius, linspace(0.95, 0.1, 10)), append(min_peak_height, linspace(0.05, 0.95, 10)))
+// until a candidate is accepted.  Row 0 = the caller's pair; row r = 1 .. 11 = the r-th radius with its 11 heights.  All candidates
+// of a row share the ring samples, the roll, the gaussian and the grounding (only the find_peaks threshold differs), so a row computes
+// that profile once; rows are independent, so the rows of a round run in parallel CTAs and every row reports its FIRST candidate
+// with a verdict (accepted or hard failure).  k_star_pick then takes the first such row in order, which is the candidate the serial
+// loop would have stopped at; best[] (smallest order index with a verdict so far) only lets later candidates stop early.
+constexpr int SS_ROWS = 12;
+constexpr int SS_ROUND_ROWS = 4;       // rows per round after round 0 (row 0 alone: no speculative work for frames that pass at once)
+
 __global__ void __launch_bounds__(SS_THREADS)
-k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ frames, const StarFrame* __restrict__ sf,
-              const double* __restrict__ gauss_w, const int* __restrict__ gauss_off, double* __restrict__ prof_a,
-              double* __restrict__ prof_b, double* __restrict__ prof_c, epid_star_result* __restrict__ res) {
+k_star_rows(const StarConst* __restrict__ cc, const FrameRef* __restrict__ frames, const StarFrame* __restrict__ sf,
+            const double* __restrict__ gauss_w, const int* __restrict__ gauss_off, double* __restrict__ prof_a,
+            double* __restrict__ prof_b, double* __restrict__ prof_c, const epid_star_result* __restrict__ res, int row0,
+            const int* __restrict__ done, int* __restrict__ best, int* __restrict__ row_verdict, epid_star_result* __restrict__ row_res) {
     __shared__ double s_prom[SS_PEAK_CAP], s_wh[SS_PEAK_CAP], s_lip[SS_PEAK_CAP], s_rip[SS_PEAK_CAP], s_skey[SS_PEAK_CAP];
     __shared__ int s_idx[SS_PEAK_CAP], s_lb[SS_PEAK_CAP], s_rb[SS_PEAK_CAP], s_flag[SS_PEAK_CAP], s_sidx[SS_PEAK_CAP];
     __shared__ int s_small[SS_THREADS + 8];
@@ -283,42 +295,48 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
     __shared__ double s_gw[SS_GW_CAP];
     const StarConst& c = *cc;
     const int fi = blockIdx.x;
-    epid_star_result& R = res[fi];
-    if (R.status != EPID_STAR_OK) return;
+    const int row = row0 + blockIdx.y;
+    if (res[fi].status != EPID_STAR_OK || done[fi]) return;
+    epid_star_result& R = row_res[(size_t)fi * SS_ROWS + row];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const FrameRef frf = frames[fi];
     const StarFrame f = sf[fi];
     const int H = c.H, W = c.W;
-    double* pa = prof_a + (size_t)fi * c.nmax;
-    double* pb = prof_b + (size_t)fi * c.nmax;
-    double* pc = prof_c + (size_t)fi * c.npad;
+    const size_t slot = (size_t)fi * gridDim.y + blockIdx.y;
+    double* pa = prof_a + slot * c.nmax;
+    double* pb = prof_b + slot * c.nmax;
+    double* pc = prof_c + slot * c.npad;
     const double dpmm = c.p.dpmm;
     const double fx = c.p.has_start_point ? c.p.start_x : (double)f.sx;
     const double fy = c.p.has_start_point ? c.p.start_y : (double)f.sy;
-    double radius = c.p.radius, mph = c.p.min_peak_height;
     PeakWork w;
     w.cap = SS_PEAK_CAP;
     w.idx = s_idx; w.prom = s_prom; w.lbase = s_lb; w.rbase = s_rb; w.width_height = s_wh; w.lip = s_lip; w.rip = s_rip;
     w.flag = s_flag; w.skey = s_skey; w.sidx = s_sidx; w.s_small = s_small;
-    // candidate generator: product(append(radius, linspace(0.95, 0.1, 10)), append(min_peak_height, linspace(0.05, 0.95, 10)))
-    int gen = -1;                      // -1: the caller's values; k >= 0: k-th element of the product
-    int iterations = 0;
     const double PI = 3.141592653589793;
-    while (true) {
-        iterations++;
-        const double min_height = mph * f.local_max;
+    // this row's radius; np.linspace(a, b, 10)[i] = i * step + a, last element = b
+    const int ri = row - 1;            // index into append(radius, linspace(0.95, 0.1, 10)); row 0: the caller's radius
+    double radius;
+    if (row <= 1) radius = c.p.radius;
+    else radius = (ri - 1) == 9 ? 0.1 : (double)(ri - 1) * ((0.1 - 0.95) / 9.0) + 0.95;
+    const int nheights = row == 0 ? 1 : 11;
+    const int order0 = row == 0 ? 0 : 1 + (row - 1) * 11;      // position of the row's first candidate in the serial order
+    if (best[fi] < order0) return;                              // an earlier candidate already has a verdict
+    int roll = 0;
+    int status = EPID_STAR_OK;
+    int n;
+    double rpx, interval;
+    {
         // StarProfile._convert_radius_perc2pix -> dist2edge_min (core/image.py:817-837)
         const double d2e = fmin(fmin((double)H - fy, (double)W - fx), fmin(fy, fx));
-        const double rpx = d2e * radius;
+        rpx = d2e * radius;
         // CollapsedCircleProfile geometry (core/profile.py:2244-2252, 2446-2455)
         const double r_lo = rpx * (1 - 0.1), r_hi = rpx * (1 + 0.1);
         const double rstep = (r_hi - r_lo) / 19.0;                  // np.linspace(start, stop, 20)
         const double size = PI * r_hi * 2 * 3;
-        const double interval = (2 * PI) / size;
+        interval = (2 * PI) / size;
         const double span = ((2 * PI) - interval) / interval;       // np.arange length = ceil((stop - start) / step)
-        int n = (span > 0.0 && span < 1e9) ? (int)ceil(span) : 0;
-        int status = EPID_STAR_OK;
-        int npk = 0;
+        n = (span > 0.0 && span < 1e9) ? (int)ceil(span) : 0;
         if (n < 3 || n > c.nmax) {
             if (n > c.nmax) status = EPID_STAR_CAPACITY;
             n = 0;
@@ -359,7 +377,7 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
                 s_ctl[0] = mi;
             }
             __syncthreads();
-            const int roll = s_ctl[0];
+            roll = s_ctl[0];
             // ---- filter(size=0.003, kind="gaussian") (core/array_utils.py:106-138): sigma = max(int(round(n * 0.003)), 1)
             int sigma = (int)rint((double)n * 0.003);
             if (sigma < 1) sigma = 1;
@@ -435,6 +453,25 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
                 s_bc[1] = m;
             }
             __syncthreads();
+        }
+    }
+    for (int hi = 0; hi < nheights; hi++) {
+        const int order = order0 + hi;
+        if (hi > 0) {
+            // uniform early exit: a candidate before this one has a verdict
+            if (tid == 0) s_ctl[0] = atomicMin(&best[fi], 0x7fffffff) < order ? 1 : 0;
+            __syncthreads();
+            const int stop = s_ctl[0];
+            __syncthreads();
+            if (stop) return;
+        }
+        double mph;
+        if (row == 0 || hi == 0) mph = c.p.min_peak_height;
+        else mph = (hi - 1) == 9 ? 0.95 : (double)(hi - 1) * ((0.95 - 0.05) / 9.0) + 0.05;
+        const double min_height = mph * f.local_max;
+        const int iterations = order + 1;                          // StarProfile constructions of the serial loop up to this candidate
+        int npk = 0;
+        if (n > 0) {
             // ---- find_fwxm_peaks(threshold=min_height, min_distance=0.02) / find_peaks (core/profile.py:2050-2176, 2545-2649)
             PeakArgs a;
             double thr = min_height;
@@ -449,7 +486,6 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
             npk = block_find_peaks(pb, n, a, w);
             __syncthreads();
             if (npk < 0 || npk > SS_MAX_PEAKS) { status = EPID_STAR_CAPACITY; npk = 0; }
-            if (tid == 0) s_ctl[1] = roll;
         }
         // ---- lines, wobble, acceptance (thread 0; a handful of scalar operations per line)
         if (tid == 0) {
@@ -459,7 +495,6 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
                 if (npk < 6 || (npk & 1)) {
                     if (!c.p.recursive) { verdict = 2; fail = EPID_STAR_NO_LINES; }
                 } else {
-                    const int roll = s_ctl[1];
                     double px[SS_MAX_PEAKS], py[SS_MAX_PEAKS];
                     for (int k = 0; k < npk; k++) {
                         int idx;
@@ -513,25 +548,45 @@ k_star_wobble(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fra
             } else {
                 verdict = 2;
             }
-            if (verdict == 0) {
-                gen++;
-                if (gen >= 121) { verdict = 2; fail = EPID_STAR_NO_WOBBLE; }
-            }
             if (verdict == 2) { R.status = fail; R.iterations = iterations; }
+            if (verdict != 0) {
+                row_verdict[fi * SS_ROWS + row] = verdict;
+                __threadfence();
+                atomicMin(&best[fi], order);
+            }
             s_ctl[2] = verdict;
-            s_ctl[3] = gen;
         }
         __syncthreads();
         const int verdict = s_ctl[2];
-        gen = s_ctl[3];
         __syncthreads();
-        if (verdict != 0) break;
-        // next (radius, min_peak_height) of the product; np.linspace(a, b, 10)[i] = i * step + a, last element = b
-        const int ri = gen / 11, hi = gen - ri * 11;
-        if (ri == 0) radius = c.p.radius;
-        else radius = (ri - 1) == 9 ? 0.1 : (double)(ri - 1) * ((0.1 - 0.95) / 9.0) + 0.95;
-        if (hi == 0) mph = c.p.min_peak_height;
-        else mph = (hi - 1) == 9 ? 0.95 : (double)(hi - 1) * ((0.95 - 0.05) / 9.0) + 0.05;
+        if (verdict != 0) return;
+    }
+}
+
+// First row (in order) of rows [row0, row0 + nrows) that has a verdict -> the frame's result; after the last round a frame without any
+// verdict has exhausted the product: RuntimeError "unable to determine a reasonable wobble" (starshot.py:372-376).
+__global__ void __launch_bounds__(128)
+k_star_pick(int row0, int nrows, int last_round, const int* __restrict__ row_verdict, const epid_star_result* __restrict__ row_res,
+            int* __restrict__ done, epid_star_result* __restrict__ res) {
+    const int fi = blockIdx.x;
+    if (res[fi].status != EPID_STAR_OK || done[fi]) return;
+    int win = -1;
+    for (int r = row0; r < row0 + nrows; r++)
+        if (row_verdict[fi * SS_ROWS + r] != 0) { win = r; break; }
+    __syncthreads();
+    if (win < 0) {
+        if (last_round && threadIdx.x == 0) { res[fi].status = EPID_STAR_NO_WOBBLE; res[fi].iterations = 1 + 11 * 11; }
+        return;
+    }
+    // the fields the candidate loop fills (iterations .. passed); status / start point / local_max come from k_star_front
+    const epid_star_result& S = row_res[(size_t)fi * SS_ROWS + win];
+    constexpr int w0 = (int)(offsetof(epid_star_result, iterations) / 4), w1 = (int)(sizeof(epid_star_result) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&res[fi]);
+    for (int k = w0 + threadIdx.x; k < w1; k += blockDim.x) dst[k] = src[k];
+    if (threadIdx.x == 0) {
+        if (row_verdict[fi * SS_ROWS + win] == 2) res[fi].status = S.status;
+        done[fi] = 1;
     }
 }
 
@@ -633,8 +688,10 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
     const size_t o_cst = sz(sizeof(StarConst)), o_rf = sz(sizeof(FrameRef) * n), o_rc = sz(sizeof(FrameRef) * n);
     const size_t o_sf = sz(sizeof(FrameStats) * n), o_sc = sz(sizeof(FrameStats) * n), o_fr = sz(sizeof(StarFrame) * n);
     const size_t o_res = sz(sizeof(epid_star_result) * n), o_gw = sz(sizeof(double) * gw_count), o_go = sz(sizeof(int) * (max_sigma + 1));
-    const size_t o_pa = sz(sizeof(double) * (size_t)n * hc.nmax), o_pb = sz(sizeof(double) * (size_t)n * hc.nmax);
-    const size_t o_pc = sz(sizeof(double) * (size_t)n * hc.npad);
+    const size_t o_pa = sz(sizeof(double) * (size_t)n * SS_ROUND_ROWS * hc.nmax), o_pb = sz(sizeof(double) * (size_t)n * SS_ROUND_ROWS * hc.nmax);
+    const size_t o_pc = sz(sizeof(double) * (size_t)n * SS_ROUND_ROWS * hc.npad);
+    const size_t o_flags = sz(sizeof(int) * (size_t)n * (2 + SS_ROWS));        // done, best, row verdicts
+    const size_t o_rows = sz(sizeof(epid_star_result) * (size_t)n * SS_ROWS);
     int rc = ensure_scratch(ctx, o);
     if (rc != EPID_OK) return rc;
     char* base = (char*)ctx->scratch;
@@ -683,8 +740,26 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
         k_star_front<<<n, SS_THREADS, smem, st>>>(d_cst, d_rf, d_sf, d_sc, d_fr, d_res);
         ctx->launches++;
     }
-    k_star_wobble<<<n, SS_THREADS, 0, st>>>(d_cst, d_rf, d_fr, d_gw, d_go, (double*)(base + o_pa), (double*)(base + o_pb), (double*)(base + o_pc), d_res);
-    ctx->launches++;
+    {
+        // candidate rows in rounds (see k_star_rows): row 0, then SS_ROUND_ROWS rows at a time; CTAs of settled frames exit at once
+        int* d_done = (int*)(base + o_flags);
+        int* d_best = d_done + n;
+        int* d_verdict = d_best + n;
+        epid_star_result* d_rows = (epid_star_result*)(base + o_rows);
+        EPID_CUDA(cudaMemsetAsync(d_done, 0, sizeof(int) * (size_t)n, st));
+        EPID_CUDA(cudaMemsetAsync(d_best, 0x7f, sizeof(int) * (size_t)n, st));
+        EPID_CUDA(cudaMemsetAsync(d_verdict, 0, sizeof(int) * (size_t)n * SS_ROWS, st));
+        EPID_CUDA(cudaMemsetAsync(d_rows, 0, sizeof(epid_star_result) * (size_t)n * SS_ROWS, st));
+        for (int row0 = 0; row0 < SS_ROWS;) {
+            const int nrows = row0 == 0 ? 1 : (SS_ROWS - row0 < SS_ROUND_ROWS ? SS_ROWS - row0 : SS_ROUND_ROWS);
+            k_star_rows<<<dim3(n, nrows), SS_THREADS, 0, st>>>(d_cst, d_rf, d_fr, d_gw, d_go, (double*)(base + o_pa), (double*)(base + o_pb),
+                                                               (double*)(base + o_pc), d_res, row0, d_done, d_best, d_verdict, d_rows);
+            k_star_pick<<<n, 128, 0, st>>>(row0, nrows, row0 + nrows >= SS_ROWS ? 1 : 0, d_verdict, d_rows, d_done, d_res);
+            ctx->launches += 2;
+            row0 += nrows;
+            if (!p->recursive) break;      // analyze(recursive=False): the first candidate always yields a verdict
+        }
+    }
     EPID_CUDA(cudaGetLastError());
     EPID_CUDA(cudaMemcpyAsync(results, d_res, sizeof(epid_star_result) * n, cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);

@@ -221,8 +221,6 @@ class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
     """winston_lutz.py:629-1231 -- same constructor keywords / analyze() signature for the single-image case."""
 
     def __init__(self, file, use_filenames: bool = False, **kwargs):
-        if use_filenames:
-            raise NotImplementedError("axis values from file names are an ingest feature outside the accelerated hot path")
         if isinstance(file, np.ndarray):
             self.image = image.ArrayImage(file, **{k: v for k, v in kwargs.items() if k in ("dpi", "sid", "dtype")})
         elif isinstance(file, image.BaseImage):
@@ -230,7 +228,7 @@ class WinstonLutz2D(ResultsDataMixin[WinstonLutz2DResult]):
         elif image._is_dicom(file):
             # the reference's WinstonLutz2D IS a LinacDicomImage (winston_lutz.py:629, 1137): axis angles come from the tags,
             # gantry= / coll= / couch= override them
-            self.image = image.LinacDicomImage(file, **kwargs)
+            self.image = image.LinacDicomImage(file, use_filenames=use_filenames, **kwargs)
         else:
             self.image = image.load(file, **{k: v for k, v in kwargs.items() if k in ("dpi", "sid", "dtype")})
         self.gantry_angle = float(kwargs["gantry"] if kwargs.get("gantry") is not None else getattr(self.image, "gantry_angle", 0.0) or 0.0)
@@ -490,8 +488,6 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
                  dpi: float | None = None, sid: float | None = None, missing_axis_value=0):
         import os
 
-        if use_filenames:
-            raise NotImplementedError("axis values from file names are an ingest feature outside the accelerated hot path")
         if isinstance(directory, (list, tuple)):
             paths = [str(p) for p in directory]
         else:
@@ -500,9 +496,9 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
             raise ValueError("<2 valid WL images were found in the folder/file or passed. Ensure you chose the correct folder/file")
         frames, axes, dpmm = [], [], None
         for pth in paths:
-            img = image.LinacDicomImage(pth, axes_precision=axes_precision, missing_axis_value=missing_axis_value)
+            img = image.LinacDicomImage(pth, use_filenames=use_filenames, axes_precision=axes_precision, missing_axis_value=missing_axis_value)
             key = os.path.basename(pth)
-            if axis_mapping and key in axis_mapping:
+            if axis_mapping and not use_filenames and key in axis_mapping:   # winston_lutz.py:1293-1306
                 axes.append(tuple(float(v) for v in axis_mapping[key]))
             else:
                 axes.append((float(img.gantry_angle), float(img.collimator_angle), float(img.couch_angle)))

@@ -114,3 +114,27 @@ def test_winston_lutz_2d_reads_axis_tags(tmp_path):
     w = wl.WinstonLutz2D(p, gantry=180.0)
     assert (w.gantry_angle, w.couch_angle) == (180.0, 45.0)
     assert w._frame_u16().dtype == np.uint16          # identity rescale -> float64 array -> stored integers
+
+
+def test_axis_values_from_file_names(tmp_path):
+    """LinacDicomImage._get_axis_value (core/image.py:1655-1730): with use_filenames the `<axis><number>` convention wins over the tags, an
+    absent keyword gives missing_axis_value (tags are not consulted), a keyword without a number raises (expected values derived by hand from that function; pydicom is not
+    installed here, so the reference cannot read the file itself)."""
+    from pylinac_b200.core import image
+    from pylinac_b200 import winston_lutz as wl
+
+    a = np.zeros((64, 64), np.uint16)
+    p = write_dicom(tmp_path / "wl_gantry45_COLL270.dcm", a, gantry=90.0, coll=0.0, couch=45.0)
+    img = image.LinacDicomImage(p, use_filenames=True)
+    assert (img.gantry_angle, img.collimator_angle, img.couch_angle) == (45.0, 270.0, 0.0)
+    img = image.LinacDicomImage(p, use_filenames=True, missing_axis_value=7)
+    assert img.couch_angle == 7
+    with pytest.raises(ValueError, match="not found in the filename"):
+        image.LinacDicomImage(p, use_filenames=True, missing_axis_value="raise").couch_angle
+    assert image.LinacDicomImage(p, use_filenames=True, couch=12).couch_angle == 12.0      # explicit values first
+    assert image.LinacDicomImage(p).gantry_angle == 90.0                                    # tags otherwise
+    bad = write_dicom(tmp_path / "wl_gantry_x.dcm", a, gantry=90.0, coll=0.0, couch=45.0)
+    with pytest.raises(ValueError, match="could not read a number"):
+        image.LinacDicomImage(bad, use_filenames=True).gantry_angle
+    w = wl.WinstonLutz2D(p, use_filenames=True)
+    assert (w.gantry_angle, w.collimator_angle, w.couch_angle) == (45.0, 270.0, 0.0)
