@@ -14,6 +14,8 @@
 namespace epid {
 
 constexpr int PK_WALK = 64;      // samples per side a lane walks on its own per round (block_find_peaks, prominences)
+constexpr int PK_MAXBLK = 512;   // 32-sample blocks of the prominence skip table (profiles of up to 16384 samples)
+constexpr int PK_RANK_MAX = 768; // distance stage: order by rank counting up to this many candidates, bitonic network beyond
 constexpr int PK_COOP = 32;      // unfinished walks in a warp after a round that the warp finishes cooperatively (32 = all: measured best on the field profiles)
 
 struct PeakArgs {          // already parsed (= after _parse_peak_args, core/profile.py:2626-2649)
@@ -150,7 +152,25 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
             if (i < count) w.flag[i] = 1;
         }
         __syncthreads();
-        block_bitonic_sort(w.skey, w.sidx, m);
+        if (count <= PK_RANK_MAX) {
+            // ascending order by counting: rank = number of entries that sort before (key, position) -- a strict total order, so the
+            // ranks are a permutation.  One barrier instead of the ~log2(m)^2 / 2 of the bitonic network; every thread streams the
+            // same keys (broadcast loads).
+            for (int i = tid; i < count; i += nt) {
+                const double ki = w.skey[i];
+                int r = 0;
+#pragma unroll 4
+                for (int j = 0; j < count; j++) r += key_less(w.skey[j], j, ki, i) ? 1 : 0;
+                w.flag[i] = r;          // parked in flag (sidx is still being read as identity by nobody, but keep the write race-free)
+            }
+            __syncthreads();
+            for (int i = tid; i < count; i += nt) { const int r = w.flag[i]; w.sidx[r] = i; }
+            __syncthreads();
+            for (int i = tid; i < count; i += nt) w.flag[i] = 1;
+            __syncthreads();
+        } else {
+            block_bitonic_sort(w.skey, w.sidx, m);
+        }
         if (tid == 0) {
             for (int i = count - 1; i >= 0; i--) {
                 const int j = w.sidx[i];
@@ -164,10 +184,98 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
         count = compact_by_flag(w, count, false);
     }
 
-    // ---- 3. prominences (wlen = None).  Lanes walk their own peaks in rounds of PK_WALK samples per side.  While many lanes of a
-    // warp are still walking that is the efficient shape; once only a few are left (the dominant peaks, whose walks cross most of
-    // the profile) the whole warp finishes each of them, 32 samples per step.  Same minima and bases as the sequential walk: the
-    // first (closest) sample wins among equal minima.
+    // ---- 3. prominences (wlen = None): for every peak the minimum between it and the nearest HIGHER sample on either side (or the
+    // end of the profile); among equal minima the sample closest to the peak is the base (scipy walks outwards and updates on "<").
+    // Profiles of up to 32 * PK_MAXBLK samples: a table of 32-sample blocks (maximum, minimum, offsets of the first / last
+    // occurrence of the minimum) lets a walk skip every block that holds no higher sample -- <= 32 + n / 32 + 32 steps instead of a
+    // walk across the profile (the dominant peaks), with the same minima and bases.  Longer profiles: per-lane walks in rounds,
+    // finished warp-cooperatively.
+    if (n <= 32 * PK_MAXBLK) {
+        __shared__ double s_bmax[PK_MAXBLK], s_bmin[PK_MAXBLK];
+        __shared__ unsigned short s_bpos[PK_MAXBLK];       // first | last << 8: offsets of the block minimum
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        const int nblk = (n + 31) >> 5;
+        __syncthreads();
+        for (int b = wid; b < nblk; b += nw) {
+            const int k = (b << 5) + lane;
+            const bool in = k < n;
+            const double v = in ? x[k] : 0.0;
+            double vmax = in ? v : -__longlong_as_double(0x7ff0000000000000LL);
+            double vmin = in ? v : __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+            }
+            const unsigned eq = __ballot_sync(0xffffffffu, in && v == vmin);
+            if (lane == 0) {
+                s_bmax[b] = vmax;
+                s_bmin[b] = vmin;
+                s_bpos[b] = (unsigned short)((__ffs(eq) - 1) | ((31 - __clz(eq)) << 8));
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < count; i += nt) {
+            const int p = w.idx[i];
+            const double xp = x[p];
+            const int pb_ = p >> 5;
+            // left: own block downwards (fixed trip count, the loads do not depend on the running state), then whole blocks
+            double lmin = xp;
+            int lb = p;
+            bool stop = false;
+            for (int k = p; k >= (pb_ << 5); k--) {
+                const double v = x[k];
+                if (!stop) {
+                    if (v > xp) stop = true;
+                    else if (v < lmin) { lmin = v; lb = k; }
+                }
+            }
+            for (int b = pb_ - 1; b >= 0 && !stop; b--) {
+                if (s_bmax[b] > xp) {
+                    for (int k = (b << 5) + 31; k >= (b << 5); k--) {
+                        const double v = x[k];
+                        if (!stop) {
+                            if (v > xp) stop = true;
+                            else if (v < lmin) { lmin = v; lb = k; }
+                        }
+                    }
+                } else if (s_bmin[b] < lmin) {
+                    lmin = s_bmin[b];
+                    lb = (b << 5) + (s_bpos[b] >> 8);
+                }
+            }
+            // right
+            double rmin = xp;
+            int rb = p;
+            stop = false;
+            const int own_end = min(n - 1, (pb_ << 5) + 31);
+            for (int k = p; k <= own_end; k++) {
+                const double v = x[k];
+                if (!stop) {
+                    if (v > xp) stop = true;
+                    else if (v < rmin) { rmin = v; rb = k; }
+                }
+            }
+            for (int b = pb_ + 1; b < nblk && !stop; b++) {
+                if (s_bmax[b] > xp) {
+                    const int e = min(n - 1, (b << 5) + 31);
+                    for (int k = b << 5; k <= e; k++) {
+                        const double v = x[k];
+                        if (!stop) {
+                            if (v > xp) stop = true;
+                            else if (v < rmin) { rmin = v; rb = k; }
+                        }
+                    }
+                } else if (s_bmin[b] < rmin) {
+                    rmin = s_bmin[b];
+                    rb = (b << 5) + (s_bpos[b] & 0xff);
+                }
+            }
+            w.prom[i] = xp - fmax(lmin, rmin);
+            w.lbase[i] = lb;
+            w.rbase[i] = rb;
+        }
+    } else
     for (int base = 0; base < count; base += nt) {
         const int i = base + tid;
         const bool act = i < count;

@@ -2,12 +2,13 @@
 
     cuobjdump -xelf all build/x.o; nvdisasm -g -c x.sm_100a.cubin > lines.txt
     ncu -i rep.ncu-rep --page source --csv --print-source sass --kernel-name K > sass.csv
-    python tools/ncu_lines.py sass.csv lines.txt <mangled kernel name substring> [top]
+    python tools/ncu_lines.py sass.csv lines.txt <mangled kernel name substring> [top] [samples]
 """
 import csv, re, sys, collections
 
 sass_csv, lines_txt, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+by_samples = len(sys.argv) > 5 and sys.argv[5] == 'samples'
 # line info: list of (offset, file:line) for the kernel and the device functions that follow it
 sections = {}
 cur = None; line = None
@@ -37,5 +38,5 @@ for k in range(n):
     agg[offs[k][1]][0] += e; agg[offs[k][1]][1] += s
     tot_i += e; tot_s += s
 print(f"instructions {tot_i:.0f}  samples {tot_s:.0f}  ({n} of {len(data)} SASS rows mapped)")
-for ln, (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for ln, (e, s) in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     print(f"{str(ln):40s} {e / tot_i * 100:6.2f}% inst  {s / max(tot_s, 1) * 100:6.2f}% samples")
