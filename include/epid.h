@@ -60,9 +60,12 @@ enum { EPID_OPT_PF_EXACT_ONLY = 1, EPID_OPT_PF_LEAFBAND = 2 /* 1 = experimental 
                                 kernels of one sub-batch overlap the streaming kernels of another (bit-identical results); 0 / 1 = one stream */,
        EPID_OPT_PF_FAST_REDO = 5 /* 1 (default): a deferred frame whose _has_noise() == True can be certified by one exact count is median-filtered
                                     and re-run by the certified fast pipeline; 0 = every deferred frame goes to the exact-histogram pipeline */,
-       EPID_OPT_PF_OVERLAP_REDO = 6 /* 1 (default): epid_pf_analyze re-runs deferred frames on a second stream while the batch's window stages run */ };
+       EPID_OPT_PF_OVERLAP_REDO = 6 /* 1 (default): epid_pf_analyze re-runs deferred frames on a second stream while the batch's window stages run */,
+       EPID_OPT_STATS_EXACT = 7 /* 1: FieldAnalysis / Starshot compute check_inversion_by_histogram from the exact histogram for every frame
+                                   (default 0: decision certified from exact counts at pilot thresholds, exact histogram only where that fails) */ };
 enum { EPID_CTR_PF_FALLBACKS = 1, EPID_CTR_PF_REDONE_FRAMES = 2 /* frames re-run individually (fast re-run or exact pipeline) */,
-       EPID_CTR_PF_EXACT_FRAMES = 3 /* of those: frames that went through the exact-histogram pipeline */ };
+       EPID_CTR_PF_EXACT_FRAMES = 3 /* of those: frames that went through the exact-histogram pipeline */,
+       EPID_CTR_STATS_UNCERTIFIED = 4 /* FieldAnalysis / Starshot frames whose check_inversion_by_histogram decision needed exact percentiles */ };
 int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value);
 int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value);
 

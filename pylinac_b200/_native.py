@@ -29,9 +29,11 @@ OPT_PF_WIN2 = 3
 OPT_PF_SPLIT = 4
 OPT_PF_FAST_REDO = 5
 OPT_PF_OVERLAP_REDO = 6
+OPT_STATS_EXACT = 7
 CTR_PF_FALLBACKS = 1
 CTR_PF_REDONE_FRAMES = 2
 CTR_PF_EXACT_FRAMES = 3
+CTR_STATS_UNCERTIFIED = 4
 PF_MAX_PICKETS = 32
 PF_MAX_LEAVES = 160
 

@@ -60,6 +60,10 @@ struct epid_ctx {
     size_t scratch2_bytes = 0;
     void* hist_scratch = nullptr;        // histograms + column partials of the multi-CTA frame statistics (stats.cu)
     size_t hist_bytes = 0;
+    void* inv_scratch = nullptr;         // thresholds / partials of the certified inversion statistics (stats.cu)
+    size_t inv_bytes = 0;
+    int stats_exact = 0;                 // 1: FieldAnalysis / Starshot take the exact histogram path for every frame (EPID_OPT_STATS_EXACT)
+    int64_t stats_uncertified = 0;       // frames whose inversion decision needed the exact histogram path
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     void* pinned_ring = nullptr;         // page-locked staging ring for pageable source frames (pf.cu)

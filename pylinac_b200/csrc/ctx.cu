@@ -116,6 +116,7 @@ int32_t epid_ctx_destroy(epid_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->hist_scratch) cudaFree(ctx->hist_scratch);
+    if (ctx->inv_scratch) cudaFree(ctx->inv_scratch);
     if (ctx->pinned_ring) cudaFreeHost(ctx->pinned_ring);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
@@ -168,6 +169,7 @@ int32_t epid_set_option(epid_ctx* ctx, int32_t key, int64_t value) {
         case EPID_OPT_PF_SPLIT: ctx->pf_split = value < 2 ? 0 : (value > 4 ? 4 : (int)value); return EPID_OK;
         case EPID_OPT_PF_FAST_REDO: ctx->pf_fast_redo = value ? 1 : 0; return EPID_OK;
         case EPID_OPT_PF_OVERLAP_REDO: ctx->pf_overlap_redo = value ? 1 : 0; return EPID_OK;
+        case EPID_OPT_STATS_EXACT: ctx->stats_exact = value ? 1 : 0; return EPID_OK;
     }
     set_error("unknown option %d", key);
     return EPID_ERR_INVALID;
@@ -179,6 +181,7 @@ int32_t epid_get_counter(epid_ctx* ctx, int32_t key, int64_t* value) {
         case EPID_CTR_PF_FALLBACKS: *value = ctx->pf_fallbacks; return EPID_OK;
         case EPID_CTR_PF_REDONE_FRAMES: *value = ctx->pf_redone_frames; return EPID_OK;
         case EPID_CTR_PF_EXACT_FRAMES: *value = ctx->pf_exact_frames; return EPID_OK;
+        case EPID_CTR_STATS_UNCERTIFIED: *value = ctx->stats_uncertified; return EPID_OK;
     }
     set_error("unknown counter %d", key);
     return EPID_ERR_INVALID;

@@ -572,10 +572,7 @@ k_field_center(const FieldConst* __restrict__ cc, const FrameStats* __restrict__
     const FrameStats fs = stats[fi];
     FieldFrame& f = ff[fi];
     // check_inversion_by_histogram() with the default percentiles (5, 50, 95) (field_analysis.py:472, core/image.py:899-926)
-    const double p_low = np_lerp((double)fs.ostat[0], (double)fs.ostat[1], c.p5.gamma);
-    const double p_mid = np_lerp((double)fs.ostat[2], (double)fs.ostat[3], c.p50.gamma);
-    const double p_high = np_lerp((double)fs.ostat[4], (double)fs.ostat[5], c.p95.gamma);
-    const int hist_inv = fabs(p_mid - p_low) > fabs(p_mid - p_high) ? 1 : 0;
+    const int hist_inv = stats_hist_inverted(fs, c.p5.gamma, c.p50.gamma, c.p95.gamma);      // certified from counts or exact percentiles
     const int flip = hist_inv ^ (c.p.invert ? 1 : 0);
     if (tid == 0 && axis == 0) {
         f.mn = fs.mn;
@@ -1073,7 +1070,7 @@ extern "C" int32_t epid_field_analyze(epid_ctx* ctx, const epid_batch* frames, c
     g.ranks[2] = hc.p50.prev; g.ranks[3] = hc.p50.next;
     g.ranks[4] = hc.p95.prev; g.ranks[5] = hc.p95.next;
     g.box = 0;
-    rc = launch_frame_stats(ctx, st, g, d_rf, nullptr, n, d_st, d_rs, d_cs);
+    rc = launch_frame_stats_inversion(ctx, st, g, d_rf, n, d_st, d_rs, d_cs);
     if (rc != EPID_OK) return rc;
     for (int c0 = 0; c0 < n; c0 += chunk) {
         const int cn = n - c0 < chunk ? n - c0 : chunk;

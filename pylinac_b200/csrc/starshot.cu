@@ -76,10 +76,7 @@ k_star_front(const StarConst* __restrict__ cc, const FrameRef* __restrict__ fram
     const FrameStats fs = full[fi], cs = central[fi];
     StarFrame& f = sf[fi];
     // ---- check_inversion_by_histogram([4, 50, 96]) (core/image.py:899-926), ground, optional invert
-    const double p_low = np_lerp((double)fs.ostat[0], (double)fs.ostat[1], c.p4.gamma);
-    const double p_mid = np_lerp((double)fs.ostat[2], (double)fs.ostat[3], c.p50.gamma);
-    const double p_high = np_lerp((double)fs.ostat[4], (double)fs.ostat[5], c.p96.gamma);
-    const int hist_inv = fabs(p_mid - p_low) > fabs(p_mid - p_high) ? 1 : 0;
+    const int hist_inv = stats_hist_inverted(fs, c.p4.gamma, c.p50.gamma, c.p96.gamma);      // certified from counts or exact percentiles
     const int flip = hist_inv ^ (c.p.invert ? 1 : 0);
     const uint32_t mn = fs.mn, mx = fs.mx;
     // ---- _get_reasonable_start_point (starshot.py:197-227): maxima of the central third along each axis
@@ -720,7 +717,7 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
     g.ranks[2] = hc.p50.prev; g.ranks[3] = hc.p50.next;
     g.ranks[4] = hc.p96.prev; g.ranks[5] = hc.p96.next;
     g.box = 0;
-    rc = launch_frame_stats(ctx, st, g, d_rf, nullptr, n, d_sf, nullptr, nullptr);
+    rc = launch_frame_stats_inversion(ctx, st, g, d_rf, n, d_sf, nullptr, nullptr);
     if (rc != EPID_OK) return rc;
     StatsGeom gc;
     rc = make_stats_geom(&gc, hc.ch, hc.cw);

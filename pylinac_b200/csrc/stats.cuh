@@ -42,5 +42,18 @@ int make_stats_geom(StatsGeom* g, int H, int W);
 // out_index == nullptr: frame i writes slot i.  rowsum: [slot][H] u32, colsum: [slot][W] u32 (may be null).
 int launch_frame_stats(epid_ctx* ctx, cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames,
                        const int* d_out_index, int n, FrameStats* d_stats, uint32_t* d_rowsum, uint32_t* d_colsum);
+// check_inversion_by_histogram statistics (three percentile pairs in g.ranks): min / max / sum / row / column sums exactly; the decision
+// certified from exact counts (FrameStats.overflow = 2 + inverted) or, where the bounds overlap, exact order statistics (overflow = 0)
+int launch_frame_stats_inversion(epid_ctx* ctx, cudaStream_t stream, const StatsGeom& g, const FrameRef* d_frames, int n, FrameStats* d_stats,
+                                 uint32_t* d_rowsum, uint32_t* d_colsum);
+// the decision of check_inversion_by_histogram from a FrameStats record of either kind
+__device__ __forceinline__ int stats_hist_inverted(const FrameStats& fs, double g_low, double g_mid, double g_high) {
+    if (fs.overflow >= 2u) return (int)(fs.overflow - 2u);
+    auto lerp = [](double a, double b, double t) { const double d = b - a; double r = a + d * t; if (t >= 0.5) r = b - d * (1.0 - t); return r; };
+    const double p_low = lerp((double)fs.ostat[0], (double)fs.ostat[1], g_low);
+    const double p_mid = lerp((double)fs.ostat[2], (double)fs.ostat[3], g_mid);
+    const double p_high = lerp((double)fs.ostat[4], (double)fs.ostat[5], g_high);
+    return fabs(p_mid - p_low) > fabs(p_mid - p_high) ? 1 : 0;
+}
 
 }  // namespace epid

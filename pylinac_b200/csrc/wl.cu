@@ -600,16 +600,32 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
         const int ncomp = min(ncomp_all, WL_MAXC);
         __syncthreads();
         if (ncomp_all > WL_MAXC) { fatal = 1; break; }
-        for (int i = tid; i < npx; i += WL_THREADS) {
-            const int r = parent[i];
-            if (r < 0) continue;
-            const int id = cid[r];
-            if (id >= WL_MAXC) continue;
-            const int y = i / ww, x = i - y * ww;
-            atomicAdd(&comp->area[id], 1);
-            atomicMin(&comp->y0[id], y); atomicMax(&comp->y1[id], y);
-            atomicMin(&comp->x0[id], x); atomicMax(&comp->x1[id], x);
-            if (y == 0 || x == 0 || y == wh - 1 || x == ww - 1) comp->border[id] = 1;      // segmentation.clear_border
+        // area / bounding box per component: the 32 raster-consecutive pixels of a warp mostly belong to one or two components, so the
+        // warp combines its lanes per component id (match.any + redux) and issues one set of atomics per id instead of one per pixel
+        for (int i0 = 0; i0 < npx; i0 += WL_THREADS) {
+            const int i = i0 + tid;
+            int id = -1, y = 0, x = 0;
+            if (i < npx) {
+                const int r = parent[i];
+                if (r >= 0) {
+                    id = cid[r];
+                    if (id >= WL_MAXC) id = -1;
+                    y = i / ww; x = i - y * ww;
+                }
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, id >= 0);
+            if (id >= 0) {
+                const unsigned peers = __match_any_sync(act, id);
+                const int cnt = __popc(peers);
+                const int ymin = __reduce_min_sync(peers, y), ymax = __reduce_max_sync(peers, y);
+                const int xmin = __reduce_min_sync(peers, x), xmax = __reduce_max_sync(peers, x);
+                if (lane == __ffs(peers) - 1) {
+                    atomicAdd(&comp->area[id], cnt);
+                    atomicMin(&comp->y0[id], ymin); atomicMax(&comp->y1[id], ymax);
+                    atomicMin(&comp->x0[id], xmin); atomicMax(&comp->x1[id], xmax);
+                    if (ymin == 0 || xmin == 0 || ymax == wh - 1 || xmax == ww - 1) comp->border[id] = 1;      // segmentation.clear_border
+                }
+            }
         }
         __syncthreads();
         // -- regions in label order through the detection conditions (metrics/features.py:7-68)

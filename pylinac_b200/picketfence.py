@@ -301,6 +301,44 @@ def analyze_batch(frames, dpmm: float, *, device: int | None = None, meas_cap: i
                          analyze_kwargs.get("separate_leaves", False))
 
 
+def analyze_files(paths, *, device: int | None = None, threads: int = 8, pinned: bool = True, **kwargs) -> PFBatchResult:
+    """Batched ``PicketFence(path).analyze()`` over DICOM files: header-only parse, then every file's pixel bytes are read straight
+    into one page-locked [n, rows, cols] array (``dicom.read_frames``: no intermediate copy between the page cache and the H2D
+    DMA), then ``analyze_batch``.  As in ``image.frame_u16`` the STORED integers are analysed (order-flipped where RescaleSlope /
+    PixelIntensityRelationshipSign make the displayed values a decreasing map of them); all files must share shape, stored dtype
+    and dpmm.  The reference loads and analyses one file at a time (core/io.py:73-84, core/image.py:1431-1444)."""
+    from . import dicom
+    from .core import image
+
+    paths = [str(p) for p in paths]
+    headers0 = dicom.read_header(paths[0])
+    shape = (len(paths), int(headers0["Rows"]), int(headers0["Columns"]))
+    if headers0["PixelDtype"] != np.dtype("<u2"):
+        raise ValueError(f"analyze_files takes 16-bit unsigned pixel data, got {headers0['PixelDtype']}; use PicketFence(path)")
+    out = None
+    if pinned:
+        try:
+            out = nat.pinned_empty(shape, np.uint16)
+        except nat.NativeError:
+            out = None
+    frames, headers = dicom.read_frames(paths, out=out, threads=threads)
+    dpmms = []
+    for i, h in enumerate(headers):
+        stub = image.DicomImage.__new__(image.DicomImage)
+        stub.metadata, stub._sid, stub._dpi, stub._sad = h, None, None, 1000
+        dpmms.append(stub.dpmm)
+        slope, intercept, sign = h.get("RescaleSlope"), h.get("RescaleIntercept"), h.get("PixelIntensityRelationshipSign")
+        decreasing = (sign == -1) != (slope is not None and intercept is not None and float(slope) < 0)
+        if decreasing:      # exact modular order flip of the stored values (image.frame_u16)
+            f = frames[i]
+            frames[i] = (int(f.max()) + int(f.min()) - f.astype(np.int64)).astype(np.uint16)
+    if any(d is None for d in dpmms):
+        raise ValueError("DPI was not a tag in the image nor was it passed in. Please pass a DPI value")
+    if max(dpmms) - min(dpmms) > 1e-12 * max(dpmms):
+        raise ValueError("the files have different pixel sizes at isocentre; analyse them in groups of equal dpmm")
+    return analyze_batch(frames, float(dpmms[0]), device=device, **kwargs)
+
+
 class PFImageMixin:
     """PFDicomImage behaviour (picketfence.py:204-260) that is not pixel arithmetic: the CAX override."""
 

@@ -138,3 +138,30 @@ def test_axis_values_from_file_names(tmp_path):
         image.LinacDicomImage(bad, use_filenames=True).gantry_angle
     w = wl.WinstonLutz2D(p, use_filenames=True)
     assert (w.gantry_angle, w.collimator_angle, w.couch_angle) == (45.0, 270.0, 0.0)
+
+
+def test_batched_ingest_reads_pixels_straight_into_one_array(tmp_path):
+    """dicom.read_frames: header-only parse + readinto of the pixel bytes into the caller's [n, rows, cols] array; equals the
+    per-file reader, for explicit / implicit VR files with and without preamble; mismatching shapes are refused."""
+    rng = np.random.default_rng(3)
+    arrs = [rng.integers(0, 65535, (48, 40)).astype(np.uint16) for _ in range(5)]
+    paths = [write_dicom(tmp_path / f"f{i}.dcm", a, explicit=bool(i % 2), preamble=i != 3, slope=1.0 if i == 2 else None,
+                         intercept=0.0 if i == 2 else None) for i, a in enumerate(arrs)]
+    out = np.zeros((5, 48, 40), np.uint16)
+    frames, headers = dicom.read_frames(paths, out=out, threads=3)
+    assert frames is out
+    for i, a in enumerate(arrs):
+        np.testing.assert_array_equal(frames[i], a)
+        np.testing.assert_array_equal(dicom.dcmread(paths[i]).pixel_array, a)
+        assert headers[i]["Rows"] == 48 and headers[i]["PixelCount"] == 48 * 40
+        assert "pixel_array" not in headers[i].__dict__
+    frames2, _ = dicom.read_frames(paths)
+    np.testing.assert_array_equal(frames2, out)
+    other = write_dicom(tmp_path / "other.dcm", np.zeros((32, 40), np.uint16))
+    with pytest.raises(ValueError, match="differs from the first"):
+        dicom.read_frames(paths + [other])
+    with pytest.raises(ValueError, match="out must be"):
+        dicom.read_frames(paths, out=np.zeros((5, 48, 41), np.uint16))
+    # a header longer than the first read is parsed from the whole file
+    h = dicom.read_header(paths[0], head_bytes=64)
+    assert h["PixelCount"] == 48 * 40

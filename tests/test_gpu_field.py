@@ -123,3 +123,43 @@ def test_field_central_roi_matches_reference(name):
         assert getattr(rd, f"central_roi_{k}") == float(GOLD[f"{name}/central_roi_{k}"]), k
     assert rd.central_roi_std == pytest.approx(float(GOLD[f"{name}/central_roi_std"]), rel=1e-12)
     assert "Central ROI stats" in f.results()
+
+
+def test_certified_inversion_statistics_equal_the_exact_histogram_path():
+    """check_inversion_by_histogram is decided from exact counts at pilot thresholds (stats.cu: k_inv_pilot / k_inv_stream / k_inv_finish);
+    where the bounds cannot separate the two distances the frame takes the exact histogram path.  Either way every result field must
+    equal the all-exact run (EPID_OPT_STATS_EXACT), for fields, inverted fields, noise (undecidable -> fallback) and Starshot frames."""
+    from oracle import synth
+    from pylinac_b200 import _native as nat
+    from pylinac_b200 import field_analysis as fa
+    from pylinac_b200 import starshot as ss
+
+    import bench
+
+    rng = np.random.default_rng(11)
+    names = ["as1200_150", "as1200_offset", "inverted", "fff"]
+    frames = [case_frame(n)[0] for n in names]
+    shape = frames[0].shape
+    frames.append(rng.integers(1000, 1100, shape).astype(np.uint16))                      # pure noise: p50 - p5 ~ p95 - p50
+    frames.append((65535 - frames[0].astype(np.int64)).astype(np.uint16))
+    frames = np.stack([f for f in frames if f.shape == shape] * 3)
+    dpmm = (25.4 / 0.336) / 25.4
+    ctx = nat.Context.default()
+    stars = np.stack([bench._gen_module_frames(("star", i)) for i in range(4)] + [(65535 - bench._gen_module_frames(("star", 1)).astype(np.int64)).astype(np.uint16)])
+    try:
+        ctx.set_option(nat.OPT_STATS_EXACT, 1)
+        exact_f = fa.analyze_batch(frames, dpmm).rows.copy()
+        exact_s = nat.starshot_analyze(ctx, stars, ss.make_params(2.56)).copy()
+        ctx.set_option(nat.OPT_STATS_EXACT, 0)
+        u0 = ctx.counter(nat.CTR_STATS_UNCERTIFIED)
+        fast_f = fa.analyze_batch(frames, dpmm).rows.copy()
+        unc_f = ctx.counter(nat.CTR_STATS_UNCERTIFIED) - u0
+        fast_s = nat.starshot_analyze(ctx, stars, ss.make_params(2.56)).copy()
+    finally:
+        ctx.set_option(nat.OPT_STATS_EXACT, 0)
+    for k in exact_f.dtype.names:
+        np.testing.assert_array_equal(exact_f[k], fast_f[k], err_msg=k)
+    for k in exact_s.dtype.names:
+        np.testing.assert_array_equal(exact_s[k], fast_s[k], err_msg=k)
+    assert 0 < unc_f < len(frames), f"{unc_f} of {len(frames)} field frames took the exact path (expected: only the noise frames)"
+    assert set(np.unique(exact_f["hist_inverted"])) == {0, 1}

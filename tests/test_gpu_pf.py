@@ -588,6 +588,31 @@ def test_picketfence_reads_the_reference_dicom_files(name, tmp_path):
     assert "Gantry Angle" in pfo.results()
 
 
+def test_analyze_files_equals_the_per_file_objects(tmp_path):
+    """f1 ingest: picketfence.analyze_files (header parse + pixel bytes straight into page-locked memory + one batched analysis) returns,
+    file by file, what PicketFence(path).analyze() returns -- including a file whose PixelIntensityRelationshipSign flips the values."""
+    from oracle import synth
+    from pylinac_b200 import picketfence as pf
+    from tests.dicom_writer import write_dicom
+
+    frames = [synth.bench_pf_frame(i) for i in range(20, 26)]
+    paths = [write_dicom(tmp_path / f"pf{i}.dcm", a, pixel_spacing_mm=0.390625, sid=1000.0, gantry=0.0, coll=0.0, couch=0.0,
+                         sign=-1 if i == 4 else None, slope=1.0 if i == 4 else None, intercept=0.0 if i == 4 else None)
+             for i, a in enumerate(frames)]
+    res = pf.analyze_files(paths, threads=4)
+    assert len(res) == len(paths)
+    for i in (0, 4, 5):
+        single = pf.PicketFence(paths[i])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            single.analyze()
+        r = res[i]
+        r.raise_for_status()
+        assert int(r.s["n_meas"]) == len(single.mlc_meas) and int(r.s["n_pickets"]) == single.num_pickets
+        assert float(r.s["max_error_mm"]) == pytest.approx(single.max_error, abs=1e-9)
+        assert float(r.s["abs_median_error_mm"]) == pytest.approx(single.abs_median_error, abs=1e-9)
+
+
 def test_picketfence_on_a_rescaled_dicom_equals_the_stored_pixels(tmp_path):
     """A clinical file with RescaleSlope / RescaleIntercept (float pixel data in the reference): the device pipeline analyses the
     stored integers (image.frame_u16); positions agree with the analysis of the raw array to fp64 rounding, counts exactly."""
