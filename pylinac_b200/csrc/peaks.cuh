@@ -103,39 +103,46 @@ __device__ inline int compact_by_flag(PeakWork& w, int count, bool have_props) {
 // returns the number of peaks (>= 0) or -1 if the capacity was exceeded
 __device__ inline int block_find_peaks(const double* __restrict__ x, int n, const PeakArgs& a, PeakWork& w) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    // ---- 1. local maxima + height filter, ordered
-    const int chunk = (n + nt - 1) / nt;
-    const int lo = max(1, tid * chunk), hi = min(n - 1, (tid + 1) * chunk);
-    int c = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        int o = 0;
-        if (pass == 1) {
-            // exclusive scan of per-thread counts (sequential by thread 0; nt <= 1024)
-            w.s_small[tid + 1] = c;
-            __syncthreads();
-            if (tid == 0) {
-                int acc = 0;
-                for (int t = 0; t < nt; t++) { int v = w.s_small[t + 1]; w.s_small[t + 1] = acc; acc += v; }
-                w.s_small[0] = acc;
-            }
-            __syncthreads();
-            o = w.s_small[tid + 1];
-            if (w.s_small[0] > w.cap) return -1;
-        }
-        for (int i = lo; i < hi; i++) {
-            if (x[i - 1] < x[i]) {
-                int ahead = i + 1;
-                while (ahead < n - 1 && x[ahead] == x[i]) ahead++;
-                if (x[ahead] < x[i]) {
-                    const int p = (i + ahead - 1) / 2;
-                    if (x[p] >= a.hmin) {
-                        if (pass == 1) w.idx[o] = p;
-                        o++;
+    // ---- 1. local maxima + height filter, ordered.  Every warp owns one contiguous segment of the profile and sweeps it 32 samples at a
+    // time (coalesced loads); a plateau is reported by its first sample (x[i-1] < x[i], look ahead over the equal samples, then a strictly
+    // lower one) at its midpoint, exactly like _local_maxima_1d.  Pass 0 counts per warp, the warp totals are scanned, pass 1 writes.
+    {
+        const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+        const int span = n - 2;                                   // candidates i = 1 .. n - 2
+        const int seg = span > 0 ? ((span + nw - 1) / nw + 31) / 32 * 32 : 0;
+        const int i0 = 1 + wid * seg, i1 = min(n - 1, i0 + seg);
+        int woff = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            int o = woff;
+            for (int b0 = i0; b0 < i1; b0 += 32) {
+                const int i = b0 + lane;
+                bool pk = false;
+                int p = 0;
+                if (i < i1) {
+                    const double xi = x[i];
+                    if (x[i - 1] < xi) {
+                        int ahead = i + 1;
+                        while (ahead < n - 1 && x[ahead] == xi) ahead++;
+                        if (x[ahead] < xi) {
+                            p = (i + ahead - 1) / 2;
+                            pk = x[p] >= a.hmin;
+                        }
                     }
                 }
+                const unsigned bal = __ballot_sync(0xffffffffu, pk);
+                if (pass == 1 && pk) w.idx[o + __popc(bal & ((1u << lane) - 1u))] = p;
+                o += __popc(bal);
+            }
+            if (pass == 0) {
+                if (lane == 0) w.s_small[1 + wid] = o;
+                __syncthreads();
+                int total = 0;
+                for (int k = 0; k < nw; k++) { const int c = w.s_small[1 + k]; if (k < wid) woff += c; total += c; }
+                __syncthreads();
+                if (tid == 0) w.s_small[0] = total;
+                if (total > w.cap) return -1;
             }
         }
-        if (pass == 0) c = o;
     }
     __syncthreads();
     int count = w.s_small[0];
