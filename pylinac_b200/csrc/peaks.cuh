@@ -159,34 +159,61 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
             if (i < count) w.flag[i] = 1;
         }
         __syncthreads();
+        // priority of every candidate = its rank in the ascending (height, position) order (a strict total order: among equal heights
+        // the right-most candidate has the higher priority, as in _select_by_peak_distance), kept in w.lbase (free until stage 3)
+        int* rank = w.lbase;
         if (count <= PK_RANK_MAX) {
-            // ascending order by counting: rank = number of entries that sort before (key, position) -- a strict total order, so the
-            // ranks are a permutation.  One barrier instead of the ~log2(m)^2 / 2 of the bitonic network; every thread streams the
-            // same keys (broadcast loads).
+            // by counting: rank = number of entries that sort before this one.  One barrier instead of the ~log2(m)^2 / 2 of the bitonic
+            // network; every thread streams the same keys (broadcast loads).
             for (int i = tid; i < count; i += nt) {
                 const double ki = w.skey[i];
                 int r = 0;
 #pragma unroll 4
                 for (int j = 0; j < count; j++) r += key_less(w.skey[j], j, ki, i) ? 1 : 0;
-                w.flag[i] = r;          // parked in flag (sidx is still being read as identity by nobody, but keep the write race-free)
+                rank[i] = r;
             }
-            __syncthreads();
-            for (int i = tid; i < count; i += nt) { const int r = w.flag[i]; w.sidx[r] = i; }
-            __syncthreads();
-            for (int i = tid; i < count; i += nt) w.flag[i] = 1;
-            __syncthreads();
         } else {
             block_bitonic_sort(w.skey, w.sidx, m);
+            for (int r = tid; r < count; r += nt) rank[w.sidx[r]] = r;
         }
-        if (tid == 0) {
-            for (int i = count - 1; i >= 0; i--) {
-                const int j = w.sidx[i];
-                if (!w.flag[j]) continue;
-                int k = j - 1;
-                while (k >= 0 && w.idx[j] - w.idx[k] < a.distance) { w.flag[k] = 0; k--; }
-                k = j + 1;
-                while (k < count && w.idx[k] - w.idx[j] < a.distance) { w.flag[k] = 0; k++; }
+        // scipy visits the candidates from the highest priority down and, for each one still kept, drops every neighbour closer than
+        // `distance`: the lexicographically first maximal independent set.  The same set in parallel rounds: an undecided candidate
+        // with a kept neighbour is dropped; one with no undecided neighbour of higher priority is kept; the others wait.  The highest
+        // undecided candidate is settled every round, typically all of them within a few rounds.
+        int* cur = w.flag;      // 2 undecided, 1 kept, 0 dropped
+        int* nxt = w.rbase;     // (free until stage 3)
+        for (int i = tid; i < count; i += nt) cur[i] = 2;
+        __syncthreads();
+        while (true) {
+            bool waiting = false;
+            for (int i = tid; i < count; i += nt) {
+                int st = cur[i];
+                if (st == 2) {
+                    const int pi = w.idx[i], ri = rank[i];
+                    bool has_kept = false, blocked = false;
+                    for (int k = i - 1; k >= 0 && pi - w.idx[k] < a.distance; k--) {
+                        const int sk = cur[k];
+                        if (sk == 1) { has_kept = true; break; }
+                        if (sk == 2 && rank[k] > ri) { blocked = true; break; }
+                    }
+                    if (!has_kept && !blocked) {
+                        for (int k = i + 1; k < count && w.idx[k] - pi < a.distance; k++) {
+                            const int sk = cur[k];
+                            if (sk == 1) { has_kept = true; break; }
+                            if (sk == 2 && rank[k] > ri) { blocked = true; break; }
+                        }
+                    }
+                    st = has_kept ? 0 : (blocked ? 2 : 1);
+                    waiting = waiting || st == 2;
+                }
+                nxt[i] = st;
             }
+            const int more = __syncthreads_or(waiting ? 1 : 0);
+            int* t = cur; cur = nxt; nxt = t;
+            if (!more) break;
+        }
+        if (cur != w.flag) {
+            for (int i = tid; i < count; i += nt) w.flag[i] = cur[i];
         }
         count = compact_by_flag(w, count, false);
     }

@@ -278,7 +278,10 @@ __device__ inline void nelder_mead3(const StarLine* lines, int nl, double x0, do
 constexpr int SS_ROWS = 12;
 constexpr int SS_ROUND_ROWS = 4;       // rows per round after round 0 (row 0 alone: no speculative work for frames that pass at once)
 
-__global__ void __launch_bounds__(SS_THREADS)
+#ifndef EPID_SS_MIN_CTAS
+#define EPID_SS_MIN_CTAS 2      // resident CTAs per SM the row kernel is compiled for (3: 80 registers with ~0.9 KB of spill traffic; variants/)
+#endif
+__global__ void __launch_bounds__(SS_THREADS, EPID_SS_MIN_CTAS)
 k_star_rows(const StarConst* __restrict__ cc, const FrameRef* __restrict__ frames, const StarFrame* __restrict__ sf,
             const double* __restrict__ gauss_w, const int* __restrict__ gauss_off, double* __restrict__ prof_a,
             double* __restrict__ prof_b, double* __restrict__ prof_c, const epid_star_result* __restrict__ res, int row0,

@@ -30,6 +30,7 @@
 #include <cmath>
 
 #include "pf_common.cuh"
+#include "ccl.cuh"
 
 namespace epid {
 
@@ -561,16 +562,32 @@ k_wl_bb(const WlConst* __restrict__ cc, const uint16_t* __restrict__ base, const
         passes++;
         nreg = 0;                              // find_features returns the regions of the LAST threshold visited
         // -- measure.label(sample > cutoff, connectivity=1): union-find, roots = first pixel in raster order
-        for (int i = tid; i < npx; i += WL_THREADS) parent[i] = smp[i] > cutoff ? i : -1;
-        __syncthreads();
-        for (int i = tid; i < npx; i += WL_THREADS) {
-            if (parent[i] < 0) continue;
-            const int y = i / ww, x = i - y * ww;
-            if (x > 0 && parent[i - 1] >= 0) wl_union(parent, i, i - 1);
-            if (y > 0 && parent[i - ww] >= 0) wl_union(parent, i, i - ww);
+        // Every pixel starts at the first pixel of its horizontal run (a warp per row: ballot + bit scan, carried across the 32-pixel
+        // chunks), so only vertical merges remain, one per pair of overlapping runs (at the first pixel of the overlap); finds halve
+        // their paths.  Roots are still the smallest index of a component.
+        for (int y = wid; y < wh; y += WL_WARPS) {
+            int carry = -1;                    // run start (column) of the run that reaches the end of the previous chunk
+            for (int x0 = 0; x0 < ww; x0 += 32) {
+                const int x = x0 + lane;
+                const bool fg = x < ww && smp[y * ww + x] > cutoff;
+                const unsigned bal = __ballot_sync(0xffffffffu, fg);
+                int start = -1;
+                if (fg) {
+                    const unsigned zb = ~bal & ((1u << lane) - 1u);        // background pixels of the chunk to the left of this lane
+                    start = zb ? x0 + (32 - __clz(zb)) : (carry >= 0 ? carry : x0);
+                }
+                if (x < ww) parent[y * ww + x] = fg ? y * ww + start : -1;
+                carry = __shfl_sync(0xffffffffu, start, 31);
+            }
         }
         __syncthreads();
-        for (int i = tid; i < npx; i += WL_THREADS) if (parent[i] >= 0) parent[i] = wl_find(parent, i);
+        for (int i = tid; i < npx; i += WL_THREADS) {
+            if (i < ww || parent[i] < 0 || parent[i - ww] < 0) continue;
+            const int x = i % ww;
+            if (x == 0 || parent[i - 1] < 0 || parent[i - ww - 1] < 0) gl_union(parent, i, i - ww);
+        }
+        __syncthreads();
+        for (int i = tid; i < npx; i += WL_THREADS) if (parent[i] >= 0) parent[i] = gl_find(parent, i);
         __syncthreads();
         // -- component ids in label (raster) order: exclusive scan of the root flags
         if (tid == 0) s_i[0] = 0;
