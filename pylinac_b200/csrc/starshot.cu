@@ -750,8 +750,13 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
         EPID_CUDA(cudaMemsetAsync(d_best, 0x7f, sizeof(int) * (size_t)n, st));
         EPID_CUDA(cudaMemsetAsync(d_verdict, 0, sizeof(int) * (size_t)n * SS_ROWS, st));
         EPID_CUDA(cudaMemsetAsync(d_rows, 0, sizeof(epid_star_result) * (size_t)n * SS_ROWS, st));
-        for (int row0 = 0; row0 < SS_ROWS;) {
-            const int nrows = row0 == 0 ? 1 : (SS_ROWS - row0 < SS_ROUND_ROWS ? SS_ROWS - row0 : SS_ROUND_ROWS);
+        // rounds: the caller's pair alone (frames that pass at once cost one candidate), the first four radii together (a frame that
+        // needs the product usually fails a few whole rows), then two rows at a time: rows after the accepted one are wasted work
+        static const int kRound[] = {1, SS_ROUND_ROWS, 2, 2, 3};
+        int round = 0;
+        for (int row0 = 0; row0 < SS_ROWS; round++) {
+            int nrows = kRound[round < 5 ? round : 4];
+            if (nrows > SS_ROWS - row0) nrows = SS_ROWS - row0;
             k_star_rows<<<dim3(n, nrows), SS_THREADS, 0, st>>>(d_cst, d_rf, d_fr, d_gw, d_go, (double*)(base + o_pa), (double*)(base + o_pb),
                                                                (double*)(base + o_pc), d_res, row0, d_done, d_best, d_verdict, d_rows);
             k_star_pick<<<n, 128, 0, st>>>(row0, nrows, row0 + nrows >= SS_ROWS ? 1 : 0, d_verdict, d_rows, d_done, d_res);
