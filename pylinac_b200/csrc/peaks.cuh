@@ -224,9 +224,10 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
     // occurrence of the minimum) lets a walk skip every block that holds no higher sample -- <= 32 + n / 32 + 32 steps instead of a
     // walk across the profile (the dominant peaks), with the same minima and bases.  Longer profiles: per-lane walks in rounds,
     // finished warp-cooperatively.
-    if (n <= 32 * PK_MAXBLK) {
-        __shared__ double s_bmax[PK_MAXBLK], s_bmin[PK_MAXBLK];
-        __shared__ unsigned short s_bpos[PK_MAXBLK];       // first | last << 8: offsets of the block minimum
+    __shared__ double s_bmax[PK_MAXBLK], s_bmin[PK_MAXBLK];
+    __shared__ unsigned short s_bpos[PK_MAXBLK];           // first | last << 8: offsets of the block minimum
+    const bool have_tab = n <= 32 * PK_MAXBLK;
+    if (have_tab) {
         const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
         const int nblk = (n + 31) >> 5;
         __syncthreads();
@@ -375,24 +376,51 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
         }
     }
     __syncthreads();
-    // ---- 4/5. widths (computed before the prominence filter is applied; independent per peak)
-    for (int i = tid; i < count; i += nt) {
-        const int p = w.idx[i];
-        const double h = x[p] - w.prom[i] * a.rel_height;
-        int k = p;
-        const int imin = w.lbase[i], imax = w.rbase[i];
-        while (imin < k && h < x[k]) k--;
-        double l = (double)k;
-        if (x[k] < h) l += (h - x[k]) / (x[k + 1] - x[k]);
-        k = p;
-        while (k < imax && h < x[k]) k++;
-        double r = (double)k;
-        if (x[k] < h) r -= (h - x[k]) / (x[k - 1] - x[k]);
-        w.width_height[i] = h;
-        w.lip[i] = l;
-        w.rip[i] = r;
-        w.flag[i] = ((a.pmin < 0 || w.prom[i] >= a.pmin) && (a.wmin <= r - l)) ? 1 : 0;
-    }
+    // ---- 4/5. widths at rel_height (independent per peak).  The walk from the peak down to the evaluation height skips whole 32-sample
+    // blocks whose minimum is still above that height (same table as the prominences): the dominant peak of a field profile would
+    // otherwise walk thousands of samples in one thread.  When no minimum width is requested the widths cannot remove a peak, so they
+    // are evaluated after the selection below, for the survivors only.
+    auto widths = [&](int cnt, bool set_flags) {
+        for (int i = tid; i < cnt; i += nt) {
+            const int p = w.idx[i];
+            const double h = x[p] - w.prom[i] * a.rel_height;
+            const int imin = w.lbase[i], imax = w.rbase[i];
+            int k = p;
+            if (have_tab) {
+                const int lim = max(imin, (p >> 5) << 5);
+                while (lim < k && h < x[k]) k--;
+                if (imin < k && h < x[k]) {                       // at the first sample of the peak's block, still above h
+                    int b = (p >> 5) - 1;
+                    while (b >= 0 && s_bmin[b] > h && (b << 5) > imin) b--;
+                    k = ((b + 1) << 5) - 1;
+                }
+            }
+            while (imin < k && h < x[k]) k--;
+            double l = (double)k;
+            if (x[k] < h) l += (h - x[k]) / (x[k + 1] - x[k]);
+            k = p;
+            if (have_tab) {
+                const int lim = min(imax, ((p >> 5) << 5) + 31);
+                while (k < lim && h < x[k]) k++;
+                if (k < imax && h < x[k]) {                       // at the last sample of the peak's block, still above h
+                    const int nblk = (n + 31) >> 5;
+                    int b = (p >> 5) + 1;
+                    while (b < nblk && s_bmin[b] > h && (b << 5) + 31 < imax) b++;
+                    k = b << 5;
+                }
+            }
+            while (k < imax && h < x[k]) k++;
+            double r = (double)k;
+            if (x[k] < h) r -= (h - x[k]) / (x[k - 1] - x[k]);
+            w.width_height[i] = h;
+            w.lip[i] = l;
+            w.rip[i] = r;
+            if (set_flags) w.flag[i] = ((a.pmin < 0 || w.prom[i] >= a.pmin) && (a.wmin <= r - l)) ? 1 : 0;
+        }
+    };
+    const bool widths_first = a.wmin > 0.0;
+    if (widths_first) widths(count, true);
+    else for (int i = tid; i < count; i += nt) w.flag[i] = (a.pmin < 0 || w.prom[i] >= a.pmin) ? 1 : 0;
     count = compact_by_flag(w, count, true);
     if (count == 0) return 0;
 
@@ -441,6 +469,10 @@ __device__ inline int block_find_peaks(const double* __restrict__ x, int n, cons
         block_bitonic_sort(w.skey, w.sidx, m);
         for (int i = tid; i < a.max_number; i += nt) w.flag[w.sidx[count - 1 - i]] = 1;
         count = compact_by_flag(w, count, true);
+    }
+    if (!widths_first) {
+        widths(count, false);
+        __syncthreads();
     }
     return count;
 }
