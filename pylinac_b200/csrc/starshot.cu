@@ -177,13 +177,20 @@ __device__ __forceinline__ double line_distance(const StarLine& l, double px, do
     return num / den;
 }
 
+// max over the lines of the distance to p, evaluated by a whole warp: lane l takes lines l, l + 32, ...; the maximum of the same
+// distances as the sequential loop (max is exact and order independent), every lane returns it, so the optimiser below runs
+// redundantly but in lock step on all 32 lanes and its objective costs one line instead of nl lines per call
 __device__ inline double wobble_objective(const StarLine* lines, int nl, const double* p) {
-    double m = line_distance(lines[0], p[0], p[1]);
-    for (int i = 1; i < nl; i++) m = fmax(m, line_distance(lines[i], p[0], p[1]));
+    const int lane = threadIdx.x & 31;
+    double m = -INFINITY;
+    for (int i = lane; i < nl; i += 32) m = fmax(m, line_distance(lines[i], p[0], p[1]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     return m;
 }
 
-// scipy.optimize._optimize._minimize_neldermead, N = 3 (x, y and the inert z of Point.as_array()), default options + fatol
+// scipy.optimize._optimize._minimize_neldermead, N = 3 (x, y and the inert z of Point.as_array()), default options + fatol.
+// Called by all 32 lanes of one warp (see wobble_objective).
 __device__ inline void nelder_mead3(const StarLine* lines, int nl, double x0, double y0, double fatol, double* xout, double* fout) {
     constexpr int N = 3;
     const double xatol = 1e-4;
@@ -487,74 +494,85 @@ k_star_rows(const StarConst* __restrict__ cc, const FrameRef* __restrict__ frame
             __syncthreads();
             if (npk < 0 || npk > SS_MAX_PEAKS) { status = EPID_STAR_CAPACITY; npk = 0; }
         }
-        // ---- lines, wobble, acceptance (thread 0; a handful of scalar operations per line)
-        if (tid == 0) {
+        // ---- lines, wobble, acceptance (warp 0: lane 0 does the scalar bookkeeping, the Nelder-Mead objective uses all lanes)
+        if (wid == 0) {
             int verdict = 0;            // 0: next candidate, 1: accepted, 2: hard failure (status)
             int fail = status;
-            if (status == EPID_STAR_OK) {
-                if (npk < 6 || (npk & 1)) {
-                    if (!c.p.recursive) { verdict = 2; fail = EPID_STAR_NO_LINES; }
+            int nl = 0, do_nm = 0;
+            if (lane == 0) {
+                if (status == EPID_STAR_OK) {
+                    if (npk < 6 || (npk & 1)) {
+                        if (!c.p.recursive) { verdict = 2; fail = EPID_STAR_NO_LINES; }
+                    } else {
+                        double px[SS_MAX_PEAKS], py[SS_MAX_PEAKS];
+                        for (int k = 0; k < npk; k++) {
+                            int idx;
+                            if (c.p.fwhm) idx = (int)rint(s_lip[k] + (s_rip[k] - s_lip[k]) / 2.0);      // int(round(.)), half to even
+                            else idx = s_idx[k];
+                            R.peak_idx[k] = idx;
+                            int j = idx + roll;                                                         // position before the roll
+                            if (j >= n) j -= n;
+                            const double rad = (double)(n - 1 - j) * interval;
+                            px[k] = cos(rad) * rpx + fx;
+                            py[k] = sin(rad) * rpx + fy;
+                            R.peak_x[k] = px[k];
+                            R.peak_y[k] = py[k];
+                        }
+                        nl = npk / 2;
+                        bool near_lines = true;
+                        for (int k = 0; k < nl; k++) {
+                            s_lines[k].x1 = px[k]; s_lines[k].y1 = py[k];
+                            s_lines[k].x2 = px[k + nl]; s_lines[k].y2 = py[k + nl];
+                            if (line_distance(s_lines[k], fx, fy) > 10 * dpmm) near_lines = false;    // LineManager raises ValueError
+                        }
+                        do_nm = near_lines ? 1 : 0;
+                    }
                 } else {
-                    double px[SS_MAX_PEAKS], py[SS_MAX_PEAKS];
-                    for (int k = 0; k < npk; k++) {
-                        int idx;
-                        if (c.p.fwhm) idx = (int)rint(s_lip[k] + (s_rip[k] - s_lip[k]) / 2.0);      // int(round(.)), half to even
-                        else idx = s_idx[k];
-                        R.peak_idx[k] = idx;
-                        int j = idx + roll;                                                         // position before the roll
-                        if (j >= n) j -= n;
-                        const double rad = (double)(n - 1 - j) * interval;
-                        px[k] = cos(rad) * rpx + fx;
-                        py[k] = sin(rad) * rpx + fy;
-                        R.peak_x[k] = px[k];
-                        R.peak_y[k] = py[k];
-                    }
-                    const int nl = npk / 2;
-                    bool near_lines = true;
-                    for (int k = 0; k < nl; k++) {
-                        s_lines[k].x1 = px[k]; s_lines[k].y1 = py[k];
-                        s_lines[k].x2 = px[k + nl]; s_lines[k].y2 = py[k + nl];
-                        if (line_distance(s_lines[k], fx, fy) > 10 * dpmm) near_lines = false;    // LineManager raises ValueError
-                    }
-                    if (near_lines) {
-                        double xo[2], fo;
-                        nelder_mead3(s_lines, nl, fx, fy, 0.001, xo, &fo);
-                        const double radius_mm = fo / dpmm;
-                        // Point.distance_to (core/geometry.py:118-132): sqrt(dx^2 + dy^2 + dz^2)
-                        const double ddx = xo[0] - fx, ddy = xo[1] - fy;
-                        const bool near_center = sqrt(ddx * ddx + ddy * ddy + 0.0) < 10 * dpmm;
-                        if ((radius_mm * 2 < c.p.max_wobble_diameter && near_center) || !c.p.recursive) {
-                            verdict = 1;
-                            R.n_peaks = npk;
-                            R.n_lines = nl;
-                            R.iterations = iterations;
-                            R.radius_px = rpx;
-                            R.profile_len = n;
-                            R.wobble_x = xo[0];
-                            R.wobble_y = xo[1];
-                            R.wobble_radius_px = fo;
-                            R.wobble_radius_mm = radius_mm;
-                            R.passed = radius_mm * 2 < c.p.tolerance ? 1 : 0;
-                            for (int k = 0; k < nl; k++) {     // calculate_angles (starshot.py:817-834)
-                                const double m = (s_lines[k].y1 - s_lines[k].y2) / (s_lines[k].x1 - s_lines[k].x2);
-                                double phi = atan(m) * (180.0 / PI) - 90;
-                                if (phi > 90) phi -= 180;
-                                else if (phi <= -90) phi += 180;
-                                R.angles[k] = phi;
-                            }
+                    verdict = 2;
+                }
+            }
+            do_nm = __shfl_sync(0xffffffffu, do_nm, 0);
+            nl = __shfl_sync(0xffffffffu, nl, 0);
+            __syncwarp();
+            if (do_nm) {
+                double xo[2], fo;
+                nelder_mead3(s_lines, nl, fx, fy, 0.001, xo, &fo);
+                if (lane == 0) {
+                    const double radius_mm = fo / dpmm;
+                    // Point.distance_to (core/geometry.py:118-132): sqrt(dx^2 + dy^2 + dz^2)
+                    const double ddx = xo[0] - fx, ddy = xo[1] - fy;
+                    const bool near_center = sqrt(ddx * ddx + ddy * ddy + 0.0) < 10 * dpmm;
+                    if ((radius_mm * 2 < c.p.max_wobble_diameter && near_center) || !c.p.recursive) {
+                        verdict = 1;
+                        R.n_peaks = npk;
+                        R.n_lines = nl;
+                        R.iterations = iterations;
+                        R.radius_px = rpx;
+                        R.profile_len = n;
+                        R.wobble_x = xo[0];
+                        R.wobble_y = xo[1];
+                        R.wobble_radius_px = fo;
+                        R.wobble_radius_mm = radius_mm;
+                        R.passed = radius_mm * 2 < c.p.tolerance ? 1 : 0;
+                        for (int k = 0; k < nl; k++) {     // calculate_angles (starshot.py:817-834)
+                            const double m = (s_lines[k].y1 - s_lines[k].y2) / (s_lines[k].x1 - s_lines[k].x2);
+                            double phi = atan(m) * (180.0 / PI) - 90;
+                            if (phi > 90) phi -= 180;
+                            else if (phi <= -90) phi += 180;
+                            R.angles[k] = phi;
                         }
                     }
                 }
-            } else {
-                verdict = 2;
             }
-            if (verdict == 2) { R.status = fail; R.iterations = iterations; }
-            if (verdict != 0) {
-                row_verdict[fi * SS_ROWS + row] = verdict;
-                __threadfence();
-                atomicMin(&best[fi], order);
+            if (lane == 0) {
+                if (verdict == 2) { R.status = fail; R.iterations = iterations; }
+                if (verdict != 0) {
+                    row_verdict[fi * SS_ROWS + row] = verdict;
+                    __threadfence();
+                    atomicMin(&best[fi], order);
+                }
+                s_ctl[2] = verdict;
             }
-            s_ctl[2] = verdict;
         }
         __syncthreads();
         const int verdict = s_ctl[2];

@@ -232,6 +232,61 @@ __device__ inline double vm_lerp_at(const double* v, int n, double x) {      // 
     return v[i] * (1.0 - u) + v[i + 1] * u;
 }
 
+// Order statistics k and k2 (= k or k + 1) of n values that are all >= +0 (no NaN): 8-bit radix select on the IEEE bit patterns (8 passes of
+// a 256-bin shared-memory histogram over the values that share the prefix found so far), then the successor: the same value when it
+// occurs again, else the smallest larger value.  Results in red[34], red[35].  O(8 n) instead of the n^2 / threads of rank counting.
+__device__ void vm_order_stat_pair(const double* v, int n, int k, int k2, double* red) {
+    __shared__ unsigned s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_k, s_dup;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (tid == 0) { s_prefix = 0; s_k = k; s_dup = 0; }
+    for (int pass = 7; pass >= 0; pass--) {
+        const int shift = pass * 8;
+        for (int b = tid; b < 256; b += nt) s_hist[b] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int j = tid; j < n; j += nt) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[j]);
+            if (pass == 7 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&s_hist[(unsigned)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            unsigned c[8], t = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) { c[e] = s_hist[lane * 8 + e]; t += c[e]; }
+            unsigned inc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            const unsigned excl = inc - t;
+            const unsigned kk = (unsigned)s_k;
+            __syncwarp();
+            if (kk >= excl && kk < inc) {
+                unsigned acc = excl;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (kk >= acc && kk < acc + c[e]) {
+                        s_prefix = prefix | ((unsigned long long)(lane * 8 + e) << shift);
+                        s_k = (int)(kk - acc);
+                        if (pass == 0) s_dup = (kk - acc + 1u < c[e]) ? 1 : 0;      // the value occurs again after rank k
+                    }
+                    acc += c[e];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const double sa = __longlong_as_double((long long)s_prefix);
+    double sb = sa;
+    if (k2 != k && !s_dup) {
+        double m = VM_INF;
+        for (int j = tid; j < n; j += nt) { const double x = v[j]; if (x > sa) m = fmin(m, x); }
+        sb = blk_reduce<OpMin>(m, red);
+    }
+    __syncthreads();
+    if (tid == 0) { red[34] = sa; red[35] = sb; }
+}
+
 // the profile of VMATLinearBase._roi_profiles for one image (vmat.py:766-783) + field_values() statistics (:741-742, 759)
 __device__ void vm_roi_profile(const unsigned long long* colsum, int H, int W, const VmMap& m, VmWork& wk, double* red, VmProfOut* out) {
     double* v = wk.vals;
@@ -275,32 +330,42 @@ __device__ void vm_roi_profile(const unsigned long long* colsum, int H, int W, c
     const double pf = floor(vi);
     const int ip = (int)pf, in = min(ip + 1, W - 1);
     const double g = vi - pf;
-    if (tid == 0) { red[34] = NAN; red[35] = NAN; }      // a profile with nan has no such ranks: numpy's percentile is nan as well
-    __syncthreads();
-    if (W <= 8 * nt) {
-        // up to 8 samples per thread in registers, ONE pass over the profile (broadcast loads) ranks all of them
-        double xi[8];
-        int ii[8], rank[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) { ii[m] = tid + m * nt; xi[m] = ii[m] < W ? v[ii[m]] : 0.0; rank[m] = 0; }
-        for (int j = 0; j < W; j++) {
-            const double xj = v[j];
-#pragma unroll
-            for (int m = 0; m < 8; m++) rank[m] += (xj < xi[m] || (xj == xi[m] && j < ii[m])) ? 1 : 0;
-        }
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            if (ii[m] < W && rank[m] == ip) red[34] = xi[m];
-            if (ii[m] < W && rank[m] == in) red[35] = xi[m];
-        }
+    // NaN anywhere (a flat / failed image): the rank-counting path below keeps its behaviour; otherwise every value is >= +0 after the
+    // grounding above, IEEE bit patterns order like the values, and the two order statistics come from an 8-bit radix select
+    int has_nan = 0;
+    for (int j = tid; j < W; j += nt) has_nan |= (v[j] != v[j]) ? 1 : 0;
+    has_nan = __syncthreads_or(has_nan);
+    if (!has_nan) {
+        vm_order_stat_pair(v, W, ip, in, red);
     } else {
-        for (int i = tid; i < W; i += nt) {
-            const double xi = v[i];
-            int rank = 0;
-            for (int j = 0; j < W; j++) { const double xj = v[j]; rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
-            if (rank == ip) red[34] = xi;
-            if (rank == in) red[35] = xi;
+        if (tid == 0) { red[34] = NAN; red[35] = NAN; }      // a profile with nan has no such ranks: numpy's percentile is nan as well
+        __syncthreads();
+        if (W <= 8 * nt) {
+            // up to 8 samples per thread in registers, ONE pass over the profile (broadcast loads) ranks all of them
+            double xi[8];
+            int ii[8], rank[8];
+    #pragma unroll
+            for (int m = 0; m < 8; m++) { ii[m] = tid + m * nt; xi[m] = ii[m] < W ? v[ii[m]] : 0.0; rank[m] = 0; }
+            for (int j = 0; j < W; j++) {
+                const double xj = v[j];
+    #pragma unroll
+                for (int m = 0; m < 8; m++) rank[m] += (xj < xi[m] || (xj == xi[m] && j < ii[m])) ? 1 : 0;
+            }
+    #pragma unroll
+            for (int m = 0; m < 8; m++) {
+                if (ii[m] < W && rank[m] == ip) red[34] = xi[m];
+                if (ii[m] < W && rank[m] == in) red[35] = xi[m];
+            }
+        } else {
+            for (int i = tid; i < W; i += nt) {
+                const double xi = v[i];
+                int rank = 0;
+                for (int j = 0; j < W; j++) { const double xj = v[j]; rank += (xj < xi || (xj == xi && j < i)) ? 1 : 0; }
+                if (rank == ip) red[34] = xi;
+                if (rank == in) red[35] = xi;
+            }
         }
+        __syncthreads();
     }
     __syncthreads();
     const double sa = red[34], sb = red[35];
