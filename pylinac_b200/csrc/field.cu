@@ -675,7 +675,10 @@ k_field_strips(const FieldConst* __restrict__ cc, const FrameRef* __restrict__ f
     }
 }
 
-__global__ void __launch_bounds__(FA_THREADS)
+#ifndef EPID_FA_MIN_CTAS
+#define EPID_FA_MIN_CTAS 2      // resident CTAs per SM k_field_profile is compiled for (3: 80 registers, ~0.9 KB of spill traffic; variants/)
+#endif
+__global__ void __launch_bounds__(FA_THREADS, EPID_FA_MIN_CTAS)
 k_field_profile(const FieldConst* __restrict__ cc, const double* __restrict__ gw_h, const double* __restrict__ gw_v,
                 double* __restrict__ work, epid_field_result* __restrict__ res) {
     __shared__ int s_small[FA_THREADS + 8];

@@ -350,14 +350,25 @@ k_star_rows(const StarConst* __restrict__ cc, const FrameRef* __restrict__ frame
         }
         if (n > 0) {
             // ---- _profile: sum over 20 radii of nearest-neighbour samples / 20
+            // The 20 pixel reads of a sample are independent, but behind the bounds test of map_coordinates they were issued one
+            // DRAM round trip after the other (the batch does not fit L2): the addresses are clamped instead, all 20 loads are issued
+            // back to back, and the test only selects between the pixel and the constant 0 afterwards (same values, same order of sums).
             for (int i = tid; i < n; i += SS_THREADS) {
                 const double rad = (double)(n - 1 - i) * interval;   // arange(...)[::-1]
                 const double cs = cos(rad), sn = sin(rad);
-                double acc = 0.0;
+                uint32_t raw[20];
+                bool inside[20];
+#pragma unroll
                 for (int k = 0; k < 20; k++) {
                     const double rk = k == 19 ? r_hi : (double)k * rstep + r_lo;
-                    acc += star_px(frf, H, W, sn * rk + fy, cs * rk + fx, f.mn, f.mx, f.flip);
+                    const double yc = sn * rk + fy, xc = cs * rk + fx;
+                    inside[k] = yc >= 0.0 && yc <= (double)(H - 1) && xc >= 0.0 && xc <= (double)(W - 1);
+                    const int iy = inside[k] ? (int)floor(yc + 0.5) : 0, ix = inside[k] ? (int)floor(xc + 0.5) : 0;
+                    raw[k] = __ldg(frf.origin + (size_t)iy * frf.pitch + ix);
                 }
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 20; k++) acc += inside[k] ? (double)(f.flip ? f.mx - raw[k] : raw[k] - f.mn) : 0.0;
                 pa[i] = acc / 20.0;
             }
             __syncthreads();
