@@ -361,7 +361,10 @@ def main():
     params = pf.make_params(DPMM, FRAME_SHAPE)
     pinned = nat.pinned_empty(frames_np.shape, np.uint16)
     pinned[...] = frames_np
-    pageable = frames_np                            # an ordinary numpy array: what a drop-in user passes
+    # an ordinary numpy array, what a drop-in user passes -- allocated (first touch) AFTER the rank bound itself to the GPU's NUMA node,
+    # like the page-locked buffer above; the generator's array was assembled before the binding and may sit on the other socket
+    pageable = np.array(pinned, copy=True)
+    del frames_np
     batch = nat.Batch.upload(ctx, pinned)
 
     if world > 1:
@@ -501,7 +504,8 @@ def main():
                                                  "the end-to-end step; growth with the rank count = host-side contention, not NVLink"}},
         "e2e_pageable": {"value": world * n / (e2e_page_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_page_ms, "steps": psteps,
                          "frac_of_pinned": (world * n / (e2e_page_ms * 1e-3)) / (frames_total / (e2e_ms * 1e-3)),
-                         "api": "the same call on an ordinary (pageable) numpy array: chunks are staged through a page-locked ring"},
+                         "api": "the same call on an ordinary (pageable) numpy array allocated on the GPU's NUMA node: chunks are staged through a page-locked "
+                                "ring by a pool of copy threads (non-temporal stores)"},
         "gpu_launches": int(launches_timed),
         "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
                      "traffic": traffic, "peak_source": peak_src,

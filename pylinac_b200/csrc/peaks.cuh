@@ -14,7 +14,10 @@
 namespace epid {
 
 constexpr int PK_WALK = 64;      // samples per side a lane walks on its own per round (block_find_peaks, prominences)
-constexpr int PK_MAXBLK = 512;   // 32-sample blocks of the prominence skip table (profiles of up to 16384 samples)
+#ifndef EPID_PK_MAXBLK
+#define EPID_PK_MAXBLK 512
+#endif
+constexpr int PK_MAXBLK = EPID_PK_MAXBLK;   // 32-sample blocks of the prominence skip table (profiles of up to 16384 samples)
 constexpr int PK_RANK_MAX = 768; // distance stage: order by rank counting up to this many candidates, bitonic network beyond
 constexpr int PK_COOP = 32;      // unfinished walks in a warp after a round that the warp finishes cooperatively (32 = all: measured best on the field profiles)
 

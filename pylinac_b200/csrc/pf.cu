@@ -26,6 +26,9 @@
 #include <mutex>
 #include <thread>
 
+// PicketFence profiles have ~1000 samples: find_peaks' 32-sample skip table (peaks.cuh) buys nothing here, and its 9 KB of static shared
+// memory cost k_pf_tail a resident CTA per SM (measured: 103 us with the table, 77 us without; profiles/r2m_summary.md)
+#define EPID_PK_MAXBLK 2
 #include "pf_common.cuh"
 
 namespace epid {
@@ -914,7 +917,10 @@ private:
         if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
             long long quota = 0, period = 0;
             if (fscanf(f, "%lld %lld", &quota, &period) == 2 && quota > 0 && period > 0) {
-                const int q = (int)(quota / period) - 2;
+                // ranks of one node (torchrun: LOCAL_WORLD_SIZE) share the quota
+                int lw = 1;
+                if (const char* e = getenv("LOCAL_WORLD_SIZE")) lw = atoi(e) > 0 ? atoi(e) : 1;
+                const int q = ((int)(quota / period) - 2) / lw;
                 if (T > q) T = q < 2 ? 2 : q;
             }
             fclose(f);

@@ -30,6 +30,9 @@
 // every lane owns up to 4 aligned 8-pixel vectors of the row, so the column sums stay in registers for a whole work item
 // (a block of rows of one frame) and are reduced across warps through shared memory once per item.  All per-pixel work is
 // packed u16x2 arithmetic (VIMNMX.U16x2, IDP.2A), branch free: ~12 integer instructions per pixel.
+// PicketFence profiles have ~1000 samples: find_peaks' 32-sample skip table (peaks.cuh) buys nothing here, and its 9 KB of static shared
+// memory cost k_pf_tail a resident CTA per SM (measured: 103 us with the table, 77 us without; profiles/r2m_summary.md)
+#define EPID_PK_MAXBLK 2
 #include "pf_common.cuh"
 #include "tma.cuh"
 
