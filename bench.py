@@ -118,6 +118,57 @@ def generate_frames(n: int, start: int, cores: int) -> np.ndarray:
     return np.stack(frames)
 
 
+def _cpu_baseline_job(sample: int, cores: int):
+    ref = CpuReference(sample, cores, start=2000)
+    fps, per = ref.step()
+    fps2, per2 = ref.step()
+    ref.close()
+    return max(fps, fps2), min(per, per2)
+
+
+def _isolated_entry(conn, func, args, chunked):
+    try:
+        out = func(*args)
+        if chunked:      # a large ndarray: 64 leading entries per message (a pipe message is limited to 2 GiB)
+            conn.send(("shape", (out.shape, str(out.dtype))))
+            for i in range(0, out.shape[0], 64):
+                conn.send(("chunk", out[i:i + 64]))
+            conn.send(("ok", None))
+        else:
+            conn.send(("ok", out))
+    except BaseException as e:       # noqa: BLE001 -- reported to the parent
+        conn.send(("err", repr(e)))
+    finally:
+        conn.close()
+
+
+def _isolated(func, *args, chunked: bool = False):
+    """Run `func` in a freshly spawned interpreter and return its result.  The CPU baseline and the frame generator fork up to 128
+    worker processes; measured on the B200 hosts (profiles/r2m_summary.md), a process that has done that stages pageable frames 1.5 x
+    slower afterwards (44.8 vs 29.9 ms per 512-frame step), so the GPU process of this benchmark never forks a pool itself."""
+    ctx = mp.get_context("spawn")
+    parent, child = ctx.Pipe(duplex=False)
+    proc = ctx.Process(target=_isolated_entry, args=(child, func, args, chunked), daemon=False)
+    proc.start()
+    child.close()
+    out, filled = None, 0
+    while True:
+        kind, val = parent.recv()
+        if kind == "shape":
+            out = np.empty(val[0], np.dtype(val[1]))
+        elif kind == "chunk":
+            out[filled:filled + len(val)] = val
+            filled += len(val)
+        elif kind == "ok":
+            result = out if chunked else val
+            break
+        else:
+            proc.join()
+            raise RuntimeError(f"{func.__name__} failed in the isolated process: {val}")
+    proc.join()
+    return result
+
+
 def _gen_module_frames(kind_i):
     from oracle import synth
 
@@ -337,16 +388,12 @@ def main():
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = cores
-        ref = CpuReference(sample, cores, start=2000)
-        fps, per = ref.step()
-        fps2, per2 = ref.step()
-        ref.close()
-        fps, per = max(fps, fps2), min(per, per2)
+        fps, per = _isolated(_cpu_baseline_job, sample, cores)
         cpu_base = {"value": fps, "unit": "frames/s", "cores": cores, "cgroup_cpu_quota": cgroup_cpu_quota(), "kind": "port",
                     "sample": f"{sample} of the batch's frames on {cores} processes, wall-clock throughput of the analysis (best of 2 "
                               f"passes); {per * 1e3:.0f} ms per frame inside a worker"}
     gen_cores = max(1, cores // world)
-    frames_np = generate_frames(n, start=rank * n, cores=gen_cores)
+    frames_np = _isolated(generate_frames, n, rank * n, gen_cores, chunked=True)
 
     from pylinac_b200 import _native as nat
     from pylinac_b200 import picketfence as pf

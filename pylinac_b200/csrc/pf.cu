@@ -25,6 +25,8 @@
 #include <cstdlib>
 #include <mutex>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
 
 // PicketFence profiles have ~1000 samples: find_peaks' 32-sample skip table (peaks.cuh) buys nothing here, and its 9 KB of static shared
 // memory cost k_pf_tail a resident CTA per SM (measured: 103 us with the table, 77 us without; profiles/r2m_summary.md)
@@ -935,6 +937,16 @@ private:
         for (auto& t : workers_) t.join();
     }
     void run(int i, int T) {
+        // The caller may have pinned itself to the GPU's NUMA node (parallel.bind_host_to_gpu) for its page-locked buffers; the copy
+        // threads inherit that mask.  EPID_COPY_UNBIND=1 lets them run on every CPU the cgroup allows.
+        if (const char* e = getenv("EPID_COPY_UNBIND")) {
+            if (atoi(e)) {
+                cpu_set_t all;
+                CPU_ZERO(&all);
+                for (int c = 0; c < CPU_SETSIZE; c++) CPU_SET(c, &all);
+                pthread_setaffinity_np(pthread_self(), sizeof(all), &all);
+            }
+        }
         unsigned long long seen = 0;
         for (;;) {
             char* d; const char* s; size_t b;
