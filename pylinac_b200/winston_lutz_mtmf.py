@@ -138,8 +138,8 @@ def align_points(measured_points: Sequence[Point], ideal_points: Sequence[Point]
     """winston_lutz.py:3608-3660: rigid alignment (Kabsch) of the measured onto the ideal points -> (translation, yaw, pitch, roll).
     The reference reads the angles with scipy's Rotation.as_euler (extrinsic, roll = y, pitch = x, yaw = z); for the default order
     R = Rz(yaw) Rx(pitch) Ry(roll), whose angles are read off the matrix directly."""
-    if [a.strip() for a in axes_order.split(",")] != ["roll", "pitch", "yaw"]:
-        raise NotImplementedError("only the reference's default axes order 'roll,pitch,yaw' is implemented")
+    order = [a.strip() for a in axes_order.split(",")]
+    euler = "".join({"pitch": "x", "yaw": "z", "roll": "y"}[a] for a in order)        # conventional_to_euler_notation (:3592-3605)
     measured = np.array([[p.x, p.y, p.z] for p in measured_points], dtype=float)
     ideal = np.array([[p.x, p.y, p.z] for p in ideal_points], dtype=float)
     mc, ic = np.mean(measured, axis=0), np.mean(ideal, axis=0)
@@ -149,10 +149,17 @@ def align_points(measured_points: Sequence[Point], ideal_points: Sequence[Point]
     if np.linalg.det(R) < 0:
         Vt[2, :] *= -1
         R = Vt.T @ U.T
-    # R = Rz(c) Rx(b) Ry(a):  R[2] = (-cos b sin a, sin b, cos b cos a),  R[0][1] = -sin c cos b,  R[1][1] = cos c cos b
-    pitch = math.degrees(math.asin(max(-1.0, min(1.0, R[2, 1]))))
-    roll = math.degrees(math.atan2(-R[2, 0], R[2, 2]))
-    yaw = math.degrees(math.atan2(-R[0, 1], R[1, 1]))
+    if order == ["roll", "pitch", "yaw"]:
+        # R = Rz(c) Rx(b) Ry(a):  R[2] = (-cos b sin a, sin b, cos b cos a),  R[0][1] = -sin c cos b,  R[1][1] = cos c cos b
+        pitch = math.degrees(math.asin(max(-1.0, min(1.0, R[2, 1]))))
+        roll = math.degrees(math.atan2(-R[2, 0], R[2, 2]))
+        yaw = math.degrees(math.atan2(-R[0, 1], R[1, 1]))
+    else:
+        # any other order: exactly the reference's call, including its positional unpacking of the three angles (:3656-3658);
+        # scalar host work on a 3 x 3 matrix, like the set-level scipy.optimize call of WinstonLutz
+        from scipy.spatial.transform import Rotation
+
+        roll, pitch, yaw = (float(v) for v in Rotation.from_matrix(R).as_euler(euler, degrees=True))
     translation = ic - R @ mc
     return Vector(*translation), yaw, pitch, roll
 

@@ -61,3 +61,38 @@ def test_align_points_recovers_a_known_rigid_motion():
     t, y, p, r = mt.align_points([Point(*q) for q in pts], [Point(*q) for q in moved])
     np.testing.assert_allclose([y, p, r], [yaw, pitch, roll], atol=1e-9)
     np.testing.assert_allclose([t.x, t.y, t.z], [0.4, -1.1, 2.0], atol=1e-9)
+
+
+def test_align_points_other_axes_orders_follow_the_reference_call():
+    """winston_lutz.py:3592-3605, 3655-3658: any order of 'roll', 'pitch', 'yaw' is turned into an extrinsic euler string and the three
+    angles of Rotation.as_euler are unpacked POSITIONALLY as (roll, pitch, yaw).  The default order also goes through scipy here and
+    must equal the closed form the module uses for it; the unmodified reference is called when it is importable."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(9)
+    pts = rng.uniform(-50, 50, size=(7, 3))
+    R = Rotation.from_euler("yxz", [2.2, -0.7, 1.5], degrees=True).as_matrix()
+    moved = pts @ R.T + np.array([0.4, -1.1, 2.0])
+    mp_, ip_ = [Point(*q) for q in pts], [Point(*q) for q in moved]
+    t0, y0, p0, r0 = mt.align_points(mp_, ip_)
+    np.testing.assert_allclose([r0, p0, y0], [2.2, -0.7, 1.5], atol=1e-9)
+    for order, euler in (("yaw,pitch,roll", "zxy"), ("pitch,roll,yaw", "xyz"), ("roll,yaw,pitch", "yzx")):
+        t, y, p, r = mt.align_points(mp_, ip_, axes_order=order)
+        expect = Rotation.from_matrix(R).as_euler(euler, degrees=True)
+        np.testing.assert_allclose([r, p, y], expect, atol=1e-9, err_msg=order)
+        np.testing.assert_allclose([t.x, t.y, t.z], [t0.x, t0.y, t0.z], atol=1e-12)
+        # the three angles, applied in that extrinsic order, reproduce the rigid motion
+        np.testing.assert_allclose(Rotation.from_euler(euler, [r, p, y], degrees=True).as_matrix(), R, atol=1e-12)
+    with pytest.raises(KeyError):
+        mt.align_points(mp_, ip_, axes_order="roll,pitch,spin")
+    try:
+        from oracle import refstub
+        ref = refstub.import_reference()
+        import pylinac.winston_lutz as rwl
+    except Exception:
+        return
+    RP = rwl.Point
+    for order in ("roll,pitch,yaw", "yaw,pitch,roll", "pitch,roll,yaw"):
+        tr, yr, pr, rr = rwl.align_points([RP(*q) for q in pts], [RP(*q) for q in moved], axes_order=order)
+        t, y, p, r = mt.align_points(mp_, ip_, axes_order=order)
+        np.testing.assert_allclose([y, p, r, t.x, t.y, t.z], [yr, pr, rr, tr.x, tr.y, tr.z], atol=1e-9, err_msg=order)
