@@ -791,7 +791,9 @@ extern "C" int32_t epid_starshot_analyze(epid_ctx* ctx, const epid_batch* frames
             k_star_pick<<<n, 128, 0, st>>>(row0, nrows, row0 + nrows >= SS_ROWS ? 1 : 0, d_verdict, d_rows, d_done, d_res);
             ctx->launches += 2;
             row0 += nrows;
-            if (!p->recursive) break;      // analyze(recursive=False): the first candidate always yields a verdict
+            // analyze(recursive=False) usually settles in round 0 (first candidate accepted or NO_LINES); a LineManager ValueError (a line
+            // too far from the start point) still moves on to the next candidate in the reference (starshot.py:346-376), so all rounds are
+            // enqueued either way -- CTAs of settled frames exit at once
         }
     }
     EPID_CUDA(cudaGetLastError());
