@@ -522,6 +522,7 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
         self._is_analyzed = False
         self.machine_scale = MachineScale.IEC61217
         self._minimized = {}
+        self._virtual_shift = False
 
     def analyze(self, bb_size_mm: float = 5, machine_scale: MachineScale = MachineScale.IEC61217, low_density_bb: bool = False,
                 open_field: bool = False, apply_virtual_shift: bool = False, snap_tolerance: float = 3, gantry_reference: float = 0,
@@ -680,6 +681,39 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
         """winston_lutz.py:1794-1810 -- as in the reference this aggregates ``epid_to_bb_distances()`` (EPID centre to BB,
         winston_lutz.py:838-843), not the per-image CAX-to-EPID distance."""
         return self._metric([im.bb_epid_distance_mm for im in self.images], metric)
+
+    def results(self, as_list: bool = False):
+        """winston_lutz.py:2501-2546: the text summary of an analysed set."""
+        if not self._is_analyzed:
+            raise ValueError("The set is not analyzed. Use .analyze() first.")
+        num_gantry_imgs = self._get_images(axis=(Axis.GANTRY, Axis.REFERENCE))[0]
+        num_gantry_coll_imgs = self._get_images(axis=(Axis.GANTRY, Axis.COLLIMATOR, Axis.GB_COMBO, Axis.REFERENCE))[0]
+        num_coll_imgs = self._get_images(axis=(Axis.COLLIMATOR, Axis.REFERENCE))[0]
+        num_couch_imgs = self._get_images(axis=(Axis.COUCH, Axis.REFERENCE))[0]
+        num_imgs = len(self.images)
+        result = [
+            "Winston-Lutz Analysis",
+            "=================================",
+            f"Number of images: {num_imgs}",
+            f"Maximum 2D CAX->BB distance: {self.cax2bb_distance('max'):.2f}mm",
+            f"Median 2D CAX->BB distance: {self.cax2bb_distance('median'):.2f}mm",
+            f"Mean 2D CAX->BB distance: {self.cax2bb_distance('mean'):.2f}mm",
+        ]
+        if getattr(self, "_virtual_shift", False):
+            result.append(f"Virtual shift applied to BB to place at isocenter: {self._virtual_shift}")
+        else:
+            result.append(f"Shift to iso: facing gantry, move BB: {self.bb_shift_instructions()}")
+        result += [
+            f"Gantry 3D isocenter diameter: {self.gantry_iso_size:.2f}mm ({num_gantry_imgs}/{num_imgs} images considered)",
+            f"Maximum Gantry RMS deviation (mm): {max(self.axis_rms_deviation((Axis.GANTRY, Axis.REFERENCE))):.2f}mm",
+            f"Maximum EPID RMS deviation (mm): {max(self.axis_rms_deviation(Axis.EPID)):.2f}mm",
+            f"Gantry+Collimator 3D isocenter diameter: {self.gantry_coll_iso_size:.2f}mm ({num_gantry_coll_imgs}/{num_imgs} images considered)",
+            f"Collimator 2D isocenter diameter: {self.collimator_iso_size:.2f}mm ({num_coll_imgs}/{num_imgs} images considered)",
+            f"Maximum Collimator RMS deviation (mm): {max(self.axis_rms_deviation((Axis.COLLIMATOR, Axis.REFERENCE))):.2f}",
+            f"Couch 2D isocenter diameter: {self.couch_iso_size:.2f}mm ({num_couch_imgs}/{num_imgs} images considered)",
+            f"Maximum Couch RMS deviation (mm): {max(self.axis_rms_deviation((Axis.COUCH, Axis.REFERENCE))):.2f}",
+        ]
+        return result if as_list else "\n".join(result)
 
     def _generate_results_data(self) -> WinstonLutzResult:
         """winston_lutz.py:2548-2609"""

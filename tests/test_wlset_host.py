@@ -81,3 +81,35 @@ def test_virtual_shift_matches_reference(name):
         np.testing.assert_allclose(getattr(rd, k), GOLD[f"{v}/{k}"], rtol=0, atol=1e-7, err_msg=k)
     sv = st.bb_shift_vector
     np.testing.assert_allclose([sv.x, sv.y, sv.z], GOLD[f"{v}/bb_shift_vector"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(SETS))
+def test_results_text_follows_the_reference_format(name):
+    """WinstonLutz.results() (winston_lutz.py:2501-2546): the lines, rebuilt here from the scalars the UNMODIFIED reference produced for
+    the same set (golden file), in the reference's format strings."""
+    rows, dpmm = rows_from_golden(name)
+    st = build_set(name, rows, dpmm)
+    g = lambda k: float(GOLD[f"{name}/{k}"])
+    n = int(g("num_total_images"))
+    expect = [
+        "Winston-Lutz Analysis",
+        "=================================",
+        f"Number of images: {n}",
+        f"Maximum 2D CAX->BB distance: {g('max_2d_cax_to_bb_mm'):.2f}mm",
+        f"Median 2D CAX->BB distance: {g('median_2d_cax_to_bb_mm'):.2f}mm",
+        f"Mean 2D CAX->BB distance: {g('mean_2d_cax_to_bb_mm'):.2f}mm",
+        f"Shift to iso: facing gantry, move BB: {str(GOLD[f'{name}/shift_instructions'])}",
+        f"Gantry 3D isocenter diameter: {g('gantry_3d_iso_diameter_mm'):.2f}mm ({int(g('num_gantry_images'))}/{n} images considered)",
+        f"Maximum Gantry RMS deviation (mm): {g('max_gantry_rms_deviation_mm'):.2f}mm",
+        f"Maximum EPID RMS deviation (mm): {g('max_epid_rms_deviation_mm'):.2f}mm",
+        f"Gantry+Collimator 3D isocenter diameter: {g('gantry_coll_3d_iso_diameter_mm'):.2f}mm ({int(g('num_gantry_coll_images'))}/{n} images considered)",
+        f"Collimator 2D isocenter diameter: {g('coll_2d_iso_diameter_mm'):.2f}mm ({int(g('num_coll_images'))}/{n} images considered)",
+        f"Maximum Collimator RMS deviation (mm): {g('max_coll_rms_deviation_mm'):.2f}",
+        f"Couch 2D isocenter diameter: {g('couch_2d_iso_diameter_mm'):.2f}mm ({int(g('num_couch_images'))}/{n} images considered)",
+        f"Maximum Couch RMS deviation (mm): {g('max_couch_rms_deviation_mm'):.2f}",
+    ]
+    assert st.results(as_list=True) == expect
+    assert st.results() == "\n".join(expect)
+    st._is_analyzed = False
+    with pytest.raises(ValueError, match="not analyzed"):
+        st.results()
