@@ -52,6 +52,38 @@ def _is_image_file(path) -> bool:
         return False
 
 
+def retrieve_image_files(path) -> list:
+    """core/image.py:233-241 + core/io.py:146-170: every file below `path` that loads as an image (DICOM or Pillow), sorted."""
+    import os
+
+    found = []
+    for root, _dirs, files in os.walk(str(path)):
+        for name in files:
+            full = os.path.join(root, name)
+            if _is_dicom(full) or _is_image_file(full):
+                found.append(full)
+    return sorted(found)
+
+
+class TemporaryZipDirectory:
+    """core/io.py:87-117: a temporary directory holding the contents of a ZIP archive (path or binary stream)."""
+
+    def __init__(self, zfile):
+        import tempfile
+        import zipfile
+
+        self._tmp = tempfile.TemporaryDirectory()
+        self.name = self._tmp.name
+        with zipfile.ZipFile(zfile) as z:
+            z.extractall(path=self.name)
+
+    def __enter__(self) -> str:
+        return self.name
+
+    def __exit__(self, *exc) -> None:
+        self._tmp.cleanup()
+
+
 def load(path, **kwargs):
     """core/image.py:244-286.  ndarray -> ArrayImage, DICOM -> DicomImage, TIFF/PNG/JPG/BMP -> FileImage."""
     if isinstance(path, BaseImage):

@@ -172,6 +172,15 @@ class Starshot(ResultsDataMixin[StarshotResults]):
         self._result: StarFrameResult | None = None
 
     @classmethod
+    def from_zip(cls, zip_file, **kwargs):
+        """starshot.py:176-195: one image, or several images of one test sequence that are superimposed."""
+        with image.TemporaryZipDirectory(zip_file) as tmp:
+            files = image.retrieve_image_files(tmp)
+            if not files:
+                raise IndexError(f"No valid starshot images were found in {zip_file}")
+            return cls.from_multiple_images(files, **kwargs) if len(files) > 1 else cls(files[0], **kwargs)
+
+    @classmethod
     def from_multiple_images(cls, filepath_list, stretch_each: bool = True, method: str = "sum", **kwargs):
         """starshot.py:148-174: superimpose the images of the individual spokes (``load_multiples``), then construct from the
         composite as the reference does after its in-memory DICOM write / read (``image._resaved``: full-range re-quantisation

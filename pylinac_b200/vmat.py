@@ -226,6 +226,12 @@ class VMATBase(ResultsDataMixin[VMATResult]):
     _result_short_header: str = ""
     text_rotation = 0
 
+    @classmethod
+    def from_zip(cls, path, **kwargs):
+        """vmat.py:288-301: both images from a ZIP archive."""
+        with image.TemporaryZipDirectory(path) as tmp:
+            return cls(image_paths=image.retrieve_image_files(tmp), **kwargs)
+
     def __init__(self, image_paths: Sequence, ground=True, check_inversion=True, **kwargs):
         super().__init__()
         ground = kwargs.pop("ground", False) or ground

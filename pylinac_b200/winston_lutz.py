@@ -507,6 +507,12 @@ class WinstonLutz(ResultsDataMixin[WinstonLutzResult]):
         self._setup(np.stack(frames), axes, dpmm)
 
     @classmethod
+    def from_zip(cls, zfile, **kwargs):
+        """winston_lutz.py:1397-1410: instantiate from a ZIP archive of the DICOM images (frames are read before the directory goes)."""
+        with image.TemporaryZipDirectory(zfile) as tmp:
+            return cls(image.retrieve_image_files(tmp), **kwargs)
+
+    @classmethod
     def from_arrays(cls, frames: np.ndarray, axes, *, dpmm: float):
         self = cls.__new__(cls)
         self._setup(np.asarray(frames), [tuple(float(v) for v in a) for a in axes], float(dpmm))

@@ -165,3 +165,36 @@ def test_batched_ingest_reads_pixels_straight_into_one_array(tmp_path):
     # a header longer than the first read is parsed from the whole file
     h = dicom.read_header(paths[0], head_bytes=64)
     assert h["PixelCount"] == 48 * 40
+
+
+def test_zip_archives_and_image_file_discovery(tmp_path):
+    """core/io.py TemporaryZipDirectory + core/image.py retrieve_image_files, and WinstonLutz.from_zip (winston_lutz.py:1397-1410): the
+    set is built from the DICOM files of the archive (frames and axis angles are read before the temporary directory is removed)."""
+    import zipfile
+
+    from pylinac_b200 import winston_lutz as wl
+
+    rng = np.random.default_rng(8)
+    d = tmp_path / "imgs"
+    d.mkdir()
+    frames, axes = [], [(0.0, 0.0, 0.0), (90.0, 0.0, 0.0), (180.0, 0.0, 0.0)]
+    for i, (g, c, p) in enumerate(axes):
+        a = rng.integers(100, 60000, (32, 32)).astype(np.uint16)
+        frames.append(a)
+        write_dicom(d / f"wl{i}.dcm", a, gantry=g, coll=c, couch=p)
+    (d / "notes.txt").write_text("not an image")
+    z = tmp_path / "set.zip"
+    with zipfile.ZipFile(z, "w") as zf:
+        for f in sorted(d.iterdir()):
+            zf.write(f, arcname=f"sub/{f.name}")
+    with image.TemporaryZipDirectory(str(z)) as tmp:
+        files = image.retrieve_image_files(tmp)
+        assert [f.rsplit("/", 1)[1] for f in files] == ["wl0.dcm", "wl1.dcm", "wl2.dcm"]
+    import os
+    assert not os.path.exists(tmp)
+    st = wl.WinstonLutz.from_zip(str(z))
+    assert st._axes == axes and st._frames.shape == (3, 32, 32)
+    for k in range(3):
+        np.testing.assert_array_equal(st._frames[k], frames[k])
+    with open(z, "rb") as fh:                       # binary stream, like the reference accepts
+        assert wl.WinstonLutz.from_zip(fh)._frames.shape == (3, 32, 32)
