@@ -439,6 +439,32 @@ class PicketFence(ResultsDataMixin[PFResult]):
         self._warnings: list = []
 
     @classmethod
+    def from_bb_setup(cls, *args, bb_image, bb_diameter: float, **kwargs):
+        """picketfence.py:402-437: find the CAX on a BB setup image first (windowed disk locator around the image centre, bright BB first,
+        dark BB on failure) and override the picket-fence image's central axis with the BB's physical offset from the image centre."""
+        from .metrics.image import SizedDiskLocator
+
+        bb_image = image.load(bb_image)
+
+        def _metrics(invert: bool):
+            return SizedDiskLocator.from_center_physical(expected_position_mm=(0, 0), search_window_mm=(30 + bb_diameter, 30 + bb_diameter),
+                                                         radius_mm=bb_diameter / 2, radius_tolerance_mm=bb_diameter * 0.1 + 1, invert=invert)
+
+        try:
+            caxs = bb_image.compute(metrics=_metrics(invert=True))
+        except ValueError:
+            caxs = bb_image.compute(metrics=_metrics(invert=False))
+        cax_shift = caxs[0] - bb_image.center
+        # physical units: the two images may differ in size / dpmm
+        cax_physical_shift = Point(x=cax_shift.x / bb_image.dpmm, y=cax_shift.y / bb_image.dpmm)
+        image_kwargs = dict(kwargs.pop("image_kwargs", None) or {})
+        image_kwargs["central_axis"] = cax_physical_shift
+        instance = cls(*args, **kwargs, image_kwargs=image_kwargs)
+        instance._from_bb_setup = True
+        instance._bb_image = bb_image
+        return instance
+
+    @classmethod
     def from_multiple_images(cls, path_list, stretch_each: bool = True, method: str = "mean", mlc=MLC.MILLENNIUM, **kwargs):
         """picketfence.py:357-400: superimpose several images (e.g. one picket each) and analyse the composite.  The reference
         combines un-cropped images, writes the composite to an in-memory DICOM (a full-range re-quantisation to the stored dtype,

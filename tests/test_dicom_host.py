@@ -198,3 +198,26 @@ def test_zip_archives_and_image_file_discovery(tmp_path):
         np.testing.assert_array_equal(st._frames[k], frames[k])
     with open(z, "rb") as fh:                       # binary stream, like the reference accepts
         assert wl.WinstonLutz.from_zip(fh)._frames.shape == (3, 32, 32)
+
+
+def test_picketfence_from_bb_setup_overrides_the_cax(monkeypatch):
+    """picketfence.py:402-437: the BB's offset from the centre of the BB image, in mm, becomes the central-axis override of the
+    picket-fence image (the locator itself is a GPU metric: stubbed here; bright BB first, dark BB when that raises)."""
+    from pylinac_b200 import picketfence as pf
+    from pylinac_b200.core.geometry import Point
+
+    bb = image.ArrayImage(np.zeros((200, 300), np.uint16), dpi=25.4 * 2.0, sid=1000)        # dpmm = 2
+    calls = []
+
+    def fake_compute(self, metrics):
+        calls.append(bool(metrics.invert))
+        if metrics.invert:
+            raise ValueError("no bright BB")
+        return [Point(x=149.5 + 10.0, y=99.5 - 4.0)]
+
+    monkeypatch.setattr(image.BaseImage, "compute", fake_compute)
+    frame = np.zeros((64, 64), np.uint16)
+    inst = pf.PicketFence.from_bb_setup(frame, bb_image=bb, bb_diameter=5, image_kwargs={"dpi": 25.4 * 2.56, "sid": 1000})
+    assert calls == [True, False]
+    assert inst._from_bb_setup and inst._bb_image is bb
+    assert (inst._central_axis.x, inst._central_axis.y) == (5.0, -2.0)
